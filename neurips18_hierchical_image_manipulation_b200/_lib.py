@@ -1,0 +1,81 @@
+"""ctypes binding of libhm_b200.so (C ABI in include/hm_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or an entry point is absent the
+import raises, so a GPU box can never silently run a PyTorch/CPU path in place of the CUDA kernels.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhm_b200.so")
+
+HM_ACT_NONE, HM_ACT_RELU, HM_ACT_LRELU, HM_ACT_TANH = 0, 1, 2, 3
+
+
+class HmError(RuntimeError):
+    pass
+
+
+class Operand(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int),
+                ("c", C.c_int), ("cs", C.c_int)]
+
+
+class OutF32(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("h_off", C.c_int),
+                ("w_off", C.c_int), ("c_off", C.c_int)]
+
+
+class OutBF16(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+                ("h_off", C.c_int), ("w_off", C.c_int), ("c_off", C.c_int)]
+
+
+_vp, _i, _f, _l, _sz = C.c_void_p, C.c_int, C.c_float, C.c_long, C.c_size_t
+_P = C.POINTER
+
+# name -> (restype, argtypes); every symbol include/hm_b200.h declares must be listed here
+# (tests/test_abi.py checks the header against this table and against the .so).
+PROTOTYPES = {
+    "hm_version": (C.c_char_p, []),
+    "hm_last_cuda_error": (_i, []),
+    "hm_pick_bn": (_i, [_i]),
+    "hm_rows_pad": (_i, [_i]),
+    "hm_k_pad": (_i, [_i]),
+    "hm_pack_weight": (_i, [_vp, _i, _i, _i, _l, _l, _l, _vp, _vp, _vp]),
+    "hm_conv_fprop": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),
+                           _P(OutBF16), _vp, _vp]),
+    "hm_conv_dgrad": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),
+                           _P(OutBF16), _vp, _vp]),
+    "hm_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "hm_conv_wgrad": (_i, [_P(Operand), _P(Operand), _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hm_wgrad_unpack": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library handle; raises HmError when it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HmError("libhm_b200.so is not built (%s). Run `python -m neurips18_hierchical_image_manipulation_b200.build`; "
+                      "there is no CPU/PyTorch fallback for the hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise HmError("libhm_b200.so lacks symbol %s" % name) from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        lib = load()
+        raise HmError("%s failed: hm_status=%d (cudaError=%d)" % (what, rc, lib.hm_last_cuda_error()))

@@ -1,0 +1,325 @@
+// hm_conv.cu -- host-side planner + C ABI for the tcgen05 convolution engines (hm_engine.cuh).
+// Every conv of the mask2image hot path (reference: models/Pix2Pix_NET.py:63-101, models/layer_util.py:333-411,
+// models/Discriminator_NET.py:61-118) is lowered here to a tap table + TMA tensor maps; nothing is im2col'ed.
+#include "../../include/hm_b200.h"
+#include "hm_engine.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    else g_last_cuda_error = int(e);
+  });
+  return fn;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// bf16 NHWC tensor [n][h][w][cs] (c valid) -> 4-D map {c, w, h, n}; box = 64 channels x (bw x bh) pixels
+// visited with element stride es (so the box spans bw*es x bh*es input pixels).
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int cs, int bw, int bh, int es) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return HM_ERR_DRIVER;
+  if ((cs & 7) || (reinterpret_cast<uintptr_t>(base) & 15) || bw * es > 256 || bh * es > 256) return HM_ERR_INVALID;
+  cuuint64_t dims[4] = {cuuint64_t(c), cuuint64_t(w), cuuint64_t(h), cuuint64_t(n)};
+  cuuint64_t strides[3] = {cuuint64_t(cs) * 2, cuuint64_t(w) * cs * 2, cuuint64_t(h) * w * cs * 2};
+  cuuint32_t box[4] = {64, cuuint32_t(bw * es), cuuint32_t(bh * es), 1};
+  cuuint32_t estr[4] = {1, cuuint32_t(es), cuuint32_t(es), 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? HM_OK : HM_ERR_TENSORMAP;
+}
+
+// packed weights [rows_total][k_pad] bf16 -> 2-D map, box = 64 (k) x bn rows
+int make_tmap_weight(CUtensorMap* m, const void* base, int rows_total, int k_pad, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return HM_ERR_DRIVER;
+  if ((k_pad & 63) || (reinterpret_cast<uintptr_t>(base) & 15)) return HM_ERR_INVALID;
+  cuuint64_t dims[2] = {cuuint64_t(k_pad), cuuint64_t(rows_total)};
+  cuuint64_t strides[1] = {cuuint64_t(k_pad) * 2};
+  cuuint32_t box[2] = {64, cuuint32_t(bn)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? HM_OK : HM_ERR_TENSORMAP;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// choose the th x tw = `pixels` rectangle that wastes the least area on a (vh x vw) tile space
+void pick_rect(int pixels, int vh, int vw, int max_side, int* tw, int* th) {
+  long best = -1;
+  for (int w = pixels; w >= 8; w >>= 1) {
+    int h = pixels / w;
+    if (w > max_side || h > max_side) continue;
+    long area = long(round_up(vw, w)) * round_up(vh, h);
+    if (best < 0 || area < best) { best = area; *tw = w; *th = h; }
+  }
+}
+
+template <int BN>
+int launch_k(const hm::KParams& p, int num_tiles, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_kgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hm::KCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = true;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_kgemm_kernel<BN><<<grid, hm::kEngineThreads, hm::KCfg<BN>::SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+int launch_k_bn(int bn, const hm::KParams& p, int num_tiles, cudaStream_t st) {
+  switch (bn) {
+    case 16: return launch_k<16>(p, num_tiles, st);
+    case 32: return launch_k<32>(p, num_tiles, st);
+    case 64: return launch_k<64>(p, num_tiles, st);
+    case 128: return launch_k<128>(p, num_tiles, st);
+    case 256: return launch_k<256>(p, num_tiles, st);
+  }
+  return HM_ERR_INVALID;
+}
+
+template <int NB>
+int launch_mn(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_mngemm_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hm::MNCfg<NB>::SMEM_BYTES);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = true;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_mngemm_kernel<NB><<<grid, hm::kEngineThreads, hm::MNCfg<NB>::SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+struct Tap { int dw, dh, slab; };
+
+// Common back end of fprop / dgrad: one K-engine launch per output parity class.
+int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad, const float* bias,
+                 const Tap* taps, int n_taps, int in_stride, int valid_h, int valid_w, int out_sh, int out_sw,
+                 int out_oh, int out_ow, int Cout, int act, float slope, const hm_out_f32* out32,
+                 const hm_out_bf16* out16, int* err_flag, cudaStream_t st) {
+  if (n_taps <= 0 || valid_h <= 0 || valid_w <= 0) return HM_OK;
+  const int bn = hm_pick_bn(Cout);
+  if (rows_pad % bn || rows_pad < Cout || (k_pad & 63)) return HM_ERR_INVALID;
+  const bool a_lo = x->lo != nullptr, b_lo = w_lo != nullptr;
+  const int prods = 1 + (a_lo ? 1 : 0) + (b_lo ? 1 : 0);
+  if (n_taps * prods > hm::kMaxEntries) return HM_ERR_INVALID;
+
+  hm::KParams p;
+  std::memset(&p, 0, sizeof(p));
+  int tw = 128, th = 1;
+  pick_rect(128, valid_h, valid_w, 256 / in_stride, &tw, &th);
+  int rc;
+  if ((rc = make_tmap_nhwc(&p.tmA[0], x->hi, x->n, x->h, x->w, x->c, x->cs, tw, th, in_stride))) return rc;
+  if (a_lo && (rc = make_tmap_nhwc(&p.tmA[1], x->lo, x->n, x->h, x->w, x->c, x->cs, tw, th, in_stride))) return rc;
+  // total rows of the weight matrix: one rows_pad slab per tap slot referenced
+  int max_slab = 0;
+  for (int t = 0; t < n_taps; ++t) max_slab = std::max(max_slab, taps[t].slab);
+  const int rows_total = (max_slab + 1) * rows_pad;
+  if ((rc = make_tmap_weight(&p.tmB[0], w_hi, rows_total, k_pad, bn))) return rc;
+  if (b_lo && (rc = make_tmap_weight(&p.tmB[1], w_lo, rows_total, k_pad, bn))) return rc;
+
+  int ne = 0;
+  for (int t = 0; t < n_taps; ++t) {
+    const int pa[3] = {0, 1, 0}, pb[3] = {0, 0, 1};
+    for (int q = 0; q < 3; ++q) {
+      if (q == 1 && !a_lo) continue;
+      if (q == 2 && !b_lo) continue;
+      hm::KEntry& e = p.entries[ne++];
+      e.a_plane = int8_t(pa[q]); e.b_plane = int8_t(pb[q]);
+      e.dw = int16_t(taps[t].dw); e.dh = int16_t(taps[t].dh); e.pad_ = 0;
+      e.b_row = taps[t].slab * rows_pad;
+    }
+  }
+  p.n_entries = ne;
+  p.chunks = k_pad / 64;
+  p.tiles_w = (valid_w + tw - 1) / tw;
+  p.tiles_h = (valid_h + th - 1) / th;
+  p.n_img = x->n;
+  p.n_tiles_n = rows_pad / bn;
+  p.tw_log2 = ilog2(tw);
+  p.th = th;
+  p.in_stride = in_stride;
+  p.cout = Cout;
+  p.valid_h = valid_h; p.valid_w = valid_w;
+  p.out_sh = out_sh; p.out_sw = out_sw; p.out_oh = out_oh; p.out_ow = out_ow;
+  if (out32 && out32->ptr) {
+    p.o32 = out32->ptr; p.o32_H = out32->H; p.o32_W = out32->W; p.o32_C = out32->C;
+    p.o32_hoff = out32->h_off; p.o32_woff = out32->w_off; p.o32_coff = out32->c_off;
+  }
+  if (out16 && out16->hi) {
+    p.ohi = static_cast<__nv_bfloat16*>(out16->hi); p.olo = static_cast<__nv_bfloat16*>(out16->lo);
+    p.o16_H = out16->H; p.o16_W = out16->W; p.o16_C = out16->C;
+    p.o16_hoff = out16->h_off; p.o16_woff = out16->w_off; p.o16_coff = out16->c_off;
+  }
+  p.bias = bias; p.act = act; p.slope = slope; p.err = err_flag;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
+  return launch_k_bn(bn, p, num_tiles, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hm_version(void) { return "hm_b200 0.1 (sm_100a, tcgen05+TMA)"; }
+int hm_last_cuda_error(void) { return g_last_cuda_error; }
+
+int hm_pick_bn(int rows) {
+  if (rows > 128) return 256;
+  if (rows > 64) return 128;
+  if (rows > 32) return 64;
+  if (rows > 16) return 32;
+  return 16;
+}
+int hm_rows_pad(int rows) { return round_up(rows, hm_pick_bn(rows)); }
+int hm_k_pad(int k) { return round_up(k, 64); }
+
+int hm_conv_fprop(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
+                  const float* bias, int KH, int KW, int stride, int pad, int Hout, int Wout, int Cout, int act,
+                  float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream) {
+  if (!x || !x->hi || !w_hi || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
+  Tap taps[64];
+  int nt = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) taps[nt++] = Tap{kw - pad, kh - pad, kh * KW + kw};
+  return run_k_engine(x, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, stride, Hout, Wout, 1, 1, 0, 0, Cout, act, slope,
+                      out32, out16, err_flag, static_cast<cudaStream_t>(stream));
+}
+
+int hm_conv_dgrad(const hm_operand* dy, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
+                  const float* bias, int KH, int KW, int stride, int pad, int Hout, int Wout, int Cout, int act,
+                  float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream) {
+  if (!dy || !dy->hi || !w_hi || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Tap taps[64];
+  if (stride == 1) {
+    int nt = 0;
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kw = 0; kw < KW; ++kw) taps[nt++] = Tap{pad - kw, pad - kh, kh * KW + kw};
+    return run_k_engine(dy, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, 1, Hout, Wout, 1, 1, 0, 0, Cout, act, slope,
+                        out32, out16, err_flag, st);
+  }
+  // stride 2: four output parity classes, each a dense unit-stride tap-GEMM over its own tap subset
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int nt = 0;
+      for (int kh = 0; kh < KH; ++kh) {
+        if ((ph + pad - kh) & 1) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          if ((pw + pad - kw) & 1) continue;
+          taps[nt++] = Tap{(pw + pad - kw) / 2, (ph + pad - kh) / 2, kh * KW + kw};
+        }
+      }
+      if (nt == 0) return HM_ERR_INVALID;  // every class must be produced (3x3/4x4 stride-2 always have taps)
+      const int vh = (Hout - ph + 1) / 2, vw = (Wout - pw + 1) / 2;
+      // NOTE: all slabs must be addressable -> rows_total is sized from the largest slab id used by this class;
+      // the caller's buffer always holds KH*KW slabs.
+      int rc = run_k_engine(dy, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, 1, vh, vw, 2, 2, ph, pw, Cout, act, slope,
+                            out32, out16, err_flag, st);
+      if (rc) return rc;
+    }
+  return HM_OK;
+}
+
+size_t hm_wgrad_ws_bytes(int KH, int KW, int cp, int cq) {
+  return size_t(KH) * KW * round_up(cp, 64) * size_t(round_up(cq, 64)) * sizeof(float);
+}
+
+int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int stride, int pad, float* G_ws,
+                  int* err_flag, void* stream) {
+  if (!P || !Q || !P->hi || !Q->hi || !G_ws || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
+  if (P->n != Q->n) return HM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hm::MNParams p;
+  std::memset(&p, 0, sizeof(p));
+  int tw = 64, th = 1;
+  pick_rect(64, Q->h, Q->w, 256 / stride, &tw, &th);
+  int rc;
+  if ((rc = make_tmap_nhwc(&p.tmP[0], P->hi, P->n, P->h, P->w, P->c, P->cs, tw, th, stride))) return rc;
+  if (P->lo && (rc = make_tmap_nhwc(&p.tmP[1], P->lo, P->n, P->h, P->w, P->c, P->cs, tw, th, stride))) return rc;
+  if ((rc = make_tmap_nhwc(&p.tmQ[0], Q->hi, Q->n, Q->h, Q->w, Q->c, Q->cs, tw, th, 1))) return rc;
+  if (Q->lo && (rc = make_tmap_nhwc(&p.tmQ[1], Q->lo, Q->n, Q->h, Q->w, Q->c, Q->cs, tw, th, 1))) return rc;
+  int np = 0;
+  p.pairP[np] = 0; p.pairQ[np] = 0; ++np;
+  if (P->lo) { p.pairP[np] = 1; p.pairQ[np] = 0; ++np; }
+  if (Q->lo) { p.pairP[np] = 0; p.pairQ[np] = 1; ++np; }
+  p.n_pairs = np;
+  p.tiles_w = (Q->w + tw - 1) / tw;
+  p.tiles_h = (Q->h + th - 1) / th;
+  p.n_img = Q->n;
+  p.tw_log2 = ilog2(tw);
+  p.th = th;
+  p.sP = stride; p.sQ = 1;
+  p.m_tapped = 1;
+  p.upt_m = round_up(P->c, 64) / 64;
+  p.n_units = round_up(Q->c, 64) / 64;
+  p.upt_n = p.n_units;
+  p.m_units = KH * KW * p.upt_m;
+  const int nb = p.n_units >= 3 ? 4 : p.n_units;
+  p.n_m_tiles = (p.m_units + 1) / 2;
+  p.n_n_tiles = (p.n_units + nb - 1) / nb;
+  p.ktiles = p.tiles_w * p.tiles_h * p.n_img;
+  const int base_tiles = p.n_m_tiles * p.n_n_tiles;
+  int splits = 1;
+  if (base_tiles < 2 * sm_count()) splits = (2 * sm_count() + base_tiles - 1) / base_tiles;
+  splits = std::max(1, std::min(splits, p.ktiles / 4 > 0 ? p.ktiles / 4 : 1));
+  // make every split non-empty
+  { int per = (p.ktiles + splits - 1) / splits; splits = (p.ktiles + per - 1) / per; }
+  p.splits = splits;
+  p.dwP0 = p.dhP0 = p.dwQ0 = p.dhQ0 = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) { p.tap_dw[kh * KW + kw] = int16_t(kw - pad); p.tap_dh[kh * KW + kw] = int16_t(kh - pad); }
+  p.G = G_ws;
+  p.ldG = p.n_units * 64;
+  p.use_atomic = splits > 1;
+  p.err = err_flag;
+  if (p.use_atomic) {
+    cudaError_t e = cudaMemsetAsync(G_ws, 0, size_t(p.m_units) * 64 * p.ldG * sizeof(float), st);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  }
+  const int num_tiles = base_tiles * splits;
+  switch (nb) {
+    case 1: return launch_mn<1>(p, num_tiles, st);
+    case 2: return launch_mn<2>(p, num_tiles, st);
+    default: return launch_mn<4>(p, num_tiles, st);
+  }
+}
+
+}  // extern "C"
