@@ -1,0 +1,136 @@
+"""CPU tests: oracle/model.py (the restatement) against golden vectors produced by the reference's own
+classes (oracle/make_golden.py).  fp32 on both sides; tolerances are accumulation-order noise only."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as O
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    sd = OrderedDict((k[3:], torch.from_numpy(z[k])) for k in z.files if k.startswith("w::"))
+    grads = OrderedDict((k[3:], torch.from_numpy(z[k])) for k in z.files if k.startswith("g::"))
+    return z, sd, grads
+
+
+def close(a, b, tol):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert err < tol, "rel err %.3e >= %.1e" % (err, tol)
+
+
+def test_global_generator_config1(golden_dir):
+    """BASELINE config #1: GlobalGenerator(38,3,64,1,1) 128x256 batch 1."""
+    z, sd, _ = load(golden_dir, "g_config1.npz")
+    lab = torch.from_numpy(z["label"].astype(np.float32))
+    img = torch.from_numpy(z["image"])
+    onehot = torch.zeros(1, 35, 128, 256).scatter_(1, lab.long(), 1.0)
+    y = O.global_generator_forward(sd, torch.cat((onehot, img), 1), 1, 1)
+    close(y, z["out"], 2e-5)
+
+
+def test_global_generator_small_gate_and_grads(golden_dir):
+    z, sd, grads = load(golden_dir, "g_small.npz")
+    par = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    y = O.global_generator_forward(par, torch.from_numpy(z["x"]), 2, 2, mask=torch.from_numpy(z["mask"]),
+                                   use_output_gate=True)
+    close(y.detach(), z["out"], 2e-5)
+    g = torch.autograd.grad((y * torch.from_numpy(z["cot"])).sum(), list(par.values()))
+    for (k, _), gi in zip(par.items(), g):
+        if k.endswith("bias") and float(grads[k].abs().max()) < 1e-4:
+            continue  # biases in front of InstanceNorm: analytically zero gradient, numerically noise
+        close(gi, grads[k], 2e-3)
+
+
+def test_local_enhancer(golden_dir):
+    z, sd, _ = load(golden_dir, "local_small.npz")
+    y = O.local_enhancer_forward(sd, torch.from_numpy(z["x"]), 2, 2, 1, 2)
+    close(y, z["out"], 2e-5)
+
+
+def test_multiscale_discriminator_taps_losses_grads(golden_dir):
+    z, sd, grads = load(golden_dir, "d_small.npz")
+    par = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    x = torch.from_numpy(z["x"]).requires_grad_(True)
+    taps = O.multiscale_discriminator_forward(par, x, 3, 3)
+    assert len(taps) == 3 and all(len(t) == 5 for t in taps)
+    for i in range(3):
+        for j in range(5):
+            close(taps[i][j].detach(), z["tap_%d_%d" % (i, j)], 5e-5)
+    l_real, l_fake = O.gan_loss(taps, True), O.gan_loss(taps, False)
+    assert abs(float(l_real) - float(z["loss_real"])) < 1e-5 * abs(float(z["loss_real"]))
+    assert abs(float(l_fake) - float(z["loss_fake"])) < 1e-5 * abs(float(z["loss_fake"]))
+    g = torch.autograd.grad(l_real, list(par.values()) + [x])
+    close(g[-1], z["gx"], 2e-3)
+    for (k, _), gi in zip(par.items(), g[:-1]):
+        if k.endswith("bias") and float(grads[k].abs().max()) < 1e-6:
+            continue
+        close(gi, grads[k], 2e-3)
+
+
+def test_resnet_block(golden_dir):
+    z, sd, _ = load(golden_dir, "resblock.npz")
+    x = torch.from_numpy(z["x"])
+    r = torch.nn.functional.conv2d(O.reflect_pad(x, 1), sd["conv_block.1.weight"], sd["conv_block.1.bias"])
+    r = torch.relu(O.instance_norm(r))
+    r = torch.nn.functional.conv2d(O.reflect_pad(r, 1), sd["conv_block.5.weight"], sd["conv_block.5.bias"])
+    close(x + O.instance_norm(r), z["out"], 2e-5)
+
+
+def test_avgpool_pyramid(golden_dir):
+    z = np.load(os.path.join(golden_dir, "avgpool.npz"))
+    close(O.avgpool_3s2(torch.from_numpy(z["x"])), z["out"], 1e-6)
+
+
+def test_spectral_norm_power_iteration(golden_dir):
+    z = np.load(os.path.join(golden_dir, "sn.npz"))
+    sigma, u = O.max_singular_value(torch.from_numpy(z["W"]), torch.from_numpy(z["u"]), 1)
+    close(sigma, z["sigma"], 1e-5)
+    close(u, z["u_out"], 1e-5)
+
+
+def test_vgg19_topology_matches_torchvision():
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(0)
+    feats = tv.models.vgg19(weights=None).features[:30].eval()
+    sd = OrderedDict()
+    for idx, _, _ in O.VGG19_CONVS:
+        k = "slice%d.%d." % (O.VGG19_SLICE_OF[idx], idx)
+        sd[k + "weight"] = feats[idx].weight.detach()
+        sd[k + "bias"] = feats[idx].bias.detach()
+    x = torch.randn(1, 3, 32, 48)
+    taps = O.vgg19_forward(sd, x)
+    cuts = [2, 7, 12, 21, 30]  # models/layer_util.py:390-399
+    h = x
+    with torch.no_grad():
+        prev = 0
+        for t, c in enumerate(cuts):
+            for i in range(prev, c):
+                h = feats[i](h)
+            prev = c
+            close(taps[t], h, 1e-5)
+
+
+def test_model_forward_and_step_run():
+    """The model-level restatement has no reference run to compare with (the class hard-codes .cuda(),
+    SURVEY 8(c)); check its structural identities instead."""
+    opt = O.Opt(ngf=4, n_downsample_global=2, n_blocks_global=1, ndf=4, num_D=2, label_nc=5)
+    torch.manual_seed(0)
+    from tests.util_weights import random_g_sd, random_d_sd
+    g_sd, d_sd = random_g_sd(5 + 3, 3, 4, 2, 1), random_d_sd(5 + 3 + 3, 4, 3, 2)
+    vgg = O.vgg19_random_state_dict()
+    b = O.synthetic_batch(2, 32, 32, label_nc=5)
+    losses, fake, ex = O.model_forward(opt, g_sd, d_sd, vgg, b["label"], b["inst"], b["image"], b["mask_in"])
+    assert fake.shape == (2, 3, 32, 32) and len(losses) == 5
+    # D_fake is evaluated on fake.detach(): same value as the G-side GAN tap but with target 0
+    assert torch.isfinite(torch.stack([l.detach() for l in losses])).all()
+    # cond image is zero inside the box, equal to the image outside (model :165-166)
+    m = b["mask_in"].bool().expand(-1, 3, -1, -1)
+    assert float(ex["cond"][m].abs().max()) == 0.0
+    assert torch.equal(ex["cond"][~m], b["image"][~m])
+    ls, fk, gG, gD, st = O.train_step(opt, g_sd, d_sd, vgg, b)
+    assert st["step"] == 1 and all(torch.isfinite(v).all() for v in gG.values())
