@@ -99,6 +99,81 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
                   int* err_flag, void* stream);
 int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* dst, int accumulate, void* stream);
 
+/* ---- HBM-bound kernels (hm_elementwise.cu) --------------------------------------------------------------
+ * fp32 tensors are dense NHWC; "operand" outputs are bf16 (hi, lo) planes with channel stride *_cs (multiple of 8),
+ * lo may be NULL. */
+
+/* K11. Pix2PixHDModel_condImg.encode_input + get_edges (models/pix2pixHD_condImg_model.py:144-174, 285-291).
+ * label / inst / mask_in are fp32 [B,1,H,W], image fp32 [B,3,H,W] (NCHW, as the reference's data loader emits them,
+ * already on the device); inst == NULL means --no_instance.  Writes
+ *   g  : generator input operand [B, H+2*g_border, W+2*g_border, g_cs], channels one-hot | edge | (1-mask)*image,
+ *        ReflectionPad2d(g_border) materialised (Pix2Pix_NET.py:74);
+ *   d  : (optional) discriminator input operand [2B,H,W,d_cs]: conditioning channels in both halves, the real
+ *        image in channels [cin, cin+3) of the second half (the fake half is filled by hm_finish_fake);
+ *   v  : (optional) VGG input operand [2B,H,W,v_cs]: real image in the second half. */
+int hm_encode_input(const float* label, const float* inst, const float* image, const float* mask_in, int B, int H,
+                    int W, int label_nc, void* g_hi, void* g_lo, int g_cs, int g_border, void* d_hi, void* d_lo,
+                    int d_cs, void* v_hi, void* v_lo, int v_cs, void* stream);
+
+/* K7. nn.InstanceNorm2d(C, affine=False) (models/layer_util.py:19-26), split in statistics / apply / backward.
+ * ws: hm_in_ws_bytes(N, H*W, C) bytes of scratch. */
+size_t hm_in_ws_bytes(int N, int HW, int C);
+int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, float* mean, float* rstd, void* stream);
+/* out = act((y-mean)*rstd) [+ skip]; mean == NULL skips the normalisation.  Emits the dense fp32 result (optional)
+ * and/or the bf16 operand with a materialised border (reflect != 0: ReflectionPad2d(border), else zeros). */
+int hm_in_apply(const float* y, const float* mean, const float* rstd, const float* skip, int N, int H, int W, int C,
+                int act, float slope, float* out32, void* o_hi, void* o_lo, int o_cs, int border, int reflect,
+                void* stream);
+/* Backward of [InstanceNorm] -> act:  dz = fold_reflect(g1) + g2 + l1coef*sign(z - tref);
+ * dy = IN'(dz * act'(.)).  g1 is fp32 [N,H+2b,W+2b,g1_ld] (read at channel offset g1_coff), g2 dense [N,H,W,C];
+ * act' is taken from y (with stats) if given, else z, else the sign of the bf16 plane mask_hi.  Result: operand
+ * [N,H,W,o_cs] and/or dense fp32. */
+int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float* z, const void* mask_hi, int mask_cs,
+              const float* g1, int g1_border, int g1_ld, int g1_coff, const float* g2, const float* tref, float l1coef,
+              int N, int H, int W, int C, int act, float slope, float* ws, void* o_hi, void* o_lo, int o_cs,
+              float* out32, void* stream);
+/* out = base + fold_reflect(g_padded)  (residual skip gradient, layer_util.py:376-378); base may be NULL */
+int hm_fold_add(const float* g_padded, int border, int N, int H, int W, int C, const float* base, float* out,
+                void* stream);
+
+/* K8. nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (Discriminator_NET.py:31-32, Pix2Pix_NET.py:45)
+ * on operands, and its adjoint accumulated into channels [c0,c1) of a finer fp32 gradient. */
+int hm_avgpool3s2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, void* o_hi, void* o_lo, void* stream);
+int hm_avgpool3s2_bwd(const float* g_coarse, int N, int Ho, int Wo, int ld_coarse, float* g_fine, int H, int W,
+                      int ld_fine, int c0, int c1, void* stream);
+/* VGG19 MaxPool2d(2,2) (torchvision features, layer_util.py:384-399) and its adjoint (first maximum wins). */
+int hm_maxpool2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, void* o_hi, void* o_lo, void* stream);
+int hm_maxpool2_bwd(const float* g, int N, int H, int W, int C, const void* a_hi, const void* a_lo, int cs, float* dz,
+                    void* stream);
+
+/* K9. loss reductions into fp64 accumulators: *acc += coef*sum|a-b| (nn.L1Loss, losses.py:75-82 and
+ * pix2pixHD_condImg_model.py:235-251) and *acc += coef*sum (a-target)^2 (LSGAN nn.MSELoss, losses.py:40-50);
+ * hm_mse_grad writes scale*(y-target) as an operand (the caller folds 2*coef/numel into scale). */
+int hm_l1_sum(const float* a, const float* b, long n, double coef, double* acc, void* stream);
+int hm_mse_sum(const float* a, long n, float target, double coef, double* acc, void* stream);
+int hm_mse_grad(const float* y, long P, int C, float target, float scale, void* o_hi, void* o_lo, int o_cs, void* stream);
+
+/* K12. generator head epilogue: output gate (Pix2Pix_NET.py:96-99), NCHW fp32 copy for the caller, fake image into
+ * channels [d_coff, d_coff+3) of the first half of the D operand and into the first half of the VGG operand;
+ * hm_fake_bwd is its adjoint: d/d(pre-tanh) of everything that reads the fake image. */
+int hm_finish_fake(const float* t, const float* image, const float* mask, int use_gate, int B, int H, int W,
+                   float* fake_nchw, void* d_hi, void* d_lo, int d_cs, int d_coff, void* v_hi, void* v_lo, int v_cs,
+                   void* stream);
+int hm_fake_bwd(const float* t, const float* mask, int use_gate, const float* gD, int gD_ld, int gD_coff,
+                const float* gV, int gV_ld, const float* real_nchw, float rec_coef, int B, int H, int W, void* o_hi,
+                void* o_lo, int o_cs, void* stream);
+
+/* misc: dense fp32 [P][ld] (channels [coff, coff+C)) * scale -> operand; per-channel sums (bias gradients). */
+int hm_f32_to_operand(const float* x, long P, int C, int ld, int coff, float scale, void* o_hi, void* o_lo, int o_cs,
+                      void* stream);
+int hm_colsum(const float* x, long P, int C, float* out, int accumulate, void* stream);
+int hm_colsum_operand(const void* hi, const void* lo, long P, int C, int cs, float* out, int accumulate, void* stream);
+
+/* K10. torch.optim.Adam(lr, betas=(beta1, 0.999)) step (pix2pixHD_condImg_model.py:135,139) over a flat fp32
+ * segment; grad_scale multiplies the gradient first (1/world_size after a sum-allreduce). step is 1-based. */
+int hm_adam_step(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                 float eps, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

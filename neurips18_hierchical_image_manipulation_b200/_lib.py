@@ -50,6 +50,26 @@ PROTOTYPES = {
     "hm_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "hm_conv_wgrad": (_i, [_P(Operand), _P(Operand), _i, _i, _i, _i, _vp, _vp, _vp]),
     "hm_wgrad_unpack": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "hm_encode_input": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "hm_in_ws_bytes": (_sz, [_i, _i, _i]),
+    "hm_in_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "hm_in_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hm_in_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _i, _i, _i, _i, _f, _vp, _vp,
+                       _vp, _i, _vp, _vp]),
+    "hm_fold_add": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hm_avgpool3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hm_avgpool3s2_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "hm_maxpool2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hm_maxpool2_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "hm_l1_sum": (_i, [_vp, _vp, _l, C.c_double, _vp, _vp]),
+    "hm_mse_sum": (_i, [_vp, _l, _f, C.c_double, _vp, _vp]),
+    "hm_mse_grad": (_i, [_vp, _l, _i, _f, _f, _vp, _vp, _i, _vp]),
+    "hm_finish_fake": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "hm_fake_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "hm_f32_to_operand": (_i, [_vp, _l, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
+    "hm_colsum": (_i, [_vp, _l, _i, _vp, _i, _vp]),
+    "hm_colsum_operand": (_i, [_vp, _vp, _l, _i, _i, _vp, _i, _vp]),
+    "hm_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,1016 @@
+// hm_elementwise.cu -- the HBM-bound kernels of the mask2image hot path (everything that is not a
+// tensor-core contraction): input encoding, InstanceNorm statistics / apply / backward, pooling,
+// loss reductions and gradients, output gate, fused Adam.  All tensors are NHWC; one thread owns a
+// group of 8 consecutive channels of one pixel so that fp32 traffic is 2 x 16 B and bf16 traffic 16 B
+// per access, fully coalesced across a warp.  Reference lines are cited per kernel.
+#include "../../include/hm_b200.h"
+#include "hm_ptx.cuh"
+
+#include <algorithm>
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kBlock = 256;
+inline int grid_for(long items, int block = kBlock, int max_blocks = 148 * 32) {
+  long g = (items + block - 1) / block;
+  return int(std::max<long>(1, std::min<long>(g, max_blocks)));
+}
+#define HM_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? HM_OK : HM_ERR_LAUNCH)
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // index into [0,n) of reflect-padded coordinate i
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// load 8 consecutive fp32 channels [c, c+8) of a pixel whose channel count is C (row pointer p); zeros past C
+__device__ __forceinline__ void load8(const float* __restrict__ p, int c, int C, float (&v)[8]) {
+  if (((C & 3) == 0) && c + 8 <= C) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (c + i < C) ? __ldg(p + c + i) : 0.f;
+  }
+}
+__device__ __forceinline__ void store8(float* __restrict__ p, int c, int C, const float (&v)[8]) {
+  if (((C & 3) == 0) && c + 8 <= C) {
+    *reinterpret_cast<float4*>(p + c) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (c + i < C) p[c + i] = v[i];
+  }
+}
+// bf16 operand planes: channel stride cs is a multiple of 8, so a group of 8 is one aligned 16 B word
+__device__ __forceinline__ void store_op8(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t off, const float (&v)[8]) {
+  alignas(16) bf16 h[8];
+  alignas(16) bf16 l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hm::split_bf16(v[i], h[i], l[i]);
+  *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+}
+__device__ __forceinline__ void load_op8(const bf16* __restrict__ hi, const bf16* __restrict__ lo, size_t off, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const bf16* h = reinterpret_cast<const bf16*>(&a);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(h[i]);
+  if (lo) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    const bf16* l = reinterpret_cast<const bf16*>(&b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += __bfloat162float(l[i]);
+  }
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == HM_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == HM_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == HM_ACT_TANH) return tanhf(v);
+  return v;
+}
+__device__ __forceinline__ float act_grad(float pre_sign_src, int act, float slope) {
+  // derivative of relu / lrelu from anything with the sign of the pre-activation
+  if (act == HM_ACT_RELU) return pre_sign_src > 0.f ? 1.f : 0.f;
+  if (act == HM_ACT_LRELU) return pre_sign_src > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// ================================================================================================
+// K11  encode_input  (models/pix2pixHD_condImg_model.py:144-174, get_edges :285-291)
+// one thread per (padded) generator-input pixel: one-hot(label) | edge(inst) | (1-mask)*image
+// ================================================================================================
+__global__ void encode_kernel(const float* __restrict__ label, const float* __restrict__ inst,
+                              const float* __restrict__ image, const float* __restrict__ mask, int B, int H, int W,
+                              int label_nc, bf16* g_hi, bf16* g_lo, int g_cs, int gb, bf16* d_hi, bf16* d_lo, int d_cs,
+                              bf16* v_hi, bf16* v_lo, int v_cs) {
+  const int Hp = H + 2 * gb, Wp = W + 2 * gb;
+  const long total = long(B) * Hp * Wp;
+  const int n_cond = label_nc + (inst ? 1 : 0);
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int wp = int(i % Wp);
+    const int hp = int((i / Wp) % Hp);
+    const int n = int(i / (long(Wp) * Hp));
+    const int h = reflect_idx(hp - gb, H), w = reflect_idx(wp - gb, W);
+    const bool interior = (hp - gb == h) && (wp - gb == w);
+    const long pix = (long(n) * H + h) * W + w;
+    const int cls = int(__ldg(label + pix));
+    float edge = 0.f;
+    if (inst) {  // :285-291: 4-neighbour instance boundary
+      const float t = __ldg(inst + pix);
+      bool e = false;
+      if (w > 0) e |= (t != __ldg(inst + pix - 1));
+      if (w < W - 1) e |= (t != __ldg(inst + pix + 1));
+      if (h > 0) e |= (t != __ldg(inst + pix - W));
+      if (h < H - 1) e |= (t != __ldg(inst + pix + W));
+      edge = e ? 1.f : 0.f;
+    }
+    const float m = __ldg(mask + pix);
+    float img[3], cond[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      img[c] = __ldg(image + (long(n) * 3 + c) * H * W + long(h) * W + w);
+      cond[c] = (1.f - m) * img[c];  // NULLVAL == 0 (:18, :165-166)
+    }
+    // generator operand (all cs channels written; padding channels are zero)
+    const size_t goff = (size_t(n) * Hp * Wp + size_t(hp) * Wp + wp) * g_cs;
+    for (int c0 = 0; c0 < g_cs; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float x = 0.f;
+        if (c < label_nc) x = (c == cls) ? 1.f : 0.f;
+        else if (inst && c == label_nc) x = edge;
+        else if (c >= n_cond && c < n_cond + 3) x = cond[c - n_cond];
+        v[j] = x;
+      }
+      store_op8(g_hi, g_lo, goff + c0, v);
+    }
+    if (interior && d_hi) {
+      for (int half = 0; half < 2; ++half) {  // half 0 = fake (image channels filled later), 1 = real
+        const size_t doff = ((size_t(n) + size_t(half) * B) * H * W + size_t(h) * W + w) * d_cs;
+        for (int c0 = 0; c0 < d_cs; c0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            float x = 0.f;
+            if (c < label_nc) x = (c == cls) ? 1.f : 0.f;
+            else if (inst && c == label_nc) x = edge;
+            else if (c >= n_cond && c < n_cond + 3) x = cond[c - n_cond];
+            else if (half == 1 && c >= n_cond + 3 && c < n_cond + 6) x = img[c - n_cond - 3];
+            v[j] = x;
+          }
+          store_op8(d_hi, d_lo, doff + c0, v);
+        }
+      }
+    }
+    if (interior && v_hi) {
+      const size_t voff = ((size_t(n) + B) * H * W + size_t(h) * W + w) * v_cs;
+      for (int c0 = 0; c0 < v_cs; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < 3) ? img[c0 + j] : 0.f;
+        store_op8(v_hi, v_lo, voff + c0, v);
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// K7  InstanceNorm2d(affine=False) statistics (models/layer_util.py:19-26): biased variance per (n,c)
+// pass 1: per-block partial (sum, sumsq) ; pass 2: combine in fp64 -> mean, rstd
+// ================================================================================================
+__global__ void in_stats_kernel(const float* __restrict__ y, int HW, int C, int gx_log2, float* __restrict__ partial) {
+  // grid (nblk, N, cgroups); thread (tx = channel quad, ty = pixel lane)
+  const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
+  const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
+  const int n = blockIdx.y, nblk = gridDim.x;
+  const int c4 = blockIdx.z * gx + tx;
+  const bool cvalid = c4 * 4 < C;
+  const int per = (HW + nblk - 1) / nblk;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (cvalid) {
+    const float* base = y + size_t(n) * HW * C + c4 * 4;
+    for (int p = p0 + ty; p < p1; p += rows) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + size_t(p) * C));
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    }
+  }
+  __shared__ float sm[kBlock * 8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sm[threadIdx.x * 8 + i] = s[i]; sm[threadIdx.x * 8 + 4 + i] = q[i]; }
+  __syncthreads();
+  // tree over ty
+  for (int step = rows >> 1; step >= 1; step >>= 1) {
+    if (ty < step) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[threadIdx.x * 8 + i] += sm[(threadIdx.x + step * gx) * 8 + i];
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && cvalid) {
+    float* dst = partial + ((size_t(n) * nblk + blockIdx.x) * 2) * C + c4 * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dst[i] = sm[tx * 8 + i]; dst[C + i] = sm[tx * 8 + 4 + i]; }
+  }
+}
+__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, int N, int nblk, int C, int HW, float eps,
+                                         float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  double s = 0, q = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const float* p = partial + ((size_t(n) * nblk + b) * 2) * C + c;
+    s += p[0]; q += p[C];
+  }
+  const double m = s / HW;
+  double var = q / HW - m * m;
+  if (var < 0) var = 0;
+  mean[i] = float(m);
+  rstd[i] = float(1.0 / sqrt(var + double(eps)));
+}
+
+// ================================================================================================
+// K7  normalise + activation (+ residual) + operand emission with materialised border
+//   out = act((y - mean) * rstd) [+ skip]     (Pix2Pix_NET.py:74-90, layer_util.py:341-378, Discriminator_NET.py:80-90)
+// ================================================================================================
+__global__ void in_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ skip, int N, int H, int W,
+                                int C, int act, float slope, float* __restrict__ out32, bf16* o_hi, bf16* o_lo, int o_cs,
+                                int border, int reflect) {
+  const int Hp = H + 2 * border, Wp = W + 2 * border;
+  const int G = (o_hi ? o_cs : ((C + 7) & ~7)) >> 3;
+  const long total = long(N) * Hp * Wp * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    long r = i / G;
+    const int wp = int(r % Wp); r /= Wp;
+    const int hp = int(r % Hp);
+    const int n = int(r / Hp);
+    const int c = g * 8;
+    int h = hp - border, w = wp - border;
+    bool interior = true, zero = false;
+    if (h < 0 || h >= H || w < 0 || w >= W) {
+      interior = false;
+      if (reflect) { h = reflect_idx(h, H); w = reflect_idx(w, W); } else zero = true;
+    }
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!zero && c < C) {
+      const size_t pix = (size_t(n) * H + h) * W + w;
+      load8(y + pix * C, c, C, v);
+      if (mean) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < C) v[j] = (v[j] - __ldg(mean + n * C + c + j)) * __ldg(rstd + n * C + c + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act, slope);
+      if (skip) {
+        float s[8];
+        load8(skip + pix * C, c, C, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += s[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c + j >= C) v[j] = 0.f;
+      if (interior && out32) store8(out32 + pix * C, c, C, v);
+    }
+    if (o_hi) store_op8(o_hi, o_lo, (size_t(n) * Hp * Wp + size_t(hp) * Wp + wp) * o_cs + c, v);
+  }
+}
+
+// ================================================================================================
+// K7 backward.  dz = fold_reflect(g1) + g2 + l1coef*sign(z - tref);  dyhat = dz * act'(.)
+//   with IN:  dy = rstd * (dyhat - mean(dyhat) - yhat * mean(dyhat*yhat))   else  dy = dyhat
+// ================================================================================================
+struct BwdArgs {
+  const float* y; const float* mean; const float* rstd;   // pre-norm conv output + stats (nullable)
+  const float* z;                                          // post-activation fp32 value (taps), nullable
+  const bf16* mask_hi; int mask_cs;                        // relu mask source when neither y nor z exist
+  const float* g1; int g1_border; int g1_ld; int g1_coff;  // gradient in (reflect-)padded space
+  const float* g2;                                         // dense gradient, same dims as y
+  const float* tref; float l1coef;                         // L1 feature-matching term
+  int N, H, W, C, act; float slope;
+};
+
+__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, int n, int h, int w, int c, float (&dyh)[8], float (&yh)[8]) {
+  const size_t pix = (size_t(n) * a.H + h) * a.W + w;
+  float dz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (a.g1) {
+    const int b = a.g1_border, Hp = a.H + 2 * b, Wp = a.W + 2 * b;
+    int hs[3], ws[3], nh = 1, nw = 1;
+    hs[0] = h + b; ws[0] = w + b;
+    if (b > 0) {  // adjoint of ReflectionPad2d(b): mirrored border cells fold back onto the interior
+      if (h >= 1 && h <= b) hs[nh++] = b - h;
+      if (h >= a.H - 1 - b && h <= a.H - 2) hs[nh++] = b + 2 * (a.H - 1) - h;
+      if (w >= 1 && w <= b) ws[nw++] = b - w;
+      if (w >= a.W - 1 - b && w <= a.W - 2) ws[nw++] = b + 2 * (a.W - 1) - w;
+    }
+    for (int ih = 0; ih < nh; ++ih)
+      for (int iw = 0; iw < nw; ++iw) {
+        float t[8];
+        const float* p = a.g1 + ((size_t(n) * Hp + hs[ih]) * Wp + ws[iw]) * a.g1_ld + a.g1_coff;
+        if (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0)) load8(p, c, a.C, t);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] += t[j];
+      }
+  }
+  if (a.g2) {
+    float t[8];
+    load8(a.g2 + pix * a.C, c, a.C, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] += t[j];
+  }
+  float zv[8];
+  bool have_z = false;
+  if (a.z) { load8(a.z + pix * a.C, c, a.C, zv); have_z = true; }
+  float yv[8];
+  bool have_y = false;
+  if (a.y) {
+    load8(a.y + pix * a.C, c, a.C, yv);
+    have_y = true;
+    if (a.mean) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j < a.C) yv[j] = (yv[j] - __ldg(a.mean + n * a.C + c + j)) * __ldg(a.rstd + n * a.C + c + j);
+    }
+  }
+  if (a.tref) {
+    float t[8];
+    load8(a.tref + pix * a.C, c, a.C, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float zz = have_z ? zv[j] : act_fwd(yv[j], a.act, a.slope);
+      const float d = zz - t[j];
+      dz[j] += a.l1coef * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+    }
+  }
+  float ms[8];
+  if (!have_y && !have_z && a.mask_hi) {
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.mask_hi + pix * a.mask_cs + c));
+    const bf16* mh = reinterpret_cast<const bf16*>(&m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ms[j] = __bfloat162float(mh[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float src = have_y ? yv[j] : (have_z ? zv[j] : (a.mask_hi ? ms[j] : 1.f));
+    dyh[j] = (c + j < a.C) ? dz[j] * act_grad(src, a.act, a.slope) : 0.f;
+    yh[j] = have_y ? yv[j] : 0.f;
+  }
+}
+
+__global__ void in_bwd_reduce_kernel(BwdArgs a, int gx_log2, float* __restrict__ partial) {
+  // same decomposition as in_stats_kernel but channel groups of 8; partial[n][blk][2][C8]
+  const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
+  const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
+  const int n = blockIdx.y, nblk = gridDim.x;
+  const int c = (blockIdx.z * gx + tx) * 8;
+  const bool cvalid = c < a.C;
+  const int HW = a.H * a.W;
+  const int per = (HW + nblk - 1) / nblk;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cvalid) {
+    for (int p = p0 + ty; p < p1; p += rows) {
+      float dyh[8], yh[8];
+      bwd_dyhat(a, n, p / a.W, p % a.W, c, dyh, yh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
+    }
+  }
+  __shared__ float sm[kBlock * 16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sm[threadIdx.x * 16 + j] = s1[j]; sm[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  __syncthreads();
+  for (int step = rows >> 1; step >= 1; step >>= 1) {
+    if (ty < step) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sm[threadIdx.x * 16 + j] += sm[(threadIdx.x + step * gx) * 16 + j];
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && cvalid) {
+    const int C8 = (a.C + 7) & ~7;
+    float* dst = partial + ((size_t(n) * nblk + blockIdx.x) * 2) * C8 + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dst[j] = sm[tx * 16 + j]; dst[C8 + j] = sm[tx * 16 + 8 + j]; }
+  }
+}
+__global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N, int nblk, int C8, int HW,
+                                       float* __restrict__ sums /*[N][2][C8] means*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C8) return;
+  const int n = i / C8, c = i % C8;
+  double s = 0, q = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const float* p = partial + ((size_t(n) * nblk + b) * 2) * C8 + c;
+    s += p[0]; q += p[C8];
+  }
+  sums[(size_t(n) * 2) * C8 + c] = float(s / HW);
+  sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
+}
+__global__ void in_bwd_apply_kernel(BwdArgs a, const float* __restrict__ sums, bf16* o_hi, bf16* o_lo, int o_cs,
+                                    float* __restrict__ out32) {
+  const int G = o_hi ? (o_cs >> 3) : ((a.C + 7) >> 3);
+  const int C8 = (a.C + 7) & ~7;
+  const long total = long(a.N) * a.H * a.W * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    long r = i / G;
+    const int w = int(r % a.W); r /= a.W;
+    const int h = int(r % a.H);
+    const int n = int(r / a.H);
+    const int c = g * 8;
+    float dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < a.C) {
+      float dyh[8], yh[8];
+      bwd_dyhat(a, n, h, w, c, dyh, yh);
+      if (a.mean) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < a.C) {
+            const float m1 = __ldg(sums + (size_t(n) * 2) * C8 + c + j);
+            const float m2 = __ldg(sums + (size_t(n) * 2 + 1) * C8 + c + j);
+            dy[j] = __ldg(a.rstd + n * a.C + c + j) * (dyh[j] - m1 - yh[j] * m2);
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[j] = dyh[j];
+      }
+    }
+    const size_t pix = (size_t(n) * a.H + h) * a.W + w;
+    if (o_hi) store_op8(o_hi, o_lo, pix * o_cs + c, dy);
+    if (out32 && c < a.C) store8(out32 + pix * a.C, c, a.C, dy);
+  }
+}
+
+// ================================================================================================
+// K8  AvgPool2d(3, stride 2, pad 1, count_include_pad=False)  (Discriminator_NET.py:31-32, Pix2Pix_NET.py:45)
+// ================================================================================================
+__global__ void avgpool_kernel(const bf16* __restrict__ i_hi, const bf16* __restrict__ i_lo, int N, int H, int W,
+                               int cs, bf16* o_hi, bf16* o_lo, int Ho, int Wo) {
+  const int G = cs >> 3;
+  const long total = long(N) * Ho * Wo * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    long r = i / G;
+    const int wo = int(r % Wo); r /= Wo;
+    const int ho = int(r % Ho);
+    const int n = int(r / Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int h = 2 * ho + dh;
+      if (h < 0 || h >= H) continue;
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int w = 2 * wo + dw;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load_op8(i_hi, i_lo, ((size_t(n) * H + h) * W + w) * cs + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        ++cnt;
+      }
+    }
+    const float inv = 1.f / float(cnt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    store_op8(o_hi, o_lo, ((size_t(n) * Ho + ho) * Wo + wo) * cs + g * 8, acc);
+  }
+}
+// adjoint, accumulated into the finer gradient for channels [c0, c1)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ gc, int N, int Ho, int Wo, int ldc, float* __restrict__ gf,
+                                   int H, int W, int ldf, int c0, int c1) {
+  const int nc = c1 - c0;
+  const long total = long(N) * H * W * nc;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int c = c0 + int(i % nc);
+    long r = i / nc;
+    const int w = int(r % W); r /= W;
+    const int h = int(r % H);
+    const int n = int(r / H);
+    float acc = 0.f;
+    for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho >= Ho) continue;
+      const int ch = min(2 * ho + 1, H - 1) - max(2 * ho - 1, 0) + 1;
+      for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        const int cw = min(2 * wo + 1, W - 1) - max(2 * wo - 1, 0) + 1;
+        acc += __ldg(gc + ((size_t(n) * Ho + ho) * Wo + wo) * ldc + c) / float(ch * cw);
+      }
+    }
+    gf[((size_t(n) * H + h) * W + w) * ldf + c] += acc;
+  }
+}
+
+// ================================================================================================
+// MaxPool2d(2,2) of the VGG19 tower (torchvision features via layer_util.py:384-399) and its adjoint
+// ================================================================================================
+__global__ void maxpool_kernel(const bf16* __restrict__ i_hi, const bf16* __restrict__ i_lo, int N, int H, int W, int cs,
+                               bf16* o_hi, bf16* o_lo) {
+  const int Ho = H / 2, Wo = W / 2, G = cs >> 3;
+  const long total = long(N) * Ho * Wo * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    long r = i / G;
+    const int wo = int(r % Wo); r /= Wo;
+    const int ho = int(r % Ho);
+    const int n = int(r / Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int dh = 0; dh < 2; ++dh)
+      for (int dw = 0; dw < 2; ++dw) {
+        float v[8];
+        load_op8(i_hi, i_lo, ((size_t(n) * H + 2 * ho + dh) * W + 2 * wo + dw) * cs + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    store_op8(o_hi, o_lo, ((size_t(n) * Ho + ho) * Wo + wo) * cs + g * 8, m);
+  }
+}
+__global__ void maxpool_bwd_kernel(const float* __restrict__ g, int N, int H, int W, int C, const bf16* __restrict__ a_hi,
+                                   const bf16* __restrict__ a_lo, int cs, float* __restrict__ dz) {
+  // one thread per pooled window x 8 channels; writes the 2x2 window of dz (first maximum wins, as ATen)
+  const int Ho = H / 2, Wo = W / 2, G = (C + 7) >> 3;
+  const long total = long(N) * Ho * Wo * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int gq = int(i % G);
+    long r = i / G;
+    const int wo = int(r % Wo); r /= Wo;
+    const int ho = int(r % Ho);
+    const int n = int(r / Ho);
+    const int c = gq * 8;
+    float v[4][8];
+    for (int k = 0; k < 4; ++k)
+      load_op8(a_hi, a_lo, ((size_t(n) * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1)) * cs + c, v[k]);
+    float gg[8];
+    load8(g + ((size_t(n) * Ho + ho) * Wo + wo) * C, c, C, gg);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int a = 0; float m = v[0][j];
+      for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
+      arg[j] = a;
+    }
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (arg[j] == k) ? gg[j] : 0.f;
+      store8(dz + ((size_t(n) * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1)) * C, c, C, o);
+    }
+  }
+}
+
+// ================================================================================================
+// K9  loss reductions: acc[slot] += coef * sum|a-b|   /   coef * sum (a-t)^2     (models/losses.py:40-50,75-82;
+//     pix2pixHD_condImg_model.py:235-251).  fp32 per-thread, fp64 block + global accumulation.
+// ================================================================================================
+__global__ void l1_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, double coef, double* acc) {
+  float s = 0.f;
+  double sd = 0.0;
+  int k = 0;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
+    s += fabsf(__ldg(a + i) - __ldg(b + i));
+    if (++k == 64) { sd += s; s = 0.f; k = 0; }
+  }
+  sd += s;
+  __shared__ double sm[kBlock];
+  sm[threadIdx.x] = sd;
+  __syncthreads();
+  for (int st = kBlock / 2; st >= 1; st >>= 1) {
+    if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(acc, sm[0] * coef);
+}
+__global__ void mse_sum_kernel(const float* __restrict__ a, long n, float target, double coef, double* acc) {
+  float s = 0.f;
+  double sd = 0.0;
+  int k = 0;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
+    const float d = __ldg(a + i) - target;
+    s += d * d;
+    if (++k == 64) { sd += s; s = 0.f; k = 0; }
+  }
+  sd += s;
+  __shared__ double sm[kBlock];
+  sm[threadIdx.x] = sd;
+  __syncthreads();
+  for (int st = kBlock / 2; st >= 1; st >>= 1) {
+    if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(acc, sm[0] * coef);
+}
+// d/dy of coef*mean((y-t)^2) written as a bf16 operand (dense [P][C] fp32 -> [P][cs])
+__global__ void mse_grad_kernel(const float* __restrict__ y, long P, int C, float target, float scale, bf16* o_hi,
+                                bf16* o_lo, int cs) {
+  const int G = cs >> 3;
+  const long total = P * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int c = int(i % G) * 8;
+    const long p = i / G;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C) {
+      load8(y + p * C, c, C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? scale * (v[j] - target) : 0.f;
+    }
+    store_op8(o_hi, o_lo, size_t(p) * cs + c, v);
+  }
+}
+
+// ================================================================================================
+// K12  generator output: gate (Pix2Pix_NET.py:96-99), NCHW copy for the caller, D / VGG operand slots
+// ================================================================================================
+__global__ void finish_fake_kernel(const float* __restrict__ t /*[B,H,W,3] tanh output*/, const float* __restrict__ image,
+                                   const float* __restrict__ mask, int use_gate, int B, int H, int W,
+                                   float* __restrict__ fake_nchw, bf16* d_hi, bf16* d_lo, int d_cs, int d_coff, bf16* v_hi,
+                                   bf16* v_lo, int v_cs) {
+  const long total = long(B) * H * W;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int w = int(i % W);
+    const int h = int((i / W) % H);
+    const int n = int(i / (long(W) * H));
+    float o[3];
+    const float m = use_gate ? __ldg(mask + i) : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = __ldg(t + i * 3 + c);
+      if (use_gate) {
+        const float img = (1.f - m) * __ldg(image + (long(n) * 3 + c) * H * W + long(h) * W + w);  // input[:, -3:] = cond image
+        v = (1.f - m) * img + m * v;
+      }
+      o[c] = v;
+      if (fake_nchw) fake_nchw[(long(n) * 3 + c) * H * W + long(h) * W + w] = v;
+    }
+    if (d_hi) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        bf16 hh, ll;
+        hm::split_bf16(o[c], hh, ll);
+        d_hi[size_t(i) * d_cs + d_coff + c] = hh;
+        if (d_lo) d_lo[size_t(i) * d_cs + d_coff + c] = ll;
+      }
+    }
+    if (v_hi) {
+      for (int c0 = 0; c0 < v_cs; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < 3) ? o[c0 + j] : 0.f;
+        store_op8(v_hi, v_lo, size_t(i) * v_cs + c0, v);
+      }
+    }
+  }
+}
+// d(loss)/d(head pre-activation) = (gD[:, coff:coff+3] + gV[:, :3] + rec term) * gate * (1 - t^2)
+__global__ void fake_bwd_kernel(const float* __restrict__ t, const float* __restrict__ mask, int use_gate,
+                                const float* __restrict__ gD, int gD_ld, int gD_coff, const float* __restrict__ gV, int gV_ld,
+                                const float* __restrict__ real_nchw, float rec_coef, int B, int H, int W, bf16* o_hi,
+                                bf16* o_lo, int o_cs) {
+  const long total = long(B) * H * W;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int w = int(i % W);
+    const int h = int((i / W) % H);
+    const int n = int(i / (long(W) * H));
+    const float m = use_gate ? __ldg(mask + i) : 1.f;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float tv = __ldg(t + i * 3 + c);
+      float g = 0.f;
+      if (gD) g += __ldg(gD + size_t(i) * gD_ld + gD_coff + c);
+      if (gV) g += __ldg(gV + size_t(i) * gV_ld + c);
+      if (rec_coef != 0.f) {
+        const float img = __ldg(real_nchw + (long(n) * 3 + c) * H * W + long(h) * W + w);
+        const float fake = use_gate ? ((1.f - m) * (1.f - m) * img + m * tv) : tv;
+        const float d = fake - img;
+        g += rec_coef * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      }
+      v[c] = g * m * (1.f - tv * tv);
+    }
+    for (int c0 = 0; c0 < o_cs; c0 += 8) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (c0 == 0) ? v[j] : 0.f;
+      store_op8(o_hi, o_lo, size_t(i) * o_cs + c0, o);
+    }
+  }
+}
+
+// dense fp32 [P][C] -> bf16 operand [P][cs]  (and the reverse direction is never needed)
+__global__ void f32_to_op_kernel(const float* __restrict__ x, long P, int C, int ld, int coff, float scale, bf16* o_hi,
+                                 bf16* o_lo, int cs) {
+  const int G = cs >> 3;
+  const long total = P * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int c = int(i % G) * 8;
+    const long p = i / G;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? scale * __ldg(x + p * ld + coff + c + j) : 0.f;
+    store_op8(o_hi, o_lo, size_t(p) * cs + c, v);
+  }
+}
+
+// per-channel sum over pixels of a dense fp32 [P][C] tensor -> bias gradient (accumulate)
+__global__ void colsum_kernel(const float* __restrict__ x, long P, int C, float* __restrict__ out, int accumulate) {
+  // grid.x = channel, block reduces over pixels
+  const int c = blockIdx.x;
+  double s = 0.0;
+  float f = 0.f;
+  int k = 0;
+  for (long p = threadIdx.x; p < P; p += blockDim.x) {
+    f += __ldg(x + p * C + c);
+    if (++k == 64) { s += f; f = 0.f; k = 0; }
+  }
+  s += f;
+  __shared__ double sm[kBlock];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = kBlock / 2; st >= 1; st >>= 1) {
+    if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = (accumulate ? out[c] : 0.f) + float(sm[0]);
+}
+// same, reading a bf16 operand (hi+lo)
+__global__ void colsum_op_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, long P, int C, int cs,
+                                 float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x;
+  double s = 0.0;
+  float f = 0.f;
+  int k = 0;
+  for (long p = threadIdx.x; p < P; p += blockDim.x) {
+    float v = __bfloat162float(hi[p * cs + c]);
+    if (lo) v += __bfloat162float(lo[p * cs + c]);
+    f += v;
+    if (++k == 64) { s += f; f = 0.f; k = 0; }
+  }
+  s += f;
+  __shared__ double sm[kBlock];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = kBlock / 2; st >= 1; st >>= 1) {
+    if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = (accumulate ? out[c] : 0.f) + float(sm[0]);
+}
+
+// ================================================================================================
+// K10  fused Adam over a flat fp32 parameter segment (torch.optim.Adam semantics, lr/betas of
+//      pix2pixHD_condImg_model.py:135,139; no weight decay, no amsgrad)
+// ================================================================================================
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float gscale) {
+  const long n4 = n >> 2;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n4; i += long(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j] * gscale;
+      M[j] = b1 * M[j] + (1.f - b1) * gr;
+      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(V[j]) / bc2_sqrt + eps;
+      P[j] -= (lr / bc1) * (M[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (long i = (n4 << 2) + blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * gscale;
+    const float mj = b1 * m[i] + (1.f - b1) * gr;
+    const float vj = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mj; v[i] = vj;
+    p[i] -= (lr / bc1) * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+  }
+}
+
+// out += fold_reflect(g)  (dense [N,H,W,C] += padded [N,H+2b,W+2b,C]); used for the residual skip gradient
+__global__ void fold_add_kernel(const float* __restrict__ g, int b, int N, int H, int W, int C, const float* __restrict__ base,
+                                float* __restrict__ out) {
+  BwdArgs a{};
+  a.g1 = g; a.g1_border = b; a.g1_ld = C; a.g1_coff = 0; a.g2 = base;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.act = HM_ACT_NONE; a.slope = 0.f;
+  const int G = (C + 7) >> 3;
+  const long total = long(N) * H * W * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int gq = int(i % G);
+    long r = i / G;
+    const int w = int(r % W); r /= W;
+    const int h = int(r % H);
+    const int n = int(r / H);
+    float dyh[8], yh[8];
+    bwd_dyhat(a, n, h, w, gq * 8, dyh, yh);
+    store8(out + ((size_t(n) * H + h) * W + w) * C, gq * 8, C, dyh);
+  }
+}
+
+int stats_geometry(int C, int quad, int* gx_log2, int* cgroups) {
+  // quad = channels per thread (4 for stats, 8 for backward)
+  const int groups = (C + quad - 1) / quad;
+  int gx = 1, l = 0;
+  while (gx < groups && gx < 32) { gx <<= 1; ++l; }
+  *gx_log2 = l;
+  *cgroups = (groups + gx - 1) / gx;
+  return 0;
+}
+inline int stats_nblk(int N, int HW) {
+  // enough blocks to fill the chip, at least ~1024 pixels per block
+  int nblk = std::max(1, std::min(HW / 1024, (148 * 8) / std::max(1, N)));
+  return std::min(nblk, 256);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hm_encode_input(const float* label, const float* inst, const float* image, const float* mask_in, int B, int H,
+                    int W, int label_nc, void* g_hi, void* g_lo, int g_cs, int g_border, void* d_hi, void* d_lo,
+                    int d_cs, void* v_hi, void* v_lo, int v_cs, void* stream) {
+  if (!label || !image || !mask_in || !g_hi || (g_cs & 7) || (d_hi && (d_cs & 7)) || (v_hi && (v_cs & 7)))
+    return HM_ERR_INVALID;
+  const int cin = label_nc + (inst ? 1 : 0) + 3;
+  if (cin > g_cs || (d_hi && cin + 3 > d_cs)) return HM_ERR_INVALID;
+  const long total = long(B) * (H + 2 * g_border) * (W + 2 * g_border);
+  encode_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      label, inst, image, mask_in, B, H, W, label_nc, static_cast<bf16*>(g_hi), static_cast<bf16*>(g_lo), g_cs,
+      g_border, static_cast<bf16*>(d_hi), static_cast<bf16*>(d_lo), d_cs, static_cast<bf16*>(v_hi),
+      static_cast<bf16*>(v_lo), v_cs);
+  return HM_LAUNCH_OK();
+}
+
+size_t hm_in_ws_bytes(int N, int HW, int C) {
+  const int C8 = (C + 7) & ~7;
+  return size_t(N) * stats_nblk(N, HW) * 2 * C8 * sizeof(float) + size_t(N) * 2 * C8 * sizeof(float);
+}
+
+int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, float* mean, float* rstd, void* stream) {
+  if (!y || !ws || !mean || !rstd || (C & 3)) return HM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int gx_log2, cgroups;
+  stats_geometry(C, 4, &gx_log2, &cgroups);
+  const int nblk = stats_nblk(N, HW);
+  in_stats_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(y, HW, C, gx_log2, ws);
+  in_stats_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(ws, N, nblk, C, HW, eps, mean, rstd);
+  return HM_LAUNCH_OK();
+}
+
+int hm_in_apply(const float* y, const float* mean, const float* rstd, const float* skip, int N, int H, int W, int C,
+                int act, float slope, float* out32, void* o_hi, void* o_lo, int o_cs, int border, int reflect,
+                void* stream) {
+  if (!y || (o_hi && ((o_cs & 7) || o_cs < C)) || (!o_hi && !out32)) return HM_ERR_INVALID;
+  if (reflect && (border >= H || border >= W)) return HM_ERR_INVALID;
+  const int G = (o_hi ? o_cs : ((C + 7) & ~7)) >> 3;
+  const long total = long(N) * (H + 2 * border) * (W + 2 * border) * G;
+  in_apply_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, mean, rstd, skip, N, H, W, C, act, slope, out32, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs,
+      border, reflect);
+  return HM_LAUNCH_OK();
+}
+
+int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float* z, const void* mask_hi, int mask_cs,
+              const float* g1, int g1_border, int g1_ld, int g1_coff, const float* g2, const float* tref, float l1coef,
+              int N, int H, int W, int C, int act, float slope, float* ws, void* o_hi, void* o_lo, int o_cs,
+              float* out32, void* stream) {
+  if ((!o_hi && !out32) || (o_hi && ((o_cs & 7) || o_cs < C))) return HM_ERR_INVALID;
+  if (mean && (!y || !ws)) return HM_ERR_INVALID;
+  if (g1 && g1_border > 0 && (g1_border >= H || g1_border >= W)) return HM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BwdArgs a;
+  a.y = y; a.mean = mean; a.rstd = rstd; a.z = z; a.mask_hi = static_cast<const bf16*>(mask_hi); a.mask_cs = mask_cs;
+  a.g1 = g1; a.g1_border = g1_border; a.g1_ld = g1_ld; a.g1_coff = g1_coff; a.g2 = g2; a.tref = tref; a.l1coef = l1coef;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.act = act; a.slope = slope;
+  const int C8 = (C + 7) & ~7;
+  float* sums = nullptr;
+  if (mean) {
+    int gx_log2, cgroups;
+    stats_geometry(C, 8, &gx_log2, &cgroups);
+    const int nblk = stats_nblk(N, H * W);
+    sums = ws + size_t(N) * nblk * 2 * C8;
+    in_bwd_reduce_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
+    in_bwd_finalize_kernel<<<(N * C8 + 127) / 128, 128, 0, st>>>(ws, N, nblk, C8, H * W, sums);
+  }
+  const int G = o_hi ? (o_cs >> 3) : (C8 >> 3);
+  in_bwd_apply_kernel<<<grid_for(long(N) * H * W * G), kBlock, 0, st>>>(a, sums, static_cast<bf16*>(o_hi),
+                                                                        static_cast<bf16*>(o_lo), o_cs, out32);
+  return HM_LAUNCH_OK();
+}
+
+int hm_fold_add(const float* g_padded, int border, int N, int H, int W, int C, const float* base, float* out,
+                void* stream) {
+  if (!g_padded || !out || (border > 0 && (border >= H || border >= W))) return HM_ERR_INVALID;
+  const long total = long(N) * H * W * ((C + 7) >> 3);
+  fold_add_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(g_padded, border, N, H, W, C, base, out);
+  return HM_LAUNCH_OK();
+}
+
+int hm_avgpool3s2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, void* o_hi, void* o_lo, void* stream) {
+  if (!i_hi || !o_hi || (cs & 7)) return HM_ERR_INVALID;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  avgpool_kernel<<<grid_for(long(N) * Ho * Wo * (cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(i_hi), static_cast<const bf16*>(i_lo), N, H, W, cs, static_cast<bf16*>(o_hi),
+      static_cast<bf16*>(o_lo), Ho, Wo);
+  return HM_LAUNCH_OK();
+}
+
+int hm_avgpool3s2_bwd(const float* g_coarse, int N, int Ho, int Wo, int ld_coarse, float* g_fine, int H, int W,
+                      int ld_fine, int c0, int c1, void* stream) {
+  if (!g_coarse || !g_fine || c1 <= c0) return HM_ERR_INVALID;
+  avgpool_bwd_kernel<<<grid_for(long(N) * H * W * (c1 - c0)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      g_coarse, N, Ho, Wo, ld_coarse, g_fine, H, W, ld_fine, c0, c1);
+  return HM_LAUNCH_OK();
+}
+
+int hm_maxpool2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, void* o_hi, void* o_lo, void* stream) {
+  if (!i_hi || !o_hi || (cs & 7)) return HM_ERR_INVALID;
+  maxpool_kernel<<<grid_for(long(N) * (H / 2) * (W / 2) * (cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(i_hi), static_cast<const bf16*>(i_lo), N, H, W, cs, static_cast<bf16*>(o_hi),
+      static_cast<bf16*>(o_lo));
+  return HM_LAUNCH_OK();
+}
+
+int hm_maxpool2_bwd(const float* g, int N, int H, int W, int C, const void* a_hi, const void* a_lo, int cs, float* dz,
+                    void* stream) {
+  if (!g || !a_hi || !dz || (H & 1) || (W & 1)) return HM_ERR_INVALID;
+  maxpool_bwd_kernel<<<grid_for(long(N) * (H / 2) * (W / 2) * ((C + 7) >> 3)), kBlock, 0,
+                       static_cast<cudaStream_t>(stream)>>>(g, N, H, W, C, static_cast<const bf16*>(a_hi),
+                                                           static_cast<const bf16*>(a_lo), cs, dz);
+  return HM_LAUNCH_OK();
+}
+
+int hm_l1_sum(const float* a, const float* b, long n, double coef, double* acc, void* stream) {
+  if (!a || !b || !acc) return HM_ERR_INVALID;
+  l1_sum_kernel<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, coef, acc);
+  return HM_LAUNCH_OK();
+}
+int hm_mse_sum(const float* a, long n, float target, double coef, double* acc, void* stream) {
+  if (!a || !acc) return HM_ERR_INVALID;
+  mse_sum_kernel<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(a, n, target, coef, acc);
+  return HM_LAUNCH_OK();
+}
+int hm_mse_grad(const float* y, long P, int C, float target, float scale, void* o_hi, void* o_lo, int o_cs, void* stream) {
+  if (!y || !o_hi || (o_cs & 7) || o_cs < C) return HM_ERR_INVALID;
+  mse_grad_kernel<<<grid_for(P * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, P, C, target, scale, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_finish_fake(const float* t, const float* image, const float* mask, int use_gate, int B, int H, int W,
+                   float* fake_nchw, void* d_hi, void* d_lo, int d_cs, int d_coff, void* v_hi, void* v_lo, int v_cs,
+                   void* stream) {
+  if (!t || (use_gate && (!image || !mask))) return HM_ERR_INVALID;
+  finish_fake_kernel<<<grid_for(long(B) * H * W), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, image, mask, use_gate, B, H, W, fake_nchw, static_cast<bf16*>(d_hi), static_cast<bf16*>(d_lo), d_cs, d_coff,
+      static_cast<bf16*>(v_hi), static_cast<bf16*>(v_lo), v_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_fake_bwd(const float* t, const float* mask, int use_gate, const float* gD, int gD_ld, int gD_coff,
+                const float* gV, int gV_ld, const float* real_nchw, float rec_coef, int B, int H, int W, void* o_hi,
+                void* o_lo, int o_cs, void* stream) {
+  if (!t || !o_hi || (o_cs & 7) || (use_gate && !mask) || (rec_coef != 0.f && !real_nchw)) return HM_ERR_INVALID;
+  fake_bwd_kernel<<<grid_for(long(B) * H * W), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, mask, use_gate, gD, gD_ld, gD_coff, gV, gV_ld, real_nchw, rec_coef, B, H, W, static_cast<bf16*>(o_hi),
+      static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_f32_to_operand(const float* x, long P, int C, int ld, int coff, float scale, void* o_hi, void* o_lo, int o_cs,
+                      void* stream) {
+  if (!x || !o_hi || (o_cs & 7) || o_cs < C) return HM_ERR_INVALID;
+  f32_to_op_kernel<<<grid_for(P * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, P, C, ld, coff, scale, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_colsum(const float* x, long P, int C, float* out, int accumulate, void* stream) {
+  if (!x || !out) return HM_ERR_INVALID;
+  colsum_kernel<<<C, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(x, P, C, out, accumulate);
+  return HM_LAUNCH_OK();
+}
+int hm_colsum_operand(const void* hi, const void* lo, long P, int C, int cs, float* out, int accumulate, void* stream) {
+  if (!hi || !out) return HM_ERR_INVALID;
+  colsum_op_kernel<<<C, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(hi),
+                                                                       static_cast<const bf16*>(lo), P, C, cs, out,
+                                                                       accumulate);
+  return HM_LAUNCH_OK();
+}
+
+int hm_adam_step(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                 float eps, int step, float grad_scale, void* stream) {
+  if (!param || !grad || !m || !v || step < 1) return HM_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return HM_ERR_INVALID;
+  const float bc1 = 1.f - powf(beta1, float(step));
+  const float bc2s = sqrtf(1.f - powf(beta2, float(step)));
+  adam_kernel<<<grid_for(n / 4 + 1, kBlock, 148 * 16), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  return HM_LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -1,0 +1,467 @@
+"""Host-side mirror of the reference's model layer for the mask2image hot path.
+
+    create_model(opt)                       <- models/models.py:6-24
+    Pix2PixHDModel_condImg                  <- models/pix2pixHD_condImg_model.py:22-327 (+ BaseModel, models/base_model.py)
+
+Same names, argument meaning and error behaviour as the reference, so train_mask2image.py:39-131 / vis_mask2image.py:22-43
+drive it with the same call sequence:
+
+    model = create_model(opt)
+    losses, generated = model(label=..., inst=..., image=..., feat=None, mask_in=..., mask_out=..., infer=...)
+    loss_G.backward(); model.module.optimizer_G.step(); loss_D.backward(); model.module.optimizer_D.step()
+
+All tensor work runs in libhm_b200.so (sm_100a); there is no torch.nn / cuDNN / CPU path behind this class.
+`optimize_parameters()` (a no-op stub in the reference, models/base_model.py:33) is the fused fast path: one forward,
+both backward passes, ONE gradient allreduce over [G | D] and both Adam steps.
+"""
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+from .networks import FlatParams, GlobalGenerator, MultiscaleDiscriminator, Vgg19, VGG19_CONVS, VGG19_SLICE_OF
+from .ops import Ctx, Operand
+
+LOSS_NAMES = ["G_GAN", "G_GAN_Feat", "G_VGG", "D_real", "D_fake"]  # pix2pixHD_condImg_model.py:118
+VGG_WEIGHTS = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]          # models/losses.py:57
+
+
+class Options(object):
+    """Flat option namespace with the reference's flag names and defaults for this path
+    (options/mask2image_base_options.py:15-74, options/mask2image_train_options.py:9-46)."""
+
+    def __init__(self, **kw):
+        d = dict(name="label2city", gpu_ids=[0], checkpoints_dir="./checkpoints", model="pix2pixHD_condImg",
+                 norm="instance", batchSize=1, label_nc=35, output_nc=3, resize_or_crop="scale_width", netG="global",
+                 ngf=64, n_downsample_global=4, n_blocks_global=9, n_blocks_local=3, n_local_enhancers=1,
+                 niter_fix_global=0, which_encoder="ctx", use_output_gate=False, use_skip=False, feat_fusion="early_add",
+                 no_instance=False, instance_feat=False, label_feat=False, feat_num=3, load_features=False,
+                 isTrain=True, continue_train=False, load_pretrain="", which_epoch="latest", niter=100, niter_decay=100,
+                 beta1=0.5, lr=0.0002, num_D=2, n_layers_D=3, ndf=64, lambda_feat=10.0, lambda_rec=0.0,
+                 no_ganFeat_loss=False, no_vgg_loss=False, no_lsgan=False, pool_size=0, no_imgCond=False,
+                 mask_gan_input=False, use_soft_mask=False, no_gan=False,
+                 # extensions of this implementation (not reference flags)
+                 precision="bf16x3",      # "bf16x3": fp32-parity mode; "bf16": single-product tensor-core mode
+                 vgg_seed=1234)           # seeded random VGG19 (no network for the ImageNet weights)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(self, k, v)
+
+
+def create_model(opt, data_size=None):
+    """models/models.py:6-24."""
+    if opt.model == "pix2pixHD_condImg":
+        model = Pix2PixHDModel_condImg(opt)
+    else:
+        # AE_maskgen_twostream / pix2pixHD_condImgColor exist in the reference factory but are outside this path
+        raise NotImplementedError("the model is not implemented")
+    print("model [%s] was created" % (model.name()))
+    if opt.isTrain and len(opt.gpu_ids):
+        model = _DataParallelShim(model)
+    return model
+
+
+class _DataParallelShim(object):
+    """What train_mask2image.py needs from nn.DataParallel (models/models.py:21-22): `.module` and a kwargs call.
+    Data parallelism itself is one process per GPU (torchrun) + an NCCL allreduce inside the optimizers."""
+
+    def __init__(self, module):
+        self.module = module
+
+    def __call__(self, *a, **kw):
+        return self.module.forward(*a, **kw)
+
+
+class FusedAdam(object):
+    """torch.optim.Adam(params, lr, betas=(beta1, 0.999)) (pix2pixHD_condImg_model.py:135,139) over a FlatParams
+    buffer: zero_grad / step / param_groups like the reference's optimizers, one kernel per param group."""
+
+    def __init__(self, ctx, fp, lr, betas=(0.5, 0.999), eps=1e-8, groups=None, dist_group=None):
+        self.ctx, self.fp = ctx, fp
+        self.betas, self.eps = betas, eps
+        self.m = torch.zeros_like(fp.flat)
+        self.v = torch.zeros_like(fp.flat)
+        self.step_count = 0
+        # param_groups: list of dicts with 'lr' and a [begin, end) range of the flat buffer
+        self.param_groups = groups if groups is not None else [dict(lr=lr, begin=0, end=fp.total, params=list(fp.params.values()))]
+        self.dist_group = dist_group
+        self.grads_reduced = False
+
+    def zero_grad(self):
+        self.fp.grad.zero_()
+        self.grads_reduced = False
+
+    def allreduce(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            if not self.grads_reduced:
+                torch.distributed.all_reduce(self.fp.grad, group=self.dist_group)
+                self.grads_reduced = True
+            return 1.0 / torch.distributed.get_world_size()
+        return 1.0
+
+    def step(self, grad_scale=None):
+        scale = self.allreduce() if grad_scale is None else grad_scale
+        self.step_count += 1
+        for g in self.param_groups:
+            b, e = g["begin"], g["end"]
+            if e > b:
+                ops.adam_step(self.ctx, self.fp.flat[b:e], self.fp.grad[b:e], self.m[b:e], self.v[b:e], float(g["lr"]),
+                              self.betas[0], self.betas[1], self.eps, self.step_count, scale)
+        self.fp.version += 1
+        self.grads_reduced = False
+
+    def state_dict(self):
+        return dict(step=self.step_count, m=self.m.cpu(), v=self.v.cpu(), lrs=[g["lr"] for g in self.param_groups])
+
+    def load_state_dict(self, sd):
+        self.step_count = sd["step"]
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
+        for g, lr in zip(self.param_groups, sd["lrs"]):
+            g["lr"] = lr
+
+
+class _LossFn(torch.autograd.Function):
+    """Autograd anchor: the losses returned to the training script are outputs of this node, and its backward
+    launches the hand-written backward schedule (writing straight into the flat .grad buffers)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, which, values):
+        ctx.model, ctx.which = model, which
+        return values.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w = [float(x) for x in grad_out.tolist()]
+        if ctx.which == "G":
+            ctx.model._backward_G(w)
+        else:
+            ctx.model._backward_D(w)
+        return None, None, None, None
+
+
+class Pix2PixHDModel_condImg(object):
+    def name(self):
+        return "Pix2PixHDModel_condImg"
+
+    def __init__(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        if not torch.cuda.is_available():
+            raise RuntimeError("Pix2PixHDModel_condImg (B200) needs a CUDA device: there is no CPU fallback")
+        dev = torch.device("cuda", self.gpu_ids[0] if len(self.gpu_ids) else torch.cuda.current_device())
+        self.device = dev
+        self.ctx = Ctx(dev, split=(getattr(opt, "precision", "bf16x3") == "bf16x3"))
+        self.netG_type = opt.netG
+        self.use_features = opt.instance_feat or opt.label_feat
+        if self.use_features:
+            raise NotImplementedError("instance/label feature encoder (netE) is broken in the reference "
+                                      "(Pix2Pix_NET.py:249-255) and not part of this path")
+        if opt.norm != "instance":
+            raise NotImplementedError("normalization layer [%s] is not found" % opt.norm)
+        if opt.label_nc == 0:
+            raise NotImplementedError("label_nc == 0 (raw label input) is not part of this path")
+        input_nc = opt.label_nc
+        netG_input_nc = input_nc + (0 if opt.no_instance else 1)
+        # ---- generator (pix2pixHD_condImg_model.py:34-56)
+        self.fpG = FlatParams(dev)
+        if opt.netG == "global":
+            netG_input_nc += 3
+            self.netG = GlobalGenerator(self.ctx, self.fpG, netG_input_nc, opt.output_nc, opt.ngf, opt.n_downsample_global,
+                                        opt.n_blocks_global, opt.use_output_gate)
+        elif opt.netG == "local":
+            from .local_enhancer import LocalEnhancer
+            netG_input_nc += 3
+            self.netG = LocalEnhancer(self.ctx, self.fpG, netG_input_nc, opt.output_nc, opt.ngf, opt.n_downsample_global,
+                                      opt.n_blocks_global, opt.n_local_enhancers, opt.n_blocks_local)
+        else:
+            raise NameError("global generator name is not defined properly: %s" % opt.netG)
+        self.netG_input_nc = netG_input_nc
+        gen = torch.Generator().manual_seed(getattr(opt, "init_seed", 0))
+        # ---- discriminator (:59-81)
+        self.netD = None
+        if self.isTrain:
+            if opt.no_imgCond or opt.mask_gan_input or opt.use_soft_mask or opt.no_lsgan:
+                raise NotImplementedError("no_imgCond / mask_gan_input / use_soft_mask / no_lsgan are outside this path")
+            netD_input_nc = input_nc + 3 + opt.output_nc + (0 if opt.no_instance else 1)
+            self.fpD = FlatParams(dev)
+            self.netD = MultiscaleDiscriminator(self.ctx, self.fpD, netD_input_nc, opt.ndf, opt.n_layers_D, opt.num_D)
+        # one flat buffer [G | D] so data parallelism is a single allreduce
+        total = self.fpG.total + (self.fpD.total if self.isTrain else 0)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.fpG.materialize(self.flat[:self.fpG.total], self.flat_grad[:self.fpG.total])
+        for c in self.netG.convs():
+            c.init_reference(gen)
+        if self.isTrain:
+            self.fpD.materialize(self.flat[self.fpG.total:], self.flat_grad[self.fpG.total:])
+            for c in self.netD.convs():
+                c.init_reference(gen)
+        print("---------- Networks initialized -------------")
+        # ---- load networks (:94-101)
+        if not self.isTrain or opt.continue_train or opt.load_pretrain:
+            pretrained_path = "" if not self.isTrain else opt.load_pretrain
+            self.load_network(self.fpG, "G", opt.which_epoch, pretrained_path)
+            if self.isTrain:
+                self.load_network(self.fpD, "D", opt.which_epoch, pretrained_path)
+        # ---- losses and optimizers (:103-139)
+        if self.isTrain:
+            if opt.pool_size > 0 and len(self.gpu_ids) > 1:
+                raise NotImplementedError("Fake Pool Not Implemented for MultiGPU")
+            if opt.pool_size > 0:
+                raise NotImplementedError("image pool (pool_size > 0) is outside this path; the default is 0")
+            self.old_lr = opt.lr
+            self.vgg = None
+            if not opt.no_vgg_loss:
+                self.vgg = Vgg19(self.ctx, random_vgg19_state_dict(getattr(opt, "vgg_seed", 1234)))
+            self.loss_names = list(LOSS_NAMES)
+            groups = None
+            if opt.niter_fix_global > 0 and opt.netG == "local":
+                print("------------- Only training the local enhancer network (for %d epochs) ------------" % opt.niter_fix_global)
+                groups = self.netG.param_groups(opt.lr, opt.n_local_enhancers)
+            self.optimizer_G = FusedAdam(self.ctx, self.fpG, opt.lr, (opt.beta1, 0.999), groups=groups)
+            self.optimizer_D = FusedAdam(self.ctx, self.fpD, opt.lr, (opt.beta1, 0.999))
+            self.loss_acc = torch.zeros(5, dtype=torch.float64, device=dev)
+            self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self._step = None
+        self._pinned = {}
+        self.fake_image = self.real_image = self.input_label = self.input_image = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _to_device(self, name, t):
+        """host (CPU) fp32 tensor -> device, through a cached pinned staging buffer (async H2D)."""
+        if t is None:
+            return None
+        if t.is_cuda:
+            return t.to(self.device, torch.float32).contiguous()
+        t = t.detach().to(torch.float32).contiguous()
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != t.shape:
+            buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
+            self._pinned[name] = buf
+        buf.copy_(t)
+        return buf.to(self.device, non_blocking=True)
+
+    def encode_input(self, label_map, inst_map=None, real_image=None, mask_in=None, train=True):
+        """pix2pixHD_condImg_model.py:144-174 -> operands for G / D / VGG (K11)."""
+        assert real_image is not None and mask_in is not None
+        opt, ctx = self.opt, self.ctx
+        label = self._to_device("label", label_map)
+        inst = None if opt.no_instance else self._to_device("inst", inst_map)
+        image = self._to_device("image", real_image)
+        mask = self._to_device("mask_in", mask_in)
+        B, _, H, W = label.shape
+        g_in = Operand(ctx, B, H, W, self.netG_input_nc, border=3)
+        d_in = v_in = None
+        if train:
+            d_in = Operand(ctx, 2 * B, H, W, self.netG_input_nc + 3)
+            if self.vgg is not None:
+                v_in = Operand(ctx, 2 * B, H, W, 3)
+        ops.encode_input(ctx, label, inst, image, mask, opt.label_nc, g_in, d_in, v_in)
+        return dict(label=label, inst=inst, image=image, mask=mask, g_in=g_in, d_in=d_in, v_in=v_in, B=B, H=H, W=W)
+
+    # ------------------------------------------------------------------------------------------------
+    def _forward_all(self, label, inst, image, mask_in):
+        """The whole forward of pix2pixHD_condImg_model.py:198-259; returns the step context."""
+        opt, ctx = self.opt, self.ctx
+        st = self.encode_input(label, inst, image, mask_in, train=True)
+        B, H, W = st["B"], st["H"], st["W"]
+        t, g_tape = self.netG.forward(st["g_in"])
+        fake = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
+        ops.finish_fake(ctx, t, st["image"], st["mask"], opt.use_output_gate, fake, st["d_in"], self.netG_input_nc, st["v_in"])
+        st.update(t=t, g_tape=g_tape, fake=fake)
+        # D on [fake ; real] (the fake.detach() pass of :218 and the pass of :231 see identical values: computed once)
+        st["d_tape"] = self.netD.forward(st["d_in"])
+        acc = self.loss_acc
+        acc.zero_()
+        for lv in st["d_tape"]:
+            pred = lv["taps"][-1]
+            half = pred.numel() // 2
+            ops.mse_sum(ctx, pred[:B], 1.0, 1.0 / half, acc, 0)      # G_GAN  (:232)
+            ops.mse_sum(ctx, pred[B:], 1.0, 1.0 / half, acc, 3)      # D_real (:223)
+            ops.mse_sum(ctx, pred[:B], 0.0, 1.0 / half, acc, 4)      # D_fake (:219)
+            if not opt.no_ganFeat_loss:                               # :235-242
+                cf = (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
+                for tap in lv["taps"][:-1]:
+                    ops.l1_sum(ctx, tap[:B], tap[B:], cf / (tap.numel() // 2), acc, 1)
+        if self.vgg is not None:                                      # :245-247
+            st["v_tape"] = self.vgg.forward(st["v_in"])
+            for li, tap in st["v_tape"]["taps"].items():
+                wi = VGG_WEIGHTS[sorted(st["v_tape"]["taps"]).index(li)]
+                ops.l1_sum(ctx, tap[:B], tap[B:], opt.lambda_feat * wi / (tap.numel() // 2), acc, 2)
+        if opt.lambda_rec > 0:                                        # :249-251
+            ops.l1_sum(ctx, fake, st["image"], opt.lambda_rec / fake.numel(), acc, 1)
+        st["losses"] = acc.to(torch.float32)
+        return st
+
+    def forward(self, label, inst, image, feat, mask_in, mask_out, infer=False):
+        """pix2pixHD_condImg_model.py:198-259.  Inputs are the reference's CPU NCHW tensors; returns
+        [[G_GAN, G_GAN_Feat, G_VGG, D_real, D_fake], fake_image | None] with differentiable scalar losses."""
+        st = self._forward_all(label, inst, image, mask_in)
+        self._step = st
+        lg = _LossFn.apply(self._anchor, self, "G", st["losses"][:3])
+        ld = _LossFn.apply(self._anchor, self, "D", st["losses"][3:])
+        self._keep_visuals(st)
+        return [[lg[0], lg[1], lg[2], ld[0], ld[1]], st["fake"] if infer else None]
+
+    def _keep_visuals(self, st):
+        # the reference copies 4 tensors to the host EVERY step (:253-256); here they stay on the device and
+        # get_current_visuals() fetches them on demand.
+        self._vis = st
+
+    # ---- backward schedules -----------------------------------------------------------------------------
+    def _backward_G(self, w):
+        """d(w0*G_GAN + w1*G_GAN_Feat + w2*G_VGG)/d(G params): VGG dgrad -> D dgrad (no D wgrad: the reference computes
+        one and discards it, train_mask2image.py:79,84) -> head -> generator dgrad + wgrad."""
+        st, opt, ctx = self._step, self.opt, self.ctx
+        B = st["B"]
+        cf = 0.0 if opt.no_ganFeat_loss else w[1] * (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
+        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.netG_input_nc)
+        gV = None
+        if self.vgg is not None and w[2] != 0.0:
+            gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
+        dy = Operand(ctx, B, st["H"], st["W"], 3)
+        rec = w[1] * opt.lambda_rec / st["fake"].numel() if opt.lambda_rec > 0 else 0.0
+        ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.netG_input_nc, gV, st["image"], rec, dy)
+        self.netG.backward(st["g_tape"], dy_head=dy)
+
+    def _backward_D(self, w):
+        """d(w0*D_real + w1*D_fake)/d(D params) over the [fake ; real] batch."""
+        st = self._step
+        self.netD.backward(st["d_tape"], st["B"], "D", w_real=w[0], w_fake=w[1])
+
+    def optimize_parameters(self, label=None, inst=None, image=None, feat=None, mask_in=None, mask_out=None):
+        """Fused step: forward, G backward, D backward, one allreduce of [G | D] grads, Adam x2.
+        Bit-identical maths to train_mask2image.py:58-86 because loss_D's graph holds no G parameter.
+        Returns the 5 losses as a device tensor (no host sync)."""
+        st = self._forward_all(label, inst, image, mask_in)
+        self._step = st
+        self._keep_visuals(st)
+        self.flat_grad.zero_()
+        self._backward_G([1.0, 1.0, 1.0])
+        self._backward_D([0.5, 0.5])
+        scale = 1.0
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.flat_grad)
+            scale = 1.0 / torch.distributed.get_world_size()
+        self.optimizer_G.step(grad_scale=scale)
+        self.optimizer_D.step(grad_scale=scale)
+        return st["losses"]
+
+    # ------------------------------------------------------------------------------------------------
+    def inference(self, label, inst, image, mask_in, mask_out):
+        """pix2pixHD_condImg_model.py:261-283."""
+        st = self.encode_input(label, inst, image, mask_in, train=False)
+        t, _ = self.netG.forward(st["g_in"])
+        fake = torch.empty(st["B"], 3, st["H"], st["W"], dtype=torch.float32, device=self.device)
+        ops.finish_fake(self.ctx, t, st["image"], st["mask"], self.opt.use_output_gate, fake, None, 0, None)
+        st["fake"] = fake
+        self._vis = st
+        return fake
+
+    def get_current_visuals(self):
+        """:293-299 -> OrderedDict of HxWx3 uint8 arrays (util/util.py:67-99 tensor2im / tensor2label)."""
+        st = self._vis
+        label = st["label"][0, 0].cpu().numpy().astype(np.int64)
+        return OrderedDict([
+            ("input_label", colorize_labels(label, self.opt.label_nc)),
+            ("input_image", tensor2im(((1 - st["mask"][0]) * st["image"][0]).cpu())),
+            ("real_image", tensor2im(st["image"][0].cpu())),
+            ("synthesized_image", tensor2im(st["fake"][0].cpu()))])
+
+    # ---- checkpoints (models/base_model.py:46-107) -------------------------------------------------------
+    def save_network(self, fp, network_label, epoch_label, gpu_ids=None):
+        os.makedirs(self.save_dir, exist_ok=True)
+        torch.save(fp.state_dict(), os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch_label, network_label)))
+
+    def load_network(self, fp, network_label, epoch_label, save_dir=""):
+        save_filename = "%s_net_%s.pth" % (epoch_label, network_label)
+        save_path = os.path.join(save_dir or self.save_dir, save_filename)
+        if not os.path.isfile(save_path):
+            print("%s not exists yet!" % save_path)
+            if network_label == "G":
+                raise RuntimeError("Generator must exist!")
+            return
+        sd = torch.load(save_path, map_location="cpu")
+        try:
+            fp.load_state_dict(sd, strict=True)
+        except KeyError:
+            own = fp.params
+            usable = {k: v for k, v in sd.items() if k in own and tuple(v.shape) == tuple(own[k].shape)}
+            not_init = sorted({k.split(".")[0] for k in own if k not in usable})
+            print("Pretrained network %s has fewer layers; The following are not initialized:" % network_label)
+            print(not_init)
+            fp.load_state_dict(usable, strict=False)
+
+    def save(self, which_epoch):
+        self.save_network(self.fpG, "G", which_epoch, self.gpu_ids)
+        self.save_network(self.fpD, "D", which_epoch, self.gpu_ids)
+
+    def delete_model(self, which_epoch):
+        for lbl in ("G", "D"):
+            p = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, lbl))
+            if os.path.isfile(p):
+                os.remove(p)
+
+    def update_fixed_params(self):
+        """:311-317: after niter_fix_global epochs, train the whole generator (fresh Adam state, as the reference)."""
+        self.optimizer_G = FusedAdam(self.ctx, self.fpG, self.opt.lr, (self.opt.beta1, 0.999))
+        print("------------ Now also finetuning global generator -----------")
+
+    def update_learning_rate(self):
+        """:319-327."""
+        lrd = self.opt.lr / self.opt.niter_decay
+        lr = self.old_lr - lrd
+        for g in self.optimizer_D.param_groups:
+            g["lr"] = lr
+        for g in self.optimizer_G.param_groups:
+            g["lr"] = lr
+        print("update learning rate: %f -> %f" % (self.old_lr, lr))
+        self.old_lr = lr
+
+
+# ------------------------------------------------------------------------------------------------------
+def random_vgg19_state_dict(seed=1234):
+    """Seeded stand-in for torchvision's ImageNet VGG19 (layer_util.py:384 downloads it; no network here):
+    torchvision's own default init (kaiming_normal_ fan_out / relu, zero bias)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for idx, cin, cout in VGG19_CONVS:
+        std = (2.0 / (cout * 9)) ** 0.5
+        k = "slice%d.%d." % (VGG19_SLICE_OF[idx], idx)
+        sd[k + "weight"] = torch.randn(cout, cin, 3, 3, generator=g) * std
+        sd[k + "bias"] = torch.zeros(cout)
+    return sd
+
+
+def tensor2im(t):
+    """util/util.py:67-80: CHW in [-1,1] -> HWC uint8."""
+    a = (np.transpose(t.float().numpy(), (1, 2, 0)) + 1) / 2.0 * 255.0
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+def colorize_labels(label_hw, n):
+    """util/util.py:141-181 (labelcolormap): bit-interleaved colour map for n != 35, Cityscapes palette for 35."""
+    if n == 35:
+        cmap = np.array([(0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0), (111, 74, 0), (81, 0, 81), (128, 64, 128),
+                         (244, 35, 232), (250, 170, 160), (230, 150, 140), (70, 70, 70), (102, 102, 156), (190, 153, 153),
+                         (180, 165, 180), (150, 100, 100), (150, 120, 90), (153, 153, 153), (153, 153, 153),
+                         (250, 170, 30), (220, 220, 0), (107, 142, 35), (152, 251, 152), (70, 130, 180), (220, 20, 60),
+                         (255, 0, 0), (0, 0, 142), (0, 0, 70), (0, 60, 100), (0, 0, 90), (0, 0, 110), (0, 80, 100),
+                         (0, 0, 230), (119, 11, 32), (0, 0, 142)], dtype=np.uint8)
+    else:
+        cmap = np.zeros((n, 3), dtype=np.uint8)
+        for i in range(n):
+            r = g = b = 0
+            idv = i
+            for j in range(7):
+                r ^= ((idv >> 0) & 1) << (7 - j)
+                g ^= ((idv >> 1) & 1) << (7 - j)
+                b ^= ((idv >> 2) & 1) << (7 - j)
+                idv >>= 3
+            cmap[i] = (r, g, b)
+    return cmap[np.clip(label_hw, 0, n - 1)]

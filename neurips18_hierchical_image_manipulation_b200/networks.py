@@ -1,0 +1,483 @@
+"""B200 executors for the networks on the mask2image hot path.
+
+Each class mirrors one reference nn.Module -- same constructor arguments, same parameter names and OIHW/IOHW
+fp32 parameter tensors (so reference checkpoints interchange) -- but forward/backward are explicit schedules of
+C-ABI kernels (ops.py): tcgen05 implicit-GEMM convolutions on bf16(x3) NHWC operands + fused InstanceNorm /
+activation / padding passes.  Nothing here calls torch.nn or autograd.
+
+  GlobalGenerator          <- models/Pix2Pix_NET.py:63-101 (+ ResnetBlock, models/layer_util.py:333-378)
+  MultiscaleDiscriminator  <- models/Discriminator_NET.py:11-118
+  Vgg19                    <- models/layer_util.py:381-411
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, Operand, PackedWeight
+
+VGG19_CONVS = [(0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256), (12, 256, 256), (14, 256, 256),
+               (16, 256, 256), (19, 256, 512), (21, 512, 512), (23, 512, 512), (25, 512, 512), (28, 512, 512)]
+VGG19_POOL_BEFORE = (5, 10, 19, 28)
+VGG19_TAP_AFTER = {0: 0, 5: 1, 10: 2, 19: 3, 28: 4}
+VGG19_SLICE_OF = {0: 1, 2: 2, 5: 2, 7: 3, 10: 3, 12: 4, 14: 4, 16: 4, 19: 4, 21: 5, 23: 5, 25: 5, 28: 5}
+
+
+class FlatParams(object):
+    """All parameters of one network as views into ONE flat fp32 buffer (and one flat gradient buffer), so the
+    optimizer is a single fused kernel and data parallelism is a single allreduce."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.specs = []  # (name, shape, offset)
+        self.total = 0
+        self.flat = None
+        self.grad = None
+        self.params = OrderedDict()  # name -> torch.nn.Parameter (view of flat, .grad = view of grad)
+        self.version = 0  # bumped whenever values change -> packed weights are refreshed lazily
+
+    def declare(self, name, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        self.specs.append((name, tuple(shape), self.total))
+        self.total += (n + 3) // 4 * 4  # keep every tensor 16 B aligned
+        return name
+
+    def materialize(self, flat=None, grad=None):
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=self.device) if flat is None else flat
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.device) if grad is None else grad
+        for name, shape, off in self.specs:
+            n = 1
+            for s in shape:
+                n *= s
+            p = torch.nn.Parameter(self.flat[off:off + n].view(shape), requires_grad=True)
+            p.grad = self.grad[off:off + n].view(shape)
+            self.params[name] = p
+
+    def state_dict(self):
+        return OrderedDict((k, v.detach().cpu().clone()) for k, v in self.params.items())
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self.params if k not in sd]
+        if strict and missing:
+            raise KeyError("missing keys: %s" % missing)
+        with torch.no_grad():
+            for k, p in self.params.items():
+                if k in sd:
+                    p.copy_(sd[k].to(self.device, torch.float32))
+        self.version += 1
+
+
+class ConvP(object):
+    """One Conv2d / ConvTranspose2d: parameter views + lazily packed bf16 weight slabs for the three engine roles."""
+
+    def __init__(self, ctx, fp, name, cin, cout, k, stride, pad, transposed=False):
+        self.ctx, self.fp, self.name = ctx, fp, name
+        self.cin, self.cout, self.k, self.stride, self.pad, self.transposed = cin, cout, k, stride, pad, transposed
+        shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+        fp.declare(name + ".weight", shape)
+        fp.declare(name + ".bias", (cout,))
+        self._pf = self._pd = None
+        self._vf = self._vd = -1
+
+    # parameter / gradient views -------------------------------------------------------------------
+    @property
+    def weight(self):
+        return self.fp.params[self.name + ".weight"]
+
+    @property
+    def bias(self):
+        return self.fp.params[self.name + ".bias"]
+
+    def init_reference(self, gen):
+        """weights_init (models/layer_util.py:9-16): N(0, 0.02) conv weights, torch-default uniform biases."""
+        with torch.no_grad():
+            w = self.weight
+            w.copy_((torch.randn(w.shape, generator=gen) * 0.02).to(w.device))
+            fan_in = w.shape[1] * self.k * self.k
+            bound = 1.0 / fan_in ** 0.5
+            self.bias.copy_(((torch.rand(self.cout, generator=gen) * 2 - 1) * bound).to(w.device))
+        self.fp.version += 1
+
+    # packed slabs ---------------------------------------------------------------------------------
+    def packed_fwd(self):
+        """rows = cout, contraction = cin."""
+        if self._pf is None:
+            self._pf = PackedWeight(self.ctx, self.cout, self.cin, self.k * self.k)
+        if self._vf != self.fp.version:
+            kk = self.k * self.k
+            if self.transposed:   # W[ci][co][t]
+                self._pf.pack(self.ctx, self.weight, kk, self.cout * kk, 1)
+            else:                 # W[co][ci][t]
+                self._pf.pack(self.ctx, self.weight, self.cin * kk, kk, 1)
+            self._vf = self.fp.version
+        return self._pf
+
+    def packed_bwd(self):
+        """rows = cin, contraction = cout."""
+        if self._pd is None:
+            self._pd = PackedWeight(self.ctx, self.cin, self.cout, self.k * self.k)
+        if self._vd != self.fp.version:
+            kk = self.k * self.k
+            if self.transposed:
+                self._pd.pack(self.ctx, self.weight, self.cout * kk, kk, 1)
+            else:
+                self._pd.pack(self.ctx, self.weight, kk, self.cin * kk, 1)
+            self._vd = self.fp.version
+        return self._pd
+
+    # geometry ---------------------------------------------------------------------------------------
+    def out_hw(self, h, w, zero_pad):
+        """h, w: stored input dims (incl. any materialised border)."""
+        if self.transposed:
+            return 2 * h, 2 * w
+        return (h + 2 * zero_pad - self.k) // self.stride + 1, (w + 2 * zero_pad - self.k) // self.stride + 1
+
+    # engine calls -----------------------------------------------------------------------------------
+    def forward(self, x, zero_pad, act=ACT_NONE, slope=0.2, out32=None, out16=None, use_bias=True):
+        ho, wo = self.out_hw(x.h, x.w, zero_pad)
+        b = self.bias if use_bias else None
+        if self.transposed:
+            ops.conv_dgrad(self.ctx, x, self.packed_fwd(), b, self.k, self.k, 2, self.pad, ho, wo, self.cout, act, slope,
+                           out32, out16)
+        else:
+            ops.conv_fprop(self.ctx, x, self.packed_fwd(), b, self.k, self.k, self.stride, zero_pad, ho, wo, self.cout,
+                           act, slope, out32, out16)
+        return ho, wo
+
+    def dgrad(self, dy, x_h, x_w, zero_pad, out32):
+        """gradient w.r.t. the stored input (dims x_h x x_w)."""
+        if self.transposed:
+            ops.conv_fprop(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, 2, self.pad, x_h, x_w, self.cin,
+                           out32=out32)
+        else:
+            ops.conv_dgrad(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, self.stride, zero_pad, x_h, x_w,
+                           self.cin, out32=out32)
+
+    def wgrad(self, x, dy, zero_pad):
+        """accumulate into .grad of weight and bias."""
+        if self.transposed:
+            ops.conv_wgrad(self.ctx, dy, x, self.k, self.k, 2, self.pad, self.weight.grad, accumulate=True)
+        else:
+            ops.conv_wgrad(self.ctx, x, dy, self.k, self.k, self.stride, zero_pad, self.weight.grad, accumulate=True)
+        ops.colsum_operand(self.ctx, dy, self.bias.grad, accumulate=True)
+
+
+def _f32(ctx, *shape):
+    return torch.empty(shape, dtype=torch.float32, device=ctx.device)
+
+
+# ======================================================================================================
+# GlobalGenerator
+# ======================================================================================================
+class GlobalGenerator(object):
+    """models/Pix2Pix_NET.py:63-101.  `with_head=False` gives the trunk LocalEnhancer embeds (Pix2Pix_NET.py:17-19)."""
+
+    IN_BORDER = {"stem": 3, "down": 0, "resA": 1, "resB": 1, "up": 0, "head": 3}
+
+    def __init__(self, ctx, fp, input_nc, output_nc, ngf=64, n_downsampling=3, n_blocks=9, use_output_gate=False,
+                 prefix="model.", with_head=True):
+        self.ctx, self.fp = ctx, fp
+        self.input_nc, self.output_nc, self.use_output_gate = input_nc, output_nc, use_output_gate
+        st = []  # (kind, ConvP)
+        st.append(("stem", ConvP(ctx, fp, prefix + "1", input_nc, ngf, 7, 1, 0)))
+        idx = 4
+        for i in range(n_downsampling):
+            m = 2 ** i
+            st.append(("down", ConvP(ctx, fp, prefix + str(idx), ngf * m, ngf * m * 2, 3, 2, 1)))
+            idx += 3
+        m = 2 ** n_downsampling
+        for i in range(n_blocks):
+            st.append(("resA", ConvP(ctx, fp, prefix + "%d.conv_block.1" % idx, ngf * m, ngf * m, 3, 1, 0)))
+            st.append(("resB", ConvP(ctx, fp, prefix + "%d.conv_block.5" % idx, ngf * m, ngf * m, 3, 1, 0)))
+            idx += 1
+        for i in range(n_downsampling):
+            m = 2 ** (n_downsampling - i)
+            st.append(("up", ConvP(ctx, fp, prefix + str(idx), ngf * m, ngf * m // 2, 3, 2, 1, transposed=True)))
+            idx += 3
+        if with_head:
+            st.append(("head", ConvP(ctx, fp, prefix + str(idx + 1), ngf, output_nc, 7, 1, 0)))
+        self.stages = st
+        self.with_head = with_head
+        self.feature_nc = ngf
+
+    def convs(self):
+        return [c for _, c in self.stages]
+
+    def forward(self, x, feature_border=0):
+        """x: Operand with ReflectionPad2d(3) materialised.  Returns (out, tape): out is the fp32 NHWC tanh output
+        (with_head) or (feature fp32 NHWC) for the trunk."""
+        ctx = self.ctx
+        tape = []
+        cur = x
+        skip32 = None      # fp32 copy of the current activation when it is a residual input
+        out = None
+        n = len(self.stages)
+        for s, (kind, conv) in enumerate(self.stages):
+            nxt = self.stages[s + 1][0] if s + 1 < n else None
+            zero_pad = conv.pad if kind == "down" else 0
+            ho, wo = conv.out_hw(cur.h, cur.w, zero_pad)
+            rec = dict(kind=kind, conv=conv, xin=cur, zero_pad=zero_pad, ho=ho, wo=wo)
+            if kind == "head":
+                y = _f32(ctx, cur.n, ho, wo, conv.cout)
+                conv.forward(cur, 0, act=ACT_TANH, out32=y)
+                rec.update(y=y)
+                tape.append(rec)
+                out = y
+                break
+            y = _f32(ctx, cur.n, ho, wo, conv.cout)
+            conv.forward(cur, zero_pad, out32=y)
+            mean, rstd = ops.in_stats(ctx, y)
+            out_border = self.IN_BORDER[nxt] if nxt is not None else feature_border
+            emit32 = (nxt == "resA") or (nxt is None)
+            act = ACT_NONE if kind == "resB" else ACT_RELU
+            o32 = _f32(ctx, cur.n, ho, wo, conv.cout) if emit32 else None
+            oop = Operand(ctx, cur.n, ho, wo, conv.cout, border=out_border) if nxt is not None else None
+            ops.in_apply(ctx, y, mean, rstd, act, skip=skip32 if kind == "resB" else None, out32=o32, out_op=oop,
+                         reflect=True)
+            rec.update(y=y, mean=mean, rstd=rstd, act=act, out_border=out_border, shape=(cur.n, ho, wo, conv.cout))
+            tape.append(rec)
+            if kind == "resA":
+                pass  # skip32 (input of the block) stays alive for resB
+            else:
+                skip32 = o32
+            cur = oop
+            out = o32
+        return out, tape
+
+    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False):
+        """dy_head: Operand gradient w.r.t. the head's pre-tanh output (with_head) or dfeat: dense fp32 gradient
+        w.r.t. the trunk feature.  Accumulates parameter gradients; returns d(input operand) (fp32, padded space)
+        when need_input_grad."""
+        ctx = self.ctx
+        G1, G1_border = None, 0   # gradient w.r.t. the current stage's OUTPUT operand (padded space)
+        T = dfeat                 # dense gradient w.r.t. the current stage's fp32 output (residual chain)
+        for s in range(len(tape) - 1, -1, -1):
+            rec = tape[s]
+            kind, conv, xin = rec["kind"], rec["conv"], rec["xin"]
+            nxt = tape[s + 1]["kind"] if s + 1 < len(tape) else None
+            if kind == "head":
+                dy = dy_head
+            else:
+                N, ho, wo, cc = rec["shape"]
+                dy = Operand(ctx, N, ho, wo, cc)
+                if kind == "resB":
+                    if nxt != "resA" and G1 is not None:   # last block: gradient arrives from the next conv only
+                        if G1_border > 0:
+                            T = _f32(ctx, N, ho, wo, cc)
+                            ops.fold_add(ctx, G1, G1_border, None, T)
+                        else:
+                            T = G1
+                    ops.in_bwd(ctx, rec["shape"], ACT_NONE, y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g2=T,
+                               out_op=dy)
+                elif nxt == "resA" or nxt is None:          # output feeds the residual chain / is the trunk feature
+                    ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g2=T,
+                               out_op=dy)
+                else:
+                    ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g1=G1,
+                               g1_border=G1_border, out_op=dy)
+            conv.wgrad(xin, dy, rec["zero_pad"])
+            if s == 0 and not need_input_grad:
+                return None
+            gin = _f32(ctx, xin.n, xin.h, xin.w, conv.cin)
+            conv.dgrad(dy, xin.h, xin.w, rec["zero_pad"], gin)
+            if kind == "resA":
+                # input of the block: T_k = T_{k+1} + fold(gin)
+                Tn = _f32(ctx, xin.n, xin.ih, xin.iw, conv.cin)
+                ops.fold_add(ctx, gin, xin.border, T, Tn)
+                T = Tn
+                G1, G1_border = None, 0
+            else:
+                G1, G1_border = gin, xin.border
+        return G1
+
+
+# ======================================================================================================
+# MultiscaleDiscriminator (getIntermFeat=True)
+# ======================================================================================================
+class MultiscaleDiscriminator(object):
+    """models/Discriminator_NET.py:11-118: num_D PatchGANs on an AvgPool(3,2,1) pyramid, every layer output kept."""
+
+    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3):
+        self.ctx, self.fp = ctx, fp
+        self.input_nc, self.n_layers, self.num_D = input_nc, n_layers, num_D
+        self.scales = []
+        for s in range(num_D):
+            layers = []
+            nf = ndf
+            layers.append(ConvP(ctx, fp, "scale%d_layer0.0" % s, input_nc, ndf, 4, 2, 2))
+            for n in range(1, n_layers):
+                nf_prev, nf = nf, min(nf * 2, 512)
+                layers.append(ConvP(ctx, fp, "scale%d_layer%d.0" % (s, n), nf_prev, nf, 4, 2, 2))
+            nf_prev, nf = nf, min(nf * 2, 512)
+            layers.append(ConvP(ctx, fp, "scale%d_layer%d.0" % (s, n_layers), nf_prev, nf, 4, 1, 2))
+            layers.append(ConvP(ctx, fp, "scale%d_layer%d.0" % (s, n_layers + 1), nf, 1, 4, 1, 2))
+            self.scales.append(layers)
+
+    def convs(self):
+        return [c for sc in self.scales for c in sc]
+
+    def forward(self, d_in):
+        """d_in: Operand [N,H,W,cs] (no border).  Returns tape: list over pyramid level i of dict(x=[operands],
+        taps=[fp32 NHWC], y/mean/rstd per layer); level i uses scale{num_D-1-i} (Discriminator_NET.py:49-57)."""
+        ctx = self.ctx
+        tape = []
+        x = d_in
+        for i in range(self.num_D):
+            layers = self.scales[self.num_D - 1 - i]
+            lv = dict(layers=layers, xs=[], taps=[], ys=[], means=[], rstds=[])
+            cur = x
+            for j, conv in enumerate(layers):
+                ho, wo = conv.out_hw(cur.h, cur.w, 2)
+                lv["xs"].append(cur)
+                last = j == len(layers) - 1
+                if j == 0:
+                    tap = _f32(ctx, cur.n, ho, wo, conv.cout)
+                    nxt = Operand(ctx, cur.n, ho, wo, conv.cout)
+                    conv.forward(cur, 2, act=ACT_LRELU, slope=0.2, out32=tap, out16=nxt)
+                    lv["ys"].append(None); lv["means"].append(None); lv["rstds"].append(None)
+                elif last:
+                    tap = _f32(ctx, cur.n, ho, wo, conv.cout)
+                    conv.forward(cur, 2, out32=tap)
+                    nxt = None
+                    lv["ys"].append(None); lv["means"].append(None); lv["rstds"].append(None)
+                else:
+                    y = _f32(ctx, cur.n, ho, wo, conv.cout)
+                    conv.forward(cur, 2, out32=y)
+                    mean, rstd = ops.in_stats(ctx, y)
+                    tap = _f32(ctx, cur.n, ho, wo, conv.cout)
+                    nxt = Operand(ctx, cur.n, ho, wo, conv.cout)
+                    ops.in_apply(ctx, y, mean, rstd, ACT_LRELU, 0.2, out32=tap, out_op=nxt)
+                    lv["ys"].append(y); lv["means"].append(mean); lv["rstds"].append(rstd)
+                lv["taps"].append(tap)
+                cur = nxt
+            tape.append(lv)
+            if i != self.num_D - 1:
+                xn = Operand(ctx, x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, cs=x.cs)
+                ops.avgpool3s2(ctx, x, xn)
+                x = xn
+        return tape
+
+    def backward(self, tape, nb, mode, w_gan=1.0, w_feat=0.0, w_real=0.5, w_fake=0.5, img_c0=0):
+        """mode 'G': d(w_gan*G_GAN + G_GAN_Feat terms)/d(input) for the first nb images (the fake half); returns the
+        fp32 gradient w.r.t. the full-resolution D input (channels [img_c0, img_c0+3) are meaningful).  No weight grads.
+        mode 'D': accumulates weight grads of w_fake*D_fake + w_real*D_real over all 2*nb images.
+        w_feat is the complete per-tap L1 coefficient numerator (D_weights*feat_weights*lambda_feat)."""
+        ctx = self.ctx
+        gins = []
+        for i, lv in enumerate(tape):
+            layers = lv["layers"]
+            nl = len(layers)
+            pred = lv["taps"][-1]
+            N = pred.shape[0]
+            half_numel = pred.numel() // 2
+            if mode == "G":
+                nimg = nb
+                dy = Operand(ctx, nimg, pred.shape[1], pred.shape[2], 1)
+                ops.mse_grad(ctx, pred[:nb], 1.0, 2.0 * w_gan / half_numel, dy)
+            else:
+                nimg = N
+                dy = Operand(ctx, N, pred.shape[1], pred.shape[2], 1)
+                ops.mse_grad(ctx, pred[:nb], 0.0, 2.0 * w_fake / half_numel, dy, 0)   # fake half: target 0
+                ops.mse_grad(ctx, pred[nb:], 1.0, 2.0 * w_real / half_numel, dy, nb)  # real half: target 1
+            for j in range(nl - 1, -1, -1):
+                conv = layers[j]
+                xin = lv["xs"][j]
+                if mode == "D":
+                    conv.wgrad(xin, dy, 2)
+                    if j == 0:
+                        break
+                gin = _f32(ctx, nimg, xin.h, xin.w, conv.cin)
+                conv.dgrad(dy, xin.h, xin.w, 2, gin)
+                if j == 0:
+                    gins.append(gin)
+                    break
+                # through layer j-1's LeakyReLU (+InstanceNorm) to its conv output
+                tap = lv["taps"][j - 1]
+                shape = (nimg,) + tuple(tap.shape[1:])
+                dyn = Operand(ctx, nimg, tap.shape[1], tap.shape[2], tap.shape[3])
+                tref, l1 = None, 0.0
+                if mode == "G" and w_feat != 0.0:
+                    tref = tap[nb:]
+                    l1 = w_feat / (tap.numel() // 2)
+                y, mean, rstd = lv["ys"][j - 1], lv["means"][j - 1], lv["rstds"][j - 1]
+                ops.in_bwd(ctx, shape, ACT_LRELU, 0.2, y=y[:nimg] if y is not None else None,
+                           mean=mean[:nimg] if mean is not None else None, rstd=rstd[:nimg] if rstd is not None else None,
+                           z=tap[:nimg], g1=gin, g1_border=0, tref=tref, l1coef=l1, out_op=dyn)
+                dy = dyn
+        if mode != "G":
+            return None
+        # total gradient at full resolution: g0 + poolT(g1 + poolT(g2 ...))
+        for i in range(len(gins) - 1, 0, -1):
+            ops.avgpool3s2_bwd(ctx, gins[i], gins[i - 1], img_c0, img_c0 + 3)
+        return gins[0]
+
+
+# ======================================================================================================
+# VGG19 feature tower (frozen)
+# ======================================================================================================
+class Vgg19(object):
+    """models/layer_util.py:381-411: torchvision VGG19 features[0:30], taps relu{1..5}_1, requires_grad=False."""
+
+    def __init__(self, ctx, state_dict):
+        self.ctx = ctx
+        self.fp = FlatParams(ctx.device)
+        self.convs_ = []
+        for idx, cin, cout in VGG19_CONVS:
+            self.convs_.append((idx, ConvP(ctx, self.fp, "slice%d.%d" % (VGG19_SLICE_OF[idx], idx), cin, cout, 3, 1, 1)))
+        self.fp.materialize()
+        self.fp.load_state_dict(state_dict)
+        for p in self.fp.params.values():
+            p.requires_grad_(False)
+            p.grad = None
+        self.fp.grad = None
+
+    def forward(self, v_in):
+        """v_in: Operand [N,H,W,8] (3 valid channels).  Returns tape with per-conv input operands / outputs and taps."""
+        ctx = self.ctx
+        tape = dict(xs=[], outs=[], taps={}, pooled_from={})
+        cur = v_in
+        for li, (idx, conv) in enumerate(self.convs_):
+            if idx in VGG19_POOL_BEFORE:
+                pooled = Operand(ctx, cur.n, cur.h // 2, cur.w // 2, cur.c, cs=cur.cs)
+                ops.maxpool2(ctx, cur, pooled)
+                tape["pooled_from"][li] = cur
+                cur = pooled
+            tape["xs"].append(cur)
+            out = Operand(ctx, cur.n, cur.h, cur.w, conv.cout)
+            tap = None
+            if idx in VGG19_TAP_AFTER:
+                tap = _f32(ctx, cur.n, cur.h, cur.w, conv.cout)
+                tape["taps"][li] = tap
+            conv.forward(cur, 1, act=ACT_RELU, out32=tap, out16=out)
+            tape["outs"].append(out)
+            cur = out
+        return tape
+
+    def backward(self, tape, nb, coefs):
+        """d(sum_i coefs[i] * mean|tap_i[:nb] - tap_i[nb:]|)/d(input[:nb]) -> fp32 [nb,H,W,3].  Frozen weights: dgrad only."""
+        ctx = self.ctx
+        g = None  # dense gradient w.r.t. the output of conv li (after relu, before any pool)
+        for li in range(len(self.convs_) - 1, -1, -1):
+            idx, conv = self.convs_[li]
+            out = tape["outs"][li]
+            shape = (nb, out.h, out.w, conv.cout)
+            dy = Operand(ctx, nb, out.h, out.w, conv.cout)
+            tap = tape["taps"].get(li)
+            if tap is not None:
+                l1 = coefs[VGG19_TAP_AFTER[idx]] / (tap.numel() // 2)
+                ops.in_bwd(ctx, shape, ACT_RELU, z=tap[:nb], g2=g, tref=tap[nb:], l1coef=l1, out_op=dy)
+            else:
+                ops.in_bwd(ctx, shape, ACT_RELU, mask_op=out, g2=g, out_op=dy)
+            xin = tape["xs"][li]
+            gin = _f32(ctx, nb, xin.h, xin.w, conv.cin)
+            conv.dgrad(dy, xin.h, xin.w, 1, gin)
+            if li in tape["pooled_from"]:
+                src = tape["pooled_from"][li]
+                dz = _f32(ctx, nb, src.h, src.w, src.c)
+                ops.maxpool2_bwd(ctx, gin, src, dz)
+                g = dz
+            else:
+                g = gin
+        return g

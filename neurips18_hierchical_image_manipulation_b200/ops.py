@@ -1,0 +1,277 @@
+"""Python faces of the C-ABI kernels (include/hm_b200.h).  torch is used for device memory and streams only:
+every function below enqueues hand-written sm_100a kernels from libhm_b200.so on torch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+
+
+def ru(v, m):
+    return (v + m - 1) // m * m
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Ctx(object):
+    """Per-device state shared by all ops: library handle, precision mode, pipeline error flag."""
+
+    def __init__(self, device, split=True):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.split = bool(split)  # True: bf16x3 (fp32-parity mode); False: plain bf16 products
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ws = {}
+        self.launches = 0  # number of hm kernels enqueued (bench.py reports it)
+
+    def ws(self, key, nbytes):
+        """Grow-only scratch buffers keyed by use."""
+        n = (int(nbytes) + 3) // 4
+        t = self._ws.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def check_pipeline(self):
+        code = int(self.err.item())
+        if code != 0:
+            raise L.HmError("tcgen05 engine pipeline wait timed out (code %d)" % code)
+
+
+class Operand(object):
+    """bf16 (hi, lo) NHWC operand [n, h, w, cs] with c valid channels; h/w include `border`."""
+
+    __slots__ = ("hi", "lo", "n", "h", "w", "c", "cs", "border")
+
+    def __init__(self, ctx, n, h, w, c, border=0, cs=None, zero=False):
+        cs = ru(c, 8) if cs is None else cs
+        hp, wp = h + 2 * border, w + 2 * border
+        alloc = torch.zeros if zero else torch.empty
+        self.hi = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device)
+        self.lo = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device) if ctx.split else None
+        self.n, self.h, self.w, self.c, self.cs, self.border = n, hp, wp, c, cs, border
+
+    def struct(self, n0=0, n=None):
+        """hm_operand for images [n0, n0+n)."""
+        n = self.n - n0 if n is None else n
+        off = n0 * self.h * self.w * self.cs * 2
+        return L.Operand(self.hi.data_ptr() + off, (self.lo.data_ptr() + off) if self.lo is not None else None, n,
+                         self.h, self.w, self.c, self.cs)
+
+    @property
+    def ih(self):
+        return self.h - 2 * self.border
+
+    @property
+    def iw(self):
+        return self.w - 2 * self.border
+
+    def dense(self):
+        """fp32 NCHW copy of the interior (tests / visuals only)."""
+        v = self.hi.float()
+        if self.lo is not None:
+            v = v + self.lo.float()
+        b = self.border
+        if b:
+            v = v[:, b:-b, b:-b]
+        return v[..., :self.c].permute(0, 3, 1, 2).contiguous()
+
+
+class PackedWeight(object):
+    """bf16 [taps][rows_pad][k_pad] slabs of one conv weight for one engine role."""
+
+    def __init__(self, ctx, rows, k, taps):
+        lib = ctx.lib
+        self.rows, self.k, self.taps = rows, k, taps
+        self.rows_pad, self.k_pad = lib.hm_rows_pad(rows), lib.hm_k_pad(k)
+        n = taps * self.rows_pad * self.k_pad
+        self.hi = torch.empty(n, dtype=torch.bfloat16, device=ctx.device)
+        self.lo = torch.empty(n, dtype=torch.bfloat16, device=ctx.device) if ctx.split else None
+
+    def pack(self, ctx, w, s_row, s_k, s_tap):
+        L.check(ctx.lib.hm_pack_weight(w.data_ptr(), self.rows, self.k, self.taps, s_row, s_k, s_tap, self.hi.data_ptr(),
+                                       _ptr(self.lo), _stream()), "hm_pack_weight")
+        ctx.launches += 1
+
+
+def conv_fprop(ctx, x, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT_NONE, slope=0.2, out32=None,
+               out16=None, out16_coff=0, n0=0, n=None):
+    """x: Operand (stored, incl. border); out32: fp32 [N,hout,wout,cout]; out16: Operand (written at its interior)."""
+    xs = x.struct(n0, n)
+    o32 = L.OutF32(out32.data_ptr(), hout, wout, out32.shape[-1], 0, 0, 0) if out32 is not None else None
+    o16 = None
+    if out16 is not None:
+        o16 = L.OutBF16(out16.hi.data_ptr(), _ptr(out16.lo), out16.h, out16.w, out16.cs, out16.border, out16.border,
+                        out16_coff)
+    L.check(ctx.lib.hm_conv_fprop(C.byref(xs), pw.hi.data_ptr(), _ptr(pw.lo), pw.k_pad, pw.rows_pad, _ptr(bias), kh, kw,
+                                  stride, pad, hout, wout, cout, act, slope, C.byref(o32) if o32 else None,
+                                  C.byref(o16) if o16 else None, ctx.err.data_ptr(), _stream()), "hm_conv_fprop")
+    ctx.launches += 1
+
+
+def conv_dgrad(ctx, dy, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT_NONE, slope=0.2, out32=None,
+               out16=None):
+    ds = dy.struct()
+    o32 = L.OutF32(out32.data_ptr(), hout, wout, out32.shape[-1], 0, 0, 0) if out32 is not None else None
+    o16 = None
+    if out16 is not None:
+        o16 = L.OutBF16(out16.hi.data_ptr(), _ptr(out16.lo), out16.h, out16.w, out16.cs, out16.border, out16.border, 0)
+    L.check(ctx.lib.hm_conv_dgrad(C.byref(ds), pw.hi.data_ptr(), _ptr(pw.lo), pw.k_pad, pw.rows_pad, _ptr(bias), kh, kw,
+                                  stride, pad, hout, wout, cout, act, slope, C.byref(o32) if o32 else None,
+                                  C.byref(o16) if o16 else None, ctx.err.data_ptr(), _stream()), "hm_conv_dgrad")
+    ctx.launches += 4 if stride == 2 else 1
+
+
+def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=0, n=None):
+    """dst[cq][cp][kh][kw] (+)= sum_pixels P[., y*stride+kh-pad, ., cp] * Q[., y, ., cq]."""
+    ps, qs = P.struct(n0P, n), Q.struct(n0Q, n)
+    ws = ctx.ws("wgrad", ctx.lib.hm_wgrad_ws_bytes(kh, kw, P.c, Q.c))
+    L.check(ctx.lib.hm_conv_wgrad(C.byref(ps), C.byref(qs), kh, kw, stride, pad, ws.data_ptr(), ctx.err.data_ptr(),
+                                  _stream()), "hm_conv_wgrad")
+    L.check(ctx.lib.hm_wgrad_unpack(ws.data_ptr(), kh, kw, P.c, Q.c, dst.data_ptr(), 1 if accumulate else 0, _stream()),
+            "hm_wgrad_unpack")
+    ctx.launches += 2
+
+
+def encode_input(ctx, label, inst, image, mask_in, label_nc, g_op, d_op=None, v_op=None):
+    B, _, H, W = label.shape
+    L.check(ctx.lib.hm_encode_input(label.data_ptr(), _ptr(inst), image.data_ptr(), mask_in.data_ptr(), B, H, W,
+                                    label_nc, g_op.hi.data_ptr(), _ptr(g_op.lo), g_op.cs, g_op.border,
+                                    _ptr(d_op.hi) if d_op else None, _ptr(d_op.lo) if d_op else None,
+                                    d_op.cs if d_op else 0, _ptr(v_op.hi) if v_op else None,
+                                    _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, _stream()),
+            "hm_encode_input")
+    ctx.launches += 1
+
+
+def in_stats(ctx, y, eps=1e-5):
+    """y fp32 [N,H,W,C] -> (mean, rstd) fp32 [N,C]."""
+    N, H, W, Cc = y.shape
+    ws = ctx.ws("in", ctx.lib.hm_in_ws_bytes(N, H * W, Cc))
+    mean = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    rstd = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    L.check(ctx.lib.hm_in_stats(y.data_ptr(), N, H * W, Cc, eps, ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                _stream()), "hm_in_stats")
+    ctx.launches += 2
+    return mean, rstd
+
+
+def in_apply(ctx, y, mean, rstd, act, slope=0.2, skip=None, out32=None, out_op=None, reflect=True):
+    N, H, W, Cc = y.shape
+    border = out_op.border if out_op is not None else 0
+    L.check(ctx.lib.hm_in_apply(y.data_ptr(), _ptr(mean), _ptr(rstd), _ptr(skip), N, H, W, Cc, act, slope, _ptr(out32),
+                                _ptr(out_op.hi) if out_op else None, _ptr(out_op.lo) if out_op else None,
+                                out_op.cs if out_op else 0, border, 1 if reflect else 0, _stream()), "hm_in_apply")
+    ctx.launches += 1
+
+
+def in_bwd(ctx, shape, act, slope=0.2, y=None, mean=None, rstd=None, z=None, mask_op=None, g1=None, g1_border=0,
+           g1_ld=None, g1_coff=0, g2=None, tref=None, l1coef=0.0, out_op=None, out32=None):
+    N, H, W, Cc = shape
+    ws = ctx.ws("in", ctx.lib.hm_in_ws_bytes(N, H * W, Cc)) if mean is not None else None
+    L.check(ctx.lib.hm_in_bwd(_ptr(y), _ptr(mean), _ptr(rstd), _ptr(z), _ptr(mask_op.hi) if mask_op else None,
+                              mask_op.cs if mask_op else 0, _ptr(g1), g1_border, Cc if g1_ld is None else g1_ld, g1_coff,
+                              _ptr(g2), _ptr(tref), float(l1coef), N, H, W, Cc, act, slope, _ptr(ws),
+                              _ptr(out_op.hi) if out_op else None, _ptr(out_op.lo) if out_op else None,
+                              out_op.cs if out_op else 0, _ptr(out32), _stream()), "hm_in_bwd")
+    ctx.launches += 3 if mean is not None else 1
+
+
+def fold_add(ctx, g_padded, border, base, out):
+    N, H, W, Cc = out.shape
+    L.check(ctx.lib.hm_fold_add(g_padded.data_ptr(), border, N, H, W, Cc, _ptr(base), out.data_ptr(), _stream()),
+            "hm_fold_add")
+    ctx.launches += 1
+
+
+def avgpool3s2(ctx, x, out):
+    L.check(ctx.lib.hm_avgpool3s2(x.hi.data_ptr(), _ptr(x.lo), x.n, x.h, x.w, x.cs, out.hi.data_ptr(), _ptr(out.lo),
+                                  _stream()), "hm_avgpool3s2")
+    ctx.launches += 1
+
+
+def avgpool3s2_bwd(ctx, g_coarse, g_fine, c0, c1):
+    N, Ho, Wo, ldc = g_coarse.shape
+    _, H, W, ldf = g_fine.shape
+    L.check(ctx.lib.hm_avgpool3s2_bwd(g_coarse.data_ptr(), N, Ho, Wo, ldc, g_fine.data_ptr(), H, W, ldf, c0, c1,
+                                      _stream()), "hm_avgpool3s2_bwd")
+    ctx.launches += 1
+
+
+def maxpool2(ctx, x, out):
+    L.check(ctx.lib.hm_maxpool2(x.hi.data_ptr(), _ptr(x.lo), x.n, x.h, x.w, x.cs, out.hi.data_ptr(), _ptr(out.lo),
+                                _stream()), "hm_maxpool2")
+    ctx.launches += 1
+
+
+def maxpool2_bwd(ctx, g, a_op, dz, n=None):
+    N, H, W, Cc = dz.shape
+    L.check(ctx.lib.hm_maxpool2_bwd(g.data_ptr(), N, H, W, Cc, a_op.hi.data_ptr(), _ptr(a_op.lo), a_op.cs, dz.data_ptr(),
+                                    _stream()), "hm_maxpool2_bwd")
+    ctx.launches += 1
+
+
+def l1_sum(ctx, a, b, coef, acc, slot):
+    L.check(ctx.lib.hm_l1_sum(a.data_ptr(), b.data_ptr(), a.numel(), float(coef), acc.data_ptr() + 8 * slot, _stream()),
+            "hm_l1_sum")
+    ctx.launches += 1
+
+
+def mse_sum(ctx, a, target, coef, acc, slot):
+    L.check(ctx.lib.hm_mse_sum(a.data_ptr(), a.numel(), float(target), float(coef), acc.data_ptr() + 8 * slot, _stream()),
+            "hm_mse_sum")
+    ctx.launches += 1
+
+
+def mse_grad(ctx, y, target, scale, out_op, op_n0=0):
+    """out_op[op_n0 : op_n0 + y.shape[0]] = scale * (y - target)"""
+    P = y.numel() // y.shape[-1]
+    off = op_n0 * out_op.h * out_op.w * out_op.cs * 2
+    L.check(ctx.lib.hm_mse_grad(y.data_ptr(), P, y.shape[-1], float(target), float(scale), out_op.hi.data_ptr() + off,
+                                (out_op.lo.data_ptr() + off) if out_op.lo is not None else None, out_op.cs, _stream()),
+            "hm_mse_grad")
+    ctx.launches += 1
+
+
+def finish_fake(ctx, t, image, mask, use_gate, fake_nchw, d_op, d_coff, v_op):
+    B, H, W, _ = t.shape
+    L.check(ctx.lib.hm_finish_fake(t.data_ptr(), _ptr(image), _ptr(mask), 1 if use_gate else 0, B, H, W, _ptr(fake_nchw),
+                                   _ptr(d_op.hi) if d_op else None, _ptr(d_op.lo) if d_op else None,
+                                   d_op.cs if d_op else 0, d_coff, _ptr(v_op.hi) if v_op else None,
+                                   _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, _stream()), "hm_finish_fake")
+    ctx.launches += 1
+
+
+def fake_bwd(ctx, t, mask, use_gate, gD, gD_coff, gV, real_nchw, rec_coef, out_op):
+    B, H, W, _ = t.shape
+    L.check(ctx.lib.hm_fake_bwd(t.data_ptr(), _ptr(mask), 1 if use_gate else 0, _ptr(gD),
+                                gD.shape[-1] if gD is not None else 0, gD_coff, _ptr(gV),
+                                gV.shape[-1] if gV is not None else 0, _ptr(real_nchw), float(rec_coef), B, H, W,
+                                out_op.hi.data_ptr(), _ptr(out_op.lo), out_op.cs, _stream()), "hm_fake_bwd")
+    ctx.launches += 1
+
+
+def colsum_operand(ctx, op, out, accumulate=True, n0=0, n=None):
+    n = op.n - n0 if n is None else n
+    off = n0 * op.h * op.w * op.cs * 2
+    P = n * op.h * op.w
+    L.check(ctx.lib.hm_colsum_operand(op.hi.data_ptr() + off, (op.lo.data_ptr() + off) if op.lo is not None else None, P,
+                                      op.c, op.cs, out.data_ptr(), 1 if accumulate else 0, _stream()),
+            "hm_colsum_operand")
+    ctx.launches += 1
+
+
+def adam_step(ctx, p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    L.check(ctx.lib.hm_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                                 step, grad_scale, _stream()), "hm_adam_step")
+    ctx.launches += 1

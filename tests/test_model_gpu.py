@@ -1,0 +1,172 @@
+"""GPU parity tests of the full mask2image hot path (through the reference-facing API and the C ABI) against the
+CPU oracle (oracle/model.py) on identical weights and synthetic batches.
+
+Precision mode bf16x3 (the fp32-parity mode): tolerance 1e-3 relative on the generator output (per pixel, relative to
+the output's max magnitude) and on every loss scalar -- the tolerance BASELINE.json's north_star states; gradients
+are compared at 1e-2 of each tensor's max magnitude.  Mode bf16 is checked at the looser 5e-2 / 1e-1.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+from oracle import model as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(precision, **kw):
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    base = dict(label_nc=5, ngf=8, n_downsample_global=2, n_blocks_global=2, ndf=8, num_D=2, n_layers_D=3,
+                no_instance=True, precision=precision, gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="t")
+    base.update(kw)
+    opt = Options(**base)
+    return opt, create_model(opt)
+
+
+def _oracle_opt(opt):
+    return O.Opt(**{k: getattr(opt, k) for k in ("label_nc", "no_instance", "output_nc", "ngf", "n_downsample_global",
+                                                 "n_blocks_global", "ndf", "n_layers_D", "num_D", "use_output_gate",
+                                                 "no_ganFeat_loss", "no_vgg_loss", "lambda_feat", "lambda_rec", "lr",
+                                                 "beta1", "netG", "n_local_enhancers", "n_blocks_local")})
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def run_parity(precision, verbose=False, **kw):
+    from neurips18_hierchical_image_manipulation_b200.models import random_vgg19_state_dict
+    opt, model = _mk(precision, **kw)
+    m = model.module
+    B, H, W = kw.get("B", 2), kw.get("H", 64), kw.get("W", 64)
+    batch = O.synthetic_batch(B, H, W, label_nc=opt.label_nc, seed=7)
+    g_sd, d_sd = m.fpG.state_dict(), m.fpD.state_dict()
+    vgg_sd = random_vgg19_state_dict(opt.vgg_seed)
+    # ---- oracle: forward, grads, one Adam step (fp32 CPU)
+    oopt = _oracle_opt(opt)
+    g_ref = {k: v.clone() for k, v in g_sd.items()}
+    d_ref = {k: v.clone() for k, v in d_sd.items()}
+    ls_ref, fake_ref, gG_ref, gD_ref, _ = O.train_step(oopt, g_ref, d_ref, vgg_sd, batch)
+    # ---- product: the reference script's call sequence (train_mask2image.py:58-86)
+    losses, fake = model(label=batch["label"], inst=batch["inst"], image=batch["image"], feat=None,
+                         mask_in=batch["mask_in"], mask_out=batch["mask_out"], infer=True)
+    losses = [torch.mean(x) for x in losses]
+    ld = dict(zip(m.loss_names, losses))
+    loss_D = (ld["D_fake"] + ld["D_real"]) * 0.5
+    loss_G = ld["G_GAN"] + ld["G_GAN_Feat"] + ld["G_VGG"]
+    m.optimizer_G.zero_grad()
+    loss_G.backward()
+    gG = {k: p.grad.detach().cpu().clone() for k, p in m.fpG.params.items()}
+    m.optimizer_G.step()
+    m.optimizer_D.zero_grad()
+    loss_D.backward()
+    gD = {k: p.grad.detach().cpu().clone() for k, p in m.fpD.params.items()}
+    m.optimizer_D.step()
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    res = dict(fake=rel(fake, fake_ref))
+    for n, a, b in zip(m.loss_names, losses, ls_ref):
+        res["loss_" + n] = abs(float(a) - b) / max(abs(b), 1e-30)
+    skip_bias = lambda k, ref: k.endswith("bias") and float(ref.abs().max()) < 1e-5  # noqa: E731 (bias before IN: ~0)
+    res["gradG"] = max(rel(gG[k], gG_ref[k]) for k in gG if not skip_bias(k, gG_ref[k]))
+    res["gradD"] = max(rel(gD[k], gD_ref[k]) for k in gD if not skip_bias(k, gD_ref[k]))
+    res["gradG_bias_abs"] = max(float(gG[k].abs().max()) for k in gG if skip_bias(k, gG_ref[k])) if any(
+        skip_bias(k, gG_ref[k]) for k in gG) else 0.0
+    # parameters after the Adam step
+    g_new, d_new = m.fpG.state_dict(), m.fpD.state_dict()
+    res["stepG"] = max(float((g_new[k] - g_ref[k]).abs().max()) for k in g_new) / opt.lr
+    res["stepD"] = max(float((d_new[k] - d_ref[k]).abs().max()) for k in d_new) / opt.lr
+    if verbose:
+        worstG = sorted(((rel(gG[k], gG_ref[k]), k) for k in gG if not skip_bias(k, gG_ref[k])), reverse=True)[:5]
+        worstD = sorted(((rel(gD[k], gD_ref[k]), k) for k in gD if not skip_bias(k, gD_ref[k])), reverse=True)[:5]
+        print("worst G grads", worstG)
+        print("worst D grads", worstD)
+    return res
+
+
+def test_parity_bf16x3_global():
+    r = run_parity("bf16x3")
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
+    assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
+    # Adam moves every weight by at most lr on the first step; the two implementations must agree to a small
+    # fraction of that (sign flips of ~zero gradients excepted, hence the loose bound)
+    assert r["stepG"] < 2.1 and r["stepD"] < 2.1, r
+
+
+def test_parity_bf16x3_gate_instance_rec():
+    r = run_parity("bf16x3", use_output_gate=True, no_instance=False, lambda_rec=5.0, num_D=3, H=64, W=96)
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
+    assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
+
+
+def test_parity_bf16_mode():
+    r = run_parity("bf16")
+    assert r["fake"] < 5e-2, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 5e-2, (k, r)
+
+
+def test_fused_step_matches_script_sequence():
+    """optimize_parameters() == {forward; G.backward; G.step; D.backward; D.step}."""
+    opt, model_a = _mk("bf16x3")
+    _, model_b = _mk("bf16x3")
+    a, b = model_a.module, model_b.module
+    b.fpG.load_state_dict(a.fpG.state_dict()); b.fpD.load_state_dict(a.fpD.state_dict())
+    batch = O.synthetic_batch(2, 64, 64, label_nc=opt.label_nc, seed=3)
+    kw = dict(label=batch["label"], inst=batch["inst"], image=batch["image"], feat=None, mask_in=batch["mask_in"],
+              mask_out=batch["mask_out"])
+    losses, _ = model_a(infer=False, **kw)
+    ld = dict(zip(a.loss_names, losses))
+    a.optimizer_G.zero_grad(); (ld["G_GAN"] + ld["G_GAN_Feat"] + ld["G_VGG"]).backward(); a.optimizer_G.step()
+    a.optimizer_D.zero_grad(); ((ld["D_fake"] + ld["D_real"]) * 0.5).backward(); a.optimizer_D.step()
+    lb = b.optimize_parameters(**kw)
+    torch.cuda.synchronize()
+    assert torch.allclose(torch.stack([x.detach() for x in losses]).cpu(), lb.cpu(), rtol=1e-6, atol=0)
+    for k in a.fpG.params:
+        assert torch.allclose(a.fpG.params[k], b.fpG.params[k], rtol=0, atol=1e-7), k
+    for k in a.fpD.params:
+        assert torch.allclose(a.fpD.params[k], b.fpD.params[k], rtol=0, atol=1e-7), k
+
+
+def test_inference_and_checkpoint_roundtrip(tmp_path):
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    opt, model = _mk("bf16x3", checkpoints_dir=str(tmp_path))
+    m = model.module
+    m.save("latest")
+    assert os.path.isfile(os.path.join(str(tmp_path), "t", "latest_net_G.pth"))
+    sd = torch.load(os.path.join(str(tmp_path), "t", "latest_net_G.pth"))
+    assert "model.1.weight" in sd and sd["model.1.weight"].shape == (8, 8, 7, 7)
+    topt = Options(label_nc=5, ngf=8, n_downsample_global=2, n_blocks_global=2, no_instance=True, isTrain=False,
+                   gpu_ids=[0], checkpoints_dir=str(tmp_path), name="t")
+    tm = create_model(topt)  # bare model when not training (models/models.py:21)
+    batch = O.synthetic_batch(1, 64, 64, label_nc=5, seed=11)
+    out = tm.inference(batch["label"], batch["inst"], batch["image"], batch["mask_in"], batch["mask_out"])
+    ref = O.global_generator_forward(sd, torch.cat(O.encode_input(batch["label"], batch["inst"], batch["image"],
+                                     batch["mask_in"], 5, True)[0::2], 1), 2, 2)
+    assert rel(out, ref) < 1e-3
+    vis = tm.get_current_visuals()
+    assert list(vis) == ["input_label", "input_image", "real_image", "synthesized_image"]
+    assert vis["synthesized_image"].shape == (64, 64, 3)
+
+
+if __name__ == "__main__":
+    for prec, kw in (("bf16x3", {}), ("bf16x3", dict(use_output_gate=True, no_instance=False, lambda_rec=5.0, num_D=3,
+                                                     H=64, W=96)), ("bf16", {})):
+        try:
+            r = run_parity(prec, verbose=True, **kw)
+            print(prec, kw, {k: "%.3e" % v for k, v in r.items()}, flush=True)
+        except Exception:
+            import traceback
+            traceback.print_exc()
