@@ -282,7 +282,19 @@ struct BwdArgs {
   int N, H, W, C, act; float slope;
 };
 
-__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, int n, int h, int w, int c, float (&dyh)[8], float (&yh)[8]) {
+// per-thread constants of one (n, 8-channel group): hoisted out of the pixel loops
+struct ChanStats { float mu[8], rs[8]; };
+__device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, ChanStats& cs) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool ok = a.mean && (c + j < a.C);
+    cs.mu[j] = ok ? __ldg(a.mean + n * a.C + c + j) : 0.f;
+    cs.rs[j] = ok ? __ldg(a.rstd + n * a.C + c + j) : 1.f;
+  }
+}
+
+__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats& cs, int n, int h, int w, int c,
+                                          float (&dyh)[8], float (&yh)[8]) {
   const size_t pix = (size_t(n) * a.H + h) * a.W + w;
   float dz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (a.g1) {
@@ -295,11 +307,12 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, int n, int h, int w,
       if (w >= 1 && w <= b) ws[nw++] = b - w;
       if (w >= a.W - 1 - b && w <= a.W - 2) ws[nw++] = b + 2 * (a.W - 1) - w;
     }
+    const bool vec = ((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0);
     for (int ih = 0; ih < nh; ++ih)
       for (int iw = 0; iw < nw; ++iw) {
         float t[8];
         const float* p = a.g1 + ((size_t(n) * Hp + hs[ih]) * Wp + ws[iw]) * a.g1_ld + a.g1_coff;
-        if (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0)) load8(p, c, a.C, t);
+        if (vec) load8(p, c, a.C, t);
         else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) t[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
@@ -315,18 +328,14 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, int n, int h, int w,
     for (int j = 0; j < 8; ++j) dz[j] += t[j];
   }
   float zv[8];
-  bool have_z = false;
-  if (a.z) { load8(a.z + pix * a.C, c, a.C, zv); have_z = true; }
+  const bool have_z = a.z != nullptr;
+  if (have_z) load8(a.z + pix * a.C, c, a.C, zv);
   float yv[8];
-  bool have_y = false;
-  if (a.y) {
+  const bool have_y = a.y != nullptr;
+  if (have_y) {
     load8(a.y + pix * a.C, c, a.C, yv);
-    have_y = true;
-    if (a.mean) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c + j < a.C) yv[j] = (yv[j] - __ldg(a.mean + n * a.C + c + j)) * __ldg(a.rstd + n * a.C + c + j);
-    }
+    for (int j = 0; j < 8; ++j) yv[j] = (yv[j] - cs.mu[j]) * cs.rs[j];
   }
   if (a.tref) {
     float t[8];
@@ -353,8 +362,8 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, int n, int h, int w,
   }
 }
 
-__global__ void in_bwd_reduce_kernel(BwdArgs a, int gx_log2, float* __restrict__ partial) {
-  // same decomposition as in_stats_kernel but channel groups of 8; partial[n][blk][2][C8]
+// grid (nblk, N, cgroups); thread (tx = 8-channel group, ty = pixel lane): per-thread channel constants are loaded once
+__global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx_log2, float* __restrict__ partial) {
   const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
   const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
   const int n = blockIdx.y, nblk = gridDim.x;
@@ -365,9 +374,11 @@ __global__ void in_bwd_reduce_kernel(BwdArgs a, int gx_log2, float* __restrict__
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cvalid) {
+    ChanStats cs;
+    load_chan_stats(a, n, c, cs);
     for (int p = p0 + ty; p < p1; p += rows) {
       float dyh[8], yh[8];
-      bwd_dyhat(a, n, p / a.W, p % a.W, c, dyh, yh);
+      bwd_dyhat(a, cs, n, p / a.W, p % a.W, c, dyh, yh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
     }
@@ -403,40 +414,48 @@ __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N,
   sums[(size_t(n) * 2) * C8 + c] = float(s / HW);
   sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
 }
-__global__ void in_bwd_apply_kernel(BwdArgs a, const float* __restrict__ sums, bf16* o_hi, bf16* o_lo, int o_cs,
-                                    float* __restrict__ out32) {
-  const int G = o_hi ? (o_cs >> 3) : ((a.C + 7) >> 3);
+// same thread decomposition; grid (pixel blocks, N, cgroups) with a grid-stride loop over the pixels of image n
+__global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_log2, const float* __restrict__ sums,
+                                                              bf16* o_hi, bf16* o_lo, int o_cs, float* __restrict__ out32) {
+  const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
+  const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
+  const int n = blockIdx.y;
+  const int c = (blockIdx.z * gx + tx) * 8;
+  const int Cout = o_hi ? o_cs : ((a.C + 7) & ~7);
+  if (c >= Cout) return;
   const int C8 = (a.C + 7) & ~7;
-  const long total = long(a.N) * a.H * a.W * G;
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    const int g = int(i % G);
-    long r = i / G;
-    const int w = int(r % a.W); r /= a.W;
-    const int h = int(r % a.H);
-    const int n = int(r / a.H);
-    const int c = g * 8;
-    float dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (c < a.C) {
-      float dyh[8], yh[8];
-      bwd_dyhat(a, n, h, w, c, dyh, yh);
-      if (a.mean) {
+  const int HW = a.H * a.W;
+  const bool cvalid = c < a.C;
+  ChanStats cs;
+  float m1[8], m2[8];
+  if (cvalid) {
+    load_chan_stats(a, n, c, cs);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c + j < a.C) {
-            const float m1 = __ldg(sums + (size_t(n) * 2) * C8 + c + j);
-            const float m2 = __ldg(sums + (size_t(n) * 2 + 1) * C8 + c + j);
-            dy[j] = __ldg(a.rstd + n * a.C + c + j) * (dyh[j] - m1 - yh[j] * m2);
-          }
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = sums && (c + j < a.C);
+      m1[j] = ok ? __ldg(sums + (size_t(n) * 2) * C8 + c + j) : 0.f;
+      m2[j] = ok ? __ldg(sums + (size_t(n) * 2 + 1) * C8 + c + j) : 0.f;
+    }
+  }
+  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
+    float dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cvalid) {
+      float dyh[8], yh[8];
+      bwd_dyhat(a, cs, n, p / a.W, p % a.W, c, dyh, yh);
+      if (sums) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[j] = (c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dy[j] = dyh[j];
       }
     }
-    const size_t pix = (size_t(n) * a.H + h) * a.W + w;
+    const size_t pix = size_t(n) * HW + p;
     if (o_hi) store_op8(o_hi, o_lo, pix * o_cs + c, dy);
-    if (out32 && c < a.C) store8(out32 + pix * a.C, c, a.C, dy);
+    if (out32 && cvalid) store8(out32 + pix * a.C, c, a.C, dy);
   }
 }
+
 
 // ================================================================================================
 // K8  AvgPool2d(3, stride 2, pad 1, count_include_pad=False)  (Discriminator_NET.py:31-32, Pix2Pix_NET.py:45)
@@ -729,28 +748,38 @@ __global__ void colsum_kernel(const float* __restrict__ x, long P, int C, float*
   }
   if (threadIdx.x == 0) out[c] = (accumulate ? out[c] : 0.f) + float(sm[0]);
 }
-// same, reading a bf16 operand (hi+lo)
-__global__ void colsum_op_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, long P, int C, int cs,
-                                 float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x;
-  double s = 0.0;
-  float f = 0.f;
-  int k = 0;
-  for (long p = threadIdx.x; p < P; p += blockDim.x) {
-    float v = __bfloat162float(hi[p * cs + c]);
-    if (lo) v += __bfloat162float(lo[p * cs + c]);
-    f += v;
-    if (++k == 64) { s += f; f = 0.f; k = 0; }
+// same, reading a bf16 operand (hi+lo): grid (pixel blocks, cgroups), thread (tx = 8-channel group, ty = pixel lane);
+// coalesced 16 B loads, block tree reduction, one fp32 atomicAdd per (block, channel)
+__global__ void __launch_bounds__(kBlock) colsum_op_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, long P,
+                                                           int C, int cs, int gx_log2, float* __restrict__ out) {
+  const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
+  const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
+  const int c = (blockIdx.y * gx + tx) * 8;
+  const bool cvalid = c < cs;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cvalid) {
+    for (long p = blockIdx.x * long(rows) + ty; p < P; p += long(gridDim.x) * rows) {
+      float v[8];
+      load_op8(hi, lo, size_t(p) * cs + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
   }
-  s += f;
-  __shared__ double sm[kBlock];
-  sm[threadIdx.x] = s;
+  __shared__ float sm[kBlock * 8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.x * 8 + j] = s[j];
   __syncthreads();
-  for (int st = kBlock / 2; st >= 1; st >>= 1) {
-    if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+  for (int step = rows >> 1; step >= 1; step >>= 1) {
+    if (ty < step) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sm[threadIdx.x * 8 + j] += sm[(threadIdx.x + step * gx) * 8 + j];
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[c] = (accumulate ? out[c] : 0.f) + float(sm[0]);
+  if (ty == 0 && cvalid) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c + j < C) atomicAdd(out + c + j, sm[tx * 8 + j]);
+  }
 }
 
 // ================================================================================================
@@ -804,7 +833,9 @@ __global__ void fold_add_kernel(const float* __restrict__ g, int b, int N, int H
     const int h = int(r % H);
     const int n = int(r / H);
     float dyh[8], yh[8];
-    bwd_dyhat(a, n, h, w, gq * 8, dyh, yh);
+    ChanStats cs;
+    load_chan_stats(a, n, gq * 8, cs);
+    bwd_dyhat(a, cs, n, h, w, gq * 8, dyh, yh);
     store8(out + ((size_t(n) * H + h) * W + w) * C, gq * 8, C, dyh);
   }
 }
@@ -818,11 +849,13 @@ int stats_geometry(int C, int quad, int* gx_log2, int* cgroups) {
   *cgroups = (groups + gx - 1) / gx;
   return 0;
 }
-inline int stats_nblk(int N, int HW) {
-  // enough blocks to fill the chip, at least ~1024 pixels per block
-  int nblk = std::max(1, std::min(HW / 1024, (148 * 8) / std::max(1, N)));
+inline int stats_nblk(int N, int HW, int cgroups = 1) {
+  // enough blocks to fill the chip (~4 per SM) while keeping >= 64 pixels per block
+  const int want = (148 * 4 + N * cgroups - 1) / std::max(1, N * cgroups);
+  int nblk = std::max(1, std::min(want, HW / 64));
   return std::min(nblk, 256);
 }
+inline int stats_nblk_max(int N, int HW) { return std::max(1, std::min(std::min((148 * 4 + N - 1) / N, HW / 64), 256)); }
 
 }  // namespace
 
@@ -845,7 +878,7 @@ int hm_encode_input(const float* label, const float* inst, const float* image, c
 
 size_t hm_in_ws_bytes(int N, int HW, int C) {
   const int C8 = (C + 7) & ~7;
-  return size_t(N) * stats_nblk(N, HW) * 2 * C8 * sizeof(float) + size_t(N) * 2 * C8 * sizeof(float);
+  return size_t(N) * stats_nblk_max(N, HW) * 2 * C8 * sizeof(float) + size_t(N) * 2 * C8 * sizeof(float);
 }
 
 int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, float* mean, float* rstd, void* stream) {
@@ -853,7 +886,7 @@ int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int gx_log2, cgroups;
   stats_geometry(C, 4, &gx_log2, &cgroups);
-  const int nblk = stats_nblk(N, HW);
+  const int nblk = stats_nblk(N, HW, cgroups);
   in_stats_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(y, HW, C, gx_log2, ws);
   in_stats_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(ws, N, nblk, C, HW, eps, mean, rstd);
   return HM_LAUNCH_OK();
@@ -886,17 +919,20 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
   a.N = N; a.H = H; a.W = W; a.C = C; a.act = act; a.slope = slope;
   const int C8 = (C + 7) & ~7;
   float* sums = nullptr;
+  int gx_log2, cgroups;
   if (mean) {
-    int gx_log2, cgroups;
     stats_geometry(C, 8, &gx_log2, &cgroups);
-    const int nblk = stats_nblk(N, H * W);
+    const int nblk = stats_nblk(N, H * W, cgroups);
     sums = ws + size_t(N) * nblk * 2 * C8;
     in_bwd_reduce_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
     in_bwd_finalize_kernel<<<(N * C8 + 127) / 128, 128, 0, st>>>(ws, N, nblk, C8, H * W, sums);
   }
-  const int G = o_hi ? (o_cs >> 3) : (C8 >> 3);
-  in_bwd_apply_kernel<<<grid_for(long(N) * H * W * G), kBlock, 0, st>>>(a, sums, static_cast<bf16*>(o_hi),
-                                                                        static_cast<bf16*>(o_lo), o_cs, out32);
+  const int Cout = o_hi ? o_cs : C8;
+  stats_geometry(Cout, 8, &gx_log2, &cgroups);
+  const int rows = kBlock >> gx_log2;
+  int pblocks = std::min((H * W + rows - 1) / rows, std::max(1, (148 * 8) / std::max(1, N * cgroups)));
+  in_bwd_apply_kernel<<<dim3(pblocks, N, cgroups), kBlock, 0, st>>>(a, gx_log2, sums, static_cast<bf16*>(o_hi),
+                                                                     static_cast<bf16*>(o_lo), o_cs, out32);
   return HM_LAUNCH_OK();
 }
 
@@ -993,10 +1029,15 @@ int hm_colsum(const float* x, long P, int C, float* out, int accumulate, void* s
   return HM_LAUNCH_OK();
 }
 int hm_colsum_operand(const void* hi, const void* lo, long P, int C, int cs, float* out, int accumulate, void* stream) {
-  if (!hi || !out) return HM_ERR_INVALID;
-  colsum_op_kernel<<<C, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(hi),
-                                                                       static_cast<const bf16*>(lo), P, C, cs, out,
-                                                                       accumulate);
+  if (!hi || !out || (cs & 7)) return HM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!accumulate && cudaMemsetAsync(out, 0, size_t(C) * sizeof(float), st) != cudaSuccess) return HM_ERR_LAUNCH;
+  int gx_log2, cgroups;
+  stats_geometry(cs, 8, &gx_log2, &cgroups);
+  const int rows = kBlock >> gx_log2;
+  const long pb = std::max<long>(1, std::min<long>((P + rows - 1) / rows, (148 * 4) / cgroups + 1));
+  colsum_op_kernel<<<dim3(unsigned(pb), cgroups), kBlock, 0, st>>>(static_cast<const bf16*>(hi), static_cast<const bf16*>(lo),
+                                                                    P, C, cs, gx_log2, out);
   return HM_LAUNCH_OK();
 }
 

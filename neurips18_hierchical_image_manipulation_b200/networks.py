@@ -155,13 +155,16 @@ class ConvP(object):
             ops.conv_dgrad(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, self.stride, zero_pad, x_h, x_w,
                            self.cin, out32=out32)
 
-    def wgrad(self, x, dy, zero_pad):
-        """accumulate into .grad of weight and bias."""
+    def wgrad(self, x, dy, zero_pad, bias_grad=True):
+        """accumulate into .grad of weight and bias.  bias_grad=False for convs that feed an InstanceNorm: the bias
+        cancels in the normalisation, its gradient is analytically zero (the reference computes ~1e-9 rounding noise),
+        so .grad stays exactly 0 and the full-resolution column reduction is skipped."""
         if self.transposed:
             ops.conv_wgrad(self.ctx, dy, x, self.k, self.k, 2, self.pad, self.weight.grad, accumulate=True)
         else:
             ops.conv_wgrad(self.ctx, x, dy, self.k, self.k, self.stride, zero_pad, self.weight.grad, accumulate=True)
-        ops.colsum_operand(self.ctx, dy, self.bias.grad, accumulate=True)
+        if bias_grad:
+            ops.colsum_operand(self.ctx, dy, self.bias.grad, accumulate=True)
 
 
 def _f32(ctx, *shape):
@@ -277,7 +280,7 @@ class GlobalGenerator(object):
                 else:
                     ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g1=G1,
                                g1_border=G1_border, out_op=dy)
-            conv.wgrad(xin, dy, rec["zero_pad"])
+            conv.wgrad(xin, dy, rec["zero_pad"], bias_grad=(kind == "head"))
             if s == 0 and not need_input_grad:
                 return None
             gin = _f32(ctx, xin.n, xin.h, xin.w, conv.cin)
@@ -385,7 +388,7 @@ class MultiscaleDiscriminator(object):
                 conv = layers[j]
                 xin = lv["xs"][j]
                 if mode == "D":
-                    conv.wgrad(xin, dy, 2)
+                    conv.wgrad(xin, dy, 2, bias_grad=(j == 0 or j == nl - 1))
                     if j == 0:
                         break
                 gin = _f32(ctx, nimg, xin.h, xin.w, conv.cin)
