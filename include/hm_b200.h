@@ -137,8 +137,11 @@ int hm_fold_add(const float* g_padded, int border, int N, int H, int W, int C, c
                 void* stream);
 
 /* K8. nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (Discriminator_NET.py:31-32, Pix2Pix_NET.py:45)
- * on operands, and its adjoint accumulated into channels [c0,c1) of a finer fp32 gradient. */
-int hm_avgpool3s2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, void* o_hi, void* o_lo, void* stream);
+ * on operands (H, W = interior extent; the input may carry a materialised border in_border, the output is written
+ * with a ReflectionPad2d(out_border) border), and its adjoint accumulated into channels [c0,c1) of a finer fp32
+ * gradient. */
+int hm_avgpool3s2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, int in_border, void* o_hi, void* o_lo,
+                  int out_border, void* stream);
 int hm_avgpool3s2_bwd(const float* g_coarse, int N, int Ho, int Wo, int ld_coarse, float* g_fine, int H, int W,
                       int ld_fine, int c0, int c1, void* stream);
 /* VGG19 MaxPool2d(2,2) (torchvision features, layer_util.py:384-399) and its adjoint (first maximum wins). */

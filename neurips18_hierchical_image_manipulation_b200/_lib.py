@@ -57,7 +57,7 @@ PROTOTYPES = {
     "hm_in_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _i, _i, _i, _i, _f, _vp, _vp,
                        _vp, _i, _vp, _vp]),
     "hm_fold_add": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "hm_avgpool3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hm_avgpool3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "hm_avgpool3s2_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "hm_maxpool2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hm_maxpool2_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -461,15 +461,19 @@ __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_
 // K8  AvgPool2d(3, stride 2, pad 1, count_include_pad=False)  (Discriminator_NET.py:31-32, Pix2Pix_NET.py:45)
 // ================================================================================================
 __global__ void avgpool_kernel(const bf16* __restrict__ i_hi, const bf16* __restrict__ i_lo, int N, int H, int W,
-                               int cs, bf16* o_hi, bf16* o_lo, int Ho, int Wo) {
+                               int cs, int ib, bf16* o_hi, bf16* o_lo, int Ho, int Wo, int ob) {
+  // H, W / Ho, Wo are interior extents; the input may carry a materialised border ib (skipped), the output gets a
+  // ReflectionPad2d(ob) border (LocalEnhancer feeds the pooled input to a 7x7 reflect-padded stem)
   const int G = cs >> 3;
-  const long total = long(N) * Ho * Wo * G;
+  const int Hs = H + 2 * ib, Ws = W + 2 * ib, Hop = Ho + 2 * ob, Wop = Wo + 2 * ob;
+  const long total = long(N) * Hop * Wop * G;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
     const int g = int(i % G);
     long r = i / G;
-    const int wo = int(r % Wo); r /= Wo;
-    const int ho = int(r % Ho);
-    const int n = int(r / Ho);
+    const int wop = int(r % Wop); r /= Wop;
+    const int hop = int(r % Hop);
+    const int n = int(r / Hop);
+    const int ho = reflect_idx(hop - ob, Ho), wo = reflect_idx(wop - ob, Wo);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int cnt = 0;
     for (int dh = -1; dh <= 1; ++dh) {
@@ -479,7 +483,7 @@ __global__ void avgpool_kernel(const bf16* __restrict__ i_hi, const bf16* __rest
         const int w = 2 * wo + dw;
         if (w < 0 || w >= W) continue;
         float v[8];
-        load_op8(i_hi, i_lo, ((size_t(n) * H + h) * W + w) * cs + g * 8, v);
+        load_op8(i_hi, i_lo, ((size_t(n) * Hs + h + ib) * Ws + w + ib) * cs + g * 8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[j];
         ++cnt;
@@ -488,7 +492,7 @@ __global__ void avgpool_kernel(const bf16* __restrict__ i_hi, const bf16* __rest
     const float inv = 1.f / float(cnt);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] *= inv;
-    store_op8(o_hi, o_lo, ((size_t(n) * Ho + ho) * Wo + wo) * cs + g * 8, acc);
+    store_op8(o_hi, o_lo, ((size_t(n) * Hop + hop) * Wop + wop) * cs + g * 8, acc);
   }
 }
 // adjoint, accumulated into the finer gradient for channels [c0, c1)
@@ -944,12 +948,15 @@ int hm_fold_add(const float* g_padded, int border, int N, int H, int W, int C, c
   return HM_LAUNCH_OK();
 }
 
-int hm_avgpool3s2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, void* o_hi, void* o_lo, void* stream) {
+int hm_avgpool3s2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs, int in_border, void* o_hi, void* o_lo,
+                  int out_border, void* stream) {
   if (!i_hi || !o_hi || (cs & 7)) return HM_ERR_INVALID;
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  avgpool_kernel<<<grid_for(long(N) * Ho * Wo * (cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(i_hi), static_cast<const bf16*>(i_lo), N, H, W, cs, static_cast<bf16*>(o_hi),
-      static_cast<bf16*>(o_lo), Ho, Wo);
+  if (out_border >= Ho || out_border >= Wo) return HM_ERR_INVALID;
+  const long total = long(N) * (Ho + 2 * out_border) * (Wo + 2 * out_border) * (cs >> 3);
+  avgpool_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(i_hi), static_cast<const bf16*>(i_lo), N, H, W, cs, in_border, static_cast<bf16*>(o_hi),
+      static_cast<bf16*>(o_lo), Ho, Wo, out_border);
   return HM_LAUNCH_OK();
 }
 

@@ -21,7 +21,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, parallel
 from .networks import FlatParams, GlobalGenerator, MultiscaleDiscriminator, Vgg19, VGG19_CONVS, VGG19_SLICE_OF
 from .ops import Ctx, Operand
 
@@ -95,12 +95,10 @@ class FusedAdam(object):
         self.grads_reduced = False
 
     def allreduce(self):
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            if not self.grads_reduced:
-                torch.distributed.all_reduce(self.fp.grad, group=self.dist_group)
-                self.grads_reduced = True
-            return 1.0 / torch.distributed.get_world_size()
-        return 1.0
+        if not self.grads_reduced:
+            parallel.allreduce_sum_(self.fp.grad, self.dist_group)
+            self.grads_reduced = True
+        return 1.0 / parallel.world()[1]
 
     def step(self, grad_scale=None):
         scale = self.allreduce() if grad_scale is None else grad_scale
@@ -344,10 +342,7 @@ class Pix2PixHDModel_condImg(object):
         self.flat_grad.zero_()
         self._backward_G([1.0, 1.0, 1.0])
         self._backward_D([0.5, 0.5])
-        scale = 1.0
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(self.flat_grad)
-            scale = 1.0 / torch.distributed.get_world_size()
+        scale = parallel.allreduce_sum_(self.flat_grad)
         self.optimizer_G.step(grad_scale=scale)
         self.optimizer_D.step(grad_scale=scale)
         return st["losses"]

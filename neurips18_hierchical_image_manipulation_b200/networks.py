@@ -208,9 +208,10 @@ class GlobalGenerator(object):
     def convs(self):
         return [c for _, c in self.stages]
 
-    def forward(self, x, feature_border=0):
+    def forward(self, x, feature_border=0, add_at=None, add_tensor=None):
         """x: Operand with ReflectionPad2d(3) materialised.  Returns (out, tape): out is the fp32 NHWC tanh output
-        (with_head) or (feature fp32 NHWC) for the trunk."""
+        (with_head) or (feature fp32 NHWC) for the trunk.  add_at/add_tensor: dense fp32 tensor added to the output of
+        stage `add_at` after its activation (LocalEnhancer: model_downsample(x) + output_prev, Pix2Pix_NET.py:60)."""
         ctx = self.ctx
         tape = []
         cur = x
@@ -237,8 +238,8 @@ class GlobalGenerator(object):
             act = ACT_NONE if kind == "resB" else ACT_RELU
             o32 = _f32(ctx, cur.n, ho, wo, conv.cout) if emit32 else None
             oop = Operand(ctx, cur.n, ho, wo, conv.cout, border=out_border) if nxt is not None else None
-            ops.in_apply(ctx, y, mean, rstd, act, skip=skip32 if kind == "resB" else None, out32=o32, out_op=oop,
-                         reflect=True)
+            skip = skip32 if kind == "resB" else (add_tensor if s == add_at else None)
+            ops.in_apply(ctx, y, mean, rstd, act, skip=skip, out32=o32, out_op=oop, reflect=True)
             rec.update(y=y, mean=mean, rstd=rstd, act=act, out_border=out_border, shape=(cur.n, ho, wo, conv.cout))
             tape.append(rec)
             if kind == "resA":
@@ -249,11 +250,12 @@ class GlobalGenerator(object):
             out = o32
         return out, tape
 
-    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False):
+    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False, add_at=None):
         """dy_head: Operand gradient w.r.t. the head's pre-tanh output (with_head) or dfeat: dense fp32 gradient
         w.r.t. the trunk feature.  Accumulates parameter gradients; returns d(input operand) (fp32, padded space)
-        when need_input_grad."""
+        when need_input_grad.  With add_at, self.add_grad holds the dense gradient w.r.t. the tensor added there."""
         ctx = self.ctx
+        self.add_grad = None
         G1, G1_border = None, 0   # gradient w.r.t. the current stage's OUTPUT operand (padded space)
         T = dfeat                 # dense gradient w.r.t. the current stage's fp32 output (residual chain)
         for s in range(len(tape) - 1, -1, -1):
@@ -265,6 +267,14 @@ class GlobalGenerator(object):
             else:
                 N, ho, wo, cc = rec["shape"]
                 dy = Operand(ctx, N, ho, wo, cc)
+                if s == add_at:   # d(out)/d(added tensor) = identity: the total gradient w.r.t. this stage's output
+                    if nxt == "resA" or nxt is None:
+                        self.add_grad = T
+                    elif G1_border > 0:
+                        self.add_grad = _f32(ctx, N, ho, wo, cc)
+                        ops.fold_add(ctx, G1, G1_border, None, self.add_grad)
+                    else:
+                        self.add_grad = G1
                 if kind == "resB":
                     if nxt != "resA" and G1 is not None:   # last block: gradient arrives from the next conv only
                         if G1_border > 0:

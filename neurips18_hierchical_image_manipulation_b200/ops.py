@@ -195,8 +195,8 @@ def fold_add(ctx, g_padded, border, base, out):
 
 
 def avgpool3s2(ctx, x, out):
-    L.check(ctx.lib.hm_avgpool3s2(x.hi.data_ptr(), _ptr(x.lo), x.n, x.h, x.w, x.cs, out.hi.data_ptr(), _ptr(out.lo),
-                                  _stream()), "hm_avgpool3s2")
+    L.check(ctx.lib.hm_avgpool3s2(x.hi.data_ptr(), _ptr(x.lo), x.n, x.ih, x.iw, x.cs, x.border, out.hi.data_ptr(),
+                                  _ptr(out.lo), out.border, _stream()), "hm_avgpool3s2")
     ctx.launches += 1
 
 

@@ -1,0 +1,36 @@
+"""Data parallelism for the mask2image hot path: one process per GPU (torchrun), replicated weights, per-rank
+minibatch shards, ONE sum-allreduce of the flat [G | D] gradient buffer per step (NCCL over NVLink on GPUs; any
+torch.distributed backend works -- the CPU tests use gloo).  InstanceNorm statistics are per sample and every loss
+is a mean over equally sized shards, so mean-of-shard-gradients == full-batch gradient:
+this replaces the reference's single-process nn.DataParallel (models/models.py:21-22)."""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place sum-allreduce of a flat gradient buffer; returns the scale (1/world_size) that turns the sum into
+    the full-batch mean gradient (folded into the fused Adam kernel's grad_scale)."""
+    _, n = world()
+    if n > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / n
+
+
+def allreduce_losses_(losses, group=None):
+    """Mean of the per-rank loss scalars (what train_mask2image.py:68 computes over DataParallel replicas)."""
+    _, n = world()
+    if n > 1:
+        dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
+        losses.div_(n)
+    return losses
+
+
+def shard_seed(base_seed, rank=None):
+    r = world()[0] if rank is None else rank
+    return base_seed + r

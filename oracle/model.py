@@ -298,7 +298,7 @@ def train_step(opt, g_sd, d_sd, vgg_sd, batch, state=None, dtype=torch.float32):
     Adam(D).  g_sd / d_sd are updated in place; returns (losses, fake, grads_G, grads_D)."""
     g_par = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(True)) for k, v in g_sd.items())
     d_par = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(True)) for k, v in d_sd.items())
-    v_sd = OrderedDict((k, v.to(dtype)) for k, v in vgg_sd.items())
+    v_sd = OrderedDict((k, v.to(dtype)) for k, v in vgg_sd.items()) if vgg_sd is not None else None
     losses, fake, _ = model_forward(opt, g_par, d_par, v_sd, batch["label"], batch["inst"], batch["image"],
                                     batch["mask_in"], dtype)
     loss_G, loss_D = step_losses(losses)

@@ -1,0 +1,103 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and exports exactly the symbols
+include/hm_b200.h declares (no compute calls -- there is no GPU here); the product never touches oracle/."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "neurips18_hierchical_image_manipulation_b200")
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "hm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(hm_\w+)\s*\(([^;{]*?)\)\s*;", src):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("void", "") else len(args.split(","))
+    return out
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from neurips18_hierchical_image_manipulation_b200 import build, _lib
+    lib_path = build.build()
+    assert os.path.exists(lib_path)
+    lib = _lib.load()
+    decl = _header_functions()
+    assert len(decl) >= 25
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", lib_path], text=True)
+    exported = set(re.findall(r"\bT (hm_\w+)", nm))
+    for name, nargs in decl.items():
+        assert name in exported, "header declares %s but the .so does not export it" % name
+        assert name in _lib.PROTOTYPES, "no ctypes prototype for %s" % name
+        assert len(_lib.PROTOTYPES[name][1]) == nargs, "arity mismatch for %s" % name
+        assert getattr(lib, name) is not None
+    assert set(_lib.PROTOTYPES) == set(decl), "ctypes table and header disagree"
+    assert b"sm_100a" in lib.hm_version()
+
+
+def test_library_is_sm100a_tcgen05_tma():
+    """The SASS carries the Blackwell-native mnemonics (B200_PROFILING.md): UTC*MMA (tcgen05.mma), LDTM (tcgen05.ld),
+    UTMALDG (TMA)."""
+    from neurips18_hierchical_image_manipulation_b200 import build
+    sass = subprocess.check_output(["cuobjdump", "-sass", build.build()], text=True)
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass
+    assert "sm_100a" in sass
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path
+
+
+def test_pure_host_abi_helpers():
+    from neurips18_hierchical_image_manipulation_b200 import _lib
+    lib = _lib.load()
+    assert [lib.hm_pick_bn(c) for c in (1, 3, 16, 17, 64, 65, 128, 129, 1024)] == [16, 16, 16, 32, 64, 128, 128, 256, 256]
+    assert lib.hm_rows_pad(1024) == 1024 and lib.hm_rows_pad(3) == 16 and lib.hm_rows_pad(192) == 256
+    assert lib.hm_k_pad(38) == 64 and lib.hm_k_pad(64) == 64 and lib.hm_k_pad(65) == 128
+    assert lib.hm_wgrad_ws_bytes(3, 3, 1024, 1024) == 9 * 1024 * 1024 * 4
+    assert lib.hm_wgrad_ws_bytes(7, 7, 38, 64) == 49 * 64 * 64 * 4
+    assert lib.hm_in_ws_bytes(4, 2048, 1024) > 0
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    import ctypes as C
+    from neurips18_hierchical_image_manipulation_b200 import _lib
+    lib = _lib.load()
+    assert lib.hm_pack_weight(None, 1, 1, 1, 1, 1, 1, None, None, None) == -1
+    assert lib.hm_conv_fprop(None, None, None, 64, 64, None, 3, 3, 1, 1, 8, 8, 64, 0, 0.0, None, None, None, None) == -1
+    op = _lib.Operand(None, None, 1, 8, 8, 64, 64)
+    assert lib.hm_conv_fprop(C.byref(op), None, None, 64, 64, None, 3, 3, 3, 1, 8, 8, 64, 0, 0.0, None, None, None, None) == -1
+    assert lib.hm_adam_step(None, None, None, None, 10, 1e-3, 0.5, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert lib.hm_in_stats(None, 1, 1, 4, 1e-5, None, None, None, None) == -1
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
+                assert "/root/reference" not in txt, os.path.join(dirpath, f)
+
+
+def test_model_fails_loudly_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    with pytest.raises(RuntimeError):
+        create_model(Options(ngf=8, n_downsample_global=1, n_blocks_global=1))
+    with pytest.raises(NotImplementedError):
+        create_model(Options(model="AE_maskgen_twostream"))
+
+
+def test_synthetic_batch_contract_matches_oracle_generator():
+    import torch
+    from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_batch
+    from oracle.model import synthetic_batch as oracle_batch
+    a, b = synthetic_batch(2, 32, 64, 35, seed=5), oracle_batch(2, 32, 64, 35, seed=5)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert a["label"].shape == (2, 1, 32, 64) and a["image"].shape == (2, 3, 32, 64)
+    assert float(a["label"].max()) <= 34 and float(a["image"].abs().max()) <= 1.0
+    assert set(a["mask_in"].unique().tolist()) <= {0.0, 1.0}
+    assert bool((a["mask_out"] >= a["mask_in"]).all())

@@ -110,6 +110,17 @@ def test_parity_bf16x3_gate_instance_rec():
     assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
 
 
+def test_parity_bf16x3_local_enhancer():
+    """BASELINE config #4 topology (LocalEnhancer, netG='local') at a reduced size, 2-scale D."""
+    r = run_parity("bf16x3", netG="local", ngf=4, n_downsample_global=2, n_blocks_global=2, n_local_enhancers=1,
+                   n_blocks_local=2, num_D=2, no_instance=False, H=64, W=96)
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
+    assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
+
+
 def test_parity_bf16_mode():
     r = run_parity("bf16")
     assert r["fake"] < 5e-2, r
