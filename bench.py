@@ -142,7 +142,7 @@ def run_cpu(budget_s, steps, warmup):
     return ips, dt * 1e3, cores, sample
 
 
-def main_reference(args):
+def main_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -152,7 +152,7 @@ def main_reference(args):
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload_desc(args.gpus),
                 cpu_baseline=dict(value=ips, unit="images/sec", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=ips, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    _emit(line, out_fd)
     return 0
 
 
@@ -241,7 +241,16 @@ def run_mode(model, precision_name, batch_dev, batch_pinned, steps, warmup, worl
                 losses=[float(x) for x in host_losses])
 
 
+def _emit(line, fd):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # stdout must carry exactly ONE JSON line: park the real stdout and send everything else (NCCL banners, library
+    # chatter) to stderr
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -252,7 +261,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
-        return main_reference(args)
+        return main_reference(args, out_fd)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -323,7 +332,8 @@ def main():
                                                  k1_tflops=r["k1"]["achieved"], k1_frac=r["k1"]["frac"],
                                                  note="plain bf16 products: NOT within the 1e-3 fp32 tolerance "
                                                       "(generator output ~1e-2 rel); reported for reference")
-        print(json.dumps(line))
+        sys.stdout.flush()
+        _emit(line, out_fd)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
