@@ -3,6 +3,9 @@
 // models/Discriminator_NET.py:61-118) is lowered here to a tap table + TMA tensor maps; nothing is im2col'ed.
 #include "../../include/hm_b200.h"
 #include "hm_engine.cuh"
+#include "hm_engine_rows.cuh"
+
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstring>
@@ -128,7 +131,135 @@ int launch_mn(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
   return HM_OK;
 }
 
+template <int BN>
+int launch_rows(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_t st) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_krows_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = smem_bytes;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_krows_kernel<BN><<<grid, hm::kEngineThreads, smem_bytes, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+// packed weights [taps][rows_pad][k_pad] bf16 -> 3-D map, box = 64 (k) x bn rows x kw taps
+int make_tmap_weight3(CUtensorMap* m, const void* base, int taps, int rows_pad, int k_pad, int bn, int kw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return HM_ERR_DRIVER;
+  if ((k_pad & 63) || (reinterpret_cast<uintptr_t>(base) & 15)) return HM_ERR_INVALID;
+  cuuint64_t dims[3] = {cuuint64_t(k_pad), cuuint64_t(rows_pad), cuuint64_t(taps)};
+  cuuint64_t strides[2] = {cuuint64_t(k_pad) * 2, cuuint64_t(rows_pad) * k_pad * 2};
+  cuuint32_t box[3] = {64, cuuint32_t(bn), cuuint32_t(kw)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? HM_OK : HM_ERR_TENSORMAP;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
 struct Tap { int dw, dh, slab; };
+
+// Row-streaming engine (hm_engine_rows.cuh): stride-1 tap grids on wide images with a narrow N tile.
+bool rows_eligible(const Tap* taps, int n_taps, int in_stride, int out_sh, int out_sw, int valid_w, int bn) {
+  static const int enabled = env_int("HM_ROWS", 1);
+  if (!enabled || in_stride != 1 || out_sh != 1 || out_sw != 1 || bn > 128 || valid_w < 96 || n_taps > 64) return false;
+  int dw_min = taps[0].dw, dw_max = taps[0].dw;
+  for (int t = 0; t < n_taps; ++t) { dw_min = std::min(dw_min, taps[t].dw); dw_max = std::max(dw_max, taps[t].dw); }
+  const int kw = dw_max - dw_min + 1;
+  if (kw < 2 || kw > hm::kRowsMaxKW || n_taps % kw) return false;
+  return 2 * (hm::RCfgCommon::A_PLANE + kw * bn * 128) <= hm::RCfgCommon::SMEM_BUDGET;
+}
+
+int run_rows_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad, const float* bias,
+                    const Tap* taps, int n_taps, int valid_h, int valid_w, int Cout, int act, float slope,
+                    const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, cudaStream_t st) {
+  const int bn = hm_pick_bn(Cout);
+  hm::RParams p;
+  std::memset(&p, 0, sizeof(p));
+  int dw_min = taps[0].dw, dw_max = taps[0].dw, max_slab = 0;
+  for (int t = 0; t < n_taps; ++t) {
+    dw_min = std::min(dw_min, taps[t].dw); dw_max = std::max(dw_max, taps[t].dw);
+    max_slab = std::max(max_slab, taps[t].slab);
+  }
+  const int kw = dw_max - dw_min + 1;
+  p.kw = kw;
+  p.box_w = 128 + kw - 1;
+  p.dw0 = dw_min;
+  const bool a_lo = x->lo != nullptr, b_lo = w_lo != nullptr;
+  int rc;
+  if ((rc = make_tmap_nhwc(&p.tmA[0], x->hi, x->n, x->h, x->w, x->c, x->cs, p.box_w, 1, 1))) return rc;
+  if (a_lo && (rc = make_tmap_nhwc(&p.tmA[1], x->lo, x->n, x->h, x->w, x->c, x->cs, p.box_w, 1, 1))) return rc;
+  if ((rc = make_tmap_weight3(&p.tmB[0], w_hi, max_slab + 1, rows_pad, k_pad, bn, kw))) return rc;
+  if (b_lo && (rc = make_tmap_weight3(&p.tmB[1], w_lo, max_slab + 1, rows_pad, k_pad, bn, kw))) return rc;
+  // one entry per (filter row, product): the row's taps must be kw consecutive slabs (true for the tap grids
+  // hm_conv_fprop / hm_conv_dgrad build: slab = kh*KW + kw')
+  bool used[64] = {false};
+  int ne = 0;
+  for (;;) {
+    int first = -1;
+    for (int t = 0; t < n_taps; ++t) if (!used[t]) { first = t; break; }
+    if (first < 0) break;
+    const int dh = taps[first].dh;
+    int slab_min = 1 << 30, cnt = 0;
+    for (int t = 0; t < n_taps; ++t) if (!used[t] && taps[t].dh == dh) { slab_min = std::min(slab_min, taps[t].slab); ++cnt; }
+    if (cnt != kw) return HM_ERR_INVALID;
+    int8_t a_off[hm::kRowsMaxKW + 3] = {0};
+    for (int t = 0; t < n_taps; ++t) {
+      if (used[t] || taps[t].dh != dh) continue;
+      used[t] = true;
+      const int j = taps[t].slab - slab_min;
+      if (j < 0 || j >= kw) return HM_ERR_INVALID;
+      a_off[j] = int8_t(taps[t].dw - dw_min);
+    }
+    const int pa[3] = {0, 1, 0}, pb[3] = {0, 0, 1};
+    for (int q = 0; q < 3; ++q) {
+      if ((q == 1 && !a_lo) || (q == 2 && !b_lo)) continue;
+      if (ne >= hm::kRowsMaxEntries) return HM_ERR_INVALID;
+      hm::REntry& e = p.entries[ne++];
+      e.a_plane = int8_t(pa[q]); e.b_plane = int8_t(pb[q]); e.dh = int16_t(dh); e.tap0 = slab_min;
+      std::memcpy(e.a_off, a_off, sizeof(a_off));
+    }
+  }
+  p.n_entries = ne;
+  p.chunks = k_pad / 64;
+  p.stage_bytes = hm::RCfgCommon::A_PLANE + kw * bn * 128;
+  p.n_stages = std::min(hm::RCfgCommon::MAX_STAGES, hm::RCfgCommon::SMEM_BUDGET / p.stage_bytes);
+  if (p.n_stages < 2) return HM_ERR_INVALID;
+  p.tiles_w = (valid_w + 127) / 128;
+  p.rows_h = valid_h;
+  p.n_img = x->n;
+  p.n_tiles_n = rows_pad / bn;
+  p.cout = Cout;
+  p.valid_w = valid_w;
+  if (out32 && out32->ptr) {
+    p.o32 = out32->ptr; p.o32_H = out32->H; p.o32_W = out32->W; p.o32_C = out32->C;
+    p.o32_hoff = out32->h_off; p.o32_woff = out32->w_off; p.o32_coff = out32->c_off;
+  }
+  if (out16 && out16->hi) {
+    p.ohi = static_cast<__nv_bfloat16*>(out16->hi); p.olo = static_cast<__nv_bfloat16*>(out16->lo);
+    p.o16_H = out16->H; p.o16_W = out16->W; p.o16_C = out16->C;
+    p.o16_hoff = out16->h_off; p.o16_woff = out16->w_off; p.o16_coff = out16->c_off;
+  }
+  p.bias = bias; p.act = act; p.slope = slope; p.err = err_flag;
+  const int num_tiles = p.tiles_w * p.rows_h * p.n_img * p.n_tiles_n;
+  const int smem_bytes = p.n_stages * p.stage_bytes + 1024 + 512;
+  switch (bn) {
+    case 16: return launch_rows<16>(p, num_tiles, smem_bytes, st);
+    case 32: return launch_rows<32>(p, num_tiles, smem_bytes, st);
+    case 64: return launch_rows<64>(p, num_tiles, smem_bytes, st);
+    case 128: return launch_rows<128>(p, num_tiles, smem_bytes, st);
+  }
+  return HM_ERR_INVALID;
+}
 
 // Common back end of fprop / dgrad: one K-engine launch per output parity class.
 int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad, const float* bias,
@@ -138,6 +269,9 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   if (n_taps <= 0 || valid_h <= 0 || valid_w <= 0) return HM_OK;
   const int bn = hm_pick_bn(Cout);
   if (rows_pad % bn || rows_pad < Cout || (k_pad & 63)) return HM_ERR_INVALID;
+  if (rows_eligible(taps, n_taps, in_stride, out_sh, out_sw, valid_w, bn))
+    return run_rows_engine(x, w_hi, w_lo, k_pad, rows_pad, bias, taps, n_taps, valid_h, valid_w, Cout, act, slope, out32,
+                           out16, err_flag, st);
   const bool a_lo = x->lo != nullptr, b_lo = w_lo != nullptr;
   const int prods = 1 + (a_lo ? 1 : 0) + (b_lo ? 1 : 0);
   if (n_taps * prods > hm::kMaxEntries) return HM_ERR_INVALID;

@@ -1,0 +1,234 @@
+// hm_engine_rows.cuh -- row-streaming variant of the K-engine for stride-1 convolutions on wide images.
+//
+// Why: with a narrow N tile (Cout <= 128) one 64-deep k-step of the generic K-engine is only 32..64 tensor cycles
+// of work per MMA but costs the single producer / issuer threads an mbarrier round trip, two TMA issues and a commit
+// (~700 cycles measured per tap, independent of the tile width): the full-resolution, few-channel layers (7x7 stem
+// and head, VGG conv1_x, the D layer-0 gradients) were issue-latency bound at 5-20 % tensor-pipe utilisation, and
+// they re-read every input pixel KH*KW times.
+// Here the pipeline stage is a whole FILTER ROW: the M tile is one output-row segment of 128 pixels; per filter row
+// and 64-channel chunk the producer issues exactly two TMA loads -- ONE box of 128+KW-1 input pixels and ONE 3-D box
+// holding the KW weight slabs of that row -- and the issuer fires KW x 4 tcgen05.mma per barrier wait.  Each tap reads
+// its shifted 128-pixel window straight out of the row box by offsetting the UMMA shared-memory descriptor by whole
+// 128-byte pixel rows (the 128B swizzle is a function of the shared-memory address bits, so a window that starts
+// inside a swizzle atom stays consistent with what TMA wrote; verified on hardware, descriptor base_offset = 0).
+// bf16x3 is three row stages per filter row (hi*hi, lo*hi, hi*lo), exactly like the generic engine's entries.
+#pragma once
+#include "hm_engine.cuh"
+
+namespace hm {
+
+constexpr int kRowsMaxKW = 9;
+constexpr int kRowsMaxEntries = 32;   // KH (<= 9) x 3 products
+
+struct __align__(8) REntry {
+  int8_t a_plane, b_plane;
+  int16_t dh;          // input row = output row + dh
+  int32_t tap0;        // first weight slab (tap index) of this filter row
+  int8_t a_off[kRowsMaxKW + 3];  // window start of tile j inside the row box, in pixels
+};
+
+struct __align__(64) RParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];     // 3-D: {k_pad, rows_pad, taps}
+  int n_entries, chunks;
+  int kw;                 // taps per filter row (tiles per B box)
+  int n_stages;           // pipeline depth (runtime: depends on kw and BN)
+  int stage_bytes;        // A_PLANE + kw * BN * 128
+  int tiles_w, rows_h, n_img, n_tiles_n;   // M tiles = tiles_w * rows_h * n_img
+  int dw0;                // row-box origin = tile origin + dw0
+  int box_w;              // pixels per row box (128 + kw - 1)
+  int cout;
+  int valid_w;
+  float* o32;  int o32_H, o32_W, o32_C, o32_hoff, o32_woff, o32_coff;
+  __nv_bfloat16* ohi; __nv_bfloat16* olo; int o16_H, o16_W, o16_C, o16_hoff, o16_woff, o16_coff;
+  const float* bias;
+  int act; float slope;
+  int* err;
+  REntry entries[kRowsMaxEntries];
+};
+
+struct RCfgCommon {
+  static constexpr int A_PLANE = 136 * 128;   // up to 136 pixel rows of 128 B (1024-aligned)
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int SMEM_BUDGET = 225 * 1024;
+};
+
+template <int BN>
+struct RCfg : RCfgCommon {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int ACC = 2;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int CH = (BN >= 32) ? 32 : 16;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __grid_constant__ RParams p) {
+  using C = RCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + C::MAX_STAGES;
+  uint64_t* tfull = empty + C::MAX_STAGES;
+  uint64_t* tempty = tfull + C::ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m_tiles = p.tiles_w * p.rows_h * p.n_img;
+  const int num_tiles = num_m_tiles * p.n_tiles_n;
+  const int nst = p.n_stages;
+  AbortCtl ab{abort_flag, p.err};
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < C::ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: 2 loads per filter-row stage =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
+      int s = 0; uint32_t ph = 0;
+      const uint32_t tx_bytes = uint32_t(p.box_w) * 128u + uint32_t(p.kw) * C::B_TILE;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+        const int h = mt % p.rows_h;
+        const int n = mt / p.rows_h;
+        const int w0 = twi * 128 + p.dw0;
+        for (int c = 0; c < p.chunks; ++c) {
+          for (int e = 0; e < p.n_entries; ++e) {
+            const int a_plane = p.entries[e].a_plane, b_plane = p.entries[e].b_plane;
+            const int dh = p.entries[e].dh, tap0 = p.entries[e].tap0;
+            mbar_wait(&empty[s], ph ^ 1, ab, 301);
+            uint8_t* dst = smem + s * p.stage_bytes;
+            mbar_arrive_expect_tx(&full[s], tx_bytes);
+            tma_load_4d(&p.tmA[a_plane], &full[s], dst, c * 64, w0, h + dh, n);
+            tma_load_3d(&p.tmB[b_plane], &full[s], dst + C::A_PLANE, c * 64, nt * BN, tap0);
+            if (++s == nst) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: kw x 4 MMAs per barrier wait =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[a], aph ^ 1, ab, 303);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.chunks; ++c) {
+          for (int e = 0; e < p.n_entries; ++e) {
+            mbar_wait(&full[s], ph, ab, 304);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
+            const uint32_t b_base = a_base + C::A_PLANE;
+            for (int j = 0; j < p.kw; ++j) {
+              const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
+              const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc); acc = 1; }
+            }
+            umma_commit(&empty[s]);
+            if (++s == nst) { s = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&tfull[a]);
+        if (++a == C::ACC) { a = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int a = 0; uint32_t aph = 0;
+    const bool v32 = p.o32 && ((p.o32_C & 3) == 0) && ((p.o32_coff & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.o32) & 15) == 0);
+    const bool v16 = p.ohi && ((p.o16_C & 7) == 0) && ((p.o16_coff & 7) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.ohi) & 15) == 0) &&
+                     (!p.olo || (reinterpret_cast<uintptr_t>(p.olo) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int oh = mt % p.rows_h;
+      const int n = mt / p.rows_h;
+      const int ow = twi * 128 + m;
+      const bool valid = ow < p.valid_w;
+      size_t off32 = 0, off16 = 0;
+      if (p.o32) off32 = ((size_t(n) * p.o32_H + oh + p.o32_hoff) * p.o32_W + ow + p.o32_woff) * p.o32_C + p.o32_coff;
+      if (p.ohi) off16 = ((size_t(n) * p.o16_H + oh + p.o16_hoff) * p.o16_W + ow + p.o16_woff) * p.o16_C + p.o16_coff;
+      mbar_wait(&tfull[a], aph, ab, 306);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += C::CH) {
+        uint32_t raw[C::CH];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + a * BN + c0;
+        if constexpr (C::CH == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+        tmem_ld_wait();
+        const int cg = nt * BN + c0;
+        if (valid && cg < p.cout) {
+          float v[C::CH];
+#pragma unroll
+          for (int i = 0; i < C::CH; ++i) {
+            float x = __uint_as_float(raw[i]);
+            if (p.bias && cg + i < p.cout) x += __ldg(p.bias + cg + i);
+            v[i] = apply_act(x, p.act, p.slope);
+          }
+          const bool full_chunk = (cg + C::CH <= p.cout);
+          if (p.o32) {
+            float* dst = p.o32 + off32 + cg;
+            if (v32 && full_chunk) {
+#pragma unroll
+              for (int i = 0; i < C::CH; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < C::CH; ++i) if (cg + i < p.cout) dst[i] = v[i];
+            }
+          }
+          if (p.ohi) {
+            __nv_bfloat16 hi[C::CH], lo[C::CH];
+#pragma unroll
+            for (int i = 0; i < C::CH; ++i) split_bf16(v[i], hi[i], lo[i]);
+            __nv_bfloat16* dh = p.ohi + off16 + cg;
+            __nv_bfloat16* dl = p.olo ? p.olo + off16 + cg : nullptr;
+            if (v16 && full_chunk) {
+#pragma unroll
+              for (int i = 0; i < C::CH; i += 8) {
+                *reinterpret_cast<uint4*>(dh + i) = *reinterpret_cast<const uint4*>(hi + i);
+                if (dl) *reinterpret_cast<uint4*>(dl + i) = *reinterpret_cast<const uint4*>(lo + i);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < C::CH; ++i)
+                if (cg + i < p.cout) { dh[i] = hi[i]; if (dl) dl[i] = lo[i]; }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+      if (++a == C::ACC) { a = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace hm

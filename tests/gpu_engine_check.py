@@ -178,6 +178,12 @@ CASES = {
         ("D4x4s1 512->1 19x35", case_fprop, dict(n=1, cin=512, cout=1, h=19, w=35, k=4, stride=1, pad=2, reflect=False)),
         ("res3x3 1024->1024 8x16 nobias", case_fprop, dict(n=1, cin=1024, cout=1024, h=8, w=16, k=3, stride=1, pad=1, reflect=True, bias=False)),
         ("wide 64->64 4x300", case_fprop, dict(n=1, cin=64, cout=64, h=4, w=300, k=3, stride=1, pad=1, reflect=False)),
+        # wide images: served by the row-streaming engine (hm_engine_rows.cuh)
+        ("rows stem7x7 38->64 9x300 reflect", case_fprop, dict(n=2, cin=38, cout=64, h=9, w=300, k=7, stride=1, pad=3, reflect=True)),
+        ("rows head7x7 64->3 9x300 tanh", case_fprop, dict(n=1, cin=64, cout=3, h=9, w=300, k=7, stride=1, pad=3, reflect=True, act=3)),
+        ("rows vgg3x3 3->64 6x260 relu +bf16out", case_fprop, dict(n=2, cin=3, cout=64, h=6, w=260, k=3, stride=1, pad=1, reflect=False, act=1, out16=True)),
+        ("rows 3x3 128->128 5x256", case_fprop, dict(n=1, cin=128, cout=128, h=5, w=256, k=3, stride=1, pad=1, reflect=False)),
+        ("rows D4x4s1 64->32 7x131", case_fprop, dict(n=1, cin=64, cout=32, h=7, w=131, k=4, stride=1, pad=2, reflect=False)),
     ],
     "dgrad": [
         ("dgrad 3x3s1p1 64<-128 16x32", case_dgrad, dict(n=2, cin=64, cout=128, h=16, w=32, k=3, stride=1, pad=1)),
@@ -187,6 +193,8 @@ CASES = {
         ("dgrad 4x4s1p2 256<-512 18x34", case_dgrad, dict(n=1, cin=256, cout=512, h=18, w=34, k=4, stride=1, pad=2)),
         ("convT fwd 3x3s2 128->64 16x32", case_dgrad, dict(n=2, cin=64, cout=128, h=16, w=32, k=3, stride=2, pad=1, transposed_fwd=True)),
         ("dgrad 7x7s1p0 64<-3 38x70", case_dgrad, dict(n=1, cin=64, cout=3, h=38, w=70, k=7, stride=1, pad=0)),
+        ("rows dgrad 7x7s1p0 64<-3 14x262", case_dgrad, dict(n=1, cin=64, cout=3, h=14, w=262, k=7, stride=1, pad=0)),
+        ("rows dgrad 3x3s1p1 64<-128 6x256", case_dgrad, dict(n=2, cin=64, cout=128, h=6, w=256, k=3, stride=1, pad=1)),
     ],
     "wgrad": [
         ("wgrad 3x3s1p1 64x64 16x32", case_wgrad, dict(n=2, cin=64, cout=64, h=16, w=32, k=3, stride=1, pad=1)),
@@ -244,7 +252,9 @@ def main(argv):
     bad = 0
     for grp in groups:
         if grp == "perf":
-            for name, kw in [("res3x3 1024->1024 32x64 B4", dict(n=4, cin=1024, cout=1024, h=32, w=64, k=3, stride=1, pad=1)),
+            for name, kw in [("stem7x7 38->64 512x1024 B1", dict(n=1, cin=38, cout=64, h=512, w=1024, k=7, stride=1, pad=3)),
+                             ("head7x7 64->3 512x1024 B1", dict(n=1, cin=64, cout=3, h=512, w=1024, k=7, stride=1, pad=3)),
+                             ("res3x3 1024->1024 32x64 B4", dict(n=4, cin=1024, cout=1024, h=32, w=64, k=3, stride=1, pad=1)),
                              ("vgg3x3 64->64 512x1024 B1", dict(n=1, cin=64, cout=64, h=512, w=1024, k=3, stride=1, pad=1)),
                              ("vgg3x3 256->256 128x256 B4", dict(n=4, cin=256, cout=256, h=128, w=256, k=3, stride=1, pad=1))]:
                 for split in (False, True):

@@ -1,0 +1,14 @@
+import ctypes as C, os, sys, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from neurips18_hierchical_image_manipulation_b200 import _lib
+lib = C.CDLL(_lib.LIB_PATH)
+lib.hm_debug_mma_issue.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+out = torch.zeros(2, dtype=torch.int64, device="cuda")
+for n in (16, 64, 256):
+    for off in (0, 1, 3, 4, 8):
+        count = 1024
+        for _ in range(2):
+            lib.hm_debug_mma_issue(n, count, off, out.data_ptr(), None)
+            torch.cuda.synchronize()
+        o = out.tolist()
+        print("N=%3d a_off=%d rows  issue %.1f cyc/MMA   complete %.1f cyc/MMA" % (n, off, o[0] / count, o[1] / count))
