@@ -4,6 +4,7 @@
 #include "../../include/hm_b200.h"
 #include "hm_engine.cuh"
 #include "hm_engine_rows.cuh"
+#include "hm_engine_mnrows.cuh"
 
 #include <cstdlib>
 
@@ -261,6 +262,79 @@ int run_rows_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int
   return HM_ERR_INVALID;
 }
 
+
+template <int NB>
+int launch_mnrows(const hm::MRParams& p, int num_tiles, int smem_bytes, cudaStream_t st) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_mnrows_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = smem_bytes;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_mnrows_kernel<NB><<<grid, hm::kEngineThreads, smem_bytes, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+// Row-streaming weight-gradient engine (hm_engine_mnrows.cuh): stride-1, wide base space.
+int run_mnrows(const hm_operand* P, const hm_operand* Q, int KH, int KW, int pad, float* G_ws, int* err_flag,
+               cudaStream_t st) {
+  hm::MRParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int n_units = round_up(Q->c, 64) / 64;
+  const int nb = n_units >= 2 ? 2 : 1;
+  p.kh = KH; p.kw = KW; p.pairs = (KW + 1) / 2;
+  p.box_w = 128 + 2 * p.pairs - 1;
+  int rc;
+  if ((rc = make_tmap_nhwc(&p.tmP[0], P->hi, P->n, P->h, P->w, P->c, P->cs, p.box_w, 1, 1))) return rc;
+  if (P->lo && (rc = make_tmap_nhwc(&p.tmP[1], P->lo, P->n, P->h, P->w, P->c, P->cs, p.box_w, 1, 1))) return rc;
+  if ((rc = make_tmap_nhwc(&p.tmQ[0], Q->hi, Q->n, Q->h, Q->w, Q->c, Q->cs, 128, 1, 1))) return rc;
+  if (Q->lo && (rc = make_tmap_nhwc(&p.tmQ[1], Q->lo, Q->n, Q->h, Q->w, Q->c, Q->cs, 128, 1, 1))) return rc;
+  int np = 0;
+  p.prodP[np] = 0; p.prodQ[np] = 0; ++np;
+  if (P->lo) { p.prodP[np] = 1; p.prodQ[np] = 0; ++np; }
+  if (Q->lo) { p.prodP[np] = 0; p.prodQ[np] = 1; ++np; }
+  p.n_prod = np;
+  p.tiles_w = (Q->w + 127) / 128;
+  p.rows_h = Q->h;
+  p.n_img = Q->n;
+  p.ktiles = p.tiles_w * p.rows_h * p.n_img;
+  p.cp_pad = round_up(P->c, 64);
+  p.m_units = p.cp_pad / 64;
+  p.n_n_tiles = (n_units + nb - 1) / nb;
+  const int base_tiles = KH * p.m_units * p.n_n_tiles;
+  int splits = 1;
+  if (base_tiles < 2 * sm_count()) splits = (2 * sm_count() + base_tiles - 1) / base_tiles;
+  splits = std::max(1, std::min(splits, p.ktiles / 4 > 0 ? p.ktiles / 4 : 1));
+  { int per = (p.ktiles + splits - 1) / splits; splits = (p.ktiles + per - 1) / per; }
+  p.splits = splits;
+  p.dw0 = -pad;
+  for (int kh = 0; kh < KH; ++kh) p.dh[kh] = int16_t(kh - pad);
+  p.stage_bytes = hm::RCfgCommon::A_PLANE + nb * 128 * 128;
+  p.n_stages = std::min(hm::RCfgCommon::MAX_STAGES, hm::RCfgCommon::SMEM_BUDGET / p.stage_bytes);
+  p.G = G_ws;
+  p.ldG = n_units * 64;
+  p.n_cols = n_units * 64;
+  p.use_atomic = splits > 1;
+  p.err = err_flag;
+  if (p.use_atomic) {
+    cudaError_t e = cudaMemsetAsync(G_ws, 0, size_t(KH) * KW * p.cp_pad * p.ldG * sizeof(float), st);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  }
+  const int num_tiles = base_tiles * splits;
+  const int smem_bytes = p.n_stages * p.stage_bytes + 1024 + 512;
+  return nb == 1 ? launch_mnrows<1>(p, num_tiles, smem_bytes, st) : launch_mnrows<2>(p, num_tiles, smem_bytes, st);
+}
+
+bool mnrows_eligible(const hm_operand* P, const hm_operand* Q, int KW, int stride) {
+  static const int enabled = env_int("HM_ROWS", 1);
+  if (!enabled || stride != 1 || KW < 2 || KW > 8 || Q->w < 96) return false;
+  const int nb = round_up(Q->c, 64) / 64 >= 2 ? 2 : 1;
+  return ((KW + 1) / 2) * nb * 64 <= 512;
+}
+
 // Common back end of fprop / dgrad: one K-engine launch per output parity class.
 int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad, const float* bias,
                  const Tap* taps, int n_taps, int in_stride, int valid_h, int valid_w, int out_sh, int out_sw,
@@ -401,6 +475,7 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
   if (!P || !Q || !P->hi || !Q->hi || !G_ws || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
   if (P->n != Q->n) return HM_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mnrows_eligible(P, Q, KW, stride)) return run_mnrows(P, Q, KH, KW, pad, G_ws, err_flag, st);
   hm::MNParams p;
   std::memset(&p, 0, sizeof(p));
   int tw = 64, th = 1;

@@ -204,6 +204,12 @@ CASES = {
         ("wgrad 7x7s1p0 38x64 38x70", case_wgrad, dict(n=1, cin=38, cout=64, h=38, w=70, k=7, stride=1, pad=0)),
         ("wgrad 7x7s1p0 64x3 38x70", case_wgrad, dict(n=1, cin=64, cout=3, h=38, w=70, k=7, stride=1, pad=0)),
         ("wgrad 3x3s1p0 512x512 10x18", case_wgrad, dict(n=2, cin=512, cout=512, h=10, w=18, k=3, stride=1, pad=0)),
+        # wide base space: row-streaming weight-gradient engine (hm_engine_mnrows.cuh)
+        ("rows wgrad 7x7s1p0 38x64 14x262", case_wgrad, dict(n=2, cin=38, cout=64, h=14, w=262, k=7, stride=1, pad=0)),
+        ("rows wgrad 7x7s1p0 64x3 14x262", case_wgrad, dict(n=1, cin=64, cout=3, h=14, w=262, k=7, stride=1, pad=0)),
+        ("rows wgrad 3x3s1p1 64x64 9x256", case_wgrad, dict(n=2, cin=64, cout=64, h=9, w=256, k=3, stride=1, pad=1)),
+        ("rows wgrad 3x3s1p1 128x192 6x130", case_wgrad, dict(n=1, cin=128, cout=192, h=6, w=130, k=3, stride=1, pad=1)),
+        ("rows wgrad 4x4s1p2 64x128 7x131", case_wgrad, dict(n=1, cin=64, cout=128, h=7, w=131, k=4, stride=1, pad=2)),
     ],
 }
 
