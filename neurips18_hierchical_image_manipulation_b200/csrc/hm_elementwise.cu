@@ -178,8 +178,12 @@ __global__ void in_stats_kernel(const float* __restrict__ y, int HW, int C, int 
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (cvalid) {
     const float* base = y + size_t(n) * HW * C + c4 * 4;
+    // shifted sums: accumulate (x - pivot) with the plane's first pixel as pivot, so that
+    // var = E[d^2] - E[d]^2 does not cancel catastrophically when |mean| >> std
+    const float4 pv = __ldg(reinterpret_cast<const float4*>(base));
     for (int p = p0 + ty; p < p1; p += rows) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + size_t(p) * C));
+      float4 v = __ldg(reinterpret_cast<const float4*>(base + size_t(p) * C));
+      v.x -= pv.x; v.y -= pv.y; v.z -= pv.z; v.w -= pv.w;
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
     }
@@ -202,8 +206,8 @@ __global__ void in_stats_kernel(const float* __restrict__ y, int HW, int C, int 
     for (int i = 0; i < 4; ++i) { dst[i] = sm[tx * 8 + i]; dst[C + i] = sm[tx * 8 + 4 + i]; }
   }
 }
-__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, int N, int nblk, int C, int HW, float eps,
-                                         float* __restrict__ mean, float* __restrict__ rstd) {
+__global__ void in_stats_finalize_kernel(const float* __restrict__ y, const float* __restrict__ partial, int N, int nblk,
+                                         int C, int HW, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
@@ -212,10 +216,10 @@ __global__ void in_stats_finalize_kernel(const float* __restrict__ partial, int 
     const float* p = partial + ((size_t(n) * nblk + b) * 2) * C + c;
     s += p[0]; q += p[C];
   }
-  const double m = s / HW;
+  const double m = s / HW;   // mean of (x - pivot)
   double var = q / HW - m * m;
   if (var < 0) var = 0;
-  mean[i] = float(m);
+  mean[i] = float(m + double(__ldg(y + size_t(n) * HW * C + c)));
   rstd[i] = float(1.0 / sqrt(var + double(eps)));
 }
 
@@ -892,7 +896,7 @@ int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, floa
   stats_geometry(C, 4, &gx_log2, &cgroups);
   const int nblk = stats_nblk(N, HW, cgroups);
   in_stats_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(y, HW, C, gx_log2, ws);
-  in_stats_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(ws, N, nblk, C, HW, eps, mean, rstd);
+  in_stats_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(y, ws, N, nblk, C, HW, eps, mean, rstd);
   return HM_LAUNCH_OK();
 }
 

@@ -204,6 +204,9 @@ CASES = {
         ("wgrad 7x7s1p0 38x64 38x70", case_wgrad, dict(n=1, cin=38, cout=64, h=38, w=70, k=7, stride=1, pad=0)),
         ("wgrad 7x7s1p0 64x3 38x70", case_wgrad, dict(n=1, cin=64, cout=3, h=38, w=70, k=7, stride=1, pad=0)),
         ("wgrad 3x3s1p0 512x512 10x18", case_wgrad, dict(n=2, cin=512, cout=512, h=10, w=18, k=3, stride=1, pad=0)),
+        ("wgrad 3x3s2p1 512x1024 16x32 n1", case_wgrad, dict(n=1, cin=512, cout=1024, h=16, w=32, k=3, stride=2, pad=1)),
+        ("wgrad 3x3s1p0 1024x1024 10x18 n1", case_wgrad, dict(n=1, cin=1024, cout=1024, h=10, w=18, k=3, stride=1, pad=0)),
+        ("wgrad 3x3s2p1 256x512 32x64 n1", case_wgrad, dict(n=1, cin=256, cout=512, h=32, w=64, k=3, stride=2, pad=1)),
         # wide base space: row-streaming weight-gradient engine (hm_engine_mnrows.cuh)
         ("rows wgrad 7x7s1p0 38x64 14x262", case_wgrad, dict(n=2, cin=38, cout=64, h=14, w=262, k=7, stride=1, pad=0)),
         ("rows wgrad 7x7s1p0 64x3 14x262", case_wgrad, dict(n=1, cin=64, cout=3, h=14, w=262, k=7, stride=1, pad=0)),
