@@ -286,115 +286,194 @@ struct BwdArgs {
   int N, H, W, C, act; float slope;
 };
 
-// per-thread constants of one (n, 8-channel group): hoisted out of the pixel loops
-struct ChanStats { float mu[8], rs[8]; };
-__device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, ChanStats& cs) {
+// ---- V-wide (V = 4 or 8 channels per thread) helpers: V = 4 halves the register footprint of the backward kernels
+// (64 regs -> 4 resident blocks/SM), which is what lets them cover HBM latency.
+template <int V>
+__device__ __forceinline__ void loadv(const float* __restrict__ p, int c, int C, float (&v)[V]) {
+  if (((C & 3) == 0) && c + V <= C) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+    for (int i = 0; i < V; i += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p + c + i));
+      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = (c + i < C) ? __ldg(p + c + i) : 0.f;
+  }
+}
+template <int V>
+__device__ __forceinline__ void storev(float* __restrict__ p, int c, int C, const float (&v)[V]) {
+  if (((C & 3) == 0) && c + V <= C) {
+#pragma unroll
+    for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(p + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) if (c + i < C) p[c + i] = v[i];
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_opv(bf16* __restrict__ hi, bf16* __restrict__ lo, size_t off, const float (&v)[V]) {
+  alignas(16) bf16 h[V];
+  alignas(16) bf16 l[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) hm::split_bf16(v[i], h[i], l[i]);
+  if constexpr (V == 8) {
+    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+  } else {
+    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<const uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// per-thread constants of one (n, V-channel group): hoisted out of the pixel loops
+template <int V>
+struct ChanStats { float mu[V], rs[V]; };
+template <int V>
+__device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, ChanStats<V>& cs) {
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
     const bool ok = a.mean && (c + j < a.C);
     cs.mu[j] = ok ? __ldg(a.mean + n * a.C + c + j) : 0.f;
     cs.rs[j] = ok ? __ldg(a.rstd + n * a.C + c + j) : 1.f;
   }
 }
 
-__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats& cs, int n, int h, int w, int c,
-                                          float (&dyh)[8], float (&yh)[8]) {
+template <int V>
+__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& cs, int n, int h, int w, int c,
+                                          float (&dyh)[V], float (&yh)[V]) {
   const size_t pix = (size_t(n) * a.H + h) * a.W + w;
-  float dz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (a.g1) {
-    const int b = a.g1_border, Hp = a.H + 2 * b, Wp = a.W + 2 * b;
-    int hs[3], ws[3], nh = 1, nw = 1;
-    hs[0] = h + b; ws[0] = w + b;
-    if (b > 0) {  // adjoint of ReflectionPad2d(b): mirrored border cells fold back onto the interior
-      if (h >= 1 && h <= b) hs[nh++] = b - h;
-      if (h >= a.H - 1 - b && h <= a.H - 2) hs[nh++] = b + 2 * (a.H - 1) - h;
-      if (w >= 1 && w <= b) ws[nw++] = b - w;
-      if (w >= a.W - 1 - b && w <= a.W - 2) ws[nw++] = b + 2 * (a.W - 1) - w;
+  float dz[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) dz[j] = 0.f;
+  if (a.g1 && a.g1_border == 0) {
+    const float* p = a.g1 + pix * a.g1_ld + a.g1_coff;
+    if (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0)) loadv<V>(p, c, a.C, dz);
+    else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) dz[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
     }
+  } else if (a.g1) {
+    const int b = a.g1_border, Hp = a.H + 2 * b, Wp = a.W + 2 * b;
     const bool vec = ((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0);
-    for (int ih = 0; ih < nh; ++ih)
-      for (int iw = 0; iw < nw; ++iw) {
-        float t[8];
-        const float* p = a.g1 + ((size_t(n) * Hp + hs[ih]) * Wp + ws[iw]) * a.g1_ld + a.g1_coff;
-        if (vec) load8(p, c, a.C, t);
+    // adjoint of ReflectionPad2d(b): the interior cell plus up to one mirrored border cell per side and axis
+#pragma unroll 1
+    for (int ih = 0; ih < 3; ++ih) {
+      int hs;
+      if (ih == 0) hs = h + b;
+      else if (ih == 1) { if (!(b > 0 && h >= 1 && h <= b)) continue; hs = b - h; }
+      else { if (!(b > 0 && h >= a.H - 1 - b && h <= a.H - 2)) continue; hs = b + 2 * (a.H - 1) - h; }
+#pragma unroll 1
+      for (int iw = 0; iw < 3; ++iw) {
+        int ws;
+        if (iw == 0) ws = w + b;
+        else if (iw == 1) { if (!(b > 0 && w >= 1 && w <= b)) continue; ws = b - w; }
+        else { if (!(b > 0 && w >= a.W - 1 - b && w <= a.W - 2)) continue; ws = b + 2 * (a.W - 1) - w; }
+        float t[V];
+        const float* p = a.g1 + ((size_t(n) * Hp + hs) * Wp + ws) * a.g1_ld + a.g1_coff;
+        if (vec) loadv<V>(p, c, a.C, t);
         else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
+          for (int j = 0; j < V; ++j) t[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dz[j] += t[j];
+        for (int j = 0; j < V; ++j) dz[j] += t[j];
       }
+    }
   }
   if (a.g2) {
-    float t[8];
-    load8(a.g2 + pix * a.C, c, a.C, t);
+    float t[V];
+    loadv<V>(a.g2 + pix * a.C, c, a.C, t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dz[j] += t[j];
+    for (int j = 0; j < V; ++j) dz[j] += t[j];
   }
-  float zv[8];
-  const bool have_z = a.z != nullptr;
-  if (have_z) load8(a.z + pix * a.C, c, a.C, zv);
-  float yv[8];
-  const bool have_y = a.y != nullptr;
+  const bool have_z = a.z != nullptr, have_y = a.y != nullptr;
+  float src[V];   // anything with the sign of the pre-activation
   if (have_y) {
-    load8(a.y + pix * a.C, c, a.C, yv);
+    loadv<V>(a.y + pix * a.C, c, a.C, yh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) yv[j] = (yv[j] - cs.mu[j]) * cs.rs[j];
+    for (int j = 0; j < V; ++j) { yh[j] = (yh[j] - cs.mu[j]) * cs.rs[j]; src[j] = yh[j]; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < V; ++j) yh[j] = 0.f;
   }
-  if (a.tref) {
-    float t[8];
-    load8(a.tref + pix * a.C, c, a.C, t);
+  if (have_z) {
+    float zv[V];
+    loadv<V>(a.z + pix * a.C, c, a.C, zv);
+    if (a.tref) {
+      float t[V];
+      loadv<V>(a.tref + pix * a.C, c, a.C, t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float zz = have_z ? zv[j] : act_fwd(yv[j], a.act, a.slope);
-      const float d = zz - t[j];
+      for (int j = 0; j < V; ++j) {
+        const float d = zv[j] - t[j];
+        dz[j] += a.l1coef * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      }
+    }
+    if (!have_y) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) src[j] = zv[j];
+    }
+  } else if (a.tref) {
+    float t[V];
+    loadv<V>(a.tref + pix * a.C, c, a.C, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float d = act_fwd(yh[j], a.act, a.slope) - t[j];
       dz[j] += a.l1coef * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
     }
   }
-  float ms[8];
-  if (!have_y && !have_z && a.mask_hi) {
-    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.mask_hi + pix * a.mask_cs + c));
-    const bf16* mh = reinterpret_cast<const bf16*>(&m);
+  if (!have_y && !have_z) {
+    if (a.mask_hi) {
+      const bf16* mh = a.mask_hi + pix * a.mask_cs + c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ms[j] = __bfloat162float(mh[j]);
+      for (int j = 0; j < V; ++j) src[j] = __bfloat162float(mh[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) src[j] = 1.f;
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float src = have_y ? yv[j] : (have_z ? zv[j] : (a.mask_hi ? ms[j] : 1.f));
-    dyh[j] = (c + j < a.C) ? dz[j] * act_grad(src, a.act, a.slope) : 0.f;
-    yh[j] = have_y ? yv[j] : 0.f;
-  }
+  for (int j = 0; j < V; ++j) dyh[j] = (c + j < a.C) ? dz[j] * act_grad(src[j], a.act, a.slope) : 0.f;
 }
 
-// grid (nblk, N, cgroups); thread (tx = 8-channel group, ty = pixel lane): per-thread channel constants are loaded once
+// grid (nblk, N, cgroups); thread (tx = V-channel group, ty = pixel lane): per-thread channel constants are loaded once
+template <int V>
 __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx_log2, float* __restrict__ partial) {
   const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
   const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
   const int n = blockIdx.y, nblk = gridDim.x;
-  const int c = (blockIdx.z * gx + tx) * 8;
+  const int c = (blockIdx.z * gx + tx) * V;
   const bool cvalid = c < a.C;
   const int HW = a.H * a.W;
   const int per = (HW + nblk - 1) / nblk;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (cvalid) {
-    ChanStats cs;
-    load_chan_stats(a, n, c, cs);
-    for (int p = p0 + ty; p < p1; p += rows) {
-      float dyh[8], yh[8];
-      bwd_dyhat(a, cs, n, p / a.W, p % a.W, c, dyh, yh);
+  float s1[V], s2[V];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
+  for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (cvalid) {
+    ChanStats<V> cs;
+    load_chan_stats<V>(a, n, c, cs);
+    // (h, w) advance incrementally: an integer division per pixel made these kernels instruction bound
+    int p = p0 + ty;
+    int h = p / a.W, w = p - h * a.W;
+    const int sh = rows / a.W, sw = rows - sh * a.W;
+    for (; p < p1; p += rows) {
+      float dyh[V], yh[V];
+      bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
+      h += sh; w += sw;
+      if (w >= a.W) { w -= a.W; ++h; }
     }
   }
-  __shared__ float sm[kBlock * 16];
+  __shared__ float sm[kBlock * 2 * V];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sm[threadIdx.x * 16 + j] = s1[j]; sm[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  for (int j = 0; j < V; ++j) { sm[threadIdx.x * 2 * V + j] = s1[j]; sm[threadIdx.x * 2 * V + V + j] = s2[j]; }
   __syncthreads();
   for (int step = rows >> 1; step >= 1; step >>= 1) {
     if (ty < step) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sm[threadIdx.x * 16 + j] += sm[(threadIdx.x + step * gx) * 16 + j];
+      for (int j = 0; j < 2 * V; ++j) sm[threadIdx.x * 2 * V + j] += sm[(threadIdx.x + step * gx) * 2 * V + j];
     }
     __syncthreads();
   }
@@ -402,7 +481,7 @@ __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx
     const int C8 = (a.C + 7) & ~7;
     float* dst = partial + ((size_t(n) * nblk + blockIdx.x) * 2) * C8 + c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dst[j] = sm[tx * 16 + j]; dst[C8 + j] = sm[tx * 16 + 8 + j]; }
+    for (int j = 0; j < V; ++j) { dst[j] = sm[tx * 2 * V + j]; dst[C8 + j] = sm[tx * 2 * V + V + j]; }
   }
 }
 __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N, int nblk, int C8, int HW,
@@ -419,47 +498,54 @@ __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N,
   sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
 }
 // same thread decomposition; grid (pixel blocks, N, cgroups) with a grid-stride loop over the pixels of image n
+template <int V>
 __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_log2, const float* __restrict__ sums,
                                                               bf16* o_hi, bf16* o_lo, int o_cs, float* __restrict__ out32) {
   const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
   const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
   const int n = blockIdx.y;
-  const int c = (blockIdx.z * gx + tx) * 8;
+  const int c = (blockIdx.z * gx + tx) * V;
   const int Cout = o_hi ? o_cs : ((a.C + 7) & ~7);
   if (c >= Cout) return;
   const int C8 = (a.C + 7) & ~7;
   const int HW = a.H * a.W;
   const bool cvalid = c < a.C;
-  ChanStats cs;
-  float m1[8], m2[8];
+  ChanStats<V> cs;
+  float m1[V], m2[V];
   if (cvalid) {
-    load_chan_stats(a, n, c, cs);
+    load_chan_stats<V>(a, n, c, cs);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < V; ++j) {
       const bool ok = sums && (c + j < a.C);
       m1[j] = ok ? __ldg(sums + (size_t(n) * 2) * C8 + c + j) : 0.f;
       m2[j] = ok ? __ldg(sums + (size_t(n) * 2 + 1) * C8 + c + j) : 0.f;
     }
   }
-  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
-    float dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int p = blockIdx.x * rows + ty;
+  int h = p / a.W, w = p - h * a.W;
+  const int step = gridDim.x * rows;
+  const int sh = step / a.W, sw = step - sh * a.W;
+  for (; p < HW; p += step, h += sh, w += sw) {
+    if (w >= a.W) { w -= a.W; ++h; }
+    float dy[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) dy[j] = 0.f;
     if (cvalid) {
-      float dyh[8], yh[8];
-      bwd_dyhat(a, cs, n, p / a.W, p % a.W, c, dyh, yh);
+      float dyh[V], yh[V];
+      bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
       if (sums) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dy[j] = (c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
+        for (int j = 0; j < V; ++j) dy[j] = (c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dy[j] = dyh[j];
+        for (int j = 0; j < V; ++j) dy[j] = dyh[j];
       }
     }
     const size_t pix = size_t(n) * HW + p;
-    if (o_hi) store_op8(o_hi, o_lo, pix * o_cs + c, dy);
-    if (out32 && cvalid) store8(out32 + pix * a.C, c, a.C, dy);
+    if (o_hi) store_opv<V>(o_hi, o_lo, pix * o_cs + c, dy);
+    if (out32 && cvalid) storev<V>(out32 + pix * a.C, c, a.C, dy);
   }
 }
-
 
 // ================================================================================================
 // K8  AvgPool2d(3, stride 2, pad 1, count_include_pad=False)  (Discriminator_NET.py:31-32, Pix2Pix_NET.py:45)
@@ -841,9 +927,9 @@ __global__ void fold_add_kernel(const float* __restrict__ g, int b, int N, int H
     const int h = int(r % H);
     const int n = int(r / H);
     float dyh[8], yh[8];
-    ChanStats cs;
-    load_chan_stats(a, n, gq * 8, cs);
-    bwd_dyhat(a, cs, n, h, w, gq * 8, dyh, yh);
+    ChanStats<8> cs;
+    load_chan_stats<8>(a, n, gq * 8, cs);
+    bwd_dyhat<8>(a, cs, n, h, w, gq * 8, dyh, yh);
     store8(out + ((size_t(n) * H + h) * W + w) * C, gq * 8, C, dyh);
   }
 }
@@ -928,19 +1014,25 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
   const int C8 = (C + 7) & ~7;
   float* sums = nullptr;
   int gx_log2, cgroups;
+  // 4 channels per thread whenever every tensor is float4-addressable (all InstanceNorm layers); 8 otherwise
+  const bool v4 = ((C & 3) == 0) && (!o_hi || (o_cs & 3) == 0) && (!mask_hi || (mask_cs & 3) == 0);
+  const int V = v4 ? 4 : 8;
   if (mean) {
-    stats_geometry(C, 8, &gx_log2, &cgroups);
+    stats_geometry(C, V, &gx_log2, &cgroups);
     const int nblk = stats_nblk(N, H * W, cgroups);
     sums = ws + size_t(N) * nblk * 2 * C8;
-    in_bwd_reduce_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
+    if (v4) in_bwd_reduce_kernel<4><<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
+    else in_bwd_reduce_kernel<8><<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
     in_bwd_finalize_kernel<<<(N * C8 + 127) / 128, 128, 0, st>>>(ws, N, nblk, C8, H * W, sums);
   }
   const int Cout = o_hi ? o_cs : C8;
-  stats_geometry(Cout, 8, &gx_log2, &cgroups);
+  stats_geometry(Cout, V, &gx_log2, &cgroups);
   const int rows = kBlock >> gx_log2;
   int pblocks = std::min((H * W + rows - 1) / rows, std::max(1, (148 * 8) / std::max(1, N * cgroups)));
-  in_bwd_apply_kernel<<<dim3(pblocks, N, cgroups), kBlock, 0, st>>>(a, gx_log2, sums, static_cast<bf16*>(o_hi),
-                                                                     static_cast<bf16*>(o_lo), o_cs, out32);
+  if (v4) in_bwd_apply_kernel<4><<<dim3(pblocks, N, cgroups), kBlock, 0, st>>>(a, gx_log2, sums, static_cast<bf16*>(o_hi),
+                                                                              static_cast<bf16*>(o_lo), o_cs, out32);
+  else in_bwd_apply_kernel<8><<<dim3(pblocks, N, cgroups), kBlock, 0, st>>>(a, gx_log2, sums, static_cast<bf16*>(o_hi),
+                                                                            static_cast<bf16*>(o_lo), o_cs, out32);
   return HM_LAUNCH_OK();
 }
 
