@@ -5,6 +5,7 @@
 #include "hm_engine.cuh"
 #include "hm_engine_rows.cuh"
 #include "hm_engine_mnrows.cuh"
+#include "hm_engine2.cuh"
 
 #include <cstdlib>
 
@@ -100,6 +101,22 @@ int launch_k(const hm::KParams& p, int num_tiles, cudaStream_t st) {
   }
   int grid = std::min(num_tiles, sm_count());
   hm::hm_kgemm_kernel<BN><<<grid, hm::kEngineThreads, hm::KCfg<BN>::SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+int launch_k2(const hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_kgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hm::K2Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = true;
+  }
+  const int pair_tiles = ((num_m_tiles + 1) / 2) * n_tiles_n;
+  const int clusters = std::min(pair_tiles, sm_count() / 2);
+  hm::hm_kgemm2_kernel<256><<<2 * clusters, hm::kEngineThreads, hm::K2Cfg::SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   return HM_OK;
@@ -361,8 +378,10 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   int max_slab = 0;
   for (int t = 0; t < n_taps; ++t) max_slab = std::max(max_slab, taps[t].slab);
   const int rows_total = (max_slab + 1) * rows_pad;
-  if ((rc = make_tmap_weight(&p.tmB[0], w_hi, rows_total, k_pad, bn))) return rc;
-  if (b_lo && (rc = make_tmap_weight(&p.tmB[1], w_lo, rows_total, k_pad, bn))) return rc;
+  static const int use_2cta = env_int("HM_2CTA", 1);
+  const bool pair = use_2cta && bn == 256;   // CTA-pair kernel: each CTA loads half (128 rows) of the weight slab
+  if ((rc = make_tmap_weight(&p.tmB[0], w_hi, rows_total, k_pad, pair ? 128 : bn))) return rc;
+  if (b_lo && (rc = make_tmap_weight(&p.tmB[1], w_lo, rows_total, k_pad, pair ? 128 : bn))) return rc;
 
   int ne = 0;
   for (int t = 0; t < n_taps; ++t) {
@@ -399,6 +418,7 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   }
   p.bias = bias; p.act = act; p.slope = slope; p.err = err_flag;
   const int num_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
+  if (pair) return launch_k2(p, p.tiles_w * p.tiles_h * p.n_img, p.n_tiles_n, st);
   return launch_k_bn(bn, p, num_tiles, st);
 }
 

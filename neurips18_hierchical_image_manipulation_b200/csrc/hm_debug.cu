@@ -1,5 +1,6 @@
 // hm_debug.cu -- micro-benchmarks used while tuning the engines (not on the product path).
 #include "hm_ptx.cuh"
+#include "hm_engine2.cuh"
 
 namespace {
 // one CTA issues `count` back-to-back tcgen05.mma (M=128, N, K=16) on arbitrary smem and reports
@@ -33,7 +34,44 @@ __global__ void mma_issue_kernel(int count, int a_off_rows, long long* out) {
   __syncthreads();
   if (threadIdx.x < 32) hm::tmem_dealloc(tm, 256);
 }
+// CTA-pair variant: leader issues `count` tcgen05.mma.cta_group::2 (M=256, N=256, K=16)
+__global__ void __cluster_dims__(2, 1, 1) mma2_issue_kernel(int count, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const bool leader = hm::cluster_ctarank() == 0;
+  if (threadIdx.x == 0) { hm::mbar_init(&bar, 1); hm::fence_barrier_init(); }
+  if (threadIdx.x < 32) hm::tmem_alloc_2sm(&slot, 256);
+  hm::tc_fence_before();
+  hm::cluster_sync_all();
+  hm::tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0 && leader) {
+    const uint32_t idesc = hm::umma_idesc_bf16(256, 256, 0, 0);
+    const uint64_t ad = hm::umma_smem_desc(hm::smem_u32(smem), 16, 1024);
+    const uint64_t bd = hm::umma_smem_desc(hm::smem_u32(smem + 32768), 16, 1024);
+    long long t0 = clock64();
+    for (int i = 0; i < count; ++i) hm::umma_bf16_2sm(tm, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, 1u);
+    long long t1 = clock64();
+    hm::umma_commit_2sm_mc(&bar, 1);
+    while (!hm::mbar_try_wait(&bar, 0)) {}
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  hm::tc_fence_before();
+  hm::cluster_sync_all();
+  if (threadIdx.x < 32) hm::tmem_dealloc_2sm(tm, 256);
+}
 }  // namespace
+
+extern "C" int hm_debug_mma2_issue(int count, long long* out_dev, void* stream) {
+  const int smem = 96 * 1024;
+  cudaFuncSetAttribute(mma2_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  mma2_issue_kernel<<<2, 64, smem, static_cast<cudaStream_t>(stream)>>>(count, out_dev);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
 
 extern "C" int hm_debug_mma_issue(int n, int count, int a_off_rows, long long* out_dev, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

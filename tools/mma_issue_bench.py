@@ -12,3 +12,10 @@ for n in (16, 64, 256):
             torch.cuda.synchronize()
         o = out.tolist()
         print("N=%3d a_off=%d rows  issue %.1f cyc/MMA   complete %.1f cyc/MMA" % (n, off, o[0] / count, o[1] / count))
+
+lib.hm_debug_mma2_issue.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+for _ in range(2):
+    lib.hm_debug_mma2_issue(1024, out.data_ptr(), None)
+    torch.cuda.synchronize()
+o = out.tolist()
+print("cta_group::2 M=256 N=256: issue %.1f cyc/MMA   complete %.1f cyc/MMA" % (o[0] / 1024, o[1] / 1024))
