@@ -44,7 +44,8 @@ class Options(object):
                  no_ganFeat_loss=False, no_vgg_loss=False, no_lsgan=False, pool_size=0, no_imgCond=False,
                  mask_gan_input=False, use_soft_mask=False, no_gan=False,
                  # extensions of this implementation (not reference flags)
-                 precision="bf16x3",      # "bf16x3": fp32-parity mode; "bf16": single-product tensor-core mode
+                 precision="bf16x3",      # "bf16x3": fp32-parity mode; "mixed": bf16x3 forward + bf16 gradient GEMMs;
+                                          # "bf16": single-product tensor-core mode
                  vgg_seed=1234)           # seeded random VGG19 (no network for the ImageNet weights)
         d.update(kw)
         for k, v in d.items():
@@ -153,7 +154,12 @@ class Pix2PixHDModel_condImg(object):
             raise RuntimeError("Pix2PixHDModel_condImg (B200) needs a CUDA device: there is no CPU fallback")
         dev = torch.device("cuda", self.gpu_ids[0] if len(self.gpu_ids) else torch.cuda.current_device())
         self.device = dev
-        self.ctx = Ctx(dev, split=(getattr(opt, "precision", "bf16x3") == "bf16x3"))
+        prec = getattr(opt, "precision", "bf16x3")
+        if prec not in ("bf16x3", "mixed", "bf16"):
+            raise ValueError("precision must be bf16x3 | mixed | bf16, got %s" % prec)
+        # bf16x3: every GEMM as 3 split products (fp32 parity); mixed: forward bf16x3 (outputs and losses keep the fp32
+        # tolerance), gradient GEMMs single bf16 products; bf16: single products everywhere
+        self.ctx = Ctx(dev, split=(prec != "bf16"), split_bwd=(prec == "bf16x3"))
         self.netG_type = opt.netG
         self.use_features = opt.instance_feat or opt.label_feat
         if self.use_features:
@@ -322,7 +328,7 @@ class Pix2PixHDModel_condImg(object):
         gV = None
         if self.vgg is not None and w[2] != 0.0:
             gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
-        dy = Operand(ctx, B, st["H"], st["W"], 3)
+        dy = Operand(ctx, B, st["H"], st["W"], 3, grad=True)
         rec = w[1] * opt.lambda_rec / st["fake"].numel() if opt.lambda_rec > 0 else 0.0
         ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.netG_input_nc, gV, st["image"], rec, dy)
         self.netG.backward(st["g_tape"], dy_head=dy)

@@ -117,7 +117,7 @@ class ConvP(object):
     def packed_bwd(self):
         """rows = cin, contraction = cout."""
         if self._pd is None:
-            self._pd = PackedWeight(self.ctx, self.cin, self.cout, self.k * self.k)
+            self._pd = PackedWeight(self.ctx, self.cin, self.cout, self.k * self.k, grad=True)
         if self._vd != self.fp.version:
             kk = self.k * self.k
             if self.transposed:
@@ -266,7 +266,7 @@ class GlobalGenerator(object):
                 dy = dy_head
             else:
                 N, ho, wo, cc = rec["shape"]
-                dy = Operand(ctx, N, ho, wo, cc)
+                dy = Operand(ctx, N, ho, wo, cc, grad=True)
                 if s == add_at:   # d(out)/d(added tensor) = identity: the total gradient w.r.t. this stage's output
                     if nxt == "resA" or nxt is None:
                         self.add_grad = T
@@ -387,11 +387,11 @@ class MultiscaleDiscriminator(object):
             half_numel = pred.numel() // 2
             if mode == "G":
                 nimg = nb
-                dy = Operand(ctx, nimg, pred.shape[1], pred.shape[2], 1)
+                dy = Operand(ctx, nimg, pred.shape[1], pred.shape[2], 1, grad=True)
                 ops.mse_grad(ctx, pred[:nb], 1.0, 2.0 * w_gan / half_numel, dy)
             else:
                 nimg = N
-                dy = Operand(ctx, N, pred.shape[1], pred.shape[2], 1)
+                dy = Operand(ctx, N, pred.shape[1], pred.shape[2], 1, grad=True)
                 ops.mse_grad(ctx, pred[:nb], 0.0, 2.0 * w_fake / half_numel, dy, 0)   # fake half: target 0
                 ops.mse_grad(ctx, pred[nb:], 1.0, 2.0 * w_real / half_numel, dy, nb)  # real half: target 1
             for j in range(nl - 1, -1, -1):
@@ -409,7 +409,7 @@ class MultiscaleDiscriminator(object):
                 # through layer j-1's LeakyReLU (+InstanceNorm) to its conv output
                 tap = lv["taps"][j - 1]
                 shape = (nimg,) + tuple(tap.shape[1:])
-                dyn = Operand(ctx, nimg, tap.shape[1], tap.shape[2], tap.shape[3])
+                dyn = Operand(ctx, nimg, tap.shape[1], tap.shape[2], tap.shape[3], grad=True)
                 tref, l1 = None, 0.0
                 if mode == "G" and w_feat != 0.0:
                     tref = tap[nb:]
@@ -476,7 +476,7 @@ class Vgg19(object):
             idx, conv = self.convs_[li]
             out = tape["outs"][li]
             shape = (nb, out.h, out.w, conv.cout)
-            dy = Operand(ctx, nb, out.h, out.w, conv.cout)
+            dy = Operand(ctx, nb, out.h, out.w, conv.cout, grad=True)
             tap = tape["taps"].get(li)
             if tap is not None:
                 l1 = coefs[VGG19_TAP_AFTER[idx]] / (tap.numel() // 2)

@@ -25,10 +25,12 @@ def _ptr(t):
 class Ctx(object):
     """Per-device state shared by all ops: library handle, precision mode, pipeline error flag."""
 
-    def __init__(self, device, split=True):
+    def __init__(self, device, split=True, split_bwd=None):
         self.lib = L.load()
         self.device = torch.device(device)
         self.split = bool(split)  # True: bf16x3 (fp32-parity mode); False: plain bf16 products
+        # gradient GEMMs (dgrad / wgrad) may run with single bf16 products while the forward stays bf16x3 ("mixed")
+        self.split_bwd = self.split if split_bwd is None else bool(split_bwd)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._ws = {}
         self.launches = 0  # number of hm kernels enqueued (bench.py reports it)
@@ -53,12 +55,13 @@ class Operand(object):
 
     __slots__ = ("hi", "lo", "n", "h", "w", "c", "cs", "border")
 
-    def __init__(self, ctx, n, h, w, c, border=0, cs=None, zero=False):
+    def __init__(self, ctx, n, h, w, c, border=0, cs=None, zero=False, grad=False):
         cs = ru(c, 8) if cs is None else cs
         hp, wp = h + 2 * border, w + 2 * border
         alloc = torch.zeros if zero else torch.empty
+        split = ctx.split_bwd if grad else ctx.split
         self.hi = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device)
-        self.lo = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device) if ctx.split else None
+        self.lo = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device) if split else None
         self.n, self.h, self.w, self.c, self.cs, self.border = n, hp, wp, c, cs, border
 
     def struct(self, n0=0, n=None):
@@ -90,13 +93,14 @@ class Operand(object):
 class PackedWeight(object):
     """bf16 [taps][rows_pad][k_pad] slabs of one conv weight for one engine role."""
 
-    def __init__(self, ctx, rows, k, taps):
+    def __init__(self, ctx, rows, k, taps, grad=False):
         lib = ctx.lib
         self.rows, self.k, self.taps = rows, k, taps
         self.rows_pad, self.k_pad = lib.hm_rows_pad(rows), lib.hm_k_pad(k)
         n = taps * self.rows_pad * self.k_pad
+        split = ctx.split_bwd if grad else ctx.split
         self.hi = torch.empty(n, dtype=torch.bfloat16, device=ctx.device)
-        self.lo = torch.empty(n, dtype=torch.bfloat16, device=ctx.device) if ctx.split else None
+        self.lo = torch.empty(n, dtype=torch.bfloat16, device=ctx.device) if split else None
 
     def pack(self, ctx, w, s_row, s_k, s_tap):
         L.check(ctx.lib.hm_pack_weight(w.data_ptr(), self.rows, self.k, self.taps, s_row, s_k, s_tap, self.hi.data_ptr(),
@@ -135,6 +139,9 @@ def conv_dgrad(ctx, dy, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT
 def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=0, n=None):
     """dst[cq][cp][kh][kw] (+)= sum_pixels P[., y*stride+kh-pad, ., cp] * Q[., y, ., cq]."""
     ps, qs = P.struct(n0P, n), Q.struct(n0Q, n)
+    if not ctx.split_bwd:   # "mixed" / bf16 modes: one bf16 product for gradient GEMMs
+        ps.lo = None
+        qs.lo = None
     ws = ctx.ws("wgrad", ctx.lib.hm_wgrad_ws_bytes(kh, kw, P.c, Q.c))
     L.check(ctx.lib.hm_conv_wgrad(C.byref(ps), C.byref(qs), kh, kw, stride, pad, ws.data_ptr(), ctx.err.data_ptr(),
                                   _stream()), "hm_conv_wgrad")

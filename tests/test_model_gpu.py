@@ -122,6 +122,16 @@ def test_parity_bf16x3_local_enhancer():
     assert r["gradG"] < 2e-2 and r["gradD"] < 1e-2, r
 
 
+def test_parity_mixed_mode_forward_is_exact():
+    """precision='mixed': forward (generator output, all five losses) keeps the fp32 tolerance, gradient GEMMs are bf16."""
+    r = run_parity("mixed")
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
+    assert r["gradG"] < 0.3 and r["gradD"] < 0.3, r
+
+
 def test_parity_bf16_mode():
     r = run_parity("bf16")
     assert r["fake"] < 5e-2, r
