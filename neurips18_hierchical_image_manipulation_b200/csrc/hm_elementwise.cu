@@ -181,6 +181,7 @@ __global__ void in_stats_kernel(const float* __restrict__ y, int HW, int C, int 
     // shifted sums: accumulate (x - pivot) with the plane's first pixel as pivot, so that
     // var = E[d^2] - E[d]^2 does not cancel catastrophically when |mean| >> std
     const float4 pv = __ldg(reinterpret_cast<const float4*>(base));
+#pragma unroll 4
     for (int p = p0 + ty; p < p1; p += rows) {
       float4 v = __ldg(reinterpret_cast<const float4*>(base + size_t(p) * C));
       v.x -= pv.x; v.y -= pv.y; v.z -= pv.z; v.w -= pv.w;
@@ -227,20 +228,31 @@ __global__ void in_stats_finalize_kernel(const float* __restrict__ y, const floa
 // K7  normalise + activation (+ residual) + operand emission with materialised border
 //   out = act((y - mean) * rstd) [+ skip]     (Pix2Pix_NET.py:74-90, layer_util.py:341-378, Discriminator_NET.py:80-90)
 // ================================================================================================
-__global__ void in_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean,
+// grid (pixel blocks, N, cgroups); thread (tx = 8-channel group, ty = padded-pixel lane); (hp, wp) advance incrementally
+__global__ void __launch_bounds__(kBlock) in_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ skip, int N, int H, int W,
                                 int C, int act, float slope, float* __restrict__ out32, bf16* o_hi, bf16* o_lo, int o_cs,
-                                int border, int reflect) {
-  const int Hp = H + 2 * border, Wp = W + 2 * border;
-  const int G = (o_hi ? o_cs : ((C + 7) & ~7)) >> 3;
-  const long total = long(N) * Hp * Wp * G;
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    const int g = int(i % G);
-    long r = i / G;
-    const int wp = int(r % Wp); r /= Wp;
-    const int hp = int(r % Hp);
-    const int n = int(r / Hp);
-    const int c = g * 8;
+                                int border, int reflect, int gx_log2) {
+  const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
+  const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
+  const int n = blockIdx.y;
+  const int c = (blockIdx.z * gx + tx) * 8;
+  const int Cout = o_hi ? o_cs : ((C + 7) & ~7);
+  if (c >= Cout) return;
+  const int Hp = H + 2 * border, Wp = W + 2 * border, HWp = Hp * Wp;
+  float mu[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool ok = mean && (c + j < C);
+    mu[j] = ok ? __ldg(mean + n * C + c + j) : 0.f;
+    rs[j] = ok ? __ldg(rstd + n * C + c + j) : 1.f;
+  }
+  int pp = blockIdx.x * rows + ty;
+  int hp = pp / Wp, wp = pp - hp * Wp;
+  const int step = gridDim.x * rows;
+  const int sh = step / Wp, sw = step - sh * Wp;
+  for (; pp < HWp; pp += step, hp += sh, wp += sw) {
+    if (wp >= Wp) { wp -= Wp; ++hp; }
     int h = hp - border, w = wp - border;
     bool interior = true, zero = false;
     if (h < 0 || h >= H || w < 0 || w >= W) {
@@ -251,24 +263,19 @@ __global__ void in_apply_kernel(const float* __restrict__ y, const float* __rest
     if (!zero && c < C) {
       const size_t pix = (size_t(n) * H + h) * W + w;
       load8(y + pix * C, c, C, v);
-      if (mean) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c + j < C) v[j] = (v[j] - __ldg(mean + n * C + c + j)) * __ldg(rstd + n * C + c + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act, slope);
+      for (int j = 0; j < 8; ++j) v[j] = act_fwd((v[j] - mu[j]) * rs[j], act, slope);
       if (skip) {
-        float s[8];
-        load8(skip + pix * C, c, C, s);
+        float sk[8];
+        load8(skip + pix * C, c, C, sk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += s[j];
+        for (int j = 0; j < 8; ++j) v[j] += sk[j];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) if (c + j >= C) v[j] = 0.f;
       if (interior && out32) store8(out32 + pix * C, c, C, v);
     }
-    if (o_hi) store_op8(o_hi, o_lo, (size_t(n) * Hp * Wp + size_t(hp) * Wp + wp) * o_cs + c, v);
+    if (o_hi) store_op8(o_hi, o_lo, (size_t(n) * HWp + size_t(hp) * Wp + wp) * o_cs + c, v);
   }
 }
 
@@ -944,12 +951,12 @@ int stats_geometry(int C, int quad, int* gx_log2, int* cgroups) {
   return 0;
 }
 inline int stats_nblk(int N, int HW, int cgroups = 1) {
-  // enough blocks to fill the chip (~4 per SM) while keeping >= 64 pixels per block
-  const int want = (148 * 4 + N * cgroups - 1) / std::max(1, N * cgroups);
+  // enough blocks to fill the chip (~8 per SM: full occupancy at <= 32 registers) while keeping >= 64 pixels per block
+  const int want = (148 * 8 + N * cgroups - 1) / std::max(1, N * cgroups);
   int nblk = std::max(1, std::min(want, HW / 64));
   return std::min(nblk, 256);
 }
-inline int stats_nblk_max(int N, int HW) { return std::max(1, std::min(std::min((148 * 4 + N - 1) / N, HW / 64), 256)); }
+inline int stats_nblk_max(int N, int HW) { return std::max(1, std::min(std::min((148 * 8 + N - 1) / N, HW / 64), 256)); }
 
 }  // namespace
 
@@ -991,11 +998,15 @@ int hm_in_apply(const float* y, const float* mean, const float* rstd, const floa
                 void* stream) {
   if (!y || (o_hi && ((o_cs & 7) || o_cs < C)) || (!o_hi && !out32)) return HM_ERR_INVALID;
   if (reflect && (border >= H || border >= W)) return HM_ERR_INVALID;
-  const int G = (o_hi ? o_cs : ((C + 7) & ~7)) >> 3;
-  const long total = long(N) * (H + 2 * border) * (W + 2 * border) * G;
-  in_apply_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int Cout = o_hi ? o_cs : ((C + 7) & ~7);
+  int gx_log2, cgroups;
+  stats_geometry(Cout, 8, &gx_log2, &cgroups);
+  const int rows = kBlock >> gx_log2;
+  const int HWp = (H + 2 * border) * (W + 2 * border);
+  const int pblocks = std::min((HWp + rows - 1) / rows, std::max(1, (148 * 16) / std::max(1, N * cgroups)));
+  in_apply_kernel<<<dim3(pblocks, N, cgroups), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       y, mean, rstd, skip, N, H, W, C, act, slope, out32, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs,
-      border, reflect);
+      border, reflect, gx_log2);
   return HM_LAUNCH_OK();
 }
 
