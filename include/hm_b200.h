@@ -99,6 +99,29 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
                   int* err_flag, void* stream);
 int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* dst, int accumulate, void* stream);
 
+/* ---- tap-unrolled lowering of thin (<= 4 channel) convolutions (hm_thin.cu) ---------------------------------
+ * The engines contract over 64-channel chunks per filter tap and emit >= 16-column N tiles, so a 3-channel side
+ * wastes most of every MMA.  Folding the horizontal taps of the thin side into its channel index gives the same
+ * arithmetic with KW x fewer MMAs.  Used for the generator head Conv2d(ngf,3,7) (models/Pix2Pix_NET.py:91), the
+ * PatchGAN output Conv2d(512,1,4) (models/Discriminator_NET.py:93) and VGG19 conv1_1 (layer_util.py:384-390).
+ *
+ * hm_pack_weight_ex: hm_pack_weight with two-level row / contraction indices and an optional DEVICE scalar
+ *   multiplier (*scale, e.g. 1/sigma of spectral normalisation, models/sn_utils.py:49-72):
+ *   element (r, k, t) = *scale * src[(r / r_div)*s_r_hi + (r % r_div)*s_r_lo + (k / k_div)*s_k_hi + (k % k_div)*s_k_lo + t*s_tap]. */
+int hm_pack_weight_ex(const float* src, int rows, int r_div, long s_r_hi, long s_r_lo, int k, int k_div, long s_k_hi,
+                      long s_k_lo, int taps, long s_tap, const float* scale, void* dst_hi, void* dst_lo, void* stream);
+/* G[(kh*round_up(cp,64) + p)][kw*cq + q] (ld = round_up(KW*cq,64), the hm_conv_wgrad workspace of P = x, Q = unrolled dy
+ * with KW' = 1) -> dst[q][p][kh][kw] (OIHW), optionally accumulating. */
+int hm_wgrad_unpack_cols(const float* G_ws, int KH, int KW, int cp, int cq, float* dst, int accumulate, void* stream);
+/* dst[n,h,w,(j*KW+i)*C + c] = src[n, h+oh+sh*j, w+ow+sw*i, c] (zero outside src; channels >= KH*KW*C of dst zero).
+ * src: operand [N,Hs,Ws,s_cs], dst: operand [N,Hd,Wd,d_cs]; s_lo / d_lo may be NULL. */
+int hm_tap_unroll(const void* s_hi, const void* s_lo, int N, int Hs, int Ws, int C, int s_cs, int KH, int KW, int oh,
+                  int ow, int sh, int sw, void* d_hi, void* d_lo, int Hd, int Wd, int d_cs, void* stream);
+/* out[n,h,w,c] = act(bias[c] + sum_{j<KH,i<KW} T[n, h+oh+sh*j, w+ow+sw*i, (j*KW+i)*C + c]), terms outside T skipped;
+ * T fp32 [N,Ht,Wt,ldT], out fp32 [N,Ho,Wo,ldo], C <= 4, bias may be NULL. */
+int hm_tap_combine(const float* T, int N, int Ht, int Wt, int ldT, int KH, int KW, int C, int oh, int ow, int sh, int sw,
+                   const float* bias, int act, float slope, float* out, int Ho, int Wo, int ldo, void* stream);
+
 /* ---- HBM-bound kernels (hm_elementwise.cu) --------------------------------------------------------------
  * fp32 tensors are dense NHWC; "operand" outputs are bf16 (hi, lo) planes with channel stride *_cs (multiple of 8),
  * lo may be NULL. */
@@ -171,6 +194,19 @@ int hm_f32_to_operand(const float* x, long P, int C, int ld, int coff, float sca
                       void* stream);
 int hm_colsum(const float* x, long P, int C, float* out, int accumulate, void* stream);
 int hm_colsum_operand(const void* hi, const void* lo, long P, int C, int cs, float* out, int accumulate, void* stream);
+
+/* K13 (opt-in). Spectral normalisation of the PatchGAN convolutions: models/sn_utils.py:11-25 max_singular_value
+ * (Ip = 1) and :49-72 SNConv2d.W_bar = W / sigma, with W viewed as [n = Cout][m = Cin*KH*KW] as stored (OIHW).
+ * `layers` is a DEVICE array with one entry per convolution; every layer of the discriminator is handled by one
+ * launch.  stash (hm_sn_stash_floats(n, m) floats per layer) receives u0 | b = W v | v | sigma, 1/sigma, |a|, |b|:
+ * stash + 2n + m + 1 is the device scalar 1/sigma that hm_pack_weight_ex takes as `scale` (the normalisation is fused
+ * into the weight load; W_bar is never materialised).  update_u != 0 stores u' back into u (SNConv2d in training mode).
+ * hm_sn_weight_grad turns grad = dL/dW_bar (as accumulated by hm_conv_wgrad + hm_wgrad_unpack) into dL/dW in place,
+ * differentiating through the power iteration exactly as autograd does in the reference. */
+typedef struct hm_sn_layer { const float* W; float* grad; float* u; float* stash; int n, m; } hm_sn_layer;
+size_t hm_sn_stash_floats(int n, int m);
+int hm_sn_power_iteration(const hm_sn_layer* layers, int n_layers, int max_n, int max_m, int update_u, void* stream);
+int hm_sn_weight_grad(const hm_sn_layer* layers, int n_layers, int max_n, int max_m, void* stream);
 
 /* K10. torch.optim.Adam(lr, betas=(beta1, 0.999)) step (pix2pixHD_condImg_model.py:135,139) over a flat fp32
  * segment; grad_scale multiplies the gradient first (1/world_size after a sum-allreduce). step is 1-based. */

@@ -31,6 +31,11 @@ class OutBF16(C.Structure):
                 ("h_off", C.c_int), ("w_off", C.c_int), ("c_off", C.c_int)]
 
 
+class SnLayer(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("grad", C.c_void_p), ("u", C.c_void_p), ("stash", C.c_void_p), ("n", C.c_int),
+                ("m", C.c_int)]
+
+
 _vp, _i, _f, _l, _sz = C.c_void_p, C.c_int, C.c_float, C.c_long, C.c_size_t
 _P = C.POINTER
 
@@ -50,6 +55,10 @@ PROTOTYPES = {
     "hm_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "hm_conv_wgrad": (_i, [_P(Operand), _P(Operand), _i, _i, _i, _i, _vp, _vp, _vp]),
     "hm_wgrad_unpack": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "hm_pack_weight_ex": (_i, [_vp, _i, _i, _l, _l, _i, _i, _l, _l, _i, _l, _vp, _vp, _vp, _vp]),
+    "hm_wgrad_unpack_cols": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "hm_tap_unroll": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "hm_tap_combine": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
     "hm_encode_input": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "hm_in_ws_bytes": (_sz, [_i, _i, _i]),
     "hm_in_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
@@ -69,6 +78,9 @@ PROTOTYPES = {
     "hm_f32_to_operand": (_i, [_vp, _l, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
     "hm_colsum": (_i, [_vp, _l, _i, _vp, _i, _vp]),
     "hm_colsum_operand": (_i, [_vp, _vp, _l, _i, _i, _vp, _i, _vp]),
+    "hm_sn_stash_floats": (_sz, [_i, _i]),
+    "hm_sn_power_iteration": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "hm_sn_weight_grad": (_i, [_vp, _i, _i, _i, _vp]),
     "hm_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
 }
 

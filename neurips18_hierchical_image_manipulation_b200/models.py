@@ -46,7 +46,9 @@ class Options(object):
                  # extensions of this implementation (not reference flags)
                  precision="bf16x3",      # "bf16x3": fp32-parity mode; "mixed": bf16x3 forward + bf16 gradient GEMMs;
                                           # "bf16": single-product tensor-core mode
-                 vgg_seed=1234)           # seeded random VGG19 (no network for the ImageNet weights)
+                 vgg_seed=1234,           # seeded random VGG19 (no network for the ImageNet weights)
+                 sn_D=False)              # K13: spectral-norm the PatchGAN convs (models/sn_utils.py SNConv2d); the
+                                          # reference's MultiscaleDiscriminator uses plain convs, so default off
         d.update(kw)
         for k, v in d.items():
             setattr(self, k, v)
@@ -193,7 +195,8 @@ class Pix2PixHDModel_condImg(object):
                 raise NotImplementedError("no_imgCond / mask_gan_input / use_soft_mask / no_lsgan are outside this path")
             netD_input_nc = input_nc + 3 + opt.output_nc + (0 if opt.no_instance else 1)
             self.fpD = FlatParams(dev)
-            self.netD = MultiscaleDiscriminator(self.ctx, self.fpD, netD_input_nc, opt.ndf, opt.n_layers_D, opt.num_D)
+            self.netD = MultiscaleDiscriminator(self.ctx, self.fpD, netD_input_nc, opt.ndf, opt.n_layers_D, opt.num_D,
+                                                spectral_norm=getattr(opt, "sn_D", False))
         # one flat buffer [G | D] so data parallelism is a single allreduce
         total = self.fpG.total + (self.fpD.total if self.isTrain else 0)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -205,6 +208,8 @@ class Pix2PixHDModel_condImg(object):
             self.fpD.materialize(self.flat[self.fpG.total:], self.flat_grad[self.fpG.total:])
             for c in self.netD.convs():
                 c.init_reference(gen)
+            if self.netD.spectral_norm:
+                self.netD.setup_spectral_norm(gen)
         print("---------- Networks initialized -------------")
         # ---- load networks (:94-101)
         if not self.isTrain or opt.continue_train or opt.load_pretrain:

@@ -9,6 +9,7 @@ activation / padding passes.  Nothing here calls torch.nn or autograd.
   MultiscaleDiscriminator  <- models/Discriminator_NET.py:11-118
   Vgg19                    <- models/layer_util.py:381-411
 """
+import os
 from collections import OrderedDict
 
 import torch
@@ -22,6 +23,9 @@ VGG19_POOL_BEFORE = (5, 10, 19, 28)
 VGG19_TAP_AFTER = {0: 0, 5: 1, 10: 2, 19: 3, 28: 4}
 VGG19_SLICE_OF = {0: 1, 2: 2, 5: 2, 7: 3, 10: 3, 12: 4, 14: 4, 16: 4, 19: 4, 21: 5, 23: 5, 25: 5, 28: 5}
 
+# HM_THIN=0 disables the tap-unrolled lowering of <= 4-channel convolutions (csrc/hm_thin.cu) for A/B measurements
+THIN = os.environ.get("HM_THIN", "1") != "0"
+
 
 class FlatParams(object):
     """All parameters of one network as views into ONE flat fp32 buffer (and one flat gradient buffer), so the
@@ -34,6 +38,7 @@ class FlatParams(object):
         self.flat = None
         self.grad = None
         self.params = OrderedDict()  # name -> torch.nn.Parameter (view of flat, .grad = view of grad)
+        self.buffers = OrderedDict()  # name -> non-trainable state outside the flat buffer (spectral-norm `u` vectors)
         self.version = 0  # bumped whenever values change -> packed weights are refreshed lazily
 
     def declare(self, name, shape):
@@ -56,7 +61,10 @@ class FlatParams(object):
             self.params[name] = p
 
     def state_dict(self):
-        return OrderedDict((k, v.detach().cpu().clone()) for k, v in self.params.items())
+        sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.params.items())
+        for k, v in self.buffers.items():
+            sd[k] = v.detach().cpu().clone()
+        return sd
 
     def load_state_dict(self, sd, strict=True):
         missing = [k for k in self.params if k not in sd]
@@ -66,6 +74,9 @@ class FlatParams(object):
             for k, p in self.params.items():
                 if k in sd:
                     p.copy_(sd[k].to(self.device, torch.float32))
+            for k, b in self.buffers.items():
+                if k in sd:
+                    b.copy_(sd[k].to(self.device, torch.float32).view(b.shape))
         self.version += 1
 
 
@@ -80,6 +91,12 @@ class ConvP(object):
         fp.declare(name + ".bias", (cout,))
         self._pf = self._pd = None
         self._vf = self._vd = -1
+        # thin sides (csrc/hm_thin.cu): generator head / PatchGAN output (cout <= 4), VGG conv1_1 (cin <= 4)
+        plain = THIN and not transposed and stride == 1 and k >= 2
+        self.thin_out = plain and cout <= 4
+        self.thin_in = plain and not self.thin_out and cin <= 4 and k * k * cin <= 64
+        self._u = None  # (dy, unrolled dy) of the last thin-output gradient call
+        self.sn_scale = None  # device scalar 1/sigma when the conv is spectrally normalised (K13), else None
 
     # parameter / gradient views -------------------------------------------------------------------
     @property
@@ -103,27 +120,55 @@ class ConvP(object):
     # packed slabs ---------------------------------------------------------------------------------
     def packed_fwd(self):
         """rows = cout, contraction = cin."""
+        kk = self.k * self.k
+        if self.thin_out:      # rows = (kw, co), contraction = ci, taps = kh
+            if self._pf is None:
+                self._pf = PackedWeight(self.ctx, self.k * self.cout, self.cin, self.k)
+            if self._vf != self.fp.version:
+                self._pf.pack_ex(self.ctx, self.weight, self.cout, 1, self.cin * kk, 1, kk, 0, self.k, self.sn_scale)
+                self._vf = self.fp.version
+            return self._pf
+        if self.thin_in:       # rows = co, contraction = (kh, kw, ci), one tap
+            if self._pf is None:
+                self._pf = PackedWeight(self.ctx, self.cout, kk * self.cin, 1)
+            if self._vf != self.fp.version:
+                self._pf.pack_ex(self.ctx, self.weight, 1, self.cin * kk, 0, self.cin, 1, kk, 0, self.sn_scale)
+                self._vf = self.fp.version
+            return self._pf
         if self._pf is None:
             self._pf = PackedWeight(self.ctx, self.cout, self.cin, self.k * self.k)
         if self._vf != self.fp.version:
-            kk = self.k * self.k
             if self.transposed:   # W[ci][co][t]
-                self._pf.pack(self.ctx, self.weight, kk, self.cout * kk, 1)
+                self._pf.pack(self.ctx, self.weight, kk, self.cout * kk, 1, self.sn_scale)
             else:                 # W[co][ci][t]
-                self._pf.pack(self.ctx, self.weight, self.cin * kk, kk, 1)
+                self._pf.pack(self.ctx, self.weight, self.cin * kk, kk, 1, self.sn_scale)
             self._vf = self.fp.version
         return self._pf
 
     def packed_bwd(self):
         """rows = cin, contraction = cout."""
+        kk = self.k * self.k
+        if self.thin_out:      # rows = ci, contraction = (kw, co), taps = kh
+            if self._pd is None:
+                self._pd = PackedWeight(self.ctx, self.cin, self.k * self.cout, self.k, grad=True)
+            if self._vd != self.fp.version:
+                self._pd.pack_ex(self.ctx, self.weight, 1, kk, 0, self.cout, 1, self.cin * kk, self.k, self.sn_scale)
+                self._vd = self.fp.version
+            return self._pd
+        if self.thin_in:       # rows = (kh, kw, ci), contraction = co, one tap
+            if self._pd is None:
+                self._pd = PackedWeight(self.ctx, kk * self.cin, self.cout, 1, grad=True)
+            if self._vd != self.fp.version:
+                self._pd.pack_ex(self.ctx, self.weight, self.cin, 1, kk, 1, self.cin * kk, 0, 0, self.sn_scale)
+                self._vd = self.fp.version
+            return self._pd
         if self._pd is None:
             self._pd = PackedWeight(self.ctx, self.cin, self.cout, self.k * self.k, grad=True)
         if self._vd != self.fp.version:
-            kk = self.k * self.k
             if self.transposed:
-                self._pd.pack(self.ctx, self.weight, self.cout * kk, kk, 1)
+                self._pd.pack(self.ctx, self.weight, self.cout * kk, kk, 1, self.sn_scale)
             else:
-                self._pd.pack(self.ctx, self.weight, kk, self.cin * kk, 1)
+                self._pd.pack(self.ctx, self.weight, kk, self.cin * kk, 1, self.sn_scale)
             self._vd = self.fp.version
         return self._pd
 
@@ -138,6 +183,21 @@ class ConvP(object):
     def forward(self, x, zero_pad, act=ACT_NONE, slope=0.2, out32=None, out16=None, use_bias=True):
         ho, wo = self.out_hw(x.h, x.w, zero_pad)
         b = self.bias if use_bias else None
+        if self.thin_out:
+            # T[n,h,w',(kw,co)] = KH x 1 conv (N = KW*cout columns), then y = act(b + sum_kw T[h, w+kw, (kw,co)])
+            assert out16 is None and out32 is not None
+            k, wt, ld = self.k, x.w + 2 * zero_pad, ops.ru(self.k * self.cout, 4)
+            T = self.ctx.ws("thinT", x.n * ho * wt * ld * 4)[:x.n * ho * wt * ld].view(x.n, ho, wt, ld)
+            ops.conv_fprop(self.ctx, x, self.packed_fwd(), None, k, 1, 1, zero_pad, ho, wt, k * self.cout, out32=T)
+            ops.tap_combine(self.ctx, T, 1, k, self.cout, 0, 0, 1, 1, b, act, slope, out32)
+            return ho, wo
+        if self.thin_in:
+            # U[n,h,w,(kh,kw,ci)] = x[n,h+kh-p,w+kw-p,ci], then a 1x1 conv with K = KH*KW*cin
+            k = self.k
+            U = Operand(self.ctx, x.n, ho, wo, k * k * self.cin)
+            ops.tap_unroll(self.ctx, x, U, self.cin, k, k, -zero_pad, -zero_pad, 1, 1)
+            ops.conv_fprop(self.ctx, U, self.packed_fwd(), b, 1, 1, 1, 0, ho, wo, self.cout, act, slope, out32, out16)
+            return ho, wo
         if self.transposed:
             ops.conv_dgrad(self.ctx, x, self.packed_fwd(), b, self.k, self.k, 2, self.pad, ho, wo, self.cout, act, slope,
                            out32, out16)
@@ -148,6 +208,16 @@ class ConvP(object):
 
     def dgrad(self, dy, x_h, x_w, zero_pad, out32):
         """gradient w.r.t. the stored input (dims x_h x x_w)."""
+        if self.thin_out:
+            ops.conv_dgrad(self.ctx, self._unrolled(dy), self.packed_bwd(), None, self.k, 1, 1, zero_pad, x_h, x_w,
+                           self.cin, out32=out32)
+            return
+        if self.thin_in:
+            k, ld = self.k, ops.ru(self.k * self.k * self.cin, 4)
+            dU = self.ctx.ws("thinT", dy.n * dy.h * dy.w * ld * 4)[:dy.n * dy.h * dy.w * ld].view(dy.n, dy.h, dy.w, ld)
+            ops.conv_dgrad(self.ctx, dy, self.packed_bwd(), None, 1, 1, 1, 0, dy.h, dy.w, k * k * self.cin, out32=dU)
+            ops.tap_combine(self.ctx, dU, k, k, self.cin, zero_pad, zero_pad, -1, -1, None, ACT_NONE, 0.0, out32)
+            return
         if self.transposed:
             ops.conv_fprop(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, 2, self.pad, x_h, x_w, self.cin,
                            out32=out32)
@@ -155,11 +225,26 @@ class ConvP(object):
             ops.conv_dgrad(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, self.stride, zero_pad, x_h, x_w,
                            self.cin, out32=out32)
 
+    def _unrolled(self, dy):
+        """U[n,h,w',(kw,co)] = dy[n,h,w'-kw,co], w' in [0, W+KW-1): the thin output gradient with its horizontal taps
+        folded into channels (shared by dgrad and wgrad of the same dy)."""
+        if self._u is not None and self._u[0] is dy:
+            return self._u[1]
+        U = Operand(self.ctx, dy.n, dy.h, dy.w + self.k - 1, self.k * self.cout, grad=True)
+        ops.tap_unroll(self.ctx, dy, U, self.cout, 1, self.k, 0, 0, 1, -1)
+        self._u = (dy, U)
+        return U
+
     def wgrad(self, x, dy, zero_pad, bias_grad=True):
         """accumulate into .grad of weight and bias.  bias_grad=False for convs that feed an InstanceNorm: the bias
         cancels in the normalisation, its gradient is analytically zero (the reference computes ~1e-9 rounding noise),
         so .grad stays exactly 0 and the full-resolution column reduction is skipped."""
-        if self.transposed:
+        if self.thin_in:
+            raise NotImplementedError("weight gradient of a thin-input conv (only the frozen VGG conv1_1 is one)")
+        if self.thin_out:
+            ops.conv_wgrad(self.ctx, x, self._unrolled(dy), self.k, 1, 1, zero_pad, self.weight.grad, accumulate=True,
+                           unpack_cols=(self.k, self.cout))
+        elif self.transposed:
             ops.conv_wgrad(self.ctx, dy, x, self.k, self.k, 2, self.pad, self.weight.grad, accumulate=True)
         else:
             ops.conv_wgrad(self.ctx, x, dy, self.k, self.k, self.stride, zero_pad, self.weight.grad, accumulate=True)
@@ -312,9 +397,11 @@ class GlobalGenerator(object):
 class MultiscaleDiscriminator(object):
     """models/Discriminator_NET.py:11-118: num_D PatchGANs on an AvgPool(3,2,1) pyramid, every layer output kept."""
 
-    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3):
+    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3, spectral_norm=False):
         self.ctx, self.fp = ctx, fp
         self.input_nc, self.n_layers, self.num_D = input_nc, n_layers, num_D
+        self.spectral_norm = bool(spectral_norm)
+        self._sn = None
         self.scales = []
         for s in range(num_D):
             layers = []
@@ -331,10 +418,40 @@ class MultiscaleDiscriminator(object):
     def convs(self):
         return [c for sc in self.scales for c in sc]
 
-    def forward(self, d_in):
+    def setup_spectral_norm(self, gen):
+        """K13 (opt-in; the reference's MultiscaleDiscriminator uses plain convs): every conv becomes an
+        SNConv2d (models/sn_utils.py:49-72) -- `u` ~ N(0,1) [1, Cout] kept as a non-trainable '<conv>.u' state entry,
+        one power iteration per discriminator evaluation, W / sigma fused into the weight pack."""
+        import ctypes as C
+        from . import _lib as L
+        convs = self.convs()
+        arr = (L.SnLayer * len(convs))()
+        self._sn_keep = []
+        max_n = max_m = 0
+        for i, c in enumerate(convs):
+            n, m = c.cout, c.cin * c.k * c.k
+            u = torch.randn(1, n, generator=gen).to(self.ctx.device)
+            stash = torch.zeros(self.ctx.lib.hm_sn_stash_floats(n, m), dtype=torch.float32, device=self.ctx.device)
+            self.fp.buffers[c.name + ".u"] = u
+            c.sn_scale = stash[2 * n + m + 1:2 * n + m + 2]
+            self._sn_keep.append((u, stash))
+            arr[i] = L.SnLayer(c.weight.data_ptr(), c.weight.grad.data_ptr(), u.data_ptr(), stash.data_ptr(), n, m)
+            max_n, max_m = max(max_n, n), max(max_m, m)
+        dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.ctx.device)
+        self._sn = dict(layers=dev, n=len(convs), max_n=max_n, max_m=max_m)
+
+    def sigma(self, conv):
+        """current spectral norm estimate of `conv` (device tensor, 1 element)."""
+        return 1.0 / conv.sn_scale
+
+    def forward(self, d_in, update_u=True):
         """d_in: Operand [N,H,W,cs] (no border).  Returns tape: list over pyramid level i of dict(x=[operands],
         taps=[fp32 NHWC], y/mean/rstd per layer); level i uses scale{num_D-1-i} (Discriminator_NET.py:49-57)."""
         ctx = self.ctx
+        if self._sn is not None:
+            ops.sn_power_iteration(ctx, self._sn["layers"], self._sn["n"], self._sn["max_n"], self._sn["max_m"], update_u)
+            for c in self.convs():   # sigma changed: the packed W / sigma slabs are stale
+                c._vf = c._vd = -1
         tape = []
         x = d_in
         for i in range(self.num_D):
@@ -420,6 +537,8 @@ class MultiscaleDiscriminator(object):
                            z=tap[:nimg], g1=gin, g1_border=0, tref=tref, l1coef=l1, out_op=dyn)
                 dy = dyn
         if mode != "G":
+            if self._sn is not None:   # dL/dW_bar -> dL/dW through sigma(W) (sn_utils.py:11-25 under autograd)
+                ops.sn_weight_grad(ctx, self._sn["layers"], self._sn["n"], self._sn["max_n"], self._sn["max_m"])
             return None
         # total gradient at full resolution: g0 + poolT(g1 + poolT(g2 ...))
         for i in range(len(gins) - 1, 0, -1):

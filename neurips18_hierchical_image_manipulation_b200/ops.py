@@ -102,9 +102,18 @@ class PackedWeight(object):
         self.hi = torch.empty(n, dtype=torch.bfloat16, device=ctx.device)
         self.lo = torch.empty(n, dtype=torch.bfloat16, device=ctx.device) if split else None
 
-    def pack(self, ctx, w, s_row, s_k, s_tap):
+    def pack(self, ctx, w, s_row, s_k, s_tap, scale=None):
+        if scale is not None:   # spectral norm: W / sigma fused into the weight load
+            return self.pack_ex(ctx, w, 1, s_row, 0, 1, s_k, 0, s_tap, scale)
         L.check(ctx.lib.hm_pack_weight(w.data_ptr(), self.rows, self.k, self.taps, s_row, s_k, s_tap, self.hi.data_ptr(),
                                        _ptr(self.lo), _stream()), "hm_pack_weight")
+        ctx.launches += 1
+
+    def pack_ex(self, ctx, w, r_div, s_r_hi, s_r_lo, k_div, s_k_hi, s_k_lo, s_tap, scale=None):
+        """two-level row / contraction strides (tap-unrolled thin convs) and an optional device scalar multiplier."""
+        L.check(ctx.lib.hm_pack_weight_ex(w.data_ptr(), self.rows, r_div, s_r_hi, s_r_lo, self.k, k_div, s_k_hi, s_k_lo,
+                                          self.taps, s_tap, _ptr(scale), self.hi.data_ptr(), _ptr(self.lo), _stream()),
+                "hm_pack_weight_ex")
         ctx.launches += 1
 
 
@@ -136,8 +145,9 @@ def conv_dgrad(ctx, dy, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT
     ctx.launches += 4 if stride == 2 else 1
 
 
-def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=0, n=None):
-    """dst[cq][cp][kh][kw] (+)= sum_pixels P[., y*stride+kh-pad, ., cp] * Q[., y, ., cq]."""
+def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=0, n=None, unpack_cols=None):
+    """dst[cq][cp][kh][kw] (+)= sum_pixels P[., y*stride+kh-pad, ., cp] * Q[., y, ., cq].
+    unpack_cols=(KW, cq): Q is a tap-unrolled operand with channels (kw, cq) and kw == 1 here; dst is [cq][cp][kh][KW]."""
     ps, qs = P.struct(n0P, n), Q.struct(n0Q, n)
     if not ctx.split_bwd:   # "mixed" / bf16 modes: one bf16 product for gradient GEMMs
         ps.lo = None
@@ -145,9 +155,30 @@ def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=
     ws = ctx.ws("wgrad", ctx.lib.hm_wgrad_ws_bytes(kh, kw, P.c, Q.c))
     L.check(ctx.lib.hm_conv_wgrad(C.byref(ps), C.byref(qs), kh, kw, stride, pad, ws.data_ptr(), ctx.err.data_ptr(),
                                   _stream()), "hm_conv_wgrad")
-    L.check(ctx.lib.hm_wgrad_unpack(ws.data_ptr(), kh, kw, P.c, Q.c, dst.data_ptr(), 1 if accumulate else 0, _stream()),
-            "hm_wgrad_unpack")
+    if unpack_cols is not None:
+        L.check(ctx.lib.hm_wgrad_unpack_cols(ws.data_ptr(), kh, unpack_cols[0], P.c, unpack_cols[1], dst.data_ptr(),
+                                             1 if accumulate else 0, _stream()), "hm_wgrad_unpack_cols")
+    else:
+        L.check(ctx.lib.hm_wgrad_unpack(ws.data_ptr(), kh, kw, P.c, Q.c, dst.data_ptr(), 1 if accumulate else 0,
+                                        _stream()), "hm_wgrad_unpack")
     ctx.launches += 2
+
+
+def tap_unroll(ctx, src, dst, C, KH, KW, oh, ow, sh, sw):
+    """dst[n,h,w,(j*KW+i)*C+c] = src[n,h+oh+sh*j,w+ow+sw*i,c] over the STORED extents of both operands (zero outside)."""
+    L.check(ctx.lib.hm_tap_unroll(src.hi.data_ptr(), _ptr(src.lo) if dst.lo is not None else None, src.n, src.h, src.w, C,
+                                  src.cs, KH, KW, oh, ow, sh, sw, dst.hi.data_ptr(), _ptr(dst.lo), dst.h, dst.w, dst.cs,
+                                  _stream()), "hm_tap_unroll")
+    ctx.launches += 1
+
+
+def tap_combine(ctx, T, KH, KW, C, oh, ow, sh, sw, bias, act, slope, out):
+    """out[n,h,w,c] = act(bias[c] + sum_{j,i} T[n,h+oh+sh*j,w+ow+sw*i,(j*KW+i)*C+c]); T, out dense fp32 NHWC."""
+    N, Ht, Wt, ldT = T.shape
+    _, Ho, Wo, ldo = out.shape
+    L.check(ctx.lib.hm_tap_combine(T.data_ptr(), N, Ht, Wt, ldT, KH, KW, C, oh, ow, sh, sw, _ptr(bias), act, slope,
+                                   out.data_ptr(), Ho, Wo, ldo, _stream()), "hm_tap_combine")
+    ctx.launches += 1
 
 
 def encode_input(ctx, label, inst, image, mask_in, label_nc, g_op, d_op=None, v_op=None):
@@ -275,6 +306,17 @@ def colsum_operand(ctx, op, out, accumulate=True, n0=0, n=None):
     L.check(ctx.lib.hm_colsum_operand(op.hi.data_ptr() + off, (op.lo.data_ptr() + off) if op.lo is not None else None, P,
                                       op.c, op.cs, out.data_ptr(), 1 if accumulate else 0, _stream()),
             "hm_colsum_operand")
+    ctx.launches += 1
+
+
+def sn_power_iteration(ctx, layers_dev, n_layers, max_n, max_m, update_u=True):
+    L.check(ctx.lib.hm_sn_power_iteration(layers_dev.data_ptr(), n_layers, max_n, max_m, 1 if update_u else 0, _stream()),
+            "hm_sn_power_iteration")
+    ctx.launches += 1
+
+
+def sn_weight_grad(ctx, layers_dev, n_layers, max_n, max_m):
+    L.check(ctx.lib.hm_sn_weight_grad(layers_dev.data_ptr(), n_layers, max_n, max_m, _stream()), "hm_sn_weight_grad")
     ctx.launches += 1
 
 

@@ -250,6 +250,9 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
     else:
         fake = global_generator_forward(g_sd, input_label, opt.n_downsample_global, opt.n_blocks_global,
                                         mask=mask_in.to(dtype), use_output_gate=opt.use_output_gate)   # :208
+    # opt-in spectral norm (SNConv2d in place of Conv2d): one power iteration per step, shared by the three D calls
+    # below -- the product evaluates D once on [fake ; real]; identity when d_sd has no '.u' entries
+    d_sd, new_u = spectral_normalize(d_sd)
     D = lambda t: multiscale_discriminator_forward(d_sd, t, opt.num_D, opt.n_layers_D)
     pred_fake_pool = D(torch.cat((input_label, fake.detach()), 1))             # :218 (discriminate :176-186)
     loss_D_fake = gan_loss(pred_fake_pool, False)                              # :219
@@ -270,7 +273,7 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
         loss_G_VGG = vgg_loss(vgg_sd, fake, real) * opt.lambda_feat
     if opt.lambda_rec > 0:                                                     # :249-251
         loss_G_GAN_Feat = loss_G_GAN_Feat + F.l1_loss(fake, real.detach()) * opt.lambda_rec
-    extras = dict(input_label=input_label, cond=cond, pred_fake=pred_fake, pred_real=pred_real)
+    extras = dict(input_label=input_label, cond=cond, pred_fake=pred_fake, pred_real=pred_real, sn_u=new_u)
     return [loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_D_real, loss_D_fake], fake, extras
 
 
@@ -297,20 +300,25 @@ def train_step(opt, g_sd, d_sd, vgg_sd, batch, state=None, dtype=torch.float32):
     """One iteration of train_mask2image.py:58-86 on CPU: forward, loss_G.backward + Adam(G), loss_D.backward +
     Adam(D).  g_sd / d_sd are updated in place; returns (losses, fake, grads_G, grads_D)."""
     g_par = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(True)) for k, v in g_sd.items())
-    d_par = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(True)) for k, v in d_sd.items())
+    d_par = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(not k.endswith(".u"))) for k, v in d_sd.items())
     v_sd = OrderedDict((k, v.to(dtype)) for k, v in vgg_sd.items()) if vgg_sd is not None else None
-    losses, fake, _ = model_forward(opt, g_par, d_par, v_sd, batch["label"], batch["inst"], batch["image"],
-                                    batch["mask_in"], dtype)
+    losses, fake, extras = model_forward(opt, g_par, d_par, v_sd, batch["label"], batch["inst"], batch["image"],
+                                         batch["mask_in"], dtype)
     loss_G, loss_D = step_losses(losses)
+    d_train = OrderedDict((k, p) for k, p in d_par.items() if p.requires_grad)
     gG = torch.autograd.grad(loss_G, list(g_par.values()), retain_graph=True, allow_unused=True)
-    gD = torch.autograd.grad(loss_D, list(d_par.values()), allow_unused=True)
+    gD = torch.autograd.grad(loss_D, list(d_train.values()), allow_unused=True)
     gG = OrderedDict((k, (g if g is not None else torch.zeros_like(p))) for (k, p), g in zip(g_par.items(), gG))
-    gD = OrderedDict((k, (g if g is not None else torch.zeros_like(p))) for (k, p), g in zip(d_par.items(), gD))
+    gD = OrderedDict((k, (g if g is not None else torch.zeros_like(p))) for (k, p), g in zip(d_train.items(), gD))
+    for k, u in extras["sn_u"].items():       # SNConv2d stores the iterated u (sn_utils.py:65-66)
+        d_sd[k].copy_(u.reshape(d_sd[k].shape))
     if state is None:
         state = dict(step=0, mG={}, vG={}, mD={}, vD={})
     state["step"] += 1
     for sd, grads, mk, vk in ((g_sd, gG, "mG", "vG"), (d_sd, gD, "mD", "vD")):
         for k in sd:
+            if k not in grads:
+                continue
             if k not in state[mk]:
                 state[mk][k] = torch.zeros_like(sd[k], dtype=dtype)
                 state[vk][k] = torch.zeros_like(sd[k], dtype=dtype)
@@ -333,6 +341,21 @@ def max_singular_value(W, u, Ip=1):
         _u = _u / (_u.norm() + 1e-12)
     sigma = (_u @ Wm @ _v.t()).reshape(())
     return sigma, _u
+
+
+def spectral_normalize(d_sd):
+    """SNConv2d.W_bar (models/sn_utils.py:57-63) for every conv of a state dict that carries a '<conv>.u' entry:
+    returns (state dict with weight / sigma, differentiable w.r.t. the weight exactly as in the reference, where
+    autograd flows through the power iteration) and {'<conv>.u': iterated u}."""
+    eff, new_u = OrderedDict(d_sd), OrderedDict()
+    for k in d_sd:
+        if k.endswith(".u"):
+            base = k[:-2]
+            w = d_sd[base + ".weight"]
+            sigma, u2 = max_singular_value(w, d_sd[k].detach().to(w.dtype).reshape(1, -1))
+            eff[base + ".weight"] = w / sigma
+            new_u[k] = u2.detach()
+    return eff, new_u
 
 
 # --------------------------------------------------------------------------------------------------

@@ -134,3 +134,39 @@ def test_model_forward_and_step_run():
     assert torch.equal(ex["cond"][~m], b["image"][~m])
     ls, fk, gG, gD, st = O.train_step(opt, g_sd, d_sd, vgg, b)
     assert st["step"] == 1 and all(torch.isfinite(v).all() for v in gG.values())
+
+
+def test_spectral_norm_conv_forward_backward(golden_dir):
+    """oracle.spectral_normalize against the reference's own SNConv2d (fixture: oracle/make_golden_sn.py), and the
+    closed-form gradient through the power iteration that csrc/hm_sn.cu implements against the reference's autograd."""
+    z = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "sn_conv.npz")).items()}
+    W = z["W"].clone().requires_grad_(True)
+    b = z["b"].clone().requires_grad_(True)
+    x = z["x"].clone().requires_grad_(True)
+    eff, new_u = O.spectral_normalize(OrderedDict([("c.weight", W), ("c.bias", b), ("c.u", z["u"])]))
+    y = torch.nn.functional.conv2d(x, eff["c.weight"], eff["c.bias"], stride=1, padding=2)
+    (y * z["g"]).sum().backward()
+    close(y, z["y"], 1e-5)
+    close(new_u["c.u"], z["u_out"], 1e-5)
+    close(W.grad, z["dW"], 1e-4)
+    close(b.grad, z["db"], 1e-5)
+    close(x.grad, z["dx"], 1e-5)
+    # closed form: dL/dW = (G - <G, W_bar> (g_b v^T + u0 g_a^T)) / sigma, G = dL/dW_bar
+    Wm = z["W"].reshape(10, -1).double()
+    u0 = z["u"].double().reshape(-1)
+    eps = 1e-12
+    a = Wm.t() @ u0
+    na = a.norm(); v = a / (na + eps)
+    bb = Wm @ v
+    nb = bb.norm(); sigma = (bb @ bb) / (nb + eps)
+    close(sigma.float(), z["sigma"].reshape(()), 1e-5)
+    Wbar = (z["W"] / z["sigma"].reshape(())).detach().requires_grad_(True)
+    y2 = torch.nn.functional.conv2d(z["x"], Wbar, z["b"], stride=1, padding=2)
+    (y2 * z["g"]).sum().backward()
+    G = Wbar.grad.reshape(10, -1).double()
+    c = (G * Wm).sum() / sigma
+    g_b = bb * (1 / (nb + eps) + eps / (nb + eps) ** 2)
+    g_v = Wm.t() @ g_b
+    g_a = g_v / (na + eps) - a * (a @ g_v) / (na * (na + eps) ** 2)
+    dW = (G - c * (torch.outer(g_b, v) + torch.outer(u0, g_a))) / sigma
+    close(dW.float().reshape(z["dW"].shape), z["dW"], 1e-4)
