@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int num_m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   const int num_tiles = num_m_tiles * p.n_tiles_n;
   const int ksteps = p.n_entries * p.chunks;
@@ -118,55 +118,55 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
-        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-        const int thi = mt % p.tiles_h;
-        const int n = mt / p.tiles_h;
-        const int w0 = (twi << p.tw_log2) * p.in_stride;
-        const int h0 = thi * p.th * p.in_stride;
-        for (int e = 0; e < p.n_entries; ++e) {
-          const KEntry en = p.entries[e];
-          for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait(&empty[s], ph ^ 1, ab, 101);
-            uint8_t* sa = smem + s * C::STAGE_BYTES;
+    // ===================== TMA producer (warp-wide loop, one elected lane issues) =====================
+    if (elect_one_sync()) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]); }
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h;
+      const int n = mt / p.tiles_h;
+      const int w0 = (twi << p.tw_log2) * p.in_stride;
+      const int h0 = thi * p.th * p.in_stride;
+      for (int e = 0; e < p.n_entries; ++e) {
+        const KEntry en = p.entries[e];
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&empty[s], ph ^ 1, ab, 101);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
             tma_load_4d(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
             tma_load_2d(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN);
-            if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[a], aph ^ 1, ab, 102);
+    // ===================== MMA issuer (warp-wide loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[a], aph ^ 1, ab, 102);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * BN;
+      for (int k = 0; k < ksteps; ++k) {
+        mbar_wait(&full[s], ph, ab, 103);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * BN;
-        for (int k = 0; k < ksteps; ++k) {
-          mbar_wait(&full[s], ph, ab, 103);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
             umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
           umma_commit(&empty[s]);
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[a]);
-        if (++a == C::ACC) { a = 0; aph ^= 1; }
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(&tfull[a]);
+      if (++a == C::ACC) { a = 0; aph ^= 1; }
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM sub-partition each) =====================
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int num_tiles = p.n_m_tiles * p.n_n_tiles * p.splits;
   AbortCtl ab{abort_flag, p.err};
 
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmP[0]); tma_prefetch_desc(&p.tmQ[0]);
+    {
+      if (elect_one_sync()) { tma_prefetch_desc(&p.tmP[0]); tma_prefetch_desc(&p.tmQ[0]); }
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_n_tiles;
@@ -342,21 +342,23 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
             const int w0 = twi << p.tw_log2, h0 = thi * p.th;
             mbar_wait(&empty[s], ph ^ 1, ab, 201);
             uint8_t* sa = smem + s * C::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-              tma_load_4d(mp, &full[s], sa + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r], h0 * p.sP + mdh[r], n);
+              for (int r = 0; r < 2; ++r)
+                tma_load_4d(mp, &full[s], sa + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r], h0 * p.sP + mdh[r], n);
 #pragma unroll
-            for (int r = 0; r < NB; ++r)
-              tma_load_4d(mq, &full[s], sa + C::A_BYTES + r * C::BOX_BYTES, nc[r], w0 * p.sQ + ndw[r],
-                          h0 * p.sQ + ndh[r], n);
+              for (int r = 0; r < NB; ++r)
+                tma_load_4d(mq, &full[s], sa + C::A_BYTES + r * C::BOX_BYTES, nc[r], w0 * p.sQ + ndw[r],
+                            h0 * p.sQ + ndh[r], n);
+            }
             if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
       int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -373,13 +375,15 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
           // MN-major SW128: LBO = distance between 64-channel groups (one TMA box), SBO = 8 K-rows = 1024 B
           const uint64_t adesc = umma_smem_desc(sa, C::BOX_BYTES, 1024);
           const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, C::BOX_BYTES, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // 16 pixels (K) per MMA = 16 rows x 128 B = 2048 B
-            umma_bf16(d_tmem, adesc + j * (2048 >> 4), bdesc + j * (2048 >> 4), idesc, (k | j) != 0);
-          umma_commit(&empty[s]);
+            for (int j = 0; j < 4; ++j)  // 16 pixels (K) per MMA = 16 rows x 128 B = 2048 B
+              umma_bf16(d_tmem, adesc + j * (2048 >> 4), bdesc + j * (2048 >> 4), idesc, (k | j) != 0);
+            umma_commit(&empty[s]);
+          }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[a]);
+        if (elect_one_sync()) umma_commit(&tfull[a]);
         if (++a == C::ACC) { a = 0; aph ^= 1; }
       }
     }

@@ -100,7 +100,7 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int num_m_tiles = p.tiles_w * p.tiles_h * p.n_img;
@@ -124,8 +124,8 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
+    {
+      if (elect_one_sync()) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]); }
       int s = 0; uint32_t ph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int nt = tile % p.n_tiles_n;
@@ -143,9 +143,11 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
             uint8_t* sa = smem + s * C::STAGE_BYTES;
             // only the leader arms its full barrier, for the bytes of BOTH CTAs; the peer's loads cannot run ahead of
             // it by a phase because they are gated by the leader's multicast commit on empty[s]
-            if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
-            tma_load_4d_2sm(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
-            tma_load_2d_2sm(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
+            if (elect_one_sync()) {
+              if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+              tma_load_4d_2sm(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
+              tma_load_2d_2sm(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
+            }
             if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -153,7 +155,7 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
       int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
@@ -166,12 +168,14 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
-          umma_commit_2sm_mc(&empty[s], 3);
+            for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
+            umma_commit_2sm_mc(&empty[s], 3);
+          }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm_mc(&tfull[a], 3);
+        if (elect_one_sync()) umma_commit_2sm_mc(&tfull[a], 3);
         if (++a == C::ACC) { a = 0; aph ^= 1; }
       }
     }

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mnrows_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int base_tiles = p.kh * p.m_units * p.n_n_tiles;
   const int num_tiles = base_tiles * p.splits;
   const int nst = p.n_stages;
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mnrows_kernel(const __gr
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmP[0]); tma_prefetch_desc(&p.tmQ[0]);
+    {
+      if (elect_one_sync()) { tma_prefetch_desc(&p.tmP[0]); tma_prefetch_desc(&p.tmQ[0]); }
       int s = 0; uint32_t ph = 0;
       const uint32_t tx_bytes = uint32_t(p.box_w) * 128u + NB * C::Q_BOX;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -100,18 +100,20 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mnrows_kernel(const __gr
             const int w0 = twi * 128;
             mbar_wait(&empty[s], ph ^ 1, ab, 401);
             uint8_t* dst = smem + s * p.stage_bytes;
-            mbar_arrive_expect_tx(&full[s], tx_bytes);
-            tma_load_4d(mp, &full[s], dst, mu * 64, w0 + p.dw0, h + p.dh[kh], n);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full[s], tx_bytes);
+              tma_load_4d(mp, &full[s], dst, mu * 64, w0 + p.dw0, h + p.dh[kh], n);
 #pragma unroll
-            for (int r = 0; r < NB; ++r)
-              tma_load_4d(mq, &full[s], dst + C::A_PLANE + r * C::Q_BOX, (nt * NB + r) * 64, w0, h, n);
+              for (int r = 0; r < NB; ++r)
+                tma_load_4d(mq, &full[s], dst + C::A_PLANE + r * C::Q_BOX, (nt * NB + r) * 64, w0, h, n);
+            }
             if (++s == nst) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
       int s = 0; uint32_t ph = 0; uint32_t tph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -125,18 +127,20 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mnrows_kernel(const __gr
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
           const uint32_t b_base = a_base + C::A_PLANE;
-          for (int pi = 0; pi < p.pairs; ++pi) {
-            // A: taps (2pi, 2pi+1) = two 64-channel groups one pixel row (128 B) apart; 8 K-rows every 1024 B
-            const uint64_t ad = umma_smem_desc(a_base + uint32_t(2 * pi) * 128u, 128, 1024);
-            const uint64_t bd = umma_smem_desc(b_base, C::Q_BOX, 1024);
+          if (elect_one_sync()) {
+            for (int pi = 0; pi < p.pairs; ++pi) {
+              // A: taps (2pi, 2pi+1) = two 64-channel groups one pixel row (128 B) apart; 8 K-rows every 1024 B
+              const uint64_t ad = umma_smem_desc(a_base + uint32_t(2 * pi) * 128u, 128, 1024);
+              const uint64_t bd = umma_smem_desc(b_base, C::Q_BOX, 1024);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)   // 16 pixels (K) per MMA = 2048 B
-              umma_bf16(tmem_base + pi * BN, ad + j * (2048 >> 4), bd + j * (2048 >> 4), idesc, (k | j) != 0);
+              for (int j = 0; j < 8; ++j)   // 16 pixels (K) per MMA = 2048 B
+                umma_bf16(tmem_base + pi * BN, ad + j * (2048 >> 4), bd + j * (2048 >> 4), idesc, (k | j) != 0);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
           if (++s == nst) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull);
+        if (elect_one_sync()) umma_commit(tfull);
         tph ^= 1;
       }
     }

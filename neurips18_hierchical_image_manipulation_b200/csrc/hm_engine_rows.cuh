@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int num_m_tiles = p.tiles_w * p.rows_h * p.n_img;
   const int num_tiles = num_m_tiles * p.n_tiles_n;
   const int nst = p.n_stages;
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
 
   if (warp == 0) {
     // ===================== TMA producer: 2 loads per filter-row stage =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
+    {
+      if (elect_one_sync()) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]); }
       int s = 0; uint32_t ph = 0;
       const uint32_t tx_bytes = uint32_t(p.box_w) * 128u + uint32_t(p.kw) * C::B_TILE;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -111,9 +111,11 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
             const int dh = p.entries[e].dh, tap0 = p.entries[e].tap0;
             mbar_wait(&empty[s], ph ^ 1, ab, 301);
             uint8_t* dst = smem + s * p.stage_bytes;
-            mbar_arrive_expect_tx(&full[s], tx_bytes);
-            tma_load_4d(&p.tmA[a_plane], &full[s], dst, c * 64, w0, h + dh, n);
-            tma_load_3d(&p.tmB[b_plane], &full[s], dst + C::A_PLANE, c * 64, nt * BN, tap0);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full[s], tx_bytes);
+              tma_load_4d(&p.tmA[a_plane], &full[s], dst, c * 64, w0, h + dh, n);
+              tma_load_3d(&p.tmB[b_plane], &full[s], dst + C::A_PLANE, c * 64, nt * BN, tap0);
+            }
             if (++s == nst) { s = 0; ph ^= 1; }
           }
         }
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: kw x 4 MMAs per barrier wait =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -135,17 +137,21 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
             const uint32_t b_base = a_base + C::A_PLANE;
-            for (int j = 0; j < p.kw; ++j) {
-              const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
-              const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
+            if (elect_one_sync()) {
+              uint32_t acc_j = acc;
+              for (int j = 0; j < p.kw; ++j) {
+                const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
+                const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc); acc = 1; }
+                for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
+              }
+              umma_commit(&empty[s]);
             }
-            umma_commit(&empty[s]);
+            acc = 1;
             if (++s == nst) { s = 0; ph ^= 1; }
           }
         }
-        umma_commit(&tfull[a]);
+        if (elect_one_sync()) umma_commit(&tfull[a]);
         if (++a == C::ACC) { a = 0; aph ^= 1; }
       }
     }

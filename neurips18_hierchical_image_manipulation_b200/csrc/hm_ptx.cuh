@@ -14,6 +14,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// warp-uniform role dispatch.  The producer / issuer roles run WARP-WIDE with only the side-effecting instruction
+// (TMA, tcgen05.mma, commit) under elect_one_sync(): a role body nested in `if (lane == 0)` is divergent code to the
+// compiler, so every descriptor / coordinate operand lives in a vector register and each UTMALDG / UTCHMMA is wrapped
+// in an ELECT + R2UR.BROADCAST "waterfall" loop -- measured (ncu source page, r01) at ~92 issue cycles per MMA, which
+// capped every N <= 128 kernel at 35 % tensor pipe.  With a shuffled (provably uniform) warp index and uniform loop
+// variables the operands stay in uniform registers and an MMA issues in a handful of cycles.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
