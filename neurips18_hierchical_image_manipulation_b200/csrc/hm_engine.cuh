@@ -83,6 +83,73 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
+
+// Epilogue of one TMEM chunk (CH consecutive output channels of this thread's pixel): + bias -> activation ->
+// fp32 NHWC store and/or bf16 hi/lo operand store.  The bias vector is fetched with 16 B loads and the activation is
+// selected ONCE per chunk: a per-element `if (bias) ... switch (act)` serialised 32 dependent __ldg + branches per
+// chunk (~4.7 k cycles per 32 columns measured, ncu r01), which made every full-resolution 64/128-channel layer
+// epilogue-bound.  P is KParams or RParams (same output fields).
+template <int CH, class P>
+__device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&raw)[CH], int cg, bool v32, bool v16,
+                                               bool vb, size_t off32, size_t off16) {
+  float v[CH];
+  const bool full_chunk = (cg + CH <= p.cout);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(raw[i]);
+  if (p.bias) {
+    if (vb && full_chunk) {
+#pragma unroll
+      for (int i = 0; i < CH; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cg + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) if (cg + i < p.cout) v[i] += __ldg(p.bias + cg + i);
+    }
+  }
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.act == ACT_LRELU) {
+    const float sl = p.slope;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+  } else if (p.act == ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = tanhf(v[i]);
+  }
+  if (p.o32) {
+    float* dst = p.o32 + off32 + cg;
+    if (v32 && full_chunk) {
+#pragma unroll
+      for (int i = 0; i < CH; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) if (cg + i < p.cout) dst[i] = v[i];
+    }
+  }
+  if (p.ohi) {
+    __nv_bfloat16 hi[CH], lo[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) split_bf16(v[i], hi[i], lo[i]);
+    __nv_bfloat16* dh = p.ohi + off16 + cg;
+    __nv_bfloat16* dl = p.olo ? p.olo + off16 + cg : nullptr;
+    if (v16 && full_chunk) {
+#pragma unroll
+      for (int i = 0; i < CH; i += 8) {
+        *reinterpret_cast<uint4*>(dh + i) = *reinterpret_cast<const uint4*>(hi + i);
+        if (dl) *reinterpret_cast<uint4*>(dl + i) = *reinterpret_cast<const uint4*>(lo + i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (cg + i < p.cout) { dh[i] = hi[i]; if (dl) dl[i] = lo[i]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K-engine
 // ------------------------------------------------------------------------------------------------
@@ -178,6 +245,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
     const bool v16 = p.ohi && ((p.o16_C & 7) == 0) && ((p.o16_coff & 7) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.ohi) & 15) == 0) &&
                      (!p.olo || (reinterpret_cast<uintptr_t>(p.olo) & 15) == 0);
+    const bool vb = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles_n;
       int mt = tile / p.n_tiles_n;
@@ -201,45 +269,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
         if constexpr (C::CH == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_ld_wait();
         const int cg = nt * BN + c0;  // first output channel of this chunk
-        if (valid && cg < p.cout) {
-          float v[C::CH];
-#pragma unroll
-          for (int i = 0; i < C::CH; ++i) {
-            float x = __uint_as_float(raw[i]);
-            if (p.bias && cg + i < p.cout) x += __ldg(p.bias + cg + i);
-            v[i] = apply_act(x, p.act, p.slope);
-          }
-          const bool full_chunk = (cg + C::CH <= p.cout);
-          if (p.o32) {
-            float* dst = p.o32 + off32 + cg;
-            if (v32 && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < C::CH; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < C::CH; ++i) if (cg + i < p.cout) dst[i] = v[i];
-            }
-          }
-          if (p.ohi) {
-            __nv_bfloat16 hi[C::CH], lo[C::CH];
-#pragma unroll
-            for (int i = 0; i < C::CH; ++i) split_bf16(v[i], hi[i], lo[i]);
-            __nv_bfloat16* dh = p.ohi + off16 + cg;
-            __nv_bfloat16* dl = p.olo ? p.olo + off16 + cg : nullptr;
-            if (v16 && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < C::CH; i += 8) {
-                *reinterpret_cast<uint4*>(dh + i) = *reinterpret_cast<const uint4*>(hi + i);
-                if (dl) *reinterpret_cast<uint4*>(dl + i) = *reinterpret_cast<const uint4*>(lo + i);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < C::CH; ++i)
-                if (cg + i < p.cout) { dh[i] = hi[i]; if (dl) dl[i] = lo[i]; }
-            }
-          }
-        }
+        if (valid && cg < p.cout) epilogue_chunk<C::CH>(p, raw, cg, v32, v16, vb, off32, off16);
       }
       tc_fence_before();
       __syncwarp();

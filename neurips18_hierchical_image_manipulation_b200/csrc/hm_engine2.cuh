@@ -189,6 +189,7 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
     const bool v16 = p.ohi && ((p.o16_C & 7) == 0) && ((p.o16_coff & 7) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.ohi) & 15) == 0) &&
                      (!p.olo || (reinterpret_cast<uintptr_t>(p.olo) & 15) == 0);
+    const bool vb = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       const int nt = tile % p.n_tiles_n;
       const int mt2 = tile / p.n_tiles_n;
@@ -213,45 +214,7 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + a * BN + c0, raw);
         tmem_ld_wait();
         const int cg = nt * BN + c0;
-        if (valid && cg < p.cout) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(raw[i]);
-            if (p.bias && cg + i < p.cout) x += __ldg(p.bias + cg + i);
-            v[i] = apply_act(x, p.act, p.slope);
-          }
-          const bool full_chunk = (cg + 32 <= p.cout);
-          if (p.o32) {
-            float* dst = p.o32 + off32 + cg;
-            if (v32 && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (cg + i < p.cout) dst[i] = v[i];
-            }
-          }
-          if (p.ohi) {
-            __nv_bfloat16 hi[32], lo[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) split_bf16(v[i], hi[i], lo[i]);
-            __nv_bfloat16* dh = p.ohi + off16 + cg;
-            __nv_bfloat16* dl = p.olo ? p.olo + off16 + cg : nullptr;
-            if (v16 && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                *reinterpret_cast<uint4*>(dh + i) = *reinterpret_cast<const uint4*>(hi + i);
-                if (dl) *reinterpret_cast<uint4*>(dl + i) = *reinterpret_cast<const uint4*>(lo + i);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (cg + i < p.cout) { dh[i] = hi[i]; if (dl) dl[i] = lo[i]; }
-            }
-          }
-        }
+        if (valid && cg < p.cout) epilogue_chunk<32>(p, raw, cg, v32, v16, vb, off32, off16);
       }
       tc_fence_before();
       __syncwarp();

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
     const bool v16 = p.ohi && ((p.o16_C & 7) == 0) && ((p.o16_coff & 7) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.ohi) & 15) == 0) &&
                      (!p.olo || (reinterpret_cast<uintptr_t>(p.olo) & 15) == 0);
+    const bool vb = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles_n;
       int mt = tile / p.n_tiles_n;
@@ -185,45 +186,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
         if constexpr (C::CH == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_ld_wait();
         const int cg = nt * BN + c0;
-        if (valid && cg < p.cout) {
-          float v[C::CH];
-#pragma unroll
-          for (int i = 0; i < C::CH; ++i) {
-            float x = __uint_as_float(raw[i]);
-            if (p.bias && cg + i < p.cout) x += __ldg(p.bias + cg + i);
-            v[i] = apply_act(x, p.act, p.slope);
-          }
-          const bool full_chunk = (cg + C::CH <= p.cout);
-          if (p.o32) {
-            float* dst = p.o32 + off32 + cg;
-            if (v32 && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < C::CH; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < C::CH; ++i) if (cg + i < p.cout) dst[i] = v[i];
-            }
-          }
-          if (p.ohi) {
-            __nv_bfloat16 hi[C::CH], lo[C::CH];
-#pragma unroll
-            for (int i = 0; i < C::CH; ++i) split_bf16(v[i], hi[i], lo[i]);
-            __nv_bfloat16* dh = p.ohi + off16 + cg;
-            __nv_bfloat16* dl = p.olo ? p.olo + off16 + cg : nullptr;
-            if (v16 && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < C::CH; i += 8) {
-                *reinterpret_cast<uint4*>(dh + i) = *reinterpret_cast<const uint4*>(hi + i);
-                if (dl) *reinterpret_cast<uint4*>(dl + i) = *reinterpret_cast<const uint4*>(lo + i);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < C::CH; ++i)
-                if (cg + i < p.cout) { dh[i] = hi[i]; if (dl) dl[i] = lo[i]; }
-            }
-          }
-        }
+        if (valid && cg < p.cout) epilogue_chunk<C::CH>(p, raw, cg, v32, v16, vb, off32, off16);
       }
       tc_fence_before();
       __syncwarp();
