@@ -363,28 +363,42 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
   } else if (a.g1) {
     const int b = a.g1_border, Hp = a.H + 2 * b, Wp = a.W + 2 * b;
     const bool vec = ((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0);
-    // adjoint of ReflectionPad2d(b): the interior cell plus up to one mirrored border cell per side and axis
-#pragma unroll 1
-    for (int ih = 0; ih < 3; ++ih) {
-      int hs;
-      if (ih == 0) hs = h + b;
-      else if (ih == 1) { if (!(b > 0 && h >= 1 && h <= b)) continue; hs = b - h; }
-      else { if (!(b > 0 && h >= a.H - 1 - b && h <= a.H - 2)) continue; hs = b + 2 * (a.H - 1) - h; }
-#pragma unroll 1
-      for (int iw = 0; iw < 3; ++iw) {
-        int ws;
-        if (iw == 0) ws = w + b;
-        else if (iw == 1) { if (!(b > 0 && w >= 1 && w <= b)) continue; ws = b - w; }
-        else { if (!(b > 0 && w >= a.W - 1 - b && w <= a.W - 2)) continue; ws = b + 2 * (a.W - 1) - w; }
-        float t[V];
-        const float* p = a.g1 + ((size_t(n) * Hp + hs) * Wp + ws) * a.g1_ld + a.g1_coff;
-        if (vec) loadv<V>(p, c, a.C, t);
-        else {
+    // adjoint of ReflectionPad2d(b): the interior cell plus up to one mirrored border cell per side and axis.
+    // Fast path first: only pixels in the 2b rows / columns next to the frame receive mirrored contributions
+    // (the generic 3x3 candidate loop cost ~250 instructions per pixel and made these kernels issue bound).
+    {
+      const float* p = a.g1 + ((size_t(n) * Hp + h + b) * Wp + w + b) * a.g1_ld + a.g1_coff;
+      if (vec) loadv<V>(p, c, a.C, dz);
+      else {
 #pragma unroll
-          for (int j = 0; j < V; ++j) t[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
+        for (int j = 0; j < V; ++j) dz[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
+      }
+    }
+    const bool near_h = (h >= 1 && h <= b) || (h >= a.H - 1 - b && h <= a.H - 2);
+    const bool near_w = (w >= 1 && w <= b) || (w >= a.W - 1 - b && w <= a.W - 2);
+    if (near_h || near_w) {
+#pragma unroll 1
+      for (int ih = 0; ih < 3; ++ih) {
+        int hs;
+        if (ih == 0) hs = h + b;
+        else if (ih == 1) { if (!(h >= 1 && h <= b)) continue; hs = b - h; }
+        else { if (!(h >= a.H - 1 - b && h <= a.H - 2)) continue; hs = b + 2 * (a.H - 1) - h; }
+#pragma unroll 1
+        for (int iw = 0; iw < 3; ++iw) {
+          int ws;
+          if (iw == 0) { if (ih == 0) continue; ws = w + b; }   // the interior cell is already in dz
+          else if (iw == 1) { if (!(w >= 1 && w <= b)) continue; ws = b - w; }
+          else { if (!(w >= a.W - 1 - b && w <= a.W - 2)) continue; ws = b + 2 * (a.W - 1) - w; }
+          float t[V];
+          const float* p = a.g1 + ((size_t(n) * Hp + hs) * Wp + ws) * a.g1_ld + a.g1_coff;
+          if (vec) loadv<V>(p, c, a.C, t);
+          else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) t[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) dz[j] += t[j];
         }
-#pragma unroll
-        for (int j = 0; j < V; ++j) dz[j] += t[j];
       }
     }
   }
@@ -464,13 +478,23 @@ __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx
     int p = p0 + ty;
     int h = p / a.W, w = p - h * a.W;
     const int sh = rows / a.W, sw = rows - sh * a.W;
-    for (; p < p1; p += rows) {
+    // two pixels per iteration: twice the independent 16 B loads in flight per thread
+    for (; p + rows < p1; p += 2 * rows) {
+      int h2 = h + sh, w2 = w + sw;
+      if (w2 >= a.W) { w2 -= a.W; ++h2; }
+      float dyh[V], yh[V], dyh2[V], yh2[V];
+      bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
+      bwd_dyhat<V>(a, cs, n, h2, w2, c, dyh2, yh2);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { s1[j] += dyh[j] + dyh2[j]; s2[j] += dyh[j] * yh[j] + dyh2[j] * yh2[j]; }
+      h = h2 + sh; w = w2 + sw;
+      if (w >= a.W) { w -= a.W; ++h; }
+    }
+    if (p < p1) {
       float dyh[V], yh[V];
       bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
 #pragma unroll
       for (int j = 0; j < V; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
-      h += sh; w += sw;
-      if (w >= a.W) { w -= a.W; ++h; }
     }
   }
   __shared__ float sm[kBlock * 2 * V];
@@ -532,25 +556,45 @@ __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_
   int h = p / a.W, w = p - h * a.W;
   const int step = gridDim.x * rows;
   const int sh = step / a.W, sw = step - sh * a.W;
-  for (; p < HW; p += step, h += sh, w += sw) {
+  // two pixels per iteration (all loads of both pixels are issued before the first store)
+  for (; p < HW; p += 2 * step) {
     if (w >= a.W) { w -= a.W; ++h; }
-    float dy[V];
+    const int p2 = p + step;
+    int h2 = h + sh, w2 = w + sw;
+    if (w2 >= a.W) { w2 -= a.W; ++h2; }
+    const bool second = p2 < HW;
+    float dy[V], dy2[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) dy[j] = 0.f;
+    for (int j = 0; j < V; ++j) { dy[j] = 0.f; dy2[j] = 0.f; }
     if (cvalid) {
-      float dyh[V], yh[V];
+      float dyh[V], yh[V], dyh2[V], yh2[V];
       bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
+      if (second) bwd_dyhat<V>(a, cs, n, h2, w2, c, dyh2, yh2);
+      else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { dyh2[j] = 0.f; yh2[j] = 0.f; }
+      }
       if (sums) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) dy[j] = (c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
+        for (int j = 0; j < V; ++j) {
+          const bool ok = c + j < a.C;
+          dy[j] = ok ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
+          dy2[j] = ok ? cs.rs[j] * (dyh2[j] - m1[j] - yh2[j] * m2[j]) : 0.f;
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) dy[j] = dyh[j];
+        for (int j = 0; j < V; ++j) { dy[j] = dyh[j]; dy2[j] = dyh2[j]; }
       }
     }
     const size_t pix = size_t(n) * HW + p;
     if (o_hi) store_opv<V>(o_hi, o_lo, pix * o_cs + c, dy);
     if (out32 && cvalid) storev<V>(out32 + pix * a.C, c, a.C, dy);
+    if (second) {
+      const size_t pix2 = size_t(n) * HW + p2;
+      if (o_hi) store_opv<V>(o_hi, o_lo, pix2 * o_cs + c, dy2);
+      if (out32 && cvalid) storev<V>(out32 + pix2 * a.C, c, a.C, dy2);
+    }
+    h = h2 + sh; w = w2 + sw;
   }
 }
 

@@ -5,35 +5,53 @@
 
 namespace {
 
+// One thread converts TWO adjacent contraction indices (k, k+1) of one row for ALL taps: the fp32 source is read once
+// (the taps of a filter are contiguous in OIHW / IOHW, so the per-tap loop walks the sectors the thread already
+// fetched) and each tap plane is written with 4-byte bf16x2 stores that are contiguous across the warp.
 __global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int kk, int taps, long s_row, long s_k,
                                    long s_tap, int rows_pad, int k_pad, __nv_bfloat16* __restrict__ hi,
                                    __nv_bfloat16* __restrict__ lo) {
-  const long total = long(taps) * rows_pad * k_pad;
+  const int kh2 = k_pad >> 1;
+  const long total = long(rows_pad) * kh2;
+  const long plane = long(rows_pad) * k_pad;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    const int k = int(i % k_pad);
-    const long rt = i / k_pad;
-    const int r = int(rt % rows_pad);
-    const int t = int(rt / rows_pad);
-    float v = 0.f;
-    if (r < rows && k < kk) v = __ldg(src + r * s_row + k * s_k + t * s_tap);
-    __nv_bfloat16 h, l;
-    hm::split_bf16(v, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    const int k = int(i % kh2) * 2;
+    const int r = int(i / kh2);
+    const bool ok0 = r < rows && k < kk, ok1 = r < rows && k + 1 < kk;
+    const float* p0 = src + r * s_row + k * s_k;
+    const float* p1 = p0 + s_k;
+    const long o = long(r) * k_pad + k;
+    for (int t = 0; t < taps; ++t) {
+      const float v0 = ok0 ? __ldg(p0 + t * s_tap) : 0.f;
+      const float v1 = ok1 ? __ldg(p1 + t * s_tap) : 0.f;
+      __nv_bfloat16 h0, l0, h1, l1;
+      hm::split_bf16(v0, h0, l0);
+      hm::split_bf16(v1, h1, l1);
+      __nv_bfloat162 hh; hh.x = h0; hh.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(hi + t * plane + o) = hh;
+      if (lo) {
+        __nv_bfloat162 ll; ll.x = l0; ll.y = l1;
+        *reinterpret_cast<__nv_bfloat162*>(lo + t * plane + o) = ll;
+      }
+    }
   }
 }
 
-// G[(t*cp_pad + p)][q] (ld = cq_pad) -> dst[q][p][t]
+// G[(t*cp_pad + p)][q] (ld = cq_pad) -> dst[q][p][t].  One thread owns one (p, q) pair for all taps: the workspace
+// reads are contiguous across the warp (q fastest) and each thread updates one contiguous run of `taps` floats.
 __global__ void wgrad_unpack_kernel(const float* __restrict__ G, int taps, int cp, int cq, int cp_pad, int cq_pad,
                                     float* __restrict__ dst, int accumulate) {
-  const long total = long(cq) * cp * taps;
+  const long total = long(cq) * cp;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    const int t = int(i % taps);
-    const long qp = i / taps;
-    const int pch = int(qp % cp);
-    const int q = int(qp / cp);
-    const float v = __ldg(G + (long(t) * cp_pad + pch) * cq_pad + q);
-    dst[i] = accumulate ? dst[i] + v : v;
+    const int q = int(i % cq);
+    const int pch = int(i / cq);
+    float* d = dst + (long(q) * cp + pch) * taps;
+    const float* g = G + long(pch) * cq_pad + q;
+    const long tstride = long(cp_pad) * cq_pad;
+    for (int t = 0; t < taps; ++t) {
+      const float v = __ldg(g + t * tstride);
+      d[t] = accumulate ? d[t] + v : v;
+    }
   }
 }
 
@@ -45,7 +63,7 @@ int hm_pack_weight(const float* src, int rows, int k, int taps, long s_row, long
                    void* dst_lo, void* stream) {
   if (!src || !dst_hi || rows <= 0 || k <= 0 || taps <= 0) return HM_ERR_INVALID;
   const int rows_pad = hm_rows_pad(rows), k_pad = hm_k_pad(k);
-  const long total = long(taps) * rows_pad * k_pad;
+  const long total = long(rows_pad) * (k_pad / 2);
   const int block = 256;
   const int grid = int(std::min<long>((total + block - 1) / block, 148L * 16));
   pack_weight_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -58,7 +76,7 @@ int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* ds
   if (!G_ws || !dst) return HM_ERR_INVALID;
   const int taps = KH * KW;
   const int cp_pad = (cp + 63) / 64 * 64, cq_pad = (cq + 63) / 64 * 64;
-  const long total = long(cq) * cp * taps;
+  const long total = long(cq) * cp;
   const int block = 256;
   const int grid = int(std::min<long>((total + block - 1) / block, 148L * 16));
   wgrad_unpack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(G_ws, taps, cp, cq, cp_pad, cq_pad, dst,
