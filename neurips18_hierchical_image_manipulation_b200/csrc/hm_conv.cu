@@ -6,6 +6,7 @@
 #include "hm_engine_rows.cuh"
 #include "hm_engine_mnrows.cuh"
 #include "hm_engine2.cuh"
+#include "hm_engine_mn2.cuh"
 
 #include <cstdlib>
 
@@ -144,6 +145,21 @@ int launch_mn(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
   }
   int grid = std::min(num_tiles, sm_count());
   hm::hm_mngemm_kernel<NB><<<grid, hm::kEngineThreads, hm::MNCfg<NB>::SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+int launch_mn2(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_mngemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hm::MN2Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = true;
+  }
+  const int clusters = std::min(num_tiles, sm_count() / 2);
+  hm::hm_mngemm2_kernel<<<2 * clusters, hm::kEngineThreads, hm::MN2Cfg::SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   return HM_OK;
@@ -522,12 +538,15 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
   p.upt_n = p.n_units;
   p.m_units = KH * KW * p.upt_m;
   const int nb = p.n_units >= 3 ? 4 : p.n_units;
-  p.n_m_tiles = (p.m_units + 1) / 2;
+  static const int use_mn2 = env_int("HM_MN2", 1);
+  const bool pair = use_mn2 && p.n_units >= 4 && p.m_units >= 4;   // CTA-pair engine: 256 x 256 tiles of G
+  p.n_m_tiles = pair ? (p.m_units + 3) / 4 : (p.m_units + 1) / 2;
   p.n_n_tiles = (p.n_units + nb - 1) / nb;
   p.ktiles = p.tiles_w * p.tiles_h * p.n_img;
   const int base_tiles = p.n_m_tiles * p.n_n_tiles;
+  const int workers = pair ? sm_count() / 2 : sm_count();
   int splits = 1;
-  if (base_tiles < 2 * sm_count()) splits = (2 * sm_count() + base_tiles - 1) / base_tiles;
+  if (base_tiles < 2 * workers) splits = (2 * workers + base_tiles - 1) / base_tiles;
   splits = std::max(1, std::min(splits, p.ktiles / 4 > 0 ? p.ktiles / 4 : 1));
   // make every split non-empty
   { int per = (p.ktiles + splits - 1) / splits; splits = (p.ktiles + per - 1) / per; }
@@ -544,6 +563,7 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
     if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   }
   const int num_tiles = base_tiles * splits;
+  if (pair) return launch_mn2(p, num_tiles, st);
   switch (nb) {
     case 1: return launch_mn<1>(p, num_tiles, st);
     case 2: return launch_mn<2>(p, num_tiles, st);

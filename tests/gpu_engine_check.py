@@ -207,6 +207,9 @@ CASES = {
         ("wgrad 3x3s2p1 512x1024 16x32 n1", case_wgrad, dict(n=1, cin=512, cout=1024, h=16, w=32, k=3, stride=2, pad=1)),
         ("wgrad 3x3s1p0 1024x1024 10x18 n1", case_wgrad, dict(n=1, cin=1024, cout=1024, h=10, w=18, k=3, stride=1, pad=0)),
         ("wgrad 3x3s2p1 256x512 32x64 n1", case_wgrad, dict(n=1, cin=256, cout=512, h=32, w=64, k=3, stride=2, pad=1)),
+        # CTA-pair MN engine with ragged M (9 units) and N (5 units) tile counts
+        ("wgrad 3x3s1p1 64x320 12x20", case_wgrad, dict(n=2, cin=64, cout=320, h=12, w=20, k=3, stride=1, pad=1)),
+        ("wgrad 4x4s1p2 256x512 9x17", case_wgrad, dict(n=2, cin=256, cout=512, h=9, w=17, k=4, stride=1, pad=2)),
         # wide base space: row-streaming weight-gradient engine (hm_engine_mnrows.cuh)
         ("rows wgrad 7x7s1p0 38x64 14x262", case_wgrad, dict(n=2, cin=38, cout=64, h=14, w=262, k=7, stride=1, pad=0)),
         ("rows wgrad 7x7s1p0 64x3 14x262", case_wgrad, dict(n=1, cin=64, cout=3, h=14, w=262, k=7, stride=1, pad=0)),
