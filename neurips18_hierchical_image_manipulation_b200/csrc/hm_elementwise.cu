@@ -295,27 +295,38 @@ struct BwdArgs {
 
 // ---- V-wide (V = 4 or 8 channels per thread) helpers: V = 4 halves the register footprint of the backward kernels
 // (64 regs -> 4 resident blocks/SM), which is what lets them cover HBM latency.
+// V == 4 is only launched when every tensor is float4-addressable and C % 4 == 0 (hm_in_bwd checks), so a valid
+// thread (c < C) always owns 4 full channels: no per-access bounds / alignment tests in the hot loops.
 template <int V>
 __device__ __forceinline__ void loadv(const float* __restrict__ p, int c, int C, float (&v)[V]) {
-  if (((C & 3) == 0) && c + V <= C) {
-#pragma unroll
-    for (int i = 0; i < V; i += 4) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p + c + i));
-      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
-    }
+  if constexpr (V == 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   } else {
+    if (((C & 3) == 0) && c + V <= C) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = (c + i < C) ? __ldg(p + c + i) : 0.f;
+      for (int i = 0; i < V; i += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p + c + i));
+        v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = (c + i < C) ? __ldg(p + c + i) : 0.f;
+    }
   }
 }
 template <int V>
 __device__ __forceinline__ void storev(float* __restrict__ p, int c, int C, const float (&v)[V]) {
-  if (((C & 3) == 0) && c + V <= C) {
-#pragma unroll
-    for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(p + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p + c) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
+    if (((C & 3) == 0) && c + V <= C) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) if (c + i < C) p[c + i] = v[i];
+      for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(p + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) if (c + i < C) p[c + i] = v[i];
+    }
   }
 }
 template <int V>
@@ -335,7 +346,7 @@ __device__ __forceinline__ void store_opv(bf16* __restrict__ hi, bf16* __restric
 
 // per-thread constants of one (n, V-channel group): hoisted out of the pixel loops
 template <int V>
-struct ChanStats { float mu[V], rs[V]; };
+struct ChanStats { float mu[V], rs[V]; float gneg; /* act'(x <= 0): 0 relu, slope lrelu, 1 none */ };
 template <int V>
 __device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, ChanStats<V>& cs) {
 #pragma unroll
@@ -344,25 +355,25 @@ __device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, 
     cs.mu[j] = ok ? __ldg(a.mean + n * a.C + c + j) : 0.f;
     cs.rs[j] = ok ? __ldg(a.rstd + n * a.C + c + j) : 1.f;
   }
+  cs.gneg = (a.act == HM_ACT_RELU) ? 0.f : ((a.act == HM_ACT_LRELU) ? a.slope : 1.f);
 }
 
 template <int V>
-__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& cs, int n, int h, int w, int c,
+__device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& cs, size_t pix, int n, int h, int w, int c,
                                           float (&dyh)[V], float (&yh)[V]) {
-  const size_t pix = (size_t(n) * a.H + h) * a.W + w;
   float dz[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) dz[j] = 0.f;
   if (a.g1 && a.g1_border == 0) {
     const float* p = a.g1 + pix * a.g1_ld + a.g1_coff;
-    if (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0)) loadv<V>(p, c, a.C, dz);
+    if (V == 4 || (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0))) loadv<V>(p, c, a.C, dz);
     else {
 #pragma unroll
       for (int j = 0; j < V; ++j) dz[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
     }
   } else if (a.g1) {
     const int b = a.g1_border, Hp = a.H + 2 * b, Wp = a.W + 2 * b;
-    const bool vec = ((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0);
+    const bool vec = V == 4 || (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0));
     // adjoint of ReflectionPad2d(b): the interior cell plus up to one mirrored border cell per side and axis.
     // Fast path first: only pixels in the 2b rows / columns next to the frame receive mirrored contributions
     // (the generic 3x3 candidate loop cost ~250 instructions per pixel and made these kernels issue bound).
@@ -446,15 +457,22 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
   if (!have_y && !have_z) {
     if (a.mask_hi) {
       const bf16* mh = a.mask_hi + pix * a.mask_cs + c;
+      if constexpr (V == 4) {
+        const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mh));
+        const bf16* m4 = reinterpret_cast<const bf16*>(&mv);
 #pragma unroll
-      for (int j = 0; j < V; ++j) src[j] = __bfloat162float(mh[j]);
+        for (int j = 0; j < 4; ++j) src[j] = __bfloat162float(m4[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) src[j] = __bfloat162float(mh[j]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < V; ++j) src[j] = 1.f;
     }
   }
 #pragma unroll
-  for (int j = 0; j < V; ++j) dyh[j] = (c + j < a.C) ? dz[j] * act_grad(src[j], a.act, a.slope) : 0.f;
+  for (int j = 0; j < V; ++j) dyh[j] = (V == 4 || c + j < a.C) ? dz[j] * (src[j] > 0.f ? 1.f : cs.gneg) : 0.f;
 }
 
 // grid (nblk, N, cgroups); thread (tx = V-channel group, ty = pixel lane): per-thread channel constants are loaded once
@@ -478,23 +496,14 @@ __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx
     int p = p0 + ty;
     int h = p / a.W, w = p - h * a.W;
     const int sh = rows / a.W, sw = rows - sh * a.W;
-    // two pixels per iteration: twice the independent 16 B loads in flight per thread
-    for (; p + rows < p1; p += 2 * rows) {
-      int h2 = h + sh, w2 = w + sw;
-      if (w2 >= a.W) { w2 -= a.W; ++h2; }
-      float dyh[V], yh[V], dyh2[V], yh2[V];
-      bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
-      bwd_dyhat<V>(a, cs, n, h2, w2, c, dyh2, yh2);
-#pragma unroll
-      for (int j = 0; j < V; ++j) { s1[j] += dyh[j] + dyh2[j]; s2[j] += dyh[j] * yh[j] + dyh2[j] * yh2[j]; }
-      h = h2 + sh; w = w2 + sw;
-      if (w >= a.W) { w -= a.W; ++h; }
-    }
-    if (p < p1) {
+    const size_t base = size_t(n) * HW;
+    for (; p < p1; p += rows) {
       float dyh[V], yh[V];
-      bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
+      bwd_dyhat<V>(a, cs, base + p, n, h, w, c, dyh, yh);
 #pragma unroll
       for (int j = 0; j < V; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
+      h += sh; w += sw;
+      if (w >= a.W) { w -= a.W; ++h; }
     }
   }
   __shared__ float sm[kBlock * 2 * V];
@@ -556,45 +565,26 @@ __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_
   int h = p / a.W, w = p - h * a.W;
   const int step = gridDim.x * rows;
   const int sh = step / a.W, sw = step - sh * a.W;
-  // two pixels per iteration (all loads of both pixels are issued before the first store)
-  for (; p < HW; p += 2 * step) {
+  const size_t base = size_t(n) * HW;
+  for (; p < HW; p += step, h += sh, w += sw) {
     if (w >= a.W) { w -= a.W; ++h; }
-    const int p2 = p + step;
-    int h2 = h + sh, w2 = w + sw;
-    if (w2 >= a.W) { w2 -= a.W; ++h2; }
-    const bool second = p2 < HW;
-    float dy[V], dy2[V];
+    float dy[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) { dy[j] = 0.f; dy2[j] = 0.f; }
+    for (int j = 0; j < V; ++j) dy[j] = 0.f;
+    const size_t pix = base + p;
     if (cvalid) {
-      float dyh[V], yh[V], dyh2[V], yh2[V];
-      bwd_dyhat<V>(a, cs, n, h, w, c, dyh, yh);
-      if (second) bwd_dyhat<V>(a, cs, n, h2, w2, c, dyh2, yh2);
-      else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) { dyh2[j] = 0.f; yh2[j] = 0.f; }
-      }
+      float dyh[V], yh[V];
+      bwd_dyhat<V>(a, cs, pix, n, h, w, c, dyh, yh);
       if (sums) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const bool ok = c + j < a.C;
-          dy[j] = ok ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
-          dy2[j] = ok ? cs.rs[j] * (dyh2[j] - m1[j] - yh2[j] * m2[j]) : 0.f;
-        }
+        for (int j = 0; j < V; ++j) dy[j] = (V == 4 || c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
       } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) { dy[j] = dyh[j]; dy2[j] = dyh2[j]; }
+        for (int j = 0; j < V; ++j) dy[j] = dyh[j];
       }
     }
-    const size_t pix = size_t(n) * HW + p;
     if (o_hi) store_opv<V>(o_hi, o_lo, pix * o_cs + c, dy);
     if (out32 && cvalid) storev<V>(out32 + pix * a.C, c, a.C, dy);
-    if (second) {
-      const size_t pix2 = size_t(n) * HW + p2;
-      if (o_hi) store_opv<V>(o_hi, o_lo, pix2 * o_cs + c, dy2);
-      if (out32 && cvalid) storev<V>(out32 + pix2 * a.C, c, a.C, dy2);
-    }
-    h = h2 + sh; w = w2 + sw;
   }
 }
 
@@ -980,7 +970,7 @@ __global__ void fold_add_kernel(const float* __restrict__ g, int b, int N, int H
     float dyh[8], yh[8];
     ChanStats<8> cs;
     load_chan_stats<8>(a, n, gq * 8, cs);
-    bwd_dyhat<8>(a, cs, n, h, w, gq * 8, dyh, yh);
+    bwd_dyhat<8>(a, cs, (size_t(n) * H + h) * W + w, n, h, w, gq * 8, dyh, yh);
     store8(out + ((size_t(n) * H + h) * W + w) * C, gq * 8, C, dyh);
   }
 }
@@ -1070,7 +1060,8 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
   float* sums = nullptr;
   int gx_log2, cgroups;
   // 4 channels per thread whenever every tensor is float4-addressable (all InstanceNorm layers); 8 otherwise
-  const bool v4 = ((C & 3) == 0) && (!o_hi || (o_cs & 3) == 0) && (!mask_hi || (mask_cs & 3) == 0);
+  const bool v4 = ((C & 3) == 0) && (!o_hi || (o_cs & 3) == 0) && (!mask_hi || (mask_cs & 3) == 0) &&
+                  (!g1 || (((g1_ld & 3) == 0) && ((g1_coff & 3) == 0)));
   const int V = v4 ? 4 : 8;
   if (mean) {
     stats_geometry(C, V, &gx_log2, &cgroups);

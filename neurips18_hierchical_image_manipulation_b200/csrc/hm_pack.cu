@@ -37,21 +37,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int 
   }
 }
 
-// G[(t*cp_pad + p)][q] (ld = cq_pad) -> dst[q][p][t].  One thread owns one (p, q) pair for all taps: the workspace
-// reads are contiguous across the warp (q fastest) and each thread updates one contiguous run of `taps` floats.
+// G[(t*cp_pad + p)][q] (ld = cq_pad) -> dst[q][p][t]
 __global__ void wgrad_unpack_kernel(const float* __restrict__ G, int taps, int cp, int cq, int cp_pad, int cq_pad,
                                     float* __restrict__ dst, int accumulate) {
-  const long total = long(cq) * cp;
+  const long total = long(cq) * cp * taps;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    const int q = int(i % cq);
-    const int pch = int(i / cq);
-    float* d = dst + (long(q) * cp + pch) * taps;
-    const float* g = G + long(pch) * cq_pad + q;
-    const long tstride = long(cp_pad) * cq_pad;
-    for (int t = 0; t < taps; ++t) {
-      const float v = __ldg(g + t * tstride);
-      d[t] = accumulate ? d[t] + v : v;
-    }
+    const int t = int(i % taps);
+    const long qp = i / taps;
+    const int pch = int(qp % cp);
+    const int q = int(qp / cp);
+    const float v = __ldg(G + (long(t) * cp_pad + pch) * cq_pad + q);
+    dst[i] = accumulate ? dst[i] + v : v;
   }
 }
 
@@ -76,7 +72,7 @@ int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* ds
   if (!G_ws || !dst) return HM_ERR_INVALID;
   const int taps = KH * KW;
   const int cp_pad = (cp + 63) / 64 * 64, cq_pad = (cq + 63) / 64 * 64;
-  const long total = long(cq) * cp;
+  const long total = long(cq) * cp * taps;
   const int block = 256;
   const int grid = int(std::min<long>((total + block - 1) / block, 148L * 16));
   wgrad_unpack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(G_ws, taps, cp, cq, cp_pad, cq_pad, dst,
