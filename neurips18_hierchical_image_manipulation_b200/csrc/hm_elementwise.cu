@@ -358,20 +358,33 @@ __device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, 
   cs.gneg = (a.act == HM_ACT_RELU) ? 0.f : ((a.act == HM_ACT_LRELU) ? a.slope : 1.f);
 }
 
-template <int V>
+// Which inputs exist is known on the host, so the hot variants are compiled with the presence flags as template
+// constants (F_* mask): with run-time flags the loop body re-tested ~10 pointers and rebuilt every 64-bit address
+// per pixel (~160 instructions per 4-channel pixel, issue bound at 25-35 % of HBM bandwidth; ncu r01).  BWD_GENERIC
+// keeps the run-time tests for the combinations that are not instantiated.
+enum : int { F_IN = 1, F_G1D = 2, F_G1B = 4, F_G2 = 8, F_Z = 16, F_TREF = 32, F_MASK = 64, BWD_GENERIC = 128 };
+template <int F> __device__ __forceinline__ bool has_in(const BwdArgs& a) { return (F & BWD_GENERIC) ? a.y != nullptr : (F & F_IN) != 0; }
+template <int F> __device__ __forceinline__ bool has_g1d(const BwdArgs& a) { return (F & BWD_GENERIC) ? (a.g1 && a.g1_border == 0) : (F & F_G1D) != 0; }
+template <int F> __device__ __forceinline__ bool has_g1b(const BwdArgs& a) { return (F & BWD_GENERIC) ? (a.g1 && a.g1_border != 0) : (F & F_G1B) != 0; }
+template <int F> __device__ __forceinline__ bool has_g2(const BwdArgs& a) { return (F & BWD_GENERIC) ? a.g2 != nullptr : (F & F_G2) != 0; }
+template <int F> __device__ __forceinline__ bool has_z(const BwdArgs& a) { return (F & BWD_GENERIC) ? a.z != nullptr : (F & F_Z) != 0; }
+template <int F> __device__ __forceinline__ bool has_tref(const BwdArgs& a) { return (F & BWD_GENERIC) ? a.tref != nullptr : (F & F_TREF) != 0; }
+template <int F> __device__ __forceinline__ bool has_mask(const BwdArgs& a) { return (F & BWD_GENERIC) ? a.mask_hi != nullptr : (F & F_MASK) != 0; }
+
+template <int V, int F>
 __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& cs, size_t pix, int n, int h, int w, int c,
                                           float (&dyh)[V], float (&yh)[V]) {
   float dz[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) dz[j] = 0.f;
-  if (a.g1 && a.g1_border == 0) {
+  if (has_g1d<F>(a)) {
     const float* p = a.g1 + pix * a.g1_ld + a.g1_coff;
     if (V == 4 || (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0))) loadv<V>(p, c, a.C, dz);
     else {
 #pragma unroll
       for (int j = 0; j < V; ++j) dz[j] = (c + j < a.C) ? __ldg(p + c + j) : 0.f;
     }
-  } else if (a.g1) {
+  } else if (has_g1b<F>(a)) {
     const int b = a.g1_border, Hp = a.H + 2 * b, Wp = a.W + 2 * b;
     const bool vec = V == 4 || (((a.g1_ld & 3) == 0) && ((a.g1_coff & 3) == 0));
     // adjoint of ReflectionPad2d(b): the interior cell plus up to one mirrored border cell per side and axis.
@@ -413,13 +426,13 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
       }
     }
   }
-  if (a.g2) {
+  if (has_g2<F>(a)) {
     float t[V];
     loadv<V>(a.g2 + pix * a.C, c, a.C, t);
 #pragma unroll
     for (int j = 0; j < V; ++j) dz[j] += t[j];
   }
-  const bool have_z = a.z != nullptr, have_y = a.y != nullptr;
+  const bool have_z = has_z<F>(a), have_y = has_in<F>(a);
   float src[V];   // anything with the sign of the pre-activation
   if (have_y) {
     loadv<V>(a.y + pix * a.C, c, a.C, yh);
@@ -432,7 +445,7 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
   if (have_z) {
     float zv[V];
     loadv<V>(a.z + pix * a.C, c, a.C, zv);
-    if (a.tref) {
+    if (has_tref<F>(a)) {
       float t[V];
       loadv<V>(a.tref + pix * a.C, c, a.C, t);
 #pragma unroll
@@ -445,7 +458,7 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
 #pragma unroll
       for (int j = 0; j < V; ++j) src[j] = zv[j];
     }
-  } else if (a.tref) {
+  } else if (has_tref<F>(a)) {
     float t[V];
     loadv<V>(a.tref + pix * a.C, c, a.C, t);
 #pragma unroll
@@ -455,7 +468,7 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
     }
   }
   if (!have_y && !have_z) {
-    if (a.mask_hi) {
+    if (has_mask<F>(a)) {
       const bf16* mh = a.mask_hi + pix * a.mask_cs + c;
       if constexpr (V == 4) {
         const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mh));
@@ -476,7 +489,7 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
 }
 
 // grid (nblk, N, cgroups); thread (tx = V-channel group, ty = pixel lane): per-thread channel constants are loaded once
-template <int V>
+template <int V, int F>
 __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx_log2, float* __restrict__ partial) {
   const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
   const int tx = threadIdx.x & (gx - 1), ty = threadIdx.x >> gx_log2;
@@ -499,7 +512,7 @@ __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx
     const size_t base = size_t(n) * HW;
     for (; p < p1; p += rows) {
       float dyh[V], yh[V];
-      bwd_dyhat<V>(a, cs, base + p, n, h, w, c, dyh, yh);
+      bwd_dyhat<V, F>(a, cs, base + p, n, h, w, c, dyh, yh);
 #pragma unroll
       for (int j = 0; j < V; ++j) { s1[j] += dyh[j]; s2[j] += dyh[j] * yh[j]; }
       h += sh; w += sw;
@@ -538,7 +551,7 @@ __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N,
   sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
 }
 // same thread decomposition; grid (pixel blocks, N, cgroups) with a grid-stride loop over the pixels of image n
-template <int V>
+template <int V, int F>
 __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_log2, const float* __restrict__ sums,
                                                               bf16* o_hi, bf16* o_lo, int o_cs, float* __restrict__ out32) {
   const int gx = 1 << gx_log2, rows = kBlock >> gx_log2;
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_
     const size_t pix = base + p;
     if (cvalid) {
       float dyh[V], yh[V];
-      bwd_dyhat<V>(a, cs, pix, n, h, w, c, dyh, yh);
+      bwd_dyhat<V, F>(a, cs, pix, n, h, w, c, dyh, yh);
       if (sums) {
 #pragma unroll
         for (int j = 0; j < V; ++j) dy[j] = (V == 4 || c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
@@ -970,7 +983,7 @@ __global__ void fold_add_kernel(const float* __restrict__ g, int b, int N, int H
     float dyh[8], yh[8];
     ChanStats<8> cs;
     load_chan_stats<8>(a, n, gq * 8, cs);
-    bwd_dyhat<8>(a, cs, (size_t(n) * H + h) * W + w, n, h, w, gq * 8, dyh, yh);
+    bwd_dyhat<8, BWD_GENERIC>(a, cs, (size_t(n) * H + h) * W + w, n, h, w, gq * 8, dyh, yh);
     store8(out + ((size_t(n) * H + h) * W + w) * C, gq * 8, C, dyh);
   }
 }
@@ -1063,22 +1076,53 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
   const bool v4 = ((C & 3) == 0) && (!o_hi || (o_cs & 3) == 0) && (!mask_hi || (mask_cs & 3) == 0) &&
                   (!g1 || (((g1_ld & 3) == 0) && ((g1_coff & 3) == 0)));
   const int V = v4 ? 4 : 8;
+  // presence mask of this call; instantiated combinations run with compile-time flags
+  const int F = (y ? F_IN : 0) | ((g1 && g1_border == 0) ? F_G1D : 0) | ((g1 && g1_border != 0) ? F_G1B : 0) |
+                (g2 ? F_G2 : 0) | (z ? F_Z : 0) | (tref ? F_TREF : 0) | ((mask_hi && !y && !z) ? F_MASK : 0);
+#define HM_BWD_CASES(X)                                                                                      \
+  X(F_IN | F_G2) X(F_IN | F_G1D) X(F_IN | F_G1B) X(F_IN | F_G1D | F_Z) X(F_IN | F_G1D | F_Z | F_TREF)          \
+  X(F_G1D | F_Z) X(F_G1D | F_Z | F_TREF) X(F_Z | F_TREF) X(F_Z | F_TREF | F_G2) X(F_MASK | F_G2) X(F_MASK)
   if (mean) {
     stats_geometry(C, V, &gx_log2, &cgroups);
     const int nblk = stats_nblk(N, H * W, cgroups);
     sums = ws + size_t(N) * nblk * 2 * C8;
-    if (v4) in_bwd_reduce_kernel<4><<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
-    else in_bwd_reduce_kernel<8><<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(a, gx_log2, ws);
+    const dim3 grid(nblk, N, cgroups);
+    bool done = false;
+    if (v4) {
+      switch (F) {
+#define X(f) case (f): in_bwd_reduce_kernel<4, (f)><<<grid, kBlock, 0, st>>>(a, gx_log2, ws); done = true; break;
+        HM_BWD_CASES(X)
+#undef X
+        default: break;
+      }
+      if (!done) in_bwd_reduce_kernel<4, BWD_GENERIC><<<grid, kBlock, 0, st>>>(a, gx_log2, ws);
+    } else {
+      in_bwd_reduce_kernel<8, BWD_GENERIC><<<grid, kBlock, 0, st>>>(a, gx_log2, ws);
+    }
     in_bwd_finalize_kernel<<<(N * C8 + 127) / 128, 128, 0, st>>>(ws, N, nblk, C8, H * W, sums);
   }
   const int Cout = o_hi ? o_cs : C8;
   stats_geometry(Cout, V, &gx_log2, &cgroups);
   const int rows = kBlock >> gx_log2;
   int pblocks = std::min((H * W + rows - 1) / rows, std::max(1, (148 * 8) / std::max(1, N * cgroups)));
-  if (v4) in_bwd_apply_kernel<4><<<dim3(pblocks, N, cgroups), kBlock, 0, st>>>(a, gx_log2, sums, static_cast<bf16*>(o_hi),
-                                                                              static_cast<bf16*>(o_lo), o_cs, out32);
-  else in_bwd_apply_kernel<8><<<dim3(pblocks, N, cgroups), kBlock, 0, st>>>(a, gx_log2, sums, static_cast<bf16*>(o_hi),
-                                                                            static_cast<bf16*>(o_lo), o_cs, out32);
+  {
+    const dim3 grid(pblocks, N, cgroups);
+    bf16* ohi = static_cast<bf16*>(o_hi);
+    bf16* olo = static_cast<bf16*>(o_lo);
+    bool done = false;
+    if (v4) {
+      switch (F) {
+#define X(f) case (f): in_bwd_apply_kernel<4, (f)><<<grid, kBlock, 0, st>>>(a, gx_log2, sums, ohi, olo, o_cs, out32); done = true; break;
+        HM_BWD_CASES(X)
+#undef X
+        default: break;
+      }
+      if (!done) in_bwd_apply_kernel<4, BWD_GENERIC><<<grid, kBlock, 0, st>>>(a, gx_log2, sums, ohi, olo, o_cs, out32);
+    } else {
+      in_bwd_apply_kernel<8, BWD_GENERIC><<<grid, kBlock, 0, st>>>(a, gx_log2, sums, ohi, olo, o_cs, out32);
+    }
+  }
+#undef HM_BWD_CASES
   return HM_LAUNCH_OK();
 }
 
