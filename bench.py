@@ -157,6 +157,17 @@ def main_reference(args, out_fd):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def k1_traffic(split):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch from the committed `ncu --set full` capture
+    (profiles/k1_traffic.json, written by tools/k1_traffic.py from the .ncu-rep); None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as fh:
+            d = json.load(fh)["bf16x3" if split else "bf16"]
+        return float(d["dram_bytes_read"] + d["dram_bytes_write"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def time_k1(model, pk, split):
     """Dominant kernel: the residual-block 3x3 conv (1024->1024 @32x64 x B) = hm_kgemm_kernel<256>, timed alone
     with CUDA events on the launching stream (burst peak applies)."""
@@ -182,8 +193,10 @@ def time_k1(model, pk, split):
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * B * 32 * 64 * 1024 * 1024 * 9          # algorithmic: 19.33 GMAC per image per conv
     executed = flops * (3 if split else 1)
+    traffic, traffic_src = k1_traffic(split)
     return dict(bound="tensor", achieved=flops / ms / 1e9, peak=pk["bf16_tflops"], unit="TFLOP/s",
-                frac=flops / ms / 1e9 / pk["bf16_tflops"], traffic=None, kernel="hm_kgemm_kernel<256> (res-block conv3x3 1024->1024, M=%d N=1024 K=9216)" % (B * 2048),
+                frac=flops / ms / 1e9 / pk["bf16_tflops"], traffic=traffic, traffic_unit="bytes per launch (DRAM read+write)",
+                traffic_source=traffic_src, kernel="hm_kgemm2_kernel<256> CTA-pair (res-block conv3x3 1024->1024, M=%d N=1024 K=9216)" % (B * 2048),
                 ms_per_launch=ms, executed_tflops=executed / ms / 1e9, executed_frac=executed / ms / 1e9 / pk["bf16_tflops"],
                 note="achieved counts ALGORITHMIC conv flops; in bf16x3 (fp32-parity) mode every product is issued 3x "
                      "(hi*hi + lo*hi + hi*lo), executed_* counts those tensor-core flops")

@@ -212,6 +212,10 @@ int hm_sn_weight_grad(const hm_sn_layer* layers, int n_layers, int max_n, int ma
  * segment; grad_scale multiplies the gradient first (1/world_size after a sum-allreduce). step is 1-based. */
 int hm_adam_step(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
                  float eps, int step, float grad_scale, void* stream);
+/* Same step with the (1-based) step count read from DEVICE memory, so that a training step captured in a CUDA graph
+ * replays with the right bias corrections. */
+int hm_adam_step_dev(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                     float eps, const int* step_dev, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

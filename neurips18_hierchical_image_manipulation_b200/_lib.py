@@ -82,6 +82,7 @@ PROTOTYPES = {
     "hm_sn_power_iteration": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hm_sn_weight_grad": (_i, [_vp, _i, _i, _i, _vp]),
     "hm_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
+    "hm_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
 }
 
 _lib = None

@@ -966,6 +966,43 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// CUDA-graph friendly variant: the (1-based) step count lives in device memory, so a captured training step replays
+// with the right bias corrections (a host-side `step` argument would be frozen into the graph).
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
+                                const int* __restrict__ step_dev, float gscale) {
+  const float step = float(__ldg(step_dev));
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  const float lrc = lr / bc1;
+  const long n4 = n >> 2;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n4; i += long(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j] * gscale;
+      M[j] = b1 * M[j] + (1.f - b1) * gr;
+      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(V[j]) / bc2_sqrt + eps;
+      P[j] -= lrc * (M[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long i = (n4 << 2) + blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * gscale;
+    const float mj = b1 * m[i] + (1.f - b1) * gr;
+    const float vj = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mj; v[i] = vj;
+    p[i] -= lrc * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+  }
+}
+
 // out += fold_reflect(g)  (dense [N,H,W,C] += padded [N,H+2b,W+2b,C]); used for the residual skip gradient
 __global__ void fold_add_kernel(const float* __restrict__ g, int b, int N, int H, int W, int C, const float* __restrict__ base,
                                 float* __restrict__ out) {
@@ -1244,6 +1281,17 @@ int hm_adam_step(float* param, const float* grad, float* m, float* v, long n, fl
   const float bc2s = sqrtf(1.f - powf(beta2, float(step)));
   adam_kernel<<<grid_for(n / 4 + 1, kBlock, 148 * 16), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  return HM_LAUNCH_OK();
+}
+
+int hm_adam_step_dev(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                     float eps, const int* step_dev, float grad_scale, void* stream) {
+  if (!param || !grad || !m || !v || !step_dev) return HM_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return HM_ERR_INVALID;
+  adam_dev_kernel<<<grid_for(n / 4 + 1, kBlock, 148 * 16), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale);
   return HM_LAUNCH_OK();
 }
 

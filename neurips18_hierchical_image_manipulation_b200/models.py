@@ -47,6 +47,8 @@ class Options(object):
                  precision="bf16x3",      # "bf16x3": fp32-parity mode; "mixed": bf16x3 forward + bf16 gradient GEMMs;
                                           # "bf16": single-product tensor-core mode
                  vgg_seed=1234,           # seeded random VGG19 (no network for the ImageNet weights)
+                 cuda_graph=True,         # optimize_parameters(): capture the fused step in a CUDA graph after two eager
+                                          # steps and replay it (same kernels, no per-launch host work / launch gaps)
                  sn_D=False)              # K13: spectral-norm the PatchGAN convs (models/sn_utils.py SNConv2d); the
                                           # reference's MultiscaleDiscriminator uses plain convs, so default off
         d.update(kw)
@@ -92,6 +94,7 @@ class FusedAdam(object):
         self.param_groups = groups if groups is not None else [dict(lr=lr, begin=0, end=fp.total, params=list(fp.params.values()))]
         self.dist_group = dist_group
         self.grads_reduced = False
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=fp.flat.device)  # step count for captured steps
 
     def zero_grad(self):
         self.fp.grad.zero_()
@@ -103,16 +106,28 @@ class FusedAdam(object):
             self.grads_reduced = True
         return 1.0 / parallel.world()[1]
 
-    def step(self, grad_scale=None):
+    def step(self, grad_scale=None, captured=False):
+        """captured=True: the step is being recorded into a CUDA graph -- the step count is advanced and read on the
+        device (hm_adam_step_dev); the host mirror `step_count` is advanced by the caller once per replay."""
         scale = self.allreduce() if grad_scale is None else grad_scale
-        self.step_count += 1
+        if captured:
+            self.step_dev.add_(1)
+        else:
+            self.step_count += 1
         for g in self.param_groups:
             b, e = g["begin"], g["end"]
             if e > b:
-                ops.adam_step(self.ctx, self.fp.flat[b:e], self.fp.grad[b:e], self.m[b:e], self.v[b:e], float(g["lr"]),
-                              self.betas[0], self.betas[1], self.eps, self.step_count, scale)
+                if captured:
+                    ops.adam_step_dev(self.ctx, self.fp.flat[b:e], self.fp.grad[b:e], self.m[b:e], self.v[b:e],
+                                      float(g["lr"]), self.betas[0], self.betas[1], self.eps, self.step_dev, scale)
+                else:
+                    ops.adam_step(self.ctx, self.fp.flat[b:e], self.fp.grad[b:e], self.m[b:e], self.v[b:e], float(g["lr"]),
+                                  self.betas[0], self.betas[1], self.eps, self.step_count, scale)
         self.fp.version += 1
         self.grads_reduced = False
+
+    def lr_signature(self):
+        return tuple(float(g["lr"]) for g in self.param_groups)
 
     def state_dict(self):
         return dict(step=self.step_count, m=self.m.cpu(), v=self.v.cpu(), lrs=[g["lr"] for g in self.param_groups])
@@ -238,6 +253,8 @@ class Pix2PixHDModel_condImg(object):
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._step = None
         self._pinned = {}
+        self._graph = None          # dict(graph, inputs, losses, st, sig) once the fused step has been captured
+        self._eager_steps = 0
         self.fake_image = self.real_image = self.input_label = self.input_image = None
 
     # ------------------------------------------------------------------------------------------------
@@ -346,7 +363,18 @@ class Pix2PixHDModel_condImg(object):
     def optimize_parameters(self, label=None, inst=None, image=None, feat=None, mask_in=None, mask_out=None):
         """Fused step: forward, G backward, D backward, one allreduce of [G | D] grads, Adam x2.
         Bit-identical maths to train_mask2image.py:58-86 because loss_D's graph holds no G parameter.
-        Returns the 5 losses as a device tensor (no host sync)."""
+        Returns the 5 losses as a device tensor (no host sync).
+
+        With opt.cuda_graph (default) the step is captured into a CUDA graph on its third call with a given batch
+        geometry and replayed afterwards: the ~700 kernel launches of a step then cost no host work and no launch
+        gaps.  Inputs are copied into the graph's static input tensors (an H2D copy when they are host tensors)."""
+        batch = dict(label=label, inst=None if self.opt.no_instance else inst, image=image, mask_in=mask_in)
+        if self._use_graph(batch):
+            return self._graph_step(batch)
+        self._eager_steps += 1
+        return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False)
+
+    def _fused_step(self, label, inst, image, mask_in, captured):
         st = self._forward_all(label, inst, image, mask_in)
         self._step = st
         self._keep_visuals(st)
@@ -354,9 +382,70 @@ class Pix2PixHDModel_condImg(object):
         self._backward_G([1.0, 1.0, 1.0])
         self._backward_D([0.5, 0.5])
         scale = parallel.allreduce_sum_(self.flat_grad)
-        self.optimizer_G.step(grad_scale=scale)
-        self.optimizer_D.step(grad_scale=scale)
+        self.optimizer_G.step(grad_scale=scale, captured=captured)
+        self.optimizer_D.step(grad_scale=scale, captured=captured)
         return st["losses"]
+
+    # ---- CUDA-graph replay of the fused step ------------------------------------------------------------
+    def _graph_signature(self, batch):
+        shapes = tuple((k, tuple(v.shape)) for k, v in batch.items() if v is not None)
+        return shapes, self.optimizer_G.lr_signature(), self.optimizer_D.lr_signature(), id(self.optimizer_G)
+
+    def _use_graph(self, batch):
+        if not getattr(self.opt, "cuda_graph", True) or os.environ.get("HM_CUDA_GRAPH", "1") == "0":
+            return False
+        if parallel.world()[1] > 1 and os.environ.get("HM_CUDA_GRAPH_DDP", "0") != "1":
+            return False     # NCCL inside a captured step is left opt-in
+        if self._graph is False:   # a capture failed earlier: stay eager
+            return False
+        if self._graph is not None and self._graph["sig"] != self._graph_signature(batch):
+            self._graph = None     # geometry or learning rate changed: re-capture
+            self._eager_steps = 2
+        return self._graph is not None or self._eager_steps >= 2
+
+    def _graph_step(self, batch):
+        if self._graph is None:
+            try:
+                self._capture(batch)
+            except Exception as e:  # noqa: BLE001 -- any capture problem: keep training eagerly
+                print("CUDA-graph capture of the fused step failed (%s: %s); staying eager" % (type(e).__name__, e))
+                self._graph = False
+                torch.cuda.synchronize()
+                self._eager_steps += 1
+                return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False)
+        g = self._graph
+        for k, dst in g["inputs"].items():
+            dst.copy_(batch[k], non_blocking=True)
+        g["graph"].replay()
+        # host mirrors of what the replay did on the device
+        self.optimizer_G.step_count += 1
+        self.optimizer_D.step_count += 1
+        self.fpG.version += 1
+        self.fpD.version += 1
+        self.ctx.launches += g["launches"]
+        self._step = g["st"]
+        self._keep_visuals(g["st"])
+        return g["losses"]
+
+    def _capture(self, batch):
+        dev = self.device
+        inputs = {k: torch.empty(tuple(v.shape), dtype=torch.float32, device=dev) for k, v in batch.items() if v is not None}
+        for k, dst in inputs.items():
+            dst.copy_(batch[k], non_blocking=True)
+        self.optimizer_G.step_dev.fill_(self.optimizer_G.step_count)
+        self.optimizer_D.step_dev.fill_(self.optimizer_D.step_count)
+        torch.cuda.synchronize()
+        l0 = self.ctx.launches
+        vG, vD = self.fpG.version, self.fpD.version
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            losses = self._fused_step(inputs["label"], inputs.get("inst"), inputs["image"], inputs["mask_in"], captured=True)
+        launches = self.ctx.launches - l0
+        self.ctx.launches = l0
+        # recording did not execute anything: undo the host-side bookkeeping of the recorded step
+        self.fpG.version, self.fpD.version = vG, vD
+        self._graph = dict(graph=graph, inputs=inputs, losses=losses, st=self._step, launches=launches,
+                           sig=self._graph_signature(batch))
 
     # ------------------------------------------------------------------------------------------------
     def inference(self, label, inst, image, mask_in, mask_out):

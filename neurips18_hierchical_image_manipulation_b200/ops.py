@@ -324,3 +324,10 @@ def adam_step(ctx, p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     L.check(ctx.lib.hm_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
                                  step, grad_scale, _stream()), "hm_adam_step")
     ctx.launches += 1
+
+
+def adam_step_dev(ctx, p, g, m, v, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
+    """Adam step whose step count is read from the device int32 tensor `step_dev` (CUDA-graph replays)."""
+    L.check(ctx.lib.hm_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                     eps, step_dev.data_ptr(), grad_scale, _stream()), "hm_adam_step_dev")
+    ctx.launches += 1

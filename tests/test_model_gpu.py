@@ -162,6 +162,35 @@ def test_fused_step_matches_script_sequence():
         assert torch.allclose(a.fpD.params[k], b.fpD.params[k], rtol=0, atol=1e-7), k
 
 
+def test_cuda_graph_replay_matches_eager_steps():
+    """optimize_parameters() captures the fused step in a CUDA graph on its third call; replays must train exactly like
+    eager steps (same kernels; only fp32 atomics order in the weight gradients differs run to run)."""
+    opt, model_a = _mk("bf16x3", cuda_graph=True)
+    _, model_b = _mk("bf16x3", cuda_graph=False)
+    a, b = model_a.module, model_b.module
+    b.fpG.load_state_dict(a.fpG.state_dict()); b.fpD.load_state_dict(a.fpD.state_dict())
+    batches = [O.synthetic_batch(2, 64, 64, label_nc=opt.label_nc, seed=s) for s in (3, 4)]
+    for i in range(6):
+        bt = batches[i % 2]
+        kw = dict(label=bt["label"], inst=bt["inst"], image=bt["image"], feat=None, mask_in=bt["mask_in"],
+                  mask_out=bt["mask_out"])
+        la = a.optimize_parameters(**kw).clone()
+        lb = b.optimize_parameters(**kw).clone()
+        torch.cuda.synchronize()
+        assert torch.allclose(la.cpu(), lb.cpu(), rtol=5e-3, atol=1e-5), (i, la, lb)
+    assert isinstance(a._graph, dict), "the fused step was not captured"
+    assert a.optimizer_G.step_count == 6 and int(a.optimizer_G.step_dev.item()) == 6
+    a.ctx.check_pipeline()
+    for k in a.fpG.params:
+        d = (a.fpG.params[k] - b.fpG.params[k]).abs()
+        assert float(d.max()) < 2.5e-3 and float(d.mean()) < 2e-5, (k, float(d.max()), float(d.mean()))
+    # host inputs (pinned) go through the same graph
+    pinned = {k: v.pin_memory() for k, v in batches[0].items()}
+    l1 = a.optimize_parameters(label=pinned["label"], inst=pinned["inst"], image=pinned["image"], feat=None,
+                               mask_in=pinned["mask_in"], mask_out=pinned["mask_out"])
+    assert torch.isfinite(l1).all()
+
+
 def test_inference_and_checkpoint_roundtrip(tmp_path):
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     opt, model = _mk("bf16x3", checkpoints_dir=str(tmp_path))
