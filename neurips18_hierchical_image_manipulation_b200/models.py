@@ -394,8 +394,8 @@ class Pix2PixHDModel_condImg(object):
     def _use_graph(self, batch):
         if not getattr(self.opt, "cuda_graph", True) or os.environ.get("HM_CUDA_GRAPH", "1") == "0":
             return False
-        if parallel.world()[1] > 1 and os.environ.get("HM_CUDA_GRAPH_DDP", "0") != "1":
-            return False     # NCCL inside a captured step is left opt-in
+        if parallel.world()[1] > 1 and os.environ.get("HM_CUDA_GRAPH_DDP", "1") == "0":
+            return False     # the NCCL allreduce is captured with the step (verified at 2 and 8 ranks); opt-out switch
         if self._graph is False:   # a capture failed earlier: stay eager
             return False
         if self._graph is not None and self._graph["sig"] != self._graph_signature(batch):
