@@ -180,6 +180,21 @@ int launch_rows(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_
   return HM_OK;
 }
 
+template <int BN>
+int launch_rows2(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_t st) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_krows2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = smem_bytes;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_krows2_kernel<BN><<<grid, hm::kEngineThreads, smem_bytes, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
 // packed weights [taps][rows_pad][k_pad] bf16 -> 3-D map, box = 64 (k) x bn rows x kw taps
 int make_tmap_weight3(CUtensorMap* m, const void* base, int taps, int rows_pad, int k_pad, int bn, int kw) {
   EncodeTiledFn enc = get_encode();
@@ -284,6 +299,25 @@ int run_rows_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int
     p.o16_hoff = out16->h_off; p.o16_woff = out16->w_off; p.o16_coff = out16->c_off;
   }
   p.bias = bias; p.act = act; p.slope = slope; p.err = err_flag;
+  // multi-row variant (weight slabs loaded once per MT output rows): separate B (2 stages) and A rings
+  static const int use_rows2 = env_int("HM_ROWS2", 1);
+  {
+    const int mt = bn <= 64 ? 4 : 2;
+    const int b_ring = 2 * kw * bn * 128;
+    const int a_stages = std::min(8, (hm::RCfgCommon::SMEM_BUDGET - b_ring) / hm::RCfgCommon::A_PLANE);
+    if (use_rows2 && a_stages >= 3 && valid_h >= 2 * mt) {
+      p.n_stages = a_stages;
+      const int groups_h = (p.rows_h + mt - 1) / mt;
+      const int tiles2 = p.tiles_w * groups_h * p.n_img * p.n_tiles_n;
+      const int smem2 = b_ring + a_stages * hm::RCfgCommon::A_PLANE + 1024 + 512;
+      switch (bn) {
+        case 16: return launch_rows2<16>(p, tiles2, smem2, st);
+        case 32: return launch_rows2<32>(p, tiles2, smem2, st);
+        case 64: return launch_rows2<64>(p, tiles2, smem2, st);
+        case 128: return launch_rows2<128>(p, tiles2, smem2, st);
+      }
+    }
+  }
   const int num_tiles = p.tiles_w * p.rows_h * p.n_img * p.n_tiles_n;
   const int smem_bytes = p.n_stages * p.stage_bytes + 1024 + 512;
   switch (bn) {
