@@ -84,81 +84,93 @@ __device__ __forceinline__ float act_grad(float pre_sign_src, int act, float slo
 // K11  encode_input  (models/pix2pixHD_condImg_model.py:144-174, get_edges :285-291)
 // one thread per (padded) generator-input pixel: one-hot(label) | edge(inst) | (1-mask)*image
 // ================================================================================================
+// One thread per (pixel, group of 8 output channels) of one of the three operands, so that the 16 B stores of a warp
+// are contiguous (a thread-per-pixel version wrote 80-96 B apart and ran at 1.4 TB/s); the few scalar inputs of a
+// pixel are re-read by its 5-6 channel-group threads through L1.
 __global__ void encode_kernel(const float* __restrict__ label, const float* __restrict__ inst,
                               const float* __restrict__ image, const float* __restrict__ mask, int B, int H, int W,
                               int label_nc, bf16* g_hi, bf16* g_lo, int g_cs, int gb, bf16* d_hi, bf16* d_lo, int d_cs,
                               bf16* v_hi, bf16* v_lo, int v_cs) {
   const int Hp = H + 2 * gb, Wp = W + 2 * gb;
-  const long total = long(B) * Hp * Wp;
+  const int gg = g_cs >> 3, dg = d_hi ? (d_cs >> 3) : 0, vg = v_hi ? (v_cs >> 3) : 0;
+  const long items_g = long(B) * Hp * Wp * gg;
+  const long items_d = long(2) * B * H * W * dg;
+  const long items_v = long(B) * H * W * vg;
+  const long total = items_g + items_d + items_v;
   const int n_cond = label_nc + (inst ? 1 : 0);
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    const int wp = int(i % Wp);
-    const int hp = int((i / Wp) % Hp);
-    const int n = int(i / (long(Wp) * Hp));
-    const int h = reflect_idx(hp - gb, H), w = reflect_idx(wp - gb, W);
-    const bool interior = (hp - gb == h) && (wp - gb == w);
+    int kind, grp, n, h, w, half = 0;
+    size_t off;
+    if (i < items_g) {
+      kind = 0;
+      grp = int(i % gg);
+      long r = i / gg;
+      const int wp = int(r % Wp); r /= Wp;
+      const int hp = int(r % Hp);
+      n = int(r / Hp);
+      h = reflect_idx(hp - gb, H); w = reflect_idx(wp - gb, W);
+      off = (size_t(n) * Hp * Wp + size_t(hp) * Wp + wp) * g_cs + grp * 8;
+    } else if (i < items_g + items_d) {
+      kind = 1;
+      long r = i - items_g;
+      grp = int(r % dg); r /= dg;
+      w = int(r % W); r /= W;
+      h = int(r % H); r /= H;
+      n = int(r % B);
+      half = int(r / B);   // 0 = fake (image channels filled by hm_finish_fake), 1 = real
+      off = ((size_t(n) + size_t(half) * B) * H * W + size_t(h) * W + w) * d_cs + grp * 8;
+    } else {
+      kind = 2;
+      long r = i - items_g - items_d;
+      grp = int(r % vg); r /= vg;
+      w = int(r % W); r /= W;
+      h = int(r % H);
+      n = int(r / H);
+      off = ((size_t(n) + B) * H * W + size_t(h) * W + w) * v_cs + grp * 8;
+    }
     const long pix = (long(n) * H + h) * W + w;
-    const int cls = int(__ldg(label + pix));
-    float edge = 0.f;
-    if (inst) {  // :285-291: 4-neighbour instance boundary
-      const float t = __ldg(inst + pix);
-      bool e = false;
-      if (w > 0) e |= (t != __ldg(inst + pix - 1));
-      if (w < W - 1) e |= (t != __ldg(inst + pix + 1));
-      if (h > 0) e |= (t != __ldg(inst + pix - W));
-      if (h < H - 1) e |= (t != __ldg(inst + pix + W));
-      edge = e ? 1.f : 0.f;
-    }
-    const float m = __ldg(mask + pix);
-    float img[3], cond[3];
+    const int c0 = grp * 8;
+    float v[8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      img[c] = __ldg(image + (long(n) * 3 + c) * H * W + long(h) * W + w);
-      cond[c] = (1.f - m) * img[c];  // NULLVAL == 0 (:18, :165-166)
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const bool need_img = (kind == 2) ? (c0 < 3) : (c0 + 8 > n_cond);
+    float img[3] = {0.f, 0.f, 0.f}, cond[3] = {0.f, 0.f, 0.f};
+    if (need_img) {
+      const float m = __ldg(mask + pix);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        img[c] = __ldg(image + (long(n) * 3 + c) * H * W + long(h) * W + w);
+        cond[c] = (1.f - m) * img[c];  // NULLVAL == 0 (:18, :165-166)
+      }
     }
-    // generator operand (all cs channels written; padding channels are zero)
-    const size_t goff = (size_t(n) * Hp * Wp + size_t(hp) * Wp + wp) * g_cs;
-    for (int c0 = 0; c0 < g_cs; c0 += 8) {
-      float v[8];
+    if (kind == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c0 + j < 3) v[j] = img[c0 + j];
+    } else {
+      if (c0 < label_nc) {
+        const int cls = int(__ldg(label + pix));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (c0 + j < label_nc && c0 + j == cls) v[j] = 1.f;
+      }
+      if (inst && c0 <= label_nc && label_nc < c0 + 8) {  // :285-291: 4-neighbour instance boundary
+        const float t = __ldg(inst + pix);
+        bool e = false;
+        if (w > 0) e |= (t != __ldg(inst + pix - 1));
+        if (w < W - 1) e |= (t != __ldg(inst + pix + 1));
+        if (h > 0) e |= (t != __ldg(inst + pix - W));
+        if (h < H - 1) e |= (t != __ldg(inst + pix + W));
+        v[label_nc - c0] = e ? 1.f : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        float x = 0.f;
-        if (c < label_nc) x = (c == cls) ? 1.f : 0.f;
-        else if (inst && c == label_nc) x = edge;
-        else if (c >= n_cond && c < n_cond + 3) x = cond[c - n_cond];
-        v[j] = x;
-      }
-      store_op8(g_hi, g_lo, goff + c0, v);
-    }
-    if (interior && d_hi) {
-      for (int half = 0; half < 2; ++half) {  // half 0 = fake (image channels filled later), 1 = real
-        const size_t doff = ((size_t(n) + size_t(half) * B) * H * W + size_t(h) * W + w) * d_cs;
-        for (int c0 = 0; c0 < d_cs; c0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            float x = 0.f;
-            if (c < label_nc) x = (c == cls) ? 1.f : 0.f;
-            else if (inst && c == label_nc) x = edge;
-            else if (c >= n_cond && c < n_cond + 3) x = cond[c - n_cond];
-            else if (half == 1 && c >= n_cond + 3 && c < n_cond + 6) x = img[c - n_cond - 3];
-            v[j] = x;
-          }
-          store_op8(d_hi, d_lo, doff + c0, v);
-        }
+        if (c >= n_cond && c < n_cond + 3) v[j] = cond[c - n_cond];
+        else if (kind == 1 && half == 1 && c >= n_cond + 3 && c < n_cond + 6) v[j] = img[c - n_cond - 3];
       }
     }
-    if (interior && v_hi) {
-      const size_t voff = ((size_t(n) + B) * H * W + size_t(h) * W + w) * v_cs;
-      for (int c0 = 0; c0 < v_cs; c0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < 3) ? img[c0 + j] : 0.f;
-        store_op8(v_hi, v_lo, voff + c0, v);
-      }
-    }
+    if (kind == 0) store_op8(g_hi, g_lo, off, v);
+    else if (kind == 1) store_op8(d_hi, d_lo, off, v);
+    else store_op8(v_hi, v_lo, off, v);
   }
 }
 
@@ -1053,7 +1065,8 @@ int hm_encode_input(const float* label, const float* inst, const float* image, c
     return HM_ERR_INVALID;
   const int cin = label_nc + (inst ? 1 : 0) + 3;
   if (cin > g_cs || (d_hi && cin + 3 > d_cs)) return HM_ERR_INVALID;
-  const long total = long(B) * (H + 2 * g_border) * (W + 2 * g_border);
+  const long total = long(B) * (H + 2 * g_border) * (W + 2 * g_border) * (g_cs >> 3) +
+                     (d_hi ? long(2) * B * H * W * (d_cs >> 3) : 0) + (v_hi ? long(B) * H * W * (v_cs >> 3) : 0);
   encode_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       label, inst, image, mask_in, B, H, W, label_nc, static_cast<bf16*>(g_hi), static_cast<bf16*>(g_lo), g_cs,
       g_border, static_cast<bf16*>(d_hi), static_cast<bf16*>(d_lo), d_cs, static_cast<bf16*>(v_hi),

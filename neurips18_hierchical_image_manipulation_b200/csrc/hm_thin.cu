@@ -103,6 +103,54 @@ __global__ void tap_unroll_kernel(const bf16* __restrict__ s_hi, const bf16* __r
   }
 }
 
+// Fast path for an 8-channel-stride source (the 3-channel image / gradient operands): one thread per destination pixel
+// reads each source pixel of its window with ONE 16 B load per plane and writes its d_cs (<= 32) channels with 16 B
+// stores (the generic kernel above spends a div/mod and a 2-byte load per destination element).
+template <int DG>   // destination channel groups of 8 (d_cs = 8 * DG)
+__global__ void tap_unroll8_kernel(const bf16* __restrict__ s_hi, const bf16* __restrict__ s_lo, int N, int Hs, int Ws, int C,
+                                   int KH, int KW, int oh, int ow, int sh, int sw, bf16* __restrict__ d_hi,
+                                   bf16* __restrict__ d_lo, int Hd, int Wd) {
+  const long total = long(N) * Hd * Wd;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int w = int(i % Wd);
+    long r = i / Wd;
+    const int h = int(r % Hd);
+    const int n = int(r / Hd);
+    alignas(16) bf16 vh[8 * DG];
+    alignas(16) bf16 vl[8 * DG];
+#pragma unroll
+    for (int e = 0; e < 8 * DG; ++e) { vh[e] = __float2bfloat16_rn(0.f); vl[e] = vh[e]; }
+    int d = 0;
+    for (int j = 0; j < KH; ++j) {
+      const int hs = h + oh + sh * j;
+      for (int t = 0; t < KW; ++t, d += C) {
+        const int ws = w + ow + sw * t;
+        if (hs < 0 || hs >= Hs || ws < 0 || ws >= Ws) continue;
+        const size_t off = ((size_t(n) * Hs + hs) * Ws + ws) * 8;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(s_hi + off));
+        const bf16* ah = reinterpret_cast<const bf16*>(&a);
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (s_lo && d_lo) b = __ldg(reinterpret_cast<const uint4*>(s_lo + off));
+        const bf16* al = reinterpret_cast<const bf16*>(&b);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < C) {
+            // d + c < 8 * DG is guaranteed by the launcher (KH*KW*C <= d_cs); constant-index the register arrays
+#pragma unroll
+            for (int e = 0; e < 8 * DG; ++e)
+              if (e == d + c) { vh[e] = ah[c]; vl[e] = al[c]; }
+          }
+      }
+    }
+    const size_t doff = size_t(i) * (8 * DG);
+#pragma unroll
+    for (int g = 0; g < DG; ++g) {
+      *reinterpret_cast<uint4*>(d_hi + doff + g * 8) = *reinterpret_cast<const uint4*>(vh + g * 8);
+      if (d_lo) *reinterpret_cast<uint4*>(d_lo + doff + g * 8) = *reinterpret_cast<const uint4*>(vl + g * 8);
+    }
+  }
+}
+
 // one thread per output pixel, C <= 4 channels each
 __global__ void tap_combine_kernel(const float* __restrict__ T, int N, int Ht, int Wt, int ldT, int KH, int KW, int C, int oh,
                                    int ow, int sh, int sw, const float* __restrict__ bias, int act, float slope,
@@ -166,6 +214,21 @@ int hm_tap_unroll(const void* s_hi, const void* s_lo, int N, int Hs, int Ws, int
                   int ow, int sh, int sw, void* d_hi, void* d_lo, int Hd, int Wd, int d_cs, void* stream) {
   if (!s_hi || !d_hi || C <= 0 || KH <= 0 || KW <= 0 || (d_cs & 7) || KH * KW * C > d_cs || N <= 0 || Hd <= 0 || Wd <= 0)
     return HM_ERR_INVALID;
+  if (s_cs == 8 && C <= 4 && (d_cs == 8 || d_cs == 16 || d_cs == 24 || d_cs == 32)) {
+    const long px = long(N) * Hd * Wd;
+    const bf16* sh_ = static_cast<const bf16*>(s_hi);
+    const bf16* sl_ = static_cast<const bf16*>(s_lo);
+    bf16* dh_ = static_cast<bf16*>(d_hi);
+    bf16* dl_ = static_cast<bf16*>(d_lo);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (d_cs >> 3) {
+      case 1: tap_unroll8_kernel<1><<<grid_for(px), kBlock, 0, st>>>(sh_, sl_, N, Hs, Ws, C, KH, KW, oh, ow, sh, sw, dh_, dl_, Hd, Wd); break;
+      case 2: tap_unroll8_kernel<2><<<grid_for(px), kBlock, 0, st>>>(sh_, sl_, N, Hs, Ws, C, KH, KW, oh, ow, sh, sw, dh_, dl_, Hd, Wd); break;
+      case 3: tap_unroll8_kernel<3><<<grid_for(px), kBlock, 0, st>>>(sh_, sl_, N, Hs, Ws, C, KH, KW, oh, ow, sh, sw, dh_, dl_, Hd, Wd); break;
+      default: tap_unroll8_kernel<4><<<grid_for(px), kBlock, 0, st>>>(sh_, sl_, N, Hs, Ws, C, KH, KW, oh, ow, sh, sw, dh_, dl_, Hd, Wd); break;
+    }
+    return HM_LAUNCH_OK();
+  }
   const long total = long(N) * Hd * Wd * (d_cs >> 3);
   tap_unroll_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(s_hi), static_cast<const bf16*>(s_lo), N, Hs, Ws, C, s_cs, KH, KW, oh, ow, sh, sw,
