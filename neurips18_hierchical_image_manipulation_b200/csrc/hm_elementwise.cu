@@ -219,21 +219,33 @@ __global__ void in_stats_kernel(const float* __restrict__ y, int HW, int C, int 
     for (int i = 0; i < 4; ++i) { dst[i] = sm[tx * 8 + i]; dst[C + i] = sm[tx * 8 + 4 + i]; }
   }
 }
+// 256 threads = 32 (n, c) pairs x 8 lanes over the partial blocks: the nblk (<= 256) dependent L2 loads of the old
+// thread-per-channel loop made this trivial kernel take ~18 us on the full-resolution layers.
 __global__ void in_stats_finalize_kernel(const float* __restrict__ y, const float* __restrict__ partial, int N, int nblk,
                                          int C, int HW, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i % C;
+  __shared__ double ss[8][32], sq[8][32];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
+  const bool ok = i < N * C;
+  const int n = ok ? i / C : 0, c = ok ? i % C : 0;
   double s = 0, q = 0;
-  for (int b = 0; b < nblk; ++b) {
-    const float* p = partial + ((size_t(n) * nblk + b) * 2) * C + c;
-    s += p[0]; q += p[C];
+  if (ok) {
+    for (int b = bl; b < nblk; b += 8) {
+      const float* p = partial + ((size_t(n) * nblk + b) * 2) * C + c;
+      s += p[0]; q += p[C];
+    }
   }
-  const double m = s / HW;   // mean of (x - pivot)
-  double var = q / HW - m * m;
-  if (var < 0) var = 0;
-  mean[i] = float(m + double(__ldg(y + size_t(n) * HW * C + c)));
-  rstd[i] = float(1.0 / sqrt(var + double(eps)));
+  ss[bl][cl] = s; sq[bl][cl] = q;
+  __syncthreads();
+  if (bl == 0 && ok) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
+    const double m = s / HW;   // mean of (x - pivot)
+    double var = q / HW - m * m;
+    if (var < 0) var = 0;
+    mean[i] = float(m + double(__ldg(y + size_t(n) * HW * C + c)));
+    rstd[i] = float(1.0 / sqrt(var + double(eps)));
+  }
 }
 
 // ================================================================================================
@@ -551,16 +563,26 @@ __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx
 }
 __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N, int nblk, int C8, int HW,
                                        float* __restrict__ sums /*[N][2][C8] means*/) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C8) return;
-  const int n = i / C8, c = i % C8;
+  __shared__ double ss[8][32], sq[8][32];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
+  const bool ok = i < N * C8;
+  const int n = ok ? i / C8 : 0, c = ok ? i % C8 : 0;
   double s = 0, q = 0;
-  for (int b = 0; b < nblk; ++b) {
-    const float* p = partial + ((size_t(n) * nblk + b) * 2) * C8 + c;
-    s += p[0]; q += p[C8];
+  if (ok) {
+    for (int b = bl; b < nblk; b += 8) {
+      const float* p = partial + ((size_t(n) * nblk + b) * 2) * C8 + c;
+      s += p[0]; q += p[C8];
+    }
   }
-  sums[(size_t(n) * 2) * C8 + c] = float(s / HW);
-  sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
+  ss[bl][cl] = s; sq[bl][cl] = q;
+  __syncthreads();
+  if (bl == 0 && ok) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
+    sums[(size_t(n) * 2) * C8 + c] = float(s / HW);
+    sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
+  }
 }
 // same thread decomposition; grid (pixel blocks, N, cgroups) with a grid-stride loop over the pixels of image n
 template <int V, int F>
@@ -1086,7 +1108,7 @@ int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, floa
   stats_geometry(C, 4, &gx_log2, &cgroups);
   const int nblk = stats_nblk(N, HW, cgroups);
   in_stats_kernel<<<dim3(nblk, N, cgroups), kBlock, 0, st>>>(y, HW, C, gx_log2, ws);
-  in_stats_finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(y, ws, N, nblk, C, HW, eps, mean, rstd);
+  in_stats_finalize_kernel<<<(N * C + 31) / 32, 256, 0, st>>>(y, ws, N, nblk, C, HW, eps, mean, rstd);
   return HM_LAUNCH_OK();
 }
 
@@ -1149,7 +1171,7 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
     } else {
       in_bwd_reduce_kernel<8, BWD_GENERIC><<<grid, kBlock, 0, st>>>(a, gx_log2, ws);
     }
-    in_bwd_finalize_kernel<<<(N * C8 + 127) / 128, 128, 0, st>>>(ws, N, nblk, C8, H * W, sums);
+    in_bwd_finalize_kernel<<<(N * C8 + 31) / 32, 256, 0, st>>>(ws, N, nblk, C8, H * W, sums);
   }
   const int Cout = o_hi ? o_cs : C8;
   stats_geometry(Cout, V, &gx_log2, &cgroups);
