@@ -319,7 +319,7 @@ def main():
         gb = PER_GPU_BATCH * world
         value = gb / (prim["ms"] / 1e3)
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # the CPU baseline leg runs on rank 0 at N=1 only
             ips, ms, cores, sample = run_cpu(25.0, 1, 0)
             cpu = dict(value=ips, unit="images/sec", cores=cores, kind="port", sample=sample)
         roof["peak_source"] = "%s (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" % pk_kind
