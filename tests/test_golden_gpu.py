@@ -1,0 +1,123 @@
+"""GPU parity of the network executors DIRECTLY against the golden vectors generated from the reference's own classes
+(oracle/make_golden.py -> tests/golden/*.npz): BASELINE config #1 (GlobalGenerator(38,3,64,1,1), 128x256, batch 1),
+the gated small generator with its parameter gradients, the LocalEnhancer, and the 15 taps + LSGAN losses of the
+MultiscaleDiscriminator.  Tolerance 1e-3 relative to each tensor's max magnitude (north_star), bf16x3 mode."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+    grads = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("g::")}
+    return z, sd, grads
+
+
+def _operand(ctx, x_nchw, border, grad=False):
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    n, c, h, w = x_nchw.shape
+    op = ops.Operand(ctx, n, h, w, c, border=border, grad=grad)
+    ops.in_apply(ctx, x_nchw.permute(0, 2, 3, 1).contiguous().cuda(), None, None, ops.ACT_NONE, out_op=op, reflect=True)
+    return op
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def test_config1_global_generator_matches_reference_golden(golden_dir):
+    """BASELINE config #1, the reference's own CPU-runnable case."""
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.networks import FlatParams, GlobalGenerator
+    z, sd, _ = _load(golden_dir, "g_config1.npz")
+    ctx = ops.Ctx("cuda:0", split=True)
+    fp = FlatParams(ctx.device)
+    net = GlobalGenerator(ctx, fp, 38, 3, 64, 1, 1)
+    fp.materialize()
+    fp.load_state_dict(sd)
+    lab = torch.from_numpy(z["label"].astype(np.float32))
+    onehot = torch.zeros(1, 35, 128, 256).scatter_(1, lab.long(), 1.0)
+    x = torch.cat((onehot, torch.from_numpy(z["image"])), 1)
+    out, _ = net.forward(_operand(ctx, x, 3))
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    assert rel(_nchw(out), z["out"]) < 1e-3
+
+
+def test_small_gated_generator_forward_and_parameter_gradients(golden_dir):
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.networks import FlatParams, GlobalGenerator
+    z, sd, grads = _load(golden_dir, "g_small.npz")
+    ctx = ops.Ctx("cuda:0", split=True)
+    fp = FlatParams(ctx.device)
+    net = GlobalGenerator(ctx, fp, 10, 3, 8, 2, 2, use_output_gate=True)
+    fp.materialize()
+    fp.load_state_dict(sd)
+    x, m, cot = torch.from_numpy(z["x"]), torch.from_numpy(z["mask"]), torch.from_numpy(z["cot"])
+    t, tape = net.forward(_operand(ctx, x, 3))
+    torch.cuda.synchronize()
+    t = _nchw(t).cpu()
+    out = (1 - m) * x[:, -3:] + m * t                       # output gate, Pix2Pix_NET.py:96-99
+    assert rel(out, z["out"]) < 1e-3
+    # d(sum(out * cot)) / d(pre-tanh) = cot * m * (1 - t^2)
+    dy = _operand(ctx, cot * m * (1 - t * t), 0, grad=True)
+    fp.grad.zero_()
+    net.backward(tape, dy_head=dy)
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    for k, g_ref in grads.items():
+        if k.endswith("bias") and float(g_ref.abs().max()) < 1e-4:
+            assert float(fp.params[k].grad.abs().max()) < 1e-4   # bias in front of InstanceNorm: zero gradient
+            continue
+        assert rel(fp.params[k].grad, g_ref) < 1e-2, k
+
+
+def test_local_enhancer_matches_reference_golden(golden_dir):
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.local_enhancer import LocalEnhancer
+    from neurips18_hierchical_image_manipulation_b200.networks import FlatParams
+    z, sd, _ = _load(golden_dir, "local_small.npz")
+    ctx = ops.Ctx("cuda:0", split=True)
+    fp = FlatParams(ctx.device)
+    net = LocalEnhancer(ctx, fp, 9, 3, 4, 2, 2, 1, 2)
+    fp.materialize()
+    fp.load_state_dict(sd)
+    out, _ = net.forward(_operand(ctx, torch.from_numpy(z["x"]), 3))
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    assert rel(_nchw(out), z["out"]) < 1e-3
+
+
+def test_multiscale_discriminator_taps_and_lsgan_losses(golden_dir):
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.networks import FlatParams, MultiscaleDiscriminator
+    z, sd, _ = _load(golden_dir, "d_small.npz")
+    ctx = ops.Ctx("cuda:0", split=True)
+    fp = FlatParams(ctx.device)
+    net = MultiscaleDiscriminator(ctx, fp, 12, ndf=8, n_layers=3, num_D=3)
+    fp.materialize()
+    fp.load_state_dict(sd)
+    tape = net.forward(_operand(ctx, torch.from_numpy(z["x"]), 0))
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for i, lv in enumerate(tape):
+        for j, tap in enumerate(lv["taps"]):
+            assert rel(_nchw(tap), z["tap_%d_%d" % (i, j)]) < 1e-3, (i, j)
+        pred = lv["taps"][-1]
+        ops.mse_sum(ctx, pred, 1.0, 1.0 / pred.numel(), acc, 0)    # GANLoss(target real), losses.py:40-50
+        ops.mse_sum(ctx, pred, 0.0, 1.0 / pred.numel(), acc, 1)
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    assert abs(float(acc[0]) - float(z["loss_real"])) < 1e-3 * abs(float(z["loss_real"]))
+    assert abs(float(acc[1]) - float(z["loss_fake"])) < 1e-3 * abs(float(z["loss_fake"]))
