@@ -195,6 +195,25 @@ int hm_f32_to_operand(const float* x, long P, int C, int ld, int coff, float sca
 int hm_colsum(const float* x, long P, int C, float* out, int accumulate, void* stream);
 int hm_colsum_operand(const void* hi, const void* lo, long P, int C, int cs, float* out, int accumulate, void* stream);
 
+/* ---- GlobalTwoStreamGenerator glue (hm_twostream.cu; models/Pix2Pix_NET.py:103-247) ---------------------------
+ * hm_mask_maxpool: nn.MaxPool2d(f, f) of the object mask (:133): mask fp32 [B,1,H,W] -> out fp32 [B,H/f,W/f].
+ * hm_mask_blend: (1-m)*a + m*b ('early_add' fusion of the context and label streams, :207-209 and
+ *   FeatureFusionBlock 'add', layer_util.py:322-323); a, b fp32 [N,H,W,C], m fp32 [N,H,W]; either of a / b may be
+ *   NULL (single-stream variants: plain copy).  Emits the dense fp32 result and/or the operand with
+ *   ReflectionPad2d(border) materialised (input of the first ResnetBlock).
+ * hm_mask_blend_bwd: da = (1-m)*g, db = m*g.
+ * hm_concat_operands: torch.cat((enc, dec), 1) of two operands over P pixels (:221, skip connections).
+ * hm_cond_image_operand: (1 - mask)*image (pix2pixHD_condImg_model.py:165-166) as the context-stream input operand
+ *   [B,H+2b,W+2b,o_cs] with ReflectionPad2d(b); image fp32 NCHW [B,3,H,W], mask fp32 [B,1,H,W]. */
+int hm_mask_maxpool(const float* mask, int B, int H, int W, int f, float* out, void* stream);
+int hm_mask_blend(const float* a, const float* b, const float* m, int N, int H, int W, int C, float* out32, void* o_hi,
+                  void* o_lo, int o_cs, int border, void* stream);
+int hm_mask_blend_bwd(const float* g, const float* m, long P, int C, float* da, float* db, void* stream);
+int hm_concat_operands(const void* a_hi, const void* a_lo, int a_cs, int Ca, const void* b_hi, const void* b_lo, int b_cs,
+                       int Cb, void* o_hi, void* o_lo, int o_cs, long P, void* stream);
+int hm_cond_image_operand(const float* image, const float* mask, int B, int H, int W, void* o_hi, void* o_lo, int o_cs,
+                          int border, void* stream);
+
 /* K13 (opt-in). Spectral normalisation of the PatchGAN convolutions: models/sn_utils.py:11-25 max_singular_value
  * (Ip = 1) and :49-72 SNConv2d.W_bar = W / sigma, with W viewed as [n = Cout][m = Cin*KH*KW] as stored (OIHW).
  * `layers` is a DEVICE array with one entry per convolution; every layer of the discriminator is handled by one

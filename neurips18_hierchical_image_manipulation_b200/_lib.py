@@ -78,6 +78,11 @@ PROTOTYPES = {
     "hm_f32_to_operand": (_i, [_vp, _l, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
     "hm_colsum": (_i, [_vp, _l, _i, _vp, _i, _vp]),
     "hm_colsum_operand": (_i, [_vp, _vp, _l, _i, _i, _vp, _i, _vp]),
+    "hm_mask_maxpool": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "hm_mask_blend": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "hm_mask_blend_bwd": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp]),
+    "hm_concat_operands": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _l, _vp]),
+    "hm_cond_image_operand": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "hm_sn_stash_floats": (_sz, [_i, _i]),
     "hm_sn_power_iteration": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hm_sn_weight_grad": (_i, [_vp, _i, _i, _i, _vp]),

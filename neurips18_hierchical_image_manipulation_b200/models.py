@@ -199,6 +199,15 @@ class Pix2PixHDModel_condImg(object):
             netG_input_nc += 3
             self.netG = LocalEnhancer(self.ctx, self.fpG, netG_input_nc, opt.output_nc, opt.ngf, opt.n_downsample_global,
                                       opt.n_blocks_global, opt.n_local_enhancers, opt.n_blocks_local)
+        elif opt.netG == "global_twostream":     # :47-50 (what scripts/train_mask2image_city.sh trains)
+            from .two_stream import GlobalTwoStreamGenerator
+            self.netG = GlobalTwoStreamGenerator(self.ctx, self.fpG, netG_input_nc, opt.output_nc, opt.ngf,
+                                                 opt.n_downsample_global, opt.n_blocks_global, opt.use_skip,
+                                                 opt.which_encoder, opt.use_output_gate, opt.feat_fusion)
+            if opt.which_encoder == "ctx":
+                raise NotImplementedError("which_encoder == 'ctx' changes the discriminator input (:71-72,178-179,227-228)"
+                                          " and is outside this path; use ctx_label or label")
+            netG_input_nc += 3    # the encode kernel still lays out [label | edge | cond image] (D conditioning, :216)
         else:
             raise NameError("global generator name is not defined properly: %s" % opt.netG)
         self.netG_input_nc = netG_input_nc
@@ -296,7 +305,7 @@ class Pix2PixHDModel_condImg(object):
         opt, ctx = self.opt, self.ctx
         st = self.encode_input(label, inst, image, mask_in, train=True)
         B, H, W = st["B"], st["H"], st["W"]
-        t, g_tape = self.netG.forward(st["g_in"])
+        t, g_tape = self._run_generator(st)
         fake = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
         ops.finish_fake(ctx, t, st["image"], st["mask"], opt.use_output_gate, fake, st["d_in"], self.netG_input_nc, st["v_in"])
         st.update(t=t, g_tape=g_tape, fake=fake)
@@ -323,6 +332,18 @@ class Pix2PixHDModel_condImg(object):
             ops.l1_sum(ctx, fake, st["image"], opt.lambda_rec / fake.numel(), acc, 1)
         st["losses"] = acc.to(torch.float32)
         return st
+
+    def _run_generator(self, st):
+        """:207-210.  'global' / 'local': netG(cat(label, cond_image)); 'global_twostream': netG(cond_image, label, mask)
+        -- the label stream reads the first input_nc channels of the same operand (a view with fewer valid channels)."""
+        if self.netG_type != "global_twostream":
+            return self.netG.forward(st["g_in"])
+        g = st["g_in"]
+        obj = Operand.__new__(Operand)
+        obj.hi, obj.lo, obj.n, obj.h, obj.w, obj.cs, obj.border = g.hi, g.lo, g.n, g.h, g.w, g.cs, g.border
+        obj.c = self.netG.input_nc
+        ctx_in = ops.cond_image_operand(self.ctx, st["image"], st["mask"], 3)
+        return self.netG.forward(ctx_in, obj, st["mask"])
 
     def forward(self, label, inst, image, feat, mask_in, mask_out, infer=False):
         """pix2pixHD_condImg_model.py:198-259.  Inputs are the reference's CPU NCHW tensors; returns
@@ -451,7 +472,7 @@ class Pix2PixHDModel_condImg(object):
     def inference(self, label, inst, image, mask_in, mask_out):
         """pix2pixHD_condImg_model.py:261-283."""
         st = self.encode_input(label, inst, image, mask_in, train=False)
-        t, _ = self.netG.forward(st["g_in"])
+        t, _ = self._run_generator(st)
         fake = torch.empty(st["B"], 3, st["H"], st["W"], dtype=torch.float32, device=self.device)
         ops.finish_fake(self.ctx, t, st["image"], st["mask"], self.opt.use_output_gate, fake, None, 0, None)
         st["fake"] = fake

@@ -293,21 +293,27 @@ class GlobalGenerator(object):
     def convs(self):
         return [c for _, c in self.stages]
 
-    def forward(self, x, feature_border=0, add_at=None, add_tensor=None):
+    def forward(self, x, feature_border=0, add_at=None, add_tensor=None, skip32_init=None, concat=None):
         """x: Operand with ReflectionPad2d(3) materialised.  Returns (out, tape): out is the fp32 NHWC tanh output
         (with_head) or (feature fp32 NHWC) for the trunk.  add_at/add_tensor: dense fp32 tensor added to the output of
-        stage `add_at` after its activation (LocalEnhancer: model_downsample(x) + output_prev, Pix2Pix_NET.py:60)."""
+        stage `add_at` after its activation (LocalEnhancer: model_downsample(x) + output_prev, Pix2Pix_NET.py:60).
+        skip32_init: fp32 value of x when the first stage is a ResnetBlock (its residual input).  concat: {stage index:
+        Operand} concatenated in FRONT of that stage's input channels (skip connections, Pix2Pix_NET.py:221)."""
         ctx = self.ctx
         tape = []
         cur = x
-        skip32 = None      # fp32 copy of the current activation when it is a residual input
+        skip32 = skip32_init   # fp32 copy of the current activation when it is a residual input
         out = None
         n = len(self.stages)
         for s, (kind, conv) in enumerate(self.stages):
             nxt = self.stages[s + 1][0] if s + 1 < n else None
             zero_pad = conv.pad if kind == "down" else 0
+            concat_c = 0
+            if concat and s in concat:
+                concat_c = concat[s].c
+                cur = ops.concat_operands(ctx, concat[s], cur)
             ho, wo = conv.out_hw(cur.h, cur.w, zero_pad)
-            rec = dict(kind=kind, conv=conv, xin=cur, zero_pad=zero_pad, ho=ho, wo=wo)
+            rec = dict(kind=kind, conv=conv, xin=cur, zero_pad=zero_pad, ho=ho, wo=wo, concat_c=concat_c)
             if kind == "head":
                 y = _f32(ctx, cur.n, ho, wo, conv.cout)
                 conv.forward(cur, 0, act=ACT_TANH, out32=y)
@@ -335,13 +341,19 @@ class GlobalGenerator(object):
             out = o32
         return out, tape
 
-    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False, add_at=None):
+    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False, add_at=None, extra_grad=None):
         """dy_head: Operand gradient w.r.t. the head's pre-tanh output (with_head) or dfeat: dense fp32 gradient
         w.r.t. the trunk feature.  Accumulates parameter gradients; returns d(input operand) (fp32, padded space)
-        when need_input_grad.  With add_at, self.add_grad holds the dense gradient w.r.t. the tensor added there."""
+        when need_input_grad.  With add_at, self.add_grad holds the dense gradient w.r.t. the tensor added there.
+        extra_grad: {stage index: (fp32 tensor [N,h,w,ld], ld, coff)} additional gradient w.r.t. that stage's output
+        (skip connections).  Afterwards self.concat_grads[stage] = (tensor, ld, coff) is the gradient w.r.t. the operand
+        concatenated at that stage and self.input_T the dense gradient w.r.t. x when the first stage is a ResnetBlock."""
         ctx = self.ctx
         self.add_grad = None
+        self.concat_grads = {}
+        self.input_T = None
         G1, G1_border = None, 0   # gradient w.r.t. the current stage's OUTPUT operand (padded space)
+        G1_ld, G1_coff = None, 0  # channel stride / offset of G1 when it is a slice of a concatenated input's gradient
         T = dfeat                 # dense gradient w.r.t. the current stage's fp32 output (residual chain)
         for s in range(len(tape) - 1, -1, -1):
             rec = tape[s]
@@ -372,9 +384,14 @@ class GlobalGenerator(object):
                 elif nxt == "resA" or nxt is None:          # output feeds the residual chain / is the trunk feature
                     ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g2=T,
                                out_op=dy)
+                elif extra_grad and s in extra_grad:          # gradient from the next conv + a skip connection
+                    eg, eg_ld, eg_coff = extra_grad[s]
+                    assert G1_border == 0 and G1_ld is None
+                    ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g1=eg,
+                               g1_border=0, g1_ld=eg_ld, g1_coff=eg_coff, g2=G1, out_op=dy)
                 else:
                     ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g1=G1,
-                               g1_border=G1_border, out_op=dy)
+                               g1_border=G1_border, g1_ld=G1_ld, g1_coff=G1_coff, out_op=dy)
             conv.wgrad(xin, dy, rec["zero_pad"], bias_grad=(kind == "head"))
             if s == 0 and not need_input_grad:
                 return None
@@ -385,9 +402,14 @@ class GlobalGenerator(object):
                 Tn = _f32(ctx, xin.n, xin.ih, xin.iw, conv.cin)
                 ops.fold_add(ctx, gin, xin.border, T, Tn)
                 T = Tn
-                G1, G1_border = None, 0
+                G1, G1_border, G1_ld, G1_coff = None, 0, None, 0
             else:
-                G1, G1_border = gin, xin.border
+                G1, G1_border, G1_ld, G1_coff = gin, xin.border, None, 0
+                cc_ = rec.get("concat_c", 0)
+                if cc_:   # input was cat((skip, prev)): the first cc_ channels belong to the skip operand
+                    self.concat_grads[s] = (gin, conv.cin, 0)
+                    G1_ld, G1_coff = conv.cin, cc_
+        self.input_T = T
         return G1
 
 

@@ -331,3 +331,50 @@ def adam_step_dev(ctx, p, g, m, v, lr, beta1, beta2, eps, step_dev, grad_scale=1
     L.check(ctx.lib.hm_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
                                      eps, step_dev.data_ptr(), grad_scale, _stream()), "hm_adam_step_dev")
     ctx.launches += 1
+
+
+# ---- GlobalTwoStreamGenerator glue (csrc/hm_twostream.cu) ------------------------------------------------------
+def mask_maxpool(ctx, mask_nchw, f):
+    B, _, H, W = mask_nchw.shape
+    out = torch.empty(B, H // f, W // f, dtype=torch.float32, device=ctx.device)
+    L.check(ctx.lib.hm_mask_maxpool(mask_nchw.data_ptr(), B, H, W, f, out.data_ptr(), _stream()), "hm_mask_maxpool")
+    ctx.launches += 1
+    return out
+
+
+def mask_blend(ctx, a, b, m, out32=None, out_op=None):
+    """(1-m)*a + m*b (a or b may be None: copy); fp32 NHWC inputs, optional dense / operand (reflect border) outputs."""
+    ref = a if a is not None else b
+    N, H, W, Cc = ref.shape
+    L.check(ctx.lib.hm_mask_blend(_ptr(a), _ptr(b), _ptr(m), N, H, W, Cc, _ptr(out32),
+                                  _ptr(out_op.hi) if out_op else None, _ptr(out_op.lo) if out_op else None,
+                                  out_op.cs if out_op else 0, out_op.border if out_op else 0, _stream()), "hm_mask_blend")
+    ctx.launches += 1
+
+
+def mask_blend_bwd(ctx, g, m, da=None, db=None):
+    Cc = g.shape[-1]
+    L.check(ctx.lib.hm_mask_blend_bwd(g.data_ptr(), m.data_ptr(), g.numel() // Cc, Cc, _ptr(da), _ptr(db), _stream()),
+            "hm_mask_blend_bwd")
+    ctx.launches += 1
+
+
+def concat_operands(ctx, a, b):
+    """torch.cat((a, b), channel) of two border-free operands with equal pixel dims."""
+    assert a.border == 0 and b.border == 0 and (a.n, a.h, a.w) == (b.n, b.h, b.w)
+    out = Operand(ctx, a.n, a.h, a.w, a.c + b.c)
+    both = a.lo is not None and b.lo is not None and out.lo is not None
+    L.check(ctx.lib.hm_concat_operands(a.hi.data_ptr(), _ptr(a.lo) if both else None, a.cs, a.c, b.hi.data_ptr(),
+                                       _ptr(b.lo) if both else None, b.cs, b.c, out.hi.data_ptr(), _ptr(out.lo), out.cs,
+                                       a.n * a.h * a.w, _stream()), "hm_concat_operands")
+    ctx.launches += 1
+    return out
+
+
+def cond_image_operand(ctx, image_nchw, mask_nchw, border):
+    B, _, H, W = image_nchw.shape
+    out = Operand(ctx, B, H, W, 3, border=border)
+    L.check(ctx.lib.hm_cond_image_operand(image_nchw.data_ptr(), mask_nchw.data_ptr(), B, H, W, out.hi.data_ptr(),
+                                          _ptr(out.lo), out.cs, border, _stream()), "hm_cond_image_operand")
+    ctx.launches += 1
+    return out

@@ -68,6 +68,50 @@ def global_generator_forward(sd, x, n_downsampling, n_blocks, mask=None, use_out
     return out
 
 
+def global_twostream_forward(sd, img, label, mask, n_downsampling, n_blocks, use_skip=False, which_stream="ctx",
+                             use_output_gate=False):
+    """GlobalTwoStreamGenerator.forward, models/Pix2Pix_NET.py:103-247 (feat_fusion='early_add')."""
+    def encode(prefix, x, keep):                                               # forward_encoder :135-142
+        h = F.relu(instance_norm(F.conv2d(reflect_pad(x, 3), sd[prefix + "_inputEmbedder.1.weight"],
+                                          sd[prefix + "_inputEmbedder.1.bias"])))
+        feats = []
+        for i in range(n_downsampling):
+            k = prefix + "_downsampler.%d." % (3 * i)
+            h = F.relu(instance_norm(F.conv2d(h, sd[k + "weight"], sd[k + "bias"], stride=2, padding=1)))
+            if keep and i < n_downsampling - 1:                                # :140-141
+                feats.append(h)
+        return h, feats
+    ctx_feat = obj_feat = None
+    ctx_feats = []
+    if "ctx" in which_stream:
+        ctx_feat, ctx_feats = encode("ctx", img, use_skip)
+    if "label" in which_stream:
+        obj_feat, _ = encode("obj", label, False)
+    if which_stream == "ctx_label":                                            # :203-209, FeatureFusionBlock 'add'
+        f = 2 ** n_downsampling
+        m = F.max_pool2d(mask, f, f)
+        h = (1 - m) * ctx_feat + m * obj_feat
+    else:
+        h = ctx_feat if which_stream == "ctx" else obj_feat
+    for i in range(n_blocks):                                                  # latent_embedder
+        k = "latent_embedder.%d.conv_block." % i
+        r = F.conv2d(reflect_pad(h, 1), sd[k + "1.weight"], sd[k + "1.bias"])
+        r = F.relu(instance_norm(r))
+        r = F.conv2d(reflect_pad(r, 1), sd[k + "5.weight"], sd[k + "5.bias"])
+        h = h + instance_norm(r)
+    for s in range(n_downsampling):                                            # forward_decoder :215-223
+        if use_skip and len(ctx_feats) > 0 and s > 0:
+            h = torch.cat((ctx_feats[-s], h), 1)
+        k = "decoder.%d." % (3 * s)
+        h = F.conv_transpose2d(h, sd[k + "weight"], sd[k + "bias"], stride=2, padding=1, output_padding=1)
+        h = F.relu(instance_norm(h))
+    out = torch.tanh(F.conv2d(reflect_pad(h, 3), sd["outputEmbedder.1.weight"], sd["outputEmbedder.1.bias"]))
+    if use_output_gate:                                                        # :243-245
+        mo = mask.repeat(1, out.shape[1], 1, 1)
+        out = (1 - mo) * img[:, :3] + mo * out
+    return out
+
+
 def avgpool_3s2(x):
     """nn.AvgPool2d(3, stride=2, padding=[1,1], count_include_pad=False) (Discriminator_NET.py:31-32)."""
     return F.avg_pool2d(x, 3, stride=2, padding=1, count_include_pad=False)
@@ -232,6 +276,8 @@ class Opt(object):
         self.lr = 0.0002
         self.beta1 = 0.5
         self.netG = "global"
+        self.use_skip = False
+        self.which_encoder = "ctx"
         self.n_local_enhancers = 1
         self.n_blocks_local = 3
         for k, v in kw.items():
@@ -247,6 +293,10 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
     if opt.netG == "local":
         fake = local_enhancer_forward(g_sd, input_label, opt.n_downsample_global, opt.n_blocks_global,
                                       opt.n_local_enhancers, opt.n_blocks_local)
+    elif opt.netG == "global_twostream":                                       # :209-210
+        fake = global_twostream_forward(g_sd, cond, input_mask, mask_in.to(dtype), opt.n_downsample_global,
+                                        opt.n_blocks_global, getattr(opt, "use_skip", False),
+                                        getattr(opt, "which_encoder", "ctx"), opt.use_output_gate)
     else:
         fake = global_generator_forward(g_sd, input_label, opt.n_downsample_global, opt.n_blocks_global,
                                         mask=mask_in.to(dtype), use_output_gate=opt.use_output_gate)   # :208

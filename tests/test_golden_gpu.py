@@ -121,3 +121,34 @@ def test_multiscale_discriminator_taps_and_lsgan_losses(golden_dir):
     ctx.check_pipeline()
     assert abs(float(acc[0]) - float(z["loss_real"])) < 1e-3 * abs(float(z["loss_real"]))
     assert abs(float(acc[1]) - float(z["loss_fake"])) < 1e-3 * abs(float(z["loss_fake"]))
+
+
+def test_two_stream_generator_forward_and_parameter_gradients(golden_dir):
+    """GlobalTwoStreamGenerator(6,3,8,3,2, use_skip, ctx_label, gate, early_add) against the reference's own class."""
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.networks import FlatParams
+    from neurips18_hierchical_image_manipulation_b200.two_stream import GlobalTwoStreamGenerator
+    z, sd, grads = _load(golden_dir, "twostream_small.npz")
+    ctx = ops.Ctx("cuda:0", split=True)
+    fp = FlatParams(ctx.device)
+    net = GlobalTwoStreamGenerator(ctx, fp, 6, 3, 8, 3, 2, use_skip=True, which_stream="ctx_label", use_output_gate=True)
+    fp.materialize()
+    fp.load_state_dict(sd)
+    img, label, m, cot = (torch.from_numpy(z[k]) for k in ("img", "label", "mask", "cot"))
+    t, tape = net.forward(_operand(ctx, img, 3), _operand(ctx, label, 3), m.cuda())
+    torch.cuda.synchronize()
+    t = _nchw(t).cpu()
+    out = (1 - m) * img[:, :3] + m * t                      # output gate, Pix2Pix_NET.py:243-245
+    assert rel(out, z["out"]) < 1e-3
+    dy = _operand(ctx, cot * m * (1 - t * t), 0, grad=True)
+    fp.grad.zero_()
+    net.backward(tape, dy)
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    worst = []
+    for k, g_ref in grads.items():
+        if k.endswith("bias") and float(g_ref.abs().max()) < 1e-4:
+            assert float(fp.params[k].grad.abs().max()) < 1e-4
+            continue
+        worst.append((rel(fp.params[k].grad, g_ref), k))
+    assert max(worst)[0] < 1e-2, sorted(worst, reverse=True)[:5]

@@ -31,7 +31,8 @@ def _oracle_opt(opt):
     return O.Opt(**{k: getattr(opt, k) for k in ("label_nc", "no_instance", "output_nc", "ngf", "n_downsample_global",
                                                  "n_blocks_global", "ndf", "n_layers_D", "num_D", "use_output_gate",
                                                  "no_ganFeat_loss", "no_vgg_loss", "lambda_feat", "lambda_rec", "lr",
-                                                 "beta1", "netG", "n_local_enhancers", "n_blocks_local")})
+                                                 "beta1", "netG", "n_local_enhancers", "n_blocks_local", "use_skip",
+                                                 "which_encoder")})
 
 
 def rel(a, b):
@@ -119,6 +120,18 @@ def test_parity_bf16x3_local_enhancer():
         if k.startswith("loss_"):
             assert v < 1e-3, (k, r)
     # 4-channel layers normalised over a few hundred pixels amplify fp32 summation-order noise in the gradients
+    assert r["gradG"] < 2e-2 and r["gradD"] < 1e-2, r
+
+
+def test_parity_bf16x3_two_stream_generator():
+    """netG='global_twostream' (what the reference's shipped scripts train): ctx_label streams, skip connections,
+    output gate, 3 downsamplings; full training step against the oracle."""
+    r = run_parity("bf16x3", netG="global_twostream", which_encoder="ctx_label", use_skip=True, use_output_gate=True,
+                   n_downsample_global=3, no_instance=False, H=64, W=96)
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
     assert r["gradG"] < 2e-2 and r["gradD"] < 1e-2, r
 
 

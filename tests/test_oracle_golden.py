@@ -170,3 +170,19 @@ def test_spectral_norm_conv_forward_backward(golden_dir):
     g_a = g_v / (na + eps) - a * (a @ g_v) / (na * (na + eps) ** 2)
     dW = (G - c * (torch.outer(g_b, v) + torch.outer(u0, g_a))) / sigma
     close(dW.float().reshape(z["dW"].shape), z["dW"], 1e-4)
+
+
+def test_global_twostream_generator_forward_and_grads(golden_dir):
+    """oracle.global_twostream_forward against the reference's own GlobalTwoStreamGenerator (ctx_label, use_skip,
+    output gate, early_add; fixture: oracle/make_golden_twostream.py)."""
+    z, sd, grads = load(golden_dir, "twostream_small.npz")
+    par = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    y = O.global_twostream_forward(par, torch.from_numpy(z["img"]), torch.from_numpy(z["label"]),
+                                   torch.from_numpy(z["mask"]), 3, 2, use_skip=True, which_stream="ctx_label",
+                                   use_output_gate=True)
+    close(y.detach(), z["out"], 2e-5)
+    g = torch.autograd.grad((y * torch.from_numpy(z["cot"])).sum(), list(par.values()))
+    for (k, _), gi in zip(par.items(), g):
+        if k.endswith("bias") and float(grads[k].abs().max()) < 1e-4:
+            continue
+        close(gi, grads[k], 2e-3)
