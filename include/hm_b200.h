@@ -133,10 +133,13 @@ int hm_tap_combine(const float* T, int N, int Ht, int Wt, int ldT, int KH, int K
  *        ReflectionPad2d(g_border) materialised (Pix2Pix_NET.py:74);
  *   d  : (optional) discriminator input operand [2B,H,W,d_cs]: conditioning channels in both halves, the real
  *        image in channels [cin, cin+3) of the second half (the fake half is filled by hm_finish_fake);
- *   v  : (optional) VGG input operand [2B,H,W,v_cs]: real image in the second half. */
+ *   v  : (optional) VGG input operand [2B,H,W,v_cs]: real image in the second half.
+ *   d_no_imgcond != 0 (--no_imgCond, :213-214): the D operand is [label | edge | image] without the masked image;
+ *   d_mask != NULL (--mask_gan_input, :180-181; mask_in, or mask_out with --use_soft_mask, :217): fp32 [B,1,H,W]
+ *   multiplied into every channel of the D operand (here, in hm_finish_fake and, for the gradient, in hm_fake_bwd). */
 int hm_encode_input(const float* label, const float* inst, const float* image, const float* mask_in, int B, int H,
                     int W, int label_nc, void* g_hi, void* g_lo, int g_cs, int g_border, void* d_hi, void* d_lo,
-                    int d_cs, void* v_hi, void* v_lo, int v_cs, void* stream);
+                    int d_cs, void* v_hi, void* v_lo, int v_cs, int d_no_imgcond, const float* d_mask, void* stream);
 
 /* K7. nn.InstanceNorm2d(C, affine=False) (models/layer_util.py:19-26), split in statistics / apply / backward.
  * ws: hm_in_ws_bytes(N, H*W, C) bytes of scratch. */
@@ -184,10 +187,10 @@ int hm_mse_grad(const float* y, long P, int C, float target, float scale, void* 
  * hm_fake_bwd is its adjoint: d/d(pre-tanh) of everything that reads the fake image. */
 int hm_finish_fake(const float* t, const float* image, const float* mask, int use_gate, int B, int H, int W,
                    float* fake_nchw, void* d_hi, void* d_lo, int d_cs, int d_coff, void* v_hi, void* v_lo, int v_cs,
-                   void* stream);
+                   const float* d_mask, void* stream);
 int hm_fake_bwd(const float* t, const float* mask, int use_gate, const float* gD, int gD_ld, int gD_coff,
                 const float* gV, int gV_ld, const float* real_nchw, float rec_coef, int B, int H, int W, void* o_hi,
-                void* o_lo, int o_cs, void* stream);
+                void* o_lo, int o_cs, const float* d_mask, void* stream);
 
 /* misc: dense fp32 [P][ld] (channels [coff, coff+C)) * scale -> operand; per-channel sums (bias gradients). */
 int hm_f32_to_operand(const float* x, long P, int C, int ld, int coff, float scale, void* o_hi, void* o_lo, int o_cs,

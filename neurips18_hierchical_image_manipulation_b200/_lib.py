@@ -59,7 +59,8 @@ PROTOTYPES = {
     "hm_wgrad_unpack_cols": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "hm_tap_unroll": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "hm_tap_combine": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
-    "hm_encode_input": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "hm_encode_input": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _vp,
+                             _vp]),
     "hm_in_ws_bytes": (_sz, [_i, _i, _i]),
     "hm_in_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "hm_in_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -73,8 +74,8 @@ PROTOTYPES = {
     "hm_l1_sum": (_i, [_vp, _vp, _l, C.c_double, _vp, _vp]),
     "hm_mse_sum": (_i, [_vp, _l, _f, C.c_double, _vp, _vp]),
     "hm_mse_grad": (_i, [_vp, _l, _i, _f, _f, _vp, _vp, _i, _vp]),
-    "hm_finish_fake": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
-    "hm_fake_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "hm_finish_fake": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "hm_fake_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "hm_f32_to_operand": (_i, [_vp, _l, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
     "hm_colsum": (_i, [_vp, _l, _i, _vp, _i, _vp]),
     "hm_colsum_operand": (_i, [_vp, _vp, _l, _i, _i, _vp, _i, _vp]),

@@ -90,7 +90,7 @@ __device__ __forceinline__ float act_grad(float pre_sign_src, int act, float slo
 __global__ void encode_kernel(const float* __restrict__ label, const float* __restrict__ inst,
                               const float* __restrict__ image, const float* __restrict__ mask, int B, int H, int W,
                               int label_nc, bf16* g_hi, bf16* g_lo, int g_cs, int gb, bf16* d_hi, bf16* d_lo, int d_cs,
-                              bf16* v_hi, bf16* v_lo, int v_cs) {
+                              bf16* v_hi, bf16* v_lo, int v_cs, int d_no_imgcond, const float* __restrict__ d_mask) {
   const int Hp = H + 2 * gb, Wp = W + 2 * gb;
   const int gg = g_cs >> 3, dg = d_hi ? (d_cs >> 3) : 0, vg = v_hi ? (v_cs >> 3) : 0;
   const long items_g = long(B) * Hp * Wp * gg;
@@ -133,7 +133,7 @@ __global__ void encode_kernel(const float* __restrict__ label, const float* __re
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    const bool need_img = (kind == 2) ? (c0 < 3) : (c0 + 8 > n_cond);
+    const bool need_img = (kind == 2) ? (c0 < 3) : (c0 + 8 > n_cond);   // (also covers the shifted no_imgCond layout)
     float img[3] = {0.f, 0.f, 0.f}, cond[3] = {0.f, 0.f, 0.f};
     if (need_img) {
       const float m = __ldg(mask + pix);
@@ -161,11 +161,18 @@ __global__ void encode_kernel(const float* __restrict__ label, const float* __re
         if (h < H - 1) e |= (t != __ldg(inst + pix + W));
         v[label_nc - c0] = e ? 1.f : 0.f;
       }
+      // D operand with no_imgCond (pix2pixHD_condImg_model.py:213-214): [label | edge | image], else [.. | cond | image]
+      const int cimg = (kind == 1 && d_no_imgcond) ? n_cond : n_cond + 3;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        if (c >= n_cond && c < n_cond + 3) v[j] = cond[c - n_cond];
-        else if (kind == 1 && half == 1 && c >= n_cond + 3 && c < n_cond + 6) v[j] = img[c - n_cond - 3];
+        if (!(kind == 1 && d_no_imgcond) && c >= n_cond && c < n_cond + 3) v[j] = cond[c - n_cond];
+        else if (kind == 1 && half == 1 && c >= cimg && c < cimg + 3) v[j] = img[c - cimg];
+      }
+      if (kind == 1 && d_mask) {   // mask_gan_input (:180-181): the whole D input is multiplied by the mask
+        const float dm = __ldg(d_mask + pix);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= dm;
       }
     }
     if (kind == 0) store_op8(g_hi, g_lo, off, v);
@@ -822,7 +829,7 @@ __global__ void mse_grad_kernel(const float* __restrict__ y, long P, int C, floa
 __global__ void finish_fake_kernel(const float* __restrict__ t /*[B,H,W,3] tanh output*/, const float* __restrict__ image,
                                    const float* __restrict__ mask, int use_gate, int B, int H, int W,
                                    float* __restrict__ fake_nchw, bf16* d_hi, bf16* d_lo, int d_cs, int d_coff, bf16* v_hi,
-                                   bf16* v_lo, int v_cs) {
+                                   bf16* v_lo, int v_cs, const float* __restrict__ d_mask) {
   const long total = long(B) * H * W;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
     const int w = int(i % W);
@@ -841,10 +848,11 @@ __global__ void finish_fake_kernel(const float* __restrict__ t /*[B,H,W,3] tanh 
       if (fake_nchw) fake_nchw[(long(n) * 3 + c) * H * W + long(h) * W + w] = v;
     }
     if (d_hi) {
+      const float dm = d_mask ? __ldg(d_mask + i) : 1.f;   // mask_gan_input (:229-230)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         bf16 hh, ll;
-        hm::split_bf16(o[c], hh, ll);
+        hm::split_bf16(o[c] * dm, hh, ll);
         d_hi[size_t(i) * d_cs + d_coff + c] = hh;
         if (d_lo) d_lo[size_t(i) * d_cs + d_coff + c] = ll;
       }
@@ -863,7 +871,7 @@ __global__ void finish_fake_kernel(const float* __restrict__ t /*[B,H,W,3] tanh 
 __global__ void fake_bwd_kernel(const float* __restrict__ t, const float* __restrict__ mask, int use_gate,
                                 const float* __restrict__ gD, int gD_ld, int gD_coff, const float* __restrict__ gV, int gV_ld,
                                 const float* __restrict__ real_nchw, float rec_coef, int B, int H, int W, bf16* o_hi,
-                                bf16* o_lo, int o_cs) {
+                                bf16* o_lo, int o_cs, const float* __restrict__ d_mask) {
   const long total = long(B) * H * W;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
     const int w = int(i % W);
@@ -875,7 +883,7 @@ __global__ void fake_bwd_kernel(const float* __restrict__ t, const float* __rest
     for (int c = 0; c < 3; ++c) {
       const float tv = __ldg(t + i * 3 + c);
       float g = 0.f;
-      if (gD) g += __ldg(gD + size_t(i) * gD_ld + gD_coff + c);
+      if (gD) g += __ldg(gD + size_t(i) * gD_ld + gD_coff + c) * (d_mask ? __ldg(d_mask + i) : 1.f);
       if (gV) g += __ldg(gV + size_t(i) * gV_ld + c);
       if (rec_coef != 0.f) {
         const float img = __ldg(real_nchw + (long(n) * 3 + c) * H * W + long(h) * W + w);
@@ -1082,17 +1090,17 @@ extern "C" {
 
 int hm_encode_input(const float* label, const float* inst, const float* image, const float* mask_in, int B, int H,
                     int W, int label_nc, void* g_hi, void* g_lo, int g_cs, int g_border, void* d_hi, void* d_lo,
-                    int d_cs, void* v_hi, void* v_lo, int v_cs, void* stream) {
+                    int d_cs, void* v_hi, void* v_lo, int v_cs, int d_no_imgcond, const float* d_mask, void* stream) {
   if (!label || !image || !mask_in || !g_hi || (g_cs & 7) || (d_hi && (d_cs & 7)) || (v_hi && (v_cs & 7)))
     return HM_ERR_INVALID;
   const int cin = label_nc + (inst ? 1 : 0) + 3;
-  if (cin > g_cs || (d_hi && cin + 3 > d_cs)) return HM_ERR_INVALID;
+  if (cin > g_cs || (d_hi && cin + (d_no_imgcond ? 0 : 3) > d_cs)) return HM_ERR_INVALID;
   const long total = long(B) * (H + 2 * g_border) * (W + 2 * g_border) * (g_cs >> 3) +
                      (d_hi ? long(2) * B * H * W * (d_cs >> 3) : 0) + (v_hi ? long(B) * H * W * (v_cs >> 3) : 0);
   encode_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       label, inst, image, mask_in, B, H, W, label_nc, static_cast<bf16*>(g_hi), static_cast<bf16*>(g_lo), g_cs,
       g_border, static_cast<bf16*>(d_hi), static_cast<bf16*>(d_lo), d_cs, static_cast<bf16*>(v_hi),
-      static_cast<bf16*>(v_lo), v_cs);
+      static_cast<bf16*>(v_lo), v_cs, d_no_imgcond, d_mask);
   return HM_LAUNCH_OK();
 }
 
@@ -1262,21 +1270,21 @@ int hm_mse_grad(const float* y, long P, int C, float target, float scale, void* 
 
 int hm_finish_fake(const float* t, const float* image, const float* mask, int use_gate, int B, int H, int W,
                    float* fake_nchw, void* d_hi, void* d_lo, int d_cs, int d_coff, void* v_hi, void* v_lo, int v_cs,
-                   void* stream) {
+                   const float* d_mask, void* stream) {
   if (!t || (use_gate && (!image || !mask))) return HM_ERR_INVALID;
   finish_fake_kernel<<<grid_for(long(B) * H * W), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       t, image, mask, use_gate, B, H, W, fake_nchw, static_cast<bf16*>(d_hi), static_cast<bf16*>(d_lo), d_cs, d_coff,
-      static_cast<bf16*>(v_hi), static_cast<bf16*>(v_lo), v_cs);
+      static_cast<bf16*>(v_hi), static_cast<bf16*>(v_lo), v_cs, d_mask);
   return HM_LAUNCH_OK();
 }
 
 int hm_fake_bwd(const float* t, const float* mask, int use_gate, const float* gD, int gD_ld, int gD_coff,
                 const float* gV, int gV_ld, const float* real_nchw, float rec_coef, int B, int H, int W, void* o_hi,
-                void* o_lo, int o_cs, void* stream) {
+                void* o_lo, int o_cs, const float* d_mask, void* stream) {
   if (!t || !o_hi || (o_cs & 7) || (use_gate && !mask) || (rec_coef != 0.f && !real_nchw)) return HM_ERR_INVALID;
   fake_bwd_kernel<<<grid_for(long(B) * H * W), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       t, mask, use_gate, gD, gD_ld, gD_coff, gV, gV_ld, real_nchw, rec_coef, B, H, W, static_cast<bf16*>(o_hi),
-      static_cast<bf16*>(o_lo), o_cs);
+      static_cast<bf16*>(o_lo), o_cs, d_mask);
   return HM_LAUNCH_OK();
 }
 

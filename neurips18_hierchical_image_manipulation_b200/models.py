@@ -215,9 +215,14 @@ class Pix2PixHDModel_condImg(object):
         # ---- discriminator (:59-81)
         self.netD = None
         if self.isTrain:
-            if opt.no_imgCond or opt.mask_gan_input or opt.use_soft_mask or opt.no_lsgan:
-                raise NotImplementedError("no_imgCond / mask_gan_input / use_soft_mask / no_lsgan are outside this path")
-            netD_input_nc = input_nc + 3 + opt.output_nc + (0 if opt.no_instance else 1)
+            if opt.no_lsgan:
+                raise NotImplementedError("no_lsgan (vanilla GAN loss) is outside this path")
+            # :61-70  --no_imgCond drops the masked image from the D conditioning, --mask_gan_input multiplies the D
+            # input by mask_in (mask_out with --use_soft_mask)
+            n_lab = input_nc + (0 if opt.no_instance else 1)
+            netD_input_nc = n_lab + (0 if opt.no_imgCond else 3) + opt.output_nc
+            self.netD_input_nc = netD_input_nc
+            self.d_img_c0 = netD_input_nc - opt.output_nc      # first image channel of the D operand
             self.fpD = FlatParams(dev)
             self.netD = MultiscaleDiscriminator(self.ctx, self.fpD, netD_input_nc, opt.ndf, opt.n_layers_D, opt.num_D,
                                                 spectral_norm=getattr(opt, "sn_D", False))
@@ -281,7 +286,7 @@ class Pix2PixHDModel_condImg(object):
         buf.copy_(t)
         return buf.to(self.device, non_blocking=True)
 
-    def encode_input(self, label_map, inst_map=None, real_image=None, mask_in=None, train=True):
+    def encode_input(self, label_map, inst_map=None, real_image=None, mask_in=None, train=True, mask_out=None):
         """pix2pixHD_condImg_model.py:144-174 -> operands for G / D / VGG (K11)."""
         assert real_image is not None and mask_in is not None
         opt, ctx = self.opt, self.ctx
@@ -291,23 +296,28 @@ class Pix2PixHDModel_condImg(object):
         mask = self._to_device("mask_in", mask_in)
         B, _, H, W = label.shape
         g_in = Operand(ctx, B, H, W, self.netG_input_nc, border=3)
-        d_in = v_in = None
+        d_in = v_in = d_mask = None
         if train:
-            d_in = Operand(ctx, 2 * B, H, W, self.netG_input_nc + 3)
+            d_in = Operand(ctx, 2 * B, H, W, self.netD_input_nc)
             if self.vgg is not None:
                 v_in = Operand(ctx, 2 * B, H, W, 3)
-        ops.encode_input(ctx, label, inst, image, mask, opt.label_nc, g_in, d_in, v_in)
-        return dict(label=label, inst=inst, image=image, mask=mask, g_in=g_in, d_in=d_in, v_in=v_in, B=B, H=H, W=W)
+            if opt.mask_gan_input:                                   # :217 mask_cond
+                d_mask = self._to_device("mask_out", mask_out) if opt.use_soft_mask else mask
+        ops.encode_input(ctx, label, inst, image, mask, opt.label_nc, g_in, d_in, v_in,
+                         d_no_imgcond=bool(train and opt.no_imgCond), d_mask=d_mask)
+        return dict(label=label, inst=inst, image=image, mask=mask, g_in=g_in, d_in=d_in, v_in=v_in, B=B, H=H, W=W,
+                    d_mask=d_mask)
 
     # ------------------------------------------------------------------------------------------------
-    def _forward_all(self, label, inst, image, mask_in):
+    def _forward_all(self, label, inst, image, mask_in, mask_out=None):
         """The whole forward of pix2pixHD_condImg_model.py:198-259; returns the step context."""
         opt, ctx = self.opt, self.ctx
-        st = self.encode_input(label, inst, image, mask_in, train=True)
+        st = self.encode_input(label, inst, image, mask_in, train=True, mask_out=mask_out)
         B, H, W = st["B"], st["H"], st["W"]
         t, g_tape = self._run_generator(st)
         fake = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
-        ops.finish_fake(ctx, t, st["image"], st["mask"], opt.use_output_gate, fake, st["d_in"], self.netG_input_nc, st["v_in"])
+        ops.finish_fake(ctx, t, st["image"], st["mask"], opt.use_output_gate, fake, st["d_in"], self.d_img_c0, st["v_in"],
+                        d_mask=st["d_mask"])
         st.update(t=t, g_tape=g_tape, fake=fake)
         # D on [fake ; real] (the fake.detach() pass of :218 and the pass of :231 see identical values: computed once)
         st["d_tape"] = self.netD.forward(st["d_in"])
@@ -348,7 +358,7 @@ class Pix2PixHDModel_condImg(object):
     def forward(self, label, inst, image, feat, mask_in, mask_out, infer=False):
         """pix2pixHD_condImg_model.py:198-259.  Inputs are the reference's CPU NCHW tensors; returns
         [[G_GAN, G_GAN_Feat, G_VGG, D_real, D_fake], fake_image | None] with differentiable scalar losses."""
-        st = self._forward_all(label, inst, image, mask_in)
+        st = self._forward_all(label, inst, image, mask_in, mask_out)
         self._step = st
         lg = _LossFn.apply(self._anchor, self, "G", st["losses"][:3])
         ld = _LossFn.apply(self._anchor, self, "D", st["losses"][3:])
@@ -367,13 +377,14 @@ class Pix2PixHDModel_condImg(object):
         st, opt, ctx = self._step, self.opt, self.ctx
         B = st["B"]
         cf = 0.0 if opt.no_ganFeat_loss else w[1] * (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
-        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.netG_input_nc)
+        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.d_img_c0)
         gV = None
         if self.vgg is not None and w[2] != 0.0:
             gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
         dy = Operand(ctx, B, st["H"], st["W"], 3, grad=True)
         rec = w[1] * opt.lambda_rec / st["fake"].numel() if opt.lambda_rec > 0 else 0.0
-        ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.netG_input_nc, gV, st["image"], rec, dy)
+        ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.d_img_c0, gV, st["image"], rec, dy,
+                     d_mask=st["d_mask"])
         self.netG.backward(st["g_tape"], dy_head=dy)
 
     def _backward_D(self, w):
@@ -389,14 +400,17 @@ class Pix2PixHDModel_condImg(object):
         With opt.cuda_graph (default) the step is captured into a CUDA graph on its third call with a given batch
         geometry and replayed afterwards: the ~700 kernel launches of a step then cost no host work and no launch
         gaps.  Inputs are copied into the graph's static input tensors (an H2D copy when they are host tensors)."""
-        batch = dict(label=label, inst=None if self.opt.no_instance else inst, image=image, mask_in=mask_in)
+        soft = self.opt.mask_gan_input and self.opt.use_soft_mask
+        batch = dict(label=label, inst=None if self.opt.no_instance else inst, image=image, mask_in=mask_in,
+                     mask_out=mask_out if soft else None)
         if self._use_graph(batch):
             return self._graph_step(batch)
         self._eager_steps += 1
-        return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False)
+        return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False,
+                                mask_out=batch["mask_out"])
 
-    def _fused_step(self, label, inst, image, mask_in, captured):
-        st = self._forward_all(label, inst, image, mask_in)
+    def _fused_step(self, label, inst, image, mask_in, captured, mask_out=None):
+        st = self._forward_all(label, inst, image, mask_in, mask_out)
         self._step = st
         self._keep_visuals(st)
         self.flat_grad.zero_()
@@ -433,7 +447,8 @@ class Pix2PixHDModel_condImg(object):
                 self._graph = False
                 torch.cuda.synchronize()
                 self._eager_steps += 1
-                return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False)
+                return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False,
+                                        mask_out=batch["mask_out"])
         g = self._graph
         for k, dst in g["inputs"].items():
             dst.copy_(batch[k], non_blocking=True)
@@ -460,7 +475,8 @@ class Pix2PixHDModel_condImg(object):
         vG, vD = self.fpG.version, self.fpD.version
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            losses = self._fused_step(inputs["label"], inputs.get("inst"), inputs["image"], inputs["mask_in"], captured=True)
+            losses = self._fused_step(inputs["label"], inputs.get("inst"), inputs["image"], inputs["mask_in"], captured=True,
+                                      mask_out=inputs.get("mask_out"))
         launches = self.ctx.launches - l0
         self.ctx.launches = l0
         # recording did not execute anything: undo the host-side bookkeeping of the recorded step

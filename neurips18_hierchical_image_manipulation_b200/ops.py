@@ -181,13 +181,15 @@ def tap_combine(ctx, T, KH, KW, C, oh, ow, sh, sw, bias, act, slope, out):
     ctx.launches += 1
 
 
-def encode_input(ctx, label, inst, image, mask_in, label_nc, g_op, d_op=None, v_op=None):
+def encode_input(ctx, label, inst, image, mask_in, label_nc, g_op, d_op=None, v_op=None, d_no_imgcond=False,
+                 d_mask=None):
     B, _, H, W = label.shape
     L.check(ctx.lib.hm_encode_input(label.data_ptr(), _ptr(inst), image.data_ptr(), mask_in.data_ptr(), B, H, W,
                                     label_nc, g_op.hi.data_ptr(), _ptr(g_op.lo), g_op.cs, g_op.border,
                                     _ptr(d_op.hi) if d_op else None, _ptr(d_op.lo) if d_op else None,
                                     d_op.cs if d_op else 0, _ptr(v_op.hi) if v_op else None,
-                                    _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, _stream()),
+                                    _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, 1 if d_no_imgcond else 0,
+                                    _ptr(d_mask), _stream()),
             "hm_encode_input")
     ctx.launches += 1
 
@@ -281,21 +283,22 @@ def mse_grad(ctx, y, target, scale, out_op, op_n0=0):
     ctx.launches += 1
 
 
-def finish_fake(ctx, t, image, mask, use_gate, fake_nchw, d_op, d_coff, v_op):
+def finish_fake(ctx, t, image, mask, use_gate, fake_nchw, d_op, d_coff, v_op, d_mask=None):
     B, H, W, _ = t.shape
     L.check(ctx.lib.hm_finish_fake(t.data_ptr(), _ptr(image), _ptr(mask), 1 if use_gate else 0, B, H, W, _ptr(fake_nchw),
                                    _ptr(d_op.hi) if d_op else None, _ptr(d_op.lo) if d_op else None,
                                    d_op.cs if d_op else 0, d_coff, _ptr(v_op.hi) if v_op else None,
-                                   _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, _stream()), "hm_finish_fake")
+                                   _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, _ptr(d_mask), _stream()),
+            "hm_finish_fake")
     ctx.launches += 1
 
 
-def fake_bwd(ctx, t, mask, use_gate, gD, gD_coff, gV, real_nchw, rec_coef, out_op):
+def fake_bwd(ctx, t, mask, use_gate, gD, gD_coff, gV, real_nchw, rec_coef, out_op, d_mask=None):
     B, H, W, _ = t.shape
     L.check(ctx.lib.hm_fake_bwd(t.data_ptr(), _ptr(mask), 1 if use_gate else 0, _ptr(gD),
                                 gD.shape[-1] if gD is not None else 0, gD_coff, _ptr(gV),
                                 gV.shape[-1] if gV is not None else 0, _ptr(real_nchw), float(rec_coef), B, H, W,
-                                out_op.hi.data_ptr(), _ptr(out_op.lo), out_op.cs, _stream()), "hm_fake_bwd")
+                                out_op.hi.data_ptr(), _ptr(out_op.lo), out_op.cs, _ptr(d_mask), _stream()), "hm_fake_bwd")
     ctx.launches += 1
 
 

@@ -278,13 +278,16 @@ class Opt(object):
         self.netG = "global"
         self.use_skip = False
         self.which_encoder = "ctx"
+        self.no_imgCond = False
+        self.mask_gan_input = False
+        self.use_soft_mask = False
         self.n_local_enhancers = 1
         self.n_blocks_local = 3
         for k, v in kw.items():
             setattr(self, k, v)
 
 
-def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=torch.float32):
+def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=torch.float32, mask_out=None):
     """Pix2PixHDModel_condImg.forward, models/pix2pixHD_condImg_model.py:198-259 (netG == 'global' or 'local',
     no_imgCond / mask_gan_input / use_soft_mask off, pool_size 0).
     Returns ([G_GAN, G_GAN_Feat, G_VGG, D_real, D_fake], fake_image, extras)."""
@@ -303,12 +306,19 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
     # opt-in spectral norm (SNConv2d in place of Conv2d): one power iteration per step, shared by the three D calls
     # below -- the product evaluates D once on [fake ; real]; identity when d_sd has no '.u' entries
     d_sd, new_u = spectral_normalize(d_sd)
-    D = lambda t: multiscale_discriminator_forward(d_sd, t, opt.num_D, opt.n_layers_D)
-    pred_fake_pool = D(torch.cat((input_label, fake.detach()), 1))             # :218 (discriminate :176-186)
+    netD_cond = input_mask if getattr(opt, "no_imgCond", False) else input_label     # :213-216
+    mask_cond = (mask_out if getattr(opt, "use_soft_mask", False) else mask_in).to(dtype)   # :217
+
+    def D(test_image):                                                         # discriminate :176-186 / :226-231
+        x = torch.cat((netD_cond, test_image), 1)
+        if getattr(opt, "mask_gan_input", False):
+            x = x * mask_cond.repeat(1, x.shape[1], 1, 1)
+        return multiscale_discriminator_forward(d_sd, x, opt.num_D, opt.n_layers_D)
+    pred_fake_pool = D(fake.detach())                                          # :218
     loss_D_fake = gan_loss(pred_fake_pool, False)                              # :219
-    pred_real = D(torch.cat((input_label, real), 1))                           # :222
+    pred_real = D(real)                                                        # :222
     loss_D_real = gan_loss(pred_real, True)                                    # :223
-    pred_fake = D(torch.cat((input_label, fake), 1))                           # :226-231
+    pred_fake = D(fake)                                                        # :226-231
     loss_G_GAN = gan_loss(pred_fake, True)                                     # :232
     loss_G_GAN_Feat = torch.zeros((), dtype=dtype)
     if not opt.no_ganFeat_loss:                                                # :235-242
@@ -353,7 +363,7 @@ def train_step(opt, g_sd, d_sd, vgg_sd, batch, state=None, dtype=torch.float32):
     d_par = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(not k.endswith(".u"))) for k, v in d_sd.items())
     v_sd = OrderedDict((k, v.to(dtype)) for k, v in vgg_sd.items()) if vgg_sd is not None else None
     losses, fake, extras = model_forward(opt, g_par, d_par, v_sd, batch["label"], batch["inst"], batch["image"],
-                                         batch["mask_in"], dtype)
+                                         batch["mask_in"], dtype, mask_out=batch.get("mask_out"))
     loss_G, loss_D = step_losses(losses)
     d_train = OrderedDict((k, p) for k, p in d_par.items() if p.requires_grad)
     gG = torch.autograd.grad(loss_G, list(g_par.values()), retain_graph=True, allow_unused=True)

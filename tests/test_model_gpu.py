@@ -32,7 +32,7 @@ def _oracle_opt(opt):
                                                  "n_blocks_global", "ndf", "n_layers_D", "num_D", "use_output_gate",
                                                  "no_ganFeat_loss", "no_vgg_loss", "lambda_feat", "lambda_rec", "lr",
                                                  "beta1", "netG", "n_local_enhancers", "n_blocks_local", "use_skip",
-                                                 "which_encoder")})
+                                                 "which_encoder", "no_imgCond", "mask_gan_input", "use_soft_mask")})
 
 
 def rel(a, b):
@@ -135,6 +135,29 @@ def test_parity_bf16x3_two_stream_generator():
     # 64-channel planes of 16x16 pixels behind three InstanceNorms amplify the sign flips of the L1 / ReLU gradients
     # (DESIGN.md section 4); the executor's backward itself is pinned to 1e-2 by the golden test of the reference class
     assert r["gradG"] < 5e-2 and r["gradD"] < 1e-2, r
+
+
+def test_parity_bf16x3_shipped_script_configuration():
+    """The flag set of scripts/train_mask2image_city.sh: --netG global_twostream --which_encoder ctx_label --use_skip
+    --use_output_gate --no_imgCond --mask_gan_input --no_instance (plus the soft-mask variant of the D input)."""
+    for soft in (False, True):
+        r = run_parity("bf16x3", netG="global_twostream", which_encoder="ctx_label", use_skip=True, use_output_gate=True,
+                       n_downsample_global=3, no_instance=True, no_imgCond=True, mask_gan_input=True, use_soft_mask=soft,
+                       H=128, W=128)
+        assert r["fake"] < 1e-3, r
+        for k, v in r.items():
+            if k.startswith("loss_"):
+                assert v < 1e-3, (k, r)
+        assert r["gradG"] < 5e-2 and r["gradD"] < 1e-2, r
+
+
+def test_parity_bf16x3_global_mask_gan_input():
+    r = run_parity("bf16x3", mask_gan_input=True)
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
+    assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
 
 
 def test_parity_mixed_mode_forward_is_exact():
