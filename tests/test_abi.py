@@ -67,6 +67,31 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert lib.hm_conv_fprop(C.byref(op), None, None, 64, 64, None, 3, 3, 3, 1, 8, 8, 64, 0, 0.0, None, None, None, None) == -1
     assert lib.hm_adam_step(None, None, None, None, 10, 1e-3, 0.5, 0.999, 1e-8, 1, 1.0, None) == -1
     assert lib.hm_in_stats(None, 1, 1, 4, 1e-5, None, None, None, None) == -1
+    # entry points added for the thin-side lowering, the two-stream generator, K13 and CUDA-graph replays
+    assert lib.hm_pack_weight_ex(None, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, None, None, None, None) == -1
+    assert lib.hm_wgrad_unpack_cols(None, 7, 7, 64, 3, None, 0, None) == -1
+    assert lib.hm_tap_unroll(None, None, 1, 8, 8, 3, 8, 1, 7, 0, 0, 1, -1, None, None, 8, 14, 24, None) == -1
+    assert lib.hm_tap_combine(None, 1, 8, 14, 24, 1, 7, 3, 0, 0, 1, 1, None, 0, 0.0, None, 8, 8, 3, None) == -1
+    assert lib.hm_mask_maxpool(None, 1, 8, 8, 2, None, None) == -1
+    assert lib.hm_mask_blend(None, None, None, 1, 4, 4, 8, None, None, None, 8, 0, None) == -1
+    assert lib.hm_mask_blend_bwd(None, None, 16, 8, None, None, None) == -1
+    assert lib.hm_concat_operands(None, None, 8, 8, None, None, 8, 8, None, None, 16, 16, None) == -1
+    assert lib.hm_cond_image_operand(None, None, 1, 8, 8, None, None, 8, 3, None) == -1
+    assert lib.hm_sn_power_iteration(None, 1, 8, 8, 1, None) == -1
+    assert lib.hm_sn_weight_grad(None, 1, 8, 8, None) == -1
+    assert lib.hm_adam_step_dev(None, None, None, None, 10, 1e-3, 0.5, 0.999, 1e-8, None, 1.0, None) == -1
+    assert lib.hm_sn_stash_floats(512, 4096) == 2 * 512 + 4096 + 8
+
+
+def test_options_mirror_the_reference_flag_names_and_defaults():
+    """options/mask2image_base_options.py:15-74, options/mask2image_train_options.py:9-46."""
+    from neurips18_hierchical_image_manipulation_b200.models import Options
+    o = Options()
+    assert (o.netG, o.ngf, o.n_downsample_global, o.n_blocks_global, o.norm) == ("global", 64, 4, 9, "instance")
+    assert (o.num_D, o.n_layers_D, o.ndf, o.lambda_feat, o.lr, o.beta1) == (2, 3, 64, 10.0, 0.0002, 0.5)
+    assert (o.which_encoder, o.feat_fusion, o.use_skip, o.use_output_gate) == ("ctx", "early_add", False, False)
+    assert not (o.no_imgCond or o.mask_gan_input or o.use_soft_mask or o.no_lsgan or o.no_vgg_loss or o.no_ganFeat_loss)
+    assert (o.precision, o.cuda_graph, o.sn_D) == ("bf16x3", True, False)
 
 
 def test_product_never_imports_the_oracle():
