@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libhm_b200.so (see build/nvcc.log)")
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(dig)
