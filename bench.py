@@ -295,7 +295,9 @@ def main():
     batch_dev = {k: v.to(dev) for k, v in batch.items()}
 
     results = {}
-    modes = [args.precision] + ([] if args.no_alt else [p for p in ("bf16x3", "mixed", "bf16") if p != args.precision])
+    # the alternate precision modes are a single-GPU side measurement; multi-GPU runs time the primary mode only
+    skip_alt = args.no_alt or world > 1
+    modes = [args.precision] + ([] if skip_alt else [p for p in ("bf16x3", "mixed", "bf16") if p != args.precision])
     roof = None
     for i, prec in enumerate(modes):
         opt = Options(label_nc=LABEL_NC, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9,
