@@ -142,6 +142,39 @@ def run_cpu(budget_s, steps, warmup):
     return ips, dt * 1e3, cores, sample
 
 
+def main_torch_gpu(args, out_fd):
+    """Opt-in extra baseline (`--impl torch_gpu`, never run by default): the oracle restatement of the reference's
+    modules executed by stock PyTorch / cuDNN on the same B200 (fp32 tensors, torch's default TF32 convolutions), one
+    full training step of config #2 per iteration -- the practical bar SURVEY section 8(d) asks to report, since the
+    reference publishes no GPU numbers.  Baseline measurement only; the product never touches this path."""
+    from oracle import model as O
+    from tests.util_weights import random_d_sd, random_g_sd
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = os.environ.get("HM_CUDNN_BENCHMARK", "0") == "1"   # the reference turns it on
+    opt = O.Opt(num_D=3)
+    cu = lambda sd: {k: v.to(dev) for k, v in sd.items()}  # noqa: E731
+    g_sd, d_sd = cu(random_g_sd(LABEL_NC + 3, 3, 64, 4, 9)), cu(random_d_sd(LABEL_NC + 6, 64, 3, 3))
+    vgg = cu(O.vgg19_random_state_dict())
+    batch = {k: v.to(dev) for k, v in O.synthetic_batch(PER_GPU_BATCH, H, W, LABEL_NC, seed=1234).items()}
+    state = None
+    for _ in range(max(1, args.warmup)):
+        _, _, _, _, state = O.train_step(opt, g_sd, d_sd, vgg, batch, state)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        _, _, _, _, state = O.train_step(opt, g_sd, d_sd, vgg, batch, state)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    _emit(dict(impl="torch_gpu", metric="mask2image train images/sec @512x1024", value=PER_GPU_BATCH / (ms / 1e3),
+               unit="images/sec", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+               dtype="f32 tensors, cuDNN TF32 convolutions (torch defaults)", data="synthetic", config=workload_desc(1),
+               note="stock PyTorch/cuDNN autograd + per-tensor Adam on the oracle restatement of the reference modules; "
+                    "includes the host syncs of float(loss); cudnn.benchmark=%s" % torch.backends.cudnn.benchmark), out_fd)
+    return 0
+
+
 def main_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -275,6 +308,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args, out_fd)
+    if args.impl == "torch_gpu":
+        return main_torch_gpu(args, out_fd)
     if args.warmup < 3:
         args.warmup = 3
 

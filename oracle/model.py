@@ -245,7 +245,7 @@ def get_edges(t):
 def encode_input(label, inst, image, mask_in, label_nc, no_instance, dtype=torch.float32):
     """models/pix2pixHD_condImg_model.py:144-174."""
     n, _, h, w = label.shape
-    onehot = torch.zeros(n, label_nc, h, w, dtype=dtype)
+    onehot = torch.zeros(n, label_nc, h, w, dtype=dtype, device=label.device)
     onehot.scatter_(1, label.long(), 1.0)                                      # :151-152
     input_label = onehot
     if not no_instance:                                                        # :155-158
