@@ -152,3 +152,48 @@ def test_two_stream_generator_forward_and_parameter_gradients(golden_dir):
             continue
         worst.append((rel(fp.params[k].grad, g_ref), k))
     assert max(worst)[0] < 1e-2, sorted(worst, reverse=True)[:5]
+
+
+@pytest.mark.parametrize("name,optkw", [
+    ("model_global_gate_edges.npz", dict(label_nc=6, no_instance=False, ngf=8, n_downsample_global=2, n_blocks_global=2,
+                                         ndf=8, num_D=2, n_layers_D=3, use_output_gate=True)),
+    ("model_shipped_twostream.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=3, n_blocks_global=2,
+                                         ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
+                                         which_encoder="ctx_label", use_skip=True, no_imgCond=True, mask_gan_input=True)),
+])
+def test_training_step_against_the_reference_models_own_forward(golden_dir, name, optkw):
+    """The whole forward of the training step (generated image, the five losses) and the gradient directions against
+    the golden vectors produced by the reference's OWN Pix2PixHDModel_condImg.forward on CPU (oracle/make_golden_model.py).
+    Gradients are compared by direction (cosine) because single tensors move by percents when one ReLU / L1 sign flips
+    on these tiny planes (see tests/test_oracle_golden.py::test_model_level_forward_against_the_reference_model)."""
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    z = np.load(os.path.join(golden_dir, name))
+    part = lambda p: {k[len(p):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(p)}  # noqa: E731
+    opt = Options(precision="bf16x3", gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="golden", **optkw)
+    model = create_model(opt)
+    m = model.module
+    m.fpG.load_state_dict(part("wG::"))
+    m.fpD.load_state_dict(part("wD::"))
+    b = part("in::")
+    losses, fake = model(label=b["label"], inst=b["inst"], image=b["image"], feat=None, mask_in=b["mask_in"],
+                         mask_out=b["mask_out"], infer=True)
+    assert rel(fake, z["fake"]) < 1e-3
+    for n_, a, r in zip(m.loss_names, losses, z["losses"]):
+        assert abs(float(a) - float(r)) <= 1e-3 * abs(float(r)), (n_, float(a), float(r))
+    ld = dict(zip(m.loss_names, [torch.mean(x) for x in losses]))
+    m.optimizer_G.zero_grad()
+    (ld["G_GAN"] + ld["G_GAN_Feat"] + ld["G_VGG"]).backward()
+    gG = {k: p.grad.detach().cpu().clone() for k, p in m.fpG.params.items()}
+    m.optimizer_D.zero_grad()
+    ((ld["D_fake"] + ld["D_real"]) * 0.5).backward()
+    gD = {k: p.grad.detach().cpu().clone() for k, p in m.fpD.params.items()}
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+
+    def cosine(got, ref):
+        keys = [k for k in ref if k.endswith("weight")]
+        a = torch.cat([got[k].reshape(-1) for k in keys]).double()
+        r = torch.cat([ref[k].reshape(-1) for k in keys]).double()
+        return float((a @ r) / (a.norm() * r.norm()))
+    assert cosine(gG, part("gG::")) > 0.99
+    assert cosine(gD, part("gD::")) > 0.95

@@ -186,3 +186,43 @@ def test_global_twostream_generator_forward_and_grads(golden_dir):
         if k.endswith("bias") and float(grads[k].abs().max()) < 1e-4:
             continue
         close(gi, grads[k], 2e-3)
+
+
+def _model_case(golden_dir, name, **optkw):
+    z = np.load(os.path.join(golden_dir, name))
+    part = lambda p: OrderedDict((k[len(p):], torch.from_numpy(z[k])) for k in z.files if k.startswith(p))  # noqa: E731
+    return z, part("wG::"), part("wD::"), part("gG::"), part("gD::"), {k: v for k, v in part("in::").items()}, O.Opt(**optkw)
+
+
+@pytest.mark.parametrize("name,optkw", [
+    ("model_global_gate_edges.npz", dict(label_nc=6, no_instance=False, ngf=8, n_downsample_global=2, n_blocks_global=2,
+                                         ndf=8, num_D=2, use_output_gate=True)),
+    ("model_shipped_twostream.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=3, n_blocks_global=2,
+                                         ndf=8, num_D=2, use_output_gate=True, netG="global_twostream",
+                                         which_encoder="ctx_label", use_skip=True, no_imgCond=True, mask_gan_input=True)),
+])
+def test_model_level_forward_against_the_reference_model(golden_dir, name, optkw):
+    """oracle.model_forward / step_losses against the reference's OWN Pix2PixHDModel_condImg.forward run on CPU
+    (oracle/make_golden_model.py): the five losses, the generated image and every parameter gradient of loss_G / loss_D.
+    The oracle is evaluated in float64: in float32 it reproduces outputs and losses to 1e-6 as well, but one fp32
+    rounding difference (nn.InstanceNorm2d vs (x-mean)/sqrt(var+eps) on the 6x8-pixel planes of the coarse PatchGAN
+    scale) flips a LeakyReLU sign and moves that scale's gradients by 0.9-4.8 % -- the float64 evaluation agrees with
+    the reference's float32 gradients to 1e-6, i.e. the restatement is exact and the gradient is that sensitive."""
+    z, g_sd, d_sd, gG, gD, b, opt = _model_case(golden_dir, name, **optkw)
+    dt = torch.float64
+    g_par = OrderedDict((k, v.clone().to(dt).requires_grad_(True)) for k, v in g_sd.items())
+    d_par = OrderedDict((k, v.clone().to(dt).requires_grad_(True)) for k, v in d_sd.items())
+    vgg = OrderedDict((k, v.to(dt)) for k, v in O.vgg19_random_state_dict().items())
+    losses, fake, _ = O.model_forward(opt, g_par, d_par, vgg, b["label"], b["inst"], b["image"], b["mask_in"], dtype=dt,
+                                      mask_out=b["mask_out"])
+    close(fake.detach().float(), z["fake"], 2e-5)
+    for a, r in zip(losses, z["losses"]):
+        assert abs(float(a) - float(r)) <= 2e-5 * abs(float(r)), (float(a), float(r))
+    loss_G, loss_D = O.step_losses(losses)
+    g1 = torch.autograd.grad(loss_G, list(g_par.values()), retain_graph=True)
+    g2 = torch.autograd.grad(loss_D, list(d_par.values()))
+    for ref, got, par in ((gG, g1, g_par), (gD, g2, d_par)):
+        for (k, _), gi in zip(par.items(), got):
+            if k.endswith("bias") and float(ref[k].abs().max()) < 1e-3 * float(ref[k[:-4] + "weight"].abs().max()):
+                continue   # bias in front of an InstanceNorm: analytically zero, fp32 noise (1e-8 .. 5e-7) in the reference
+            close(gi.float(), ref[k], 1e-4)
