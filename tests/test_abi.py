@@ -126,3 +126,15 @@ def test_synthetic_batch_contract_matches_oracle_generator():
     assert float(a["label"].max()) <= 34 and float(a["image"].abs().max()) <= 1.0
     assert set(a["mask_in"].unique().tolist()) <= {0.0, 1.0}
     assert bool((a["mask_out"] >= a["mask_in"]).all())
+
+
+def test_visual_conversions_match_the_reference_util(golden_dir):
+    """get_current_visuals (pix2pixHD_condImg_model.py:293-299): tensor2im and the label colour maps against golden
+    vectors produced by the reference's own util/util.py (oracle/make_golden_visuals.py)."""
+    import numpy as np
+    import torch
+    from neurips18_hierchical_image_manipulation_b200.models import colorize_labels, tensor2im
+    z = np.load(os.path.join(golden_dir, "visuals.npz"))
+    for n in (35, 20, 6):
+        assert np.array_equal(colorize_labels(z["label_%d" % n], n), z["color_%d" % n]), n
+    assert np.array_equal(tensor2im(torch.from_numpy(z["img"])), z["img_u8"])
