@@ -22,9 +22,27 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, LABEL_NC, PER_GPU_BATCH = 512, 1024, 35, 4
-# conv MACs only, 2 FLOP/MAC, BASELINE.md section 3 (fwd 1000.0 + bwd 1312.0 GMAC per image)
+LABEL_NC = 35
+# conv MACs only, 2 FLOP/MAC, BASELINE.md section 3 (fwd 1000.0 + bwd 1312.0 GMAC per image) -- config #2
 TFLOP_PER_IMAGE = 4.624
+
+# BASELINE.json configs this script can time.  "2" (= "3" per GPU) is the headline workload the metric is quoted on;
+# "4" is the LocalEnhancer configuration (one image per GPU: batch 8 on 8 GPUs), a side line selected with --config 4.
+CONFIGS = {
+    "2": dict(H=512, W=1024, per_gpu_batch=4, metric="mask2image train images/sec @512x1024",
+              opt=dict(label_nc=LABEL_NC, no_instance=True, netG="global", ngf=64, n_downsample_global=4,
+                       n_blocks_global=9, num_D=3, n_layers_D=3, ndf=64),
+              desc="BASELINE config #2/#3: mask2image 512x1024, 35-class synthetic labels, --no_instance, "
+                   "GlobalGenerator(ngf64, 4 down, 9 res) + 3-scale MultiscaleDiscriminator + VGG19 feat-match, "
+                   "full train step, 4 images/GPU"),
+    "4": dict(H=1024, W=2048, per_gpu_batch=1, metric="mask2image train images/sec @1024x2048 (LocalEnhancer)",
+              opt=dict(label_nc=LABEL_NC, no_instance=False, netG="local", ngf=32, n_downsample_global=4,
+                       n_blocks_global=9, n_local_enhancers=1, n_blocks_local=3, num_D=2, n_layers_D=3, ndf=64),
+              desc="BASELINE config #4: mask2image LocalEnhancer two-scale 1024x2048 (ngf 32, global trunk 4 down / 9 res "
+                   "at 512x1024, 1 local enhancer with 3 res-blocks), synthetic labels + instance maps, 2-scale D, VGG19 "
+                   "feat-match, full train step, 1 image/GPU (batch 8 on 8 GPUs)"),
+}
+H, W, PER_GPU_BATCH = CONFIGS["2"]["H"], CONFIGS["2"]["W"], CONFIGS["2"]["per_gpu_batch"]
 
 
 def peaks():
@@ -83,95 +101,110 @@ class ClockSampler(object):
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def workload_desc(n_gpus):
-    return dict(workload="BASELINE config #2/#3: mask2image 512x1024, 35-class synthetic labels, --no_instance, "
-                         "GlobalGenerator(ngf64, 4 down, 9 res) + 3-scale MultiscaleDiscriminator + VGG19 feat-match, "
-                         "full train step, %d images/GPU" % PER_GPU_BATCH,
-                global_batch=PER_GPU_BATCH * n_gpus, per_gpu_batch=PER_GPU_BATCH, parallelism="dp%d" % n_gpus,
+def workload_desc(n_gpus, cfg="2"):
+    c = CONFIGS[cfg]
+    return dict(workload=c["desc"], global_batch=c["per_gpu_batch"] * n_gpus, per_gpu_batch=c["per_gpu_batch"],
+                parallelism="dp%d" % n_gpus,
                 l2="per-step working set (tens of GB of activations) >> 126 MB L2: no flush needed",
                 vgg_weights="seeded random (no network for ImageNet weights)")
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's own CPU algorithm (oracle restatement of its PyTorch modules)
+# reference arm / cpu baseline: the reference's own CPU algorithm (oracle restatement of its PyTorch modules).
+# FIXED protocol: config #2 network, ONE full 512x1024 frame per step (batch 1), all host
+# cores, 1 warm-up + 2 timed training steps -- the same in every invocation, whatever --steps / --warmup say
+# (a CPU step takes tens of seconds); no size adaptation, no extrapolation.
 # ------------------------------------------------------------------------------------------------------------
-def cpu_step_time(h, w, reps=1):
+CPU_WARMUP, CPU_TIMED = 1, 2
+
+
+def run_cpu():
     from oracle import model as O
-    from tests.util_weights import random_d_sd, random_g_sd
-    opt = O.Opt(num_D=3)
-    g_sd, d_sd = random_g_sd(LABEL_NC + 3, 3, 64, 4, 9), random_d_sd(LABEL_NC + 6, 64, 3, 3)
-    vgg = O.vgg19_random_state_dict()
-    batch = O.synthetic_batch(1, h, w, LABEL_NC, seed=1234)
-    ts = []
-    for _ in range(reps):
-        t0 = time.time()
-        O.train_step(opt, g_sd, d_sd, vgg, batch)
-        ts.append(time.time() - t0)
-    return min(ts)
-
-
-def run_cpu(budget_s, steps, warmup):
-    """Time `steps` CPU training steps (after `warmup`) on a sample of the workload that fits the budget."""
+    from oracle.weights import random_d_sd, random_g_sd
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t_probe = cpu_step_time(64, 128)  # 1/64 of the pixels
-    per_step = budget_s / max(1, steps + warmup)
-    size = (64, 128)
-    for hh, ww in ((512, 1024), (256, 512), (128, 256)):
-        est = t_probe * (hh * ww) / (64 * 128)
-        if est <= per_step:
-            size = (hh, ww)
-            break
-    from oracle import model as O
-    from tests.util_weights import random_d_sd, random_g_sd
     opt = O.Opt(num_D=3)
     g_sd, d_sd = random_g_sd(LABEL_NC + 3, 3, 64, 4, 9), random_d_sd(LABEL_NC + 6, 64, 3, 3)
     vgg = O.vgg19_random_state_dict()
-    batch = O.synthetic_batch(1, size[0], size[1], LABEL_NC, seed=1234)
+    batch = O.synthetic_batch(1, H, W, LABEL_NC, seed=1234)
     state = None
-    for _ in range(warmup):
+    for _ in range(CPU_WARMUP):
         _, _, _, _, state = O.train_step(opt, g_sd, d_sd, vgg, batch, state)
     t0 = time.time()
-    for _ in range(steps):
+    for _ in range(CPU_TIMED):
         _, _, _, _, state = O.train_step(opt, g_sd, d_sd, vgg, batch, state)
-    dt = (time.time() - t0) / max(1, steps)
-    frac = size[0] * size[1] / float(H * W)
-    ips = frac / dt  # 512x1024-image equivalents per second
-    sample = "1 image of %dx%d per step (%.4g of a 512x1024 image; images/sec in 512x1024-equivalents), %d timed + %d " \
-             "warm-up steps, torch CPU fp32 oracle of the reference modules" % (size[0], size[1], frac, steps, warmup)
-    return ips, dt * 1e3, cores, sample
+    dt = (time.time() - t0) / CPU_TIMED
+    sample = "config #2 network, 1 full 512x1024 image per step (batch 1), %d warm-up + %d timed training steps (fixed, " \
+             "independent of --steps/--warmup), torch CPU fp32 oracle of the reference modules on %d threads" % (
+                 CPU_WARMUP, CPU_TIMED, cores)
+    return 1.0 / dt, dt * 1e3, cores, sample
+
+
+def torch_gpu_leg(variant, warmup=5, steps=10, device_index=0):
+    """The practical bar: the oracle restatement of the reference's modules executed by STOCK
+    PyTorch / cuDNN on the same B200 -- autograd + per-tensor Adam, one full training step of config #2 (4 images) per
+    iteration, cudnn.benchmark on as the reference sets it (pix2pixHD_condImg_model.py:26-27), F.instance_norm as
+    nn.InstanceNorm2d uses.  variant "tf32": fp32 tensors with torch's default TF32 convolutions (what the reference
+    runs on an Ampere+ GPU); "bf16_channels_last": channels_last activations / weights under bf16 autocast (the bar
+    for the plain-bf16 mode).  Baseline measurement only; the product never touches this path."""
+    import torch.nn.functional as F
+    from oracle import model as O
+    from oracle.weights import random_d_sd, random_g_sd
+    dev = torch.device("cuda", device_index)
+    old_bench, old_in = torch.backends.cudnn.benchmark, O.instance_norm
+    torch.backends.cudnn.benchmark = True
+    O.instance_norm = lambda x, eps=1e-5: F.instance_norm(x, eps=eps)
+    cl = variant == "bf16_channels_last"
+    try:
+        def cu(sd):
+            out = {}
+            for k, v in sd.items():
+                v = v.to(dev)
+                out[k] = v.contiguous(memory_format=torch.channels_last) if (cl and v.dim() == 4) else v
+            return out
+        opt = O.Opt(num_D=3)
+        g_sd, d_sd = cu(random_g_sd(LABEL_NC + 3, 3, 64, 4, 9)), cu(random_d_sd(LABEL_NC + 6, 64, 3, 3))
+        vgg = cu(O.vgg19_random_state_dict())
+        batch = {k: v.to(dev) for k, v in O.synthetic_batch(PER_GPU_BATCH, H, W, LABEL_NC, seed=1234).items()}
+        if cl:
+            batch = {k: v.contiguous(memory_format=torch.channels_last) for k, v in batch.items()}
+        state = None
+
+        def step(state):
+            if cl:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return O.train_step(opt, g_sd, d_sd, vgg, batch, state)[4]
+            return O.train_step(opt, g_sd, d_sd, vgg, batch, state)[4]
+        for _ in range(warmup):
+            state = step(state)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            state = step(state)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cudnn.benchmark, O.instance_norm = old_bench, old_in
+    del g_sd, d_sd, vgg, batch, state
+    torch.cuda.empty_cache()
+    return dict(value=PER_GPU_BATCH / (ms / 1e3), unit="images/sec", ms_per_step=ms, warmup=warmup, steps=steps,
+                variant=variant, cudnn_benchmark=True,
+                dtype="f32 tensors, cuDNN TF32 convolutions (torch defaults)" if not cl else
+                      "bf16 autocast, channels_last",
+                note="stock PyTorch %s / cuDNN autograd + per-tensor Adam on the oracle restatement of the reference "
+                     "modules, same synthetic config #2 batch (4 images); includes the host syncs of float(loss)" %
+                     torch.__version__)
 
 
 def main_torch_gpu(args, out_fd):
-    """Opt-in extra baseline (`--impl torch_gpu`, never run by default): the oracle restatement of the reference's
-    modules executed by stock PyTorch / cuDNN on the same B200 (fp32 tensors, torch's default TF32 convolutions), one
-    full training step of config #2 per iteration -- the practical bar SURVEY section 8(d) asks to report, since the
-    reference publishes no GPU numbers.  Baseline measurement only; the product never touches this path."""
-    from oracle import model as O
-    from tests.util_weights import random_d_sd, random_g_sd
-    dev = torch.device("cuda", 0)
-    torch.backends.cudnn.benchmark = os.environ.get("HM_CUDNN_BENCHMARK", "0") == "1"   # the reference turns it on
-    opt = O.Opt(num_D=3)
-    cu = lambda sd: {k: v.to(dev) for k, v in sd.items()}  # noqa: E731
-    g_sd, d_sd = cu(random_g_sd(LABEL_NC + 3, 3, 64, 4, 9)), cu(random_d_sd(LABEL_NC + 6, 64, 3, 3))
-    vgg = cu(O.vgg19_random_state_dict())
-    batch = {k: v.to(dev) for k, v in O.synthetic_batch(PER_GPU_BATCH, H, W, LABEL_NC, seed=1234).items()}
-    state = None
-    for _ in range(max(1, args.warmup)):
-        _, _, _, _, state = O.train_step(opt, g_sd, d_sd, vgg, batch, state)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        _, _, _, _, state = O.train_step(opt, g_sd, d_sd, vgg, batch, state)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    _emit(dict(impl="torch_gpu", metric="mask2image train images/sec @512x1024", value=PER_GPU_BATCH / (ms / 1e3),
-               unit="images/sec", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
-               dtype="f32 tensors, cuDNN TF32 convolutions (torch defaults)", data="synthetic", config=workload_desc(1),
-               note="stock PyTorch/cuDNN autograd + per-tensor Adam on the oracle restatement of the reference modules; "
-                    "includes the host syncs of float(loss); cudnn.benchmark=%s" % torch.backends.cudnn.benchmark), out_fd)
+    """`--impl torch_gpu`: only the stock PyTorch / cuDNN legs (the default run embeds them under "torch_gpu")."""
+    legs = {v: torch_gpu_leg(v, max(5, args.warmup), max(10, args.steps)) for v in ("tf32", "bf16_channels_last")}
+    t = legs["tf32"]
+    _emit(dict(impl="torch_gpu", metric=CONFIGS["2"]["metric"], value=t["value"], unit="images/sec", n_gpus=1,
+               steps=t["steps"], warmup=t["warmup"], ms_per_step=t["ms_per_step"], higher_is_better=True, dtype=t["dtype"],
+               data="synthetic", config=workload_desc(1), torch_gpu=legs), out_fd)
     return 0
 
 
@@ -179,10 +212,14 @@ def main_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ips, ms, cores, sample = run_cpu(150.0, args.steps, args.warmup)
-    line = dict(impl="reference", metric="mask2image train images/sec @512x1024", value=ips, unit="images/sec",
+    ips, ms, cores, sample = run_cpu()
+    cfg = workload_desc(args.gpus)
+    cfg["measured"] = "reference arm: 1 image/step on the host CPU (see cpu_baseline.sample); images/sec is per full " \
+                      "512x1024 training step, directly comparable with the GPU arm's images/sec"
+    line = dict(impl="reference", metric=CONFIGS["2"]["metric"], value=ips, unit="images/sec",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload_desc(args.gpus),
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
+                timed_steps=CPU_TIMED, warmup_steps=CPU_WARMUP,
                 cpu_baseline=dict(value=ips, unit="images/sec", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=ips, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     _emit(line, out_fd)
@@ -282,9 +319,20 @@ def run_mode(model, precision_name, batch_dev, batch_pinned, steps, warmup, worl
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, steps)
-    h2d = sum(batch_pinned[k].numel() * 4 for k in ("label", "image", "mask_in"))
+    keys = ["label", "image", "mask_in"] + ([] if m.opt.no_instance else ["inst"])
+    h2d = sum(batch_pinned[k].numel() * 4 for k in keys)
+    # data-parallel replicas must hold bit-identical weights after the timed steps (each rank saw different data, the
+    # allreduced gradients are what every rank applied): integer checksum of the parameter bit patterns, MAX - MIN == 0
+    identical = None
+    if world > 1:
+        chk = m.flat.view(torch.int32).to(torch.int64).sum().reshape(1)
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        identical = bool((hi - lo).item() == 0)
     return dict(ms=ms_dev, ms_e2e=ms_e2e, launches=launches, clocks=clocks, h2d=h2d, d2h=20,
-                losses=[float(x) for x in host_losses])
+                losses=[float(x) for x in host_losses], replicas_identical=identical,
+                graph=isinstance(m._graph, dict), peak_mem_gb=torch.cuda.max_memory_allocated(m.device) / 2 ** 30)
 
 
 def _emit(line, fd):
@@ -302,9 +350,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200")
+    ap.add_argument("--config", type=str, default="2", choices=sorted(CONFIGS),
+                    help="BASELINE config: 2 (= 3 per GPU; headline) or 4 (LocalEnhancer 1024x2048, side line)")
     ap.add_argument("--precision", type=str, default="bf16x3", help="primary precision mode (bf16x3 = fp32 parity)")
-    ap.add_argument("--no-alt", action="store_true", help="skip the secondary (plain bf16) measurement")
+    ap.add_argument("--no-alt", action="store_true", help="skip the secondary precision modes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the stock PyTorch / cuDNN legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args, out_fd)
@@ -312,6 +363,8 @@ def main():
         return main_torch_gpu(args, out_fd)
     if args.warmup < 3:
         args.warmup = 3
+    cfg = CONFIGS[args.config]
+    headline = args.config == "2"
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -324,26 +377,27 @@ def main():
     from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_batch
 
     pk, pk_kind = peaks()
-    batch = synthetic_batch(PER_GPU_BATCH, H, W, LABEL_NC, seed=1234 + rank)
+    pgb = cfg["per_gpu_batch"]
+    batch = synthetic_batch(pgb, cfg["H"], cfg["W"], LABEL_NC, seed=1234 + rank)
     batch_pinned = {k: v.pin_memory() for k, v in batch.items()}
     dev = torch.device("cuda", local)
     batch_dev = {k: v.to(dev) for k, v in batch.items()}
 
     results = {}
     # the alternate precision modes are a single-GPU side measurement; multi-GPU runs time the primary mode only
-    skip_alt = args.no_alt or world > 1
+    skip_alt = args.no_alt or world > 1 or not headline
     modes = [args.precision] + ([] if skip_alt else [p for p in ("bf16x3", "mixed", "bf16") if p != args.precision])
     roof = None
     for i, prec in enumerate(modes):
-        opt = Options(label_nc=LABEL_NC, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9,
-                      num_D=3, n_layers_D=3, ndf=64, gpu_ids=[local], precision=prec, name="bench")
+        opt = Options(gpu_ids=[local], precision=prec, name="bench", vgg_weights="random", **cfg["opt"])
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):
             model = create_model(opt).module
+        torch.cuda.reset_peak_memory_stats(dev)
         sampler = ClockSampler(local) if (rank == 0 and i == 0) else None
         results[prec] = run_mode(model, prec, batch_dev, batch_pinned, args.steps, args.warmup, world, rank, sampler)
-        if rank == 0:
+        if rank == 0 and headline:
             r = time_k1(model, pk, prec != "bf16")
             results[prec]["k1"] = r
             if i == 0:
@@ -353,37 +407,50 @@ def main():
 
     if rank == 0:
         prim = results[args.precision]
-        gb = PER_GPU_BATCH * world
+        gb = pgb * world
         value = gb / (prim["ms"] / 1e3)
-        cpu = None
-        if not args.no_cpu and world == 1:   # the CPU baseline leg runs on rank 0 at N=1 only
-            ips, ms, cores, sample = run_cpu(25.0, 1, 0)
-            cpu = dict(value=ips, unit="images/sec", cores=cores, kind="port", sample=sample)
-        roof["peak_source"] = "%s (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" % pk_kind
-        # whole-step tensor roofline against the sustained peak
-        step_flops = TFLOP_PER_IMAGE * PER_GPU_BATCH
-        line = dict(metric="mask2image train images/sec @512x1024", value=value, unit="images/sec", n_gpus=world,
+        cpu = tgpu = None
+        if headline and world == 1:   # the baseline legs run on rank 0 at N=1 only
+            if not args.no_cpu:
+                ips, ms, cores, sample = run_cpu()
+                cpu = dict(value=ips, unit="images/sec", cores=cores, kind="port", sample=sample, ms_per_step=ms)
+            if not args.no_torch_gpu:
+                tgpu = {}
+                for variant in ("tf32", "bf16_channels_last"):
+                    try:
+                        tgpu[variant] = torch_gpu_leg(variant, device_index=local)
+                    except Exception as e:  # noqa: BLE001 -- a baseline leg must never take the product line down
+                        tgpu[variant] = dict(unavailable="%s: %s" % (type(e).__name__, str(e)[:200]))
+                t32 = tgpu["tf32"].get("ms_per_step")
+                if t32:
+                    tgpu["speedup_vs_tf32"] = t32 / prim["ms"]
+        dtype = {"bf16x3": "bf16x3 (bf16 hi/lo split operands, 3 tcgen05 products, fp32 accumulate; fp32-parity mode)",
+                 "mixed": "mixed (bf16x3 forward, single-product bf16 gradient GEMMs, fp32 accumulate)",
+                 "bf16": "bf16 (fp32 accumulate)"}[args.precision]
+        line = dict(metric=cfg["metric"], value=value, unit="images/sec", n_gpus=world,
                     steps=args.steps, warmup=args.warmup, ms_per_step=prim["ms"], higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="bf16x3 (bf16 hi/lo split operands, 3 tcgen05 products, fp32 accumulate; "
-                    "fp32-parity mode)" if args.precision == "bf16x3" else "bf16 (fp32 accumulate)", data="synthetic",
-                    config=workload_desc(world), clocks=prim["clocks"],
+                    vs_baseline=None, dtype=dtype, data="synthetic",
+                    config=workload_desc(world, args.config), clocks=prim["clocks"],
                     e2e=dict(value=gb / (prim["ms_e2e"] / 1e3), unit="images/sec", h2d_bytes_per_step=prim["h2d"],
                              d2h_bytes_per_step=prim["d2h"], ms_per_step=prim["ms_e2e"]),
-                    gpu_launches=prim["launches"], roofline=roof, cpu_baseline=cpu,
-                    step_tensor_roofline=dict(algorithmic_tflop_per_step=step_flops,
-                                              achieved_tflops=step_flops / (prim["ms"] / 1e3),
-                                              peak_sustained=pk.get("bf16_tflops_sustained"),
-                                              frac=step_flops / (prim["ms"] / 1e3) / pk.get("bf16_tflops_sustained", 1400.0)),
+                    gpu_launches=prim["launches"], cuda_graph=prim["graph"], peak_mem_gb=prim["peak_mem_gb"],
                     losses_last_step=prim["losses"])
+        if world > 1:
+            line["replicas_identical"] = prim["replicas_identical"]
+        if headline:
+            roof["peak_source"] = "%s (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" % pk_kind
+            step_flops = TFLOP_PER_IMAGE * pgb     # whole-step tensor roofline against the sustained peak
+            line.update(roofline=roof, cpu_baseline=cpu, torch_gpu=tgpu,
+                        step_tensor_roofline=dict(algorithmic_tflop_per_step=step_flops,
+                                                  achieved_tflops=step_flops / (prim["ms"] / 1e3),
+                                                  peak_sustained=pk.get("bf16_tflops_sustained"),
+                                                  frac=step_flops / (prim["ms"] / 1e3) / pk.get("bf16_tflops_sustained", 1400.0)))
         for prec in modes[1:]:
             r = results[prec]
             line["alt_precision_" + prec] = dict(value=gb / (r["ms"] / 1e3), unit="images/sec", ms_per_step=r["ms"],
                                                  e2e=gb / (r["ms_e2e"] / 1e3), gpu_launches=r["launches"],
                                                  k1_tflops=r["k1"]["achieved"], k1_frac=r["k1"]["frac"],
-                                                 note=("forward bf16x3 (outputs / losses within the fp32 tolerance), gradient GEMMs "
-                                                       "single bf16 products" if prec == "mixed" else
-                                                       "plain bf16 products: NOT within the 1e-3 fp32 tolerance "
-                                                       "(generator output ~1e-2 rel); reported for reference"))
+                                                 note=MODE_NOTES[prec])
         sys.stdout.flush()
         _emit(line, out_fd)
     if world > 1:
@@ -391,6 +458,14 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+MODE_NOTES = {
+    "bf16x3": "fp32-parity mode: every product as 3 split bf16 products",
+    "mixed": "forward bf16x3 (outputs / losses within the 1e-3 fp32 tolerance), gradient GEMMs single bf16 products; "
+             "trajectory evidence: tests/test_trajectory_gpu.py, DESIGN.md section 4",
+    "bf16": "plain bf16 products: NOT within the 1e-3 fp32 tolerance (generator output ~1e-2 rel); reported for reference",
+}
 
 
 if __name__ == "__main__":

@@ -31,7 +31,7 @@ def main():
     torch.cuda.set_device(local)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-    opt = Options(name="synthetic_city", model="pix2pixHD_condImg", label_nc=35, output_nc=3, no_instance=True,
+    opt = Options(vgg_weights="random", name="synthetic_city", model="pix2pixHD_condImg", label_nc=35, output_nc=3, no_instance=True,
                   netG="global_twostream", which_encoder="ctx_label", use_skip=True, use_output_gate=True, no_imgCond=True,
                   mask_gan_input=True, n_downsample_global=4, n_layers_D=3, batchSize=args.batchSize, gpu_ids=[local],
                   precision=args.precision, checkpoints_dir="./checkpoints")

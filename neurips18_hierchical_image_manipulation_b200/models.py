@@ -46,7 +46,10 @@ class Options(object):
                  # extensions of this implementation (not reference flags)
                  precision="bf16x3",      # "bf16x3": fp32-parity mode; "mixed": bf16x3 forward + bf16 gradient GEMMs;
                                           # "bf16": single-product tensor-core mode
-                 vgg_seed=1234,           # seeded random VGG19 (no network for the ImageNet weights)
+                 vgg_weights=None,        # path of a torchvision vgg19 state dict ('features.N.*' keys) for VGGLoss
+                                          # (layer_util.py:384 uses the ImageNet weights); None: $HM_VGG19_WEIGHTS, then
+                                          # torch hub's cache; "random": seeded random stand-in (bench / parity tests)
+                 vgg_seed=1234,           # seed of that stand-in
                  cuda_graph=True,         # optimize_parameters(): capture the fused step in a CUDA graph after two eager
                                           # steps and replay it (same kernels, no per-launch host work / launch gaps)
                  sn_D=False)              # K13: spectral-norm the PatchGAN convs (models/sn_utils.py SNConv2d); the
@@ -225,7 +228,8 @@ class Pix2PixHDModel_condImg(object):
             self.d_img_c0 = netD_input_nc - opt.output_nc      # first image channel of the D operand
             self.fpD = FlatParams(dev)
             self.netD = MultiscaleDiscriminator(self.ctx, self.fpD, netD_input_nc, opt.ndf, opt.n_layers_D, opt.num_D,
-                                                spectral_norm=getattr(opt, "sn_D", False))
+                                                spectral_norm=getattr(opt, "sn_D", False),
+                                                getIntermFeat=not opt.no_ganFeat_loss)   # :75 (state-dict key names)
         # one flat buffer [G | D] so data parallelism is a single allreduce
         total = self.fpG.total + (self.fpD.total if self.isTrain else 0)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -255,7 +259,7 @@ class Pix2PixHDModel_condImg(object):
             self.old_lr = opt.lr
             self.vgg = None
             if not opt.no_vgg_loss:
-                self.vgg = Vgg19(self.ctx, random_vgg19_state_dict(getattr(opt, "vgg_seed", 1234)))
+                self.vgg = Vgg19(self.ctx, load_vgg19_state_dict(opt))
             self.loss_names = list(LOSS_NAMES)
             groups = None
             if opt.niter_fix_global > 0 and opt.netG == "local":
@@ -279,12 +283,18 @@ class Pix2PixHDModel_condImg(object):
         if t.is_cuda:
             return t.to(self.device, torch.float32).contiguous()
         t = t.detach().to(torch.float32).contiguous()
-        buf = self._pinned.get(name)
-        if buf is None or buf.shape != t.shape:
-            buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
-            self._pinned[name] = buf
+        ent = self._pinned.get(name)
+        if ent is None or ent[0].shape != t.shape:
+            ent = (torch.empty(t.shape, dtype=torch.float32, pin_memory=True), torch.cuda.Event())
+            self._pinned[name] = ent
+        buf, ev = ent
+        # the previous step's asynchronous H2D copy out of this staging buffer may still be queued behind ~700 kernel
+        # launches: wait for it before overwriting the buffer (otherwise step N would train on step N+1's data)
+        ev.synchronize()
         buf.copy_(t)
-        return buf.to(self.device, non_blocking=True)
+        out = buf.to(self.device, non_blocking=True)
+        ev.record()
+        return out
 
     def encode_input(self, label_map, inst_map=None, real_image=None, mask_in=None, train=True, mask_out=None):
         """pix2pixHD_condImg_model.py:144-174 -> operands for G / D / VGG (K11)."""
@@ -414,10 +424,19 @@ class Pix2PixHDModel_condImg(object):
         self._step = st
         self._keep_visuals(st)
         self.flat_grad.zero_()
+        nG = self.fpG.total
+        scale = 1.0 / parallel.world()[1]
+        # the two allreduce segments run on the communicator's stream: G's overlaps the D backward pass, D's overlaps
+        # the generator's Adam step (the sum over both is the ONE [G | D] allreduce of SURVEY section 8(e))
         self._backward_G([1.0, 1.0, 1.0])
+        hG = parallel.allreduce_sum_async_(self.flat_grad[:nG])
         self._backward_D([0.5, 0.5])
-        scale = parallel.allreduce_sum_(self.flat_grad)
+        hD = parallel.allreduce_sum_async_(self.flat_grad[nG:])
+        if hG is not None:
+            hG.wait()
         self.optimizer_G.step(grad_scale=scale, captured=captured)
+        if hD is not None:
+            hD.wait()
         self.optimizer_D.step(grad_scale=scale, captured=captured)
         return st["losses"]
 
@@ -519,12 +538,26 @@ class Pix2PixHDModel_condImg(object):
                 raise RuntimeError("Generator must exist!")
             return
         sd = torch.load(save_path, map_location="cpu")
+        own = dict(fp.params)
+        own.update(fp.buffers)
         try:
+            # strict like nn.Module.load_state_dict: no missing, no unexpected, no mis-shaped entry (validated before
+            # anything is copied)
+            unexpected = [k for k in sd if k not in own]
+            if unexpected:
+                raise KeyError("unexpected keys: %s" % unexpected)
             fp.load_state_dict(sd, strict=True)
         except KeyError:
-            own = fp.params
-            usable = {k: v for k, v in sd.items() if k in own and tuple(v.shape) == tuple(own[k].shape)}
-            not_init = sorted({k.split(".")[0] for k in own if k not in usable})
+            # base_model.py:84-107: first try the entries this network knows ...
+            known = {k: v for k, v in sd.items() if k in own}
+            if all(k in known for k in fp.params) and all(v.numel() == own[k].numel() and (k in fp.buffers or tuple(
+                    v.shape) == tuple(own[k].shape)) for k, v in known.items()):
+                fp.load_state_dict(known, strict=True)
+                print("Pretrained network %s has excessive layers; Only loading layers that are used" % network_label)
+                return
+            # ... else every entry whose size matches; the rest keeps its initialisation
+            usable = {k: v for k, v in known.items() if tuple(v.shape) == tuple(own[k].shape)}
+            not_init = sorted({k.split(".")[0] for k in fp.params if k not in usable})
             print("Pretrained network %s has fewer layers; The following are not initialized:" % network_label)
             print(not_init)
             fp.load_state_dict(usable, strict=False)
@@ -557,6 +590,50 @@ class Pix2PixHDModel_condImg(object):
 
 
 # ------------------------------------------------------------------------------------------------------
+def load_vgg19_state_dict(opt):
+    """VGG19 weights for VGGLoss (layer_util.py:384: torchvision.models.vgg19(pretrained=True).features[0:30]).
+    opt.vgg_weights: path of a torchvision vgg19 state dict, or None to look at $HM_VGG19_WEIGHTS and torch hub's cache
+    (where torchvision leaves vgg19-dcbb9e9d.pth), or "random" for the seeded stand-in.  Without the real weights
+    G_VGG is computed on random features: fine for throughput and parity work, NOT the reference's training objective
+    -- hence the loud warning when the fallback is taken implicitly."""
+    path = getattr(opt, "vgg_weights", None)
+    seed = getattr(opt, "vgg_seed", 1234)
+    if path == "random":
+        return random_vgg19_state_dict(seed)
+    cands = [path] if path else [os.environ.get("HM_VGG19_WEIGHTS"),
+                                 os.path.join(torch.hub.get_dir(), "checkpoints", "vgg19-dcbb9e9d.pth")]
+    for c in cands:
+        if c and os.path.isfile(c):
+            return remap_torchvision_vgg19(torch.load(c, map_location="cpu"))
+    if path:
+        raise FileNotFoundError("opt.vgg_weights: %s does not exist" % path)
+    sys.stderr.write("WARNING: no ImageNet VGG19 weights found (opt.vgg_weights / $HM_VGG19_WEIGHTS / torch hub cache): "
+                     "VGGLoss uses a SEEDED RANDOM VGG19 -- G_VGG does not match the reference's training objective. "
+                     "Pass vgg_weights='random' to silence this for benchmarks and parity tests.\n")
+    return random_vgg19_state_dict(seed)
+
+
+def remap_torchvision_vgg19(tv_sd):
+    """torchvision vgg19 keys 'features.N.{weight,bias}' -> the reference Vgg19 module tree 'slice{K}.N.*'
+    (layer_util.py:388-399); classifier / deeper feature entries are dropped like features[0:30] does."""
+    sd = OrderedDict()
+    for idx, cin, cout in VGG19_CONVS:
+        for leaf in ("weight", "bias"):
+            src = "features.%d.%s" % (idx, leaf)
+            alt = "slice%d.%d.%s" % (VGG19_SLICE_OF[idx], idx, leaf)
+            if src in tv_sd:
+                t = tv_sd[src]
+            elif alt in tv_sd:
+                t = tv_sd[alt]
+            else:
+                raise KeyError("VGG19 state dict lacks %s" % src)
+            want = (cout, cin, 3, 3) if leaf == "weight" else (cout,)
+            if tuple(t.shape) != want:
+                raise KeyError("VGG19 %s has shape %s, expected %s" % (src, tuple(t.shape), want))
+            sd[alt] = t.detach().to(torch.float32).clone()
+    return sd
+
+
 def random_vgg19_state_dict(seed=1234):
     """Seeded stand-in for torchvision's ImageNet VGG19 (layer_util.py:384 downloads it; no network here):
     torchvision's own default init (kaiming_normal_ fan_out / relu, zero bias)."""

@@ -67,9 +67,15 @@ class FlatParams(object):
         return sd
 
     def load_state_dict(self, sd, strict=True):
+        """Nothing is copied unless every key that will be copied has the right shape (a failed load must not leave a
+        half-overwritten network behind); strict additionally requires every parameter to be present."""
         missing = [k for k in self.params if k not in sd]
         if strict and missing:
             raise KeyError("missing keys: %s" % missing)
+        bad = [k for k, p in self.params.items() if k in sd and tuple(sd[k].shape) != tuple(p.shape)]
+        bad += [k for k, b in self.buffers.items() if k in sd and sd[k].numel() != b.numel()]
+        if bad:
+            raise KeyError("size mismatch for: %s" % bad)
         with torch.no_grad():
             for k, p in self.params.items():
                 if k in sd:
@@ -419,22 +425,30 @@ class GlobalGenerator(object):
 class MultiscaleDiscriminator(object):
     """models/Discriminator_NET.py:11-118: num_D PatchGANs on an AvgPool(3,2,1) pyramid, every layer output kept."""
 
-    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3, spectral_norm=False):
+    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3, spectral_norm=False, getIntermFeat=True):
         self.ctx, self.fp = ctx, fp
         self.input_nc, self.n_layers, self.num_D = input_nc, n_layers, num_D
         self.spectral_norm = bool(spectral_norm)
         self._sn = None
         self.scales = []
+
+        def key(s, j):
+            # parameter names of the reference module tree (Discriminator_NET.py:24-29,99-106): per-layer Sequentials
+            # 'scale{s}_layer{j}.0' with getIntermFeat, else ONE flattened Sequential 'layer{s}' in which layer j's
+            # conv sits at index 0, 2, 5, 8, ... (conv [+ norm] + LeakyReLU per layer)
+            if getIntermFeat:
+                return "scale%d_layer%d.0" % (s, j)
+            return "layer%d.%d" % (s, 0 if j == 0 else 2 + 3 * (j - 1))
         for s in range(num_D):
             layers = []
             nf = ndf
-            layers.append(ConvP(ctx, fp, "scale%d_layer0.0" % s, input_nc, ndf, 4, 2, 2))
+            layers.append(ConvP(ctx, fp, key(s, 0), input_nc, ndf, 4, 2, 2))
             for n in range(1, n_layers):
                 nf_prev, nf = nf, min(nf * 2, 512)
-                layers.append(ConvP(ctx, fp, "scale%d_layer%d.0" % (s, n), nf_prev, nf, 4, 2, 2))
+                layers.append(ConvP(ctx, fp, key(s, n), nf_prev, nf, 4, 2, 2))
             nf_prev, nf = nf, min(nf * 2, 512)
-            layers.append(ConvP(ctx, fp, "scale%d_layer%d.0" % (s, n_layers), nf_prev, nf, 4, 1, 2))
-            layers.append(ConvP(ctx, fp, "scale%d_layer%d.0" % (s, n_layers + 1), nf, 1, 4, 1, 2))
+            layers.append(ConvP(ctx, fp, key(s, n_layers), nf_prev, nf, 4, 1, 2))
+            layers.append(ConvP(ctx, fp, key(s, n_layers + 1), nf, 1, 4, 1, 2))
             self.scales.append(layers)
 
     def convs(self):
@@ -486,7 +500,9 @@ class MultiscaleDiscriminator(object):
                 last = j == len(layers) - 1
                 if j == 0:
                     tap = _f32(ctx, cur.n, ho, wo, conv.cout)
-                    nxt = Operand(ctx, cur.n, ho, wo, conv.cout)
+                    # the conv epilogue writes channels [0, cout) only: zero the padding channels when cout % 8 != 0
+                    # (uninitialised bf16 NaN patterns x zero weights would poison the next GEMM)
+                    nxt = Operand(ctx, cur.n, ho, wo, conv.cout, zero=(conv.cout % 8 != 0))
                     conv.forward(cur, 2, act=ACT_LRELU, slope=0.2, out32=tap, out16=nxt)
                     lv["ys"].append(None); lv["means"].append(None); lv["rstds"].append(None)
                 elif last:
@@ -599,7 +615,7 @@ class Vgg19(object):
                 tape["pooled_from"][li] = cur
                 cur = pooled
             tape["xs"].append(cur)
-            out = Operand(ctx, cur.n, cur.h, cur.w, conv.cout)
+            out = Operand(ctx, cur.n, cur.h, cur.w, conv.cout, zero=(conv.cout % 8 != 0))
             tap = None
             if idx in VGG19_TAP_AFTER:
                 tap = _f32(ctx, cur.n, cur.h, cur.w, conv.cout)
@@ -629,7 +645,10 @@ class Vgg19(object):
             conv.dgrad(dy, xin.h, xin.w, 1, gin)
             if li in tape["pooled_from"]:
                 src = tape["pooled_from"][li]
-                dz = _f32(ctx, nb, src.h, src.w, src.c)
+                if (src.h | src.w) & 1:   # odd extent: the last row / column is outside every 2x2 window -> zero gradient
+                    dz = torch.zeros(nb, src.h, src.w, src.c, dtype=torch.float32, device=ctx.device)
+                else:
+                    dz = _f32(ctx, nb, src.h, src.w, src.c)
                 ops.maxpool2_bwd(ctx, gin, src, dz)
                 g = dz
             else:

@@ -22,6 +22,16 @@ def allreduce_sum_(flat, group=None):
     return 1.0 / n
 
 
+def allreduce_sum_async_(flat, group=None):
+    """Start an in-place sum-allreduce of `flat` on the communicator's own stream and return a handle whose .wait()
+    makes the CURRENT stream wait for it (None when there is a single rank).  The fused step starts the generator
+    segment right after the generator's backward pass so that it overlaps the discriminator's backward pass."""
+    _, n = world()
+    if n > 1:
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return None
+
+
 def allreduce_losses_(losses, group=None):
     """Mean of the per-rank loss scalars (what train_mask2image.py:68 computes over DataParallel replicas)."""
     _, n = world()

@@ -385,7 +385,7 @@ def train_step(opt, g_sd, d_sd, vgg_sd, batch, state=None, dtype=torch.float32):
             p = sd[k].to(dtype)
             adam_step(p, grads[k], state[mk][k], state[vk][k], state["step"], opt.lr, opt.beta1)
             sd[k].copy_(p)
-    return [float(l) for l in losses], fake.detach(), gG, gD, state
+    return [float(l.detach()) for l in losses], fake.detach(), gG, gD, state
 
 
 # --------------------------------------------------------------------------------------------------

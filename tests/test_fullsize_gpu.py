@@ -25,7 +25,7 @@ def _model(precision="bf16x3"):
     import io
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     opt = Options(label_nc=35, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9,
-                  num_D=3, gpu_ids=[0], precision=precision, name="full", checkpoints_dir="/tmp/hm_full")
+                  num_D=3, gpu_ids=[0], precision=precision, name="full", checkpoints_dir="/tmp/hm_full", vgg_weights="random")
     with contextlib.redirect_stdout(io.StringIO()):
         return create_model(opt).module
 
@@ -92,9 +92,17 @@ def test_fused_step_equals_script_sequence_and_modes_agree_full_size():
     assert dG < 0.05 * a.opt.lr * 10, dG
     del b2
     c = _model("bf16")
-    c.fpG.load_state_dict(a.fpG.state_dict())
+    c.fpG.load_state_dict(a.fpG.state_dict()); c.fpD.load_state_dict(a.fpD.state_dict())
+    la, _ = a.forward(infer=False, **kw)      # both modes at the same (post-step) weights
     lc, _ = c.forward(infer=False, **kw)
     torch.cuda.synchronize()
+    c.ctx.check_pipeline()
+    la = torch.stack([x.detach() for x in la])
+    lc = torch.stack([x.detach() for x in lc])
+    # plain bf16 products: every loss within 2e-2 (relative) of the bf16x3 / fp32-parity value on the same weights
+    e = ((lc - la).abs() / la.abs()).cpu()
+    assert float(e.max()) < 2e-2, (e.tolist(), la.tolist(), lc.tolist())
+    assert float(e.max()) > 0, "bf16 and bf16x3 cannot agree bitwise: the precision switch is not wired through"
 
 
 def test_resblock_conv_is_linear_at_full_size():

@@ -169,7 +169,8 @@ def test_training_step_against_the_reference_models_own_forward(golden_dir, name
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     z = np.load(os.path.join(golden_dir, name))
     part = lambda p: {k[len(p):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(p)}  # noqa: E731
-    opt = Options(precision="bf16x3", gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="golden", **optkw)
+    opt = Options(precision="bf16x3", gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="golden", vgg_weights="random",
+                  **optkw)
     model = create_model(opt)
     m = model.module
     m.fpG.load_state_dict(part("wG::"))

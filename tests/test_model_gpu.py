@@ -21,8 +21,9 @@ pytestmark = pytest.mark.gpu
 def _mk(precision, **kw):
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     base = dict(label_nc=5, ngf=8, n_downsample_global=2, n_blocks_global=2, ndf=8, num_D=2, n_layers_D=3,
-                no_instance=True, precision=precision, gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="t")
-    base.update(kw)
+                no_instance=True, precision=precision, gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="t",
+                vgg_weights="random")
+    base.update({k: v for k, v in kw.items() if k not in ("B", "H", "W", "d_keys")})
     opt = Options(**base)
     return opt, create_model(opt)
 
@@ -73,6 +74,9 @@ def run_parity(precision, verbose=False, **kw):
     res = dict(fake=rel(fake, fake_ref))
     for n, a, b in zip(m.loss_names, losses, ls_ref):
         res["loss_" + n] = abs(float(a) - b) / max(abs(b), 1e-30)
+        res["abs_" + n] = abs(float(a))
+    if kw.get("d_keys"):
+        res["d_keys"] = list(d_sd)
     def skip_bias(k, ref):
         """biases in front of an InstanceNorm: analytically zero gradient (exactly 0 here), fp32 rounding noise in the
         reference -- noise = below 1e-5 absolute or below 1e-3 of the same conv's weight gradient"""
@@ -88,8 +92,24 @@ def run_parity(precision, verbose=False, **kw):
         skip_bias(k, gG_ref[k]) for k in gG) else 0.0
     # parameters after the Adam step
     g_new, d_new = m.fpG.state_dict(), m.fpD.state_dict()
-    res["stepG"] = max(float((g_new[k] - g_ref[k]).abs().max()) for k in g_new) / opt.lr
-    res["stepD"] = max(float((d_new[k] - d_ref[k]).abs().max()) for k in d_new) / opt.lr
+    # Adam's FIRST step moves every weight by ~lr * sign(-grad) whatever the gradient's magnitude, so |new - ref| can
+    # never exceed 2 lr: a max-norm bound on it is vacuous.  What the first step does expose is the SIGN of every
+    # gradient element: fraction of elements (with a non-negligible reference gradient) whose update direction
+    # disagrees with the oracle's, and the mean step error in units of lr over the same elements.
+    def step_stats(new, ref_after, before, gref):
+        bad = tot = 0
+        err = 0.0
+        for k in new:
+            if skip_bias(k, gref[k]):
+                continue
+            sel = gref[k].abs() > 1e-3 * gref[k].abs().max()
+            dm, dr = (new[k] - before[k])[sel], (ref_after[k] - before[k])[sel]
+            bad += int((torch.sign(dm) != torch.sign(dr)).sum())
+            err += float((dm - dr).abs().sum()) / opt.lr
+            tot += int(sel.sum())
+        return bad / max(tot, 1), err / max(tot, 1)
+    res["stepG_sign"], res["stepG"] = step_stats(g_new, g_ref, g_sd, gG_ref)
+    res["stepD_sign"], res["stepD"] = step_stats(d_new, d_ref, d_sd, gD_ref)
     if verbose:
         worstG = sorted(((rel(gG[k], gG_ref[k]), k) for k in gG if not skip_bias(k, gG_ref[k])), reverse=True)[:5]
         worstD = sorted(((rel(gD[k], gD_ref[k]), k) for k in gD if not skip_bias(k, gD_ref[k])), reverse=True)[:5]
@@ -105,9 +125,10 @@ def test_parity_bf16x3_global():
         if k.startswith("loss_"):
             assert v < 1e-3, (k, r)
     assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
-    # Adam moves every weight by at most lr on the first step; the two implementations must agree to a small
-    # fraction of that (sign flips of ~zero gradients excepted, hence the loose bound)
-    assert r["stepG"] < 2.1 and r["stepD"] < 2.1, r
+    # first Adam step: update directions agree element-wise with the oracle's (a wrong-signed gradient would give a
+    # disagreement fraction near 1 and a mean step error near 2 lr)
+    assert r["stepG_sign"] < 5e-3 and r["stepD_sign"] < 5e-3, r
+    assert r["stepG"] < 2e-2 and r["stepD"] < 2e-2, r
 
 
 def test_parity_bf16x3_gate_instance_rec():
@@ -186,6 +207,171 @@ def test_parity_bf16_mode():
     for k, v in r.items():
         if k.startswith("loss_"):
             assert v < 5e-2, (k, r)
+
+
+def test_parity_bf16x3_no_vgg_loss():
+    """--no_vgg_loss (pix2pixHD_condImg_model.py:245): no VGG tower, G_VGG == 0, gradients from the GAN terms only."""
+    r = run_parity("bf16x3", no_vgg_loss=True)
+    assert r["fake"] < 1e-3, r
+    for k in ("loss_G_GAN", "loss_G_GAN_Feat", "loss_D_real", "loss_D_fake"):
+        assert r[k] < 1e-3, (k, r)
+    assert r["abs_G_VGG"] == 0.0, r
+    assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
+    assert r["stepG_sign"] < 5e-3 and r["stepD_sign"] < 5e-3, r
+
+
+def test_parity_bf16x3_no_ganFeat_loss():
+    """--no_ganFeat_loss (:235): G_GAN_Feat == 0; the discriminator's state dict uses the reference's flattened
+    'layer{i}.{k}' key names of getIntermFeat=False (Discriminator_NET.py:28-29)."""
+    r = run_parity("bf16x3", no_ganFeat_loss=True, d_keys=True)
+    assert r["fake"] < 1e-3, r
+    for k in ("loss_G_GAN", "loss_G_VGG", "loss_D_real", "loss_D_fake"):
+        assert r[k] < 1e-3, (k, r)
+    assert r["abs_G_GAN_Feat"] == 0.0, r
+    assert r["gradG"] < 1e-2 and r["gradD"] < 1e-2, r
+    assert sorted(r["d_keys"])[:4] == ["layer0.0.bias", "layer0.0.weight", "layer0.11.bias", "layer0.11.weight"], r["d_keys"][:6]
+
+
+def _kw(bt):
+    return dict(label=bt["label"], inst=bt["inst"], image=bt["image"], feat=None, mask_in=bt["mask_in"],
+                mask_out=bt["mask_out"])
+
+
+def test_update_learning_rate_recaptures_the_graph_and_matches_eager():
+    """update_learning_rate (:319-327): linear decay by lr / niter_decay on both optimizers; the captured CUDA graph
+    bakes the learning rate in, so it must be re-captured, and the replayed steps must train like eager steps."""
+    opt, model_a = _mk("bf16x3", cuda_graph=True, niter_decay=4)
+    _, model_b = _mk("bf16x3", cuda_graph=False, niter_decay=4)
+    a, b = model_a.module, model_b.module
+    b.fpG.load_state_dict(a.fpG.state_dict()); b.fpD.load_state_dict(a.fpD.state_dict())
+    bt = O.synthetic_batch(2, 64, 64, label_nc=opt.label_nc, seed=3)
+    for _ in range(4):
+        a.optimize_parameters(**_kw(bt)); b.optimize_parameters(**_kw(bt))
+    g0 = a._graph
+    assert isinstance(g0, dict), "the fused step was not captured"
+    for mm in (a, b):
+        mm.update_learning_rate()
+        assert abs(mm.old_lr - (opt.lr - opt.lr / 4)) < 1e-12
+        assert all(abs(g["lr"] - mm.old_lr) < 1e-12 for g in mm.optimizer_G.param_groups + mm.optimizer_D.param_groups)
+    before = a.flat.clone()
+    for i in range(3):
+        la = a.optimize_parameters(**_kw(bt)).clone(); lb = b.optimize_parameters(**_kw(bt)).clone()
+        torch.cuda.synchronize()
+        assert torch.allclose(la.cpu(), lb.cpu(), rtol=5e-3, atol=1e-5), (i, la, lb)
+    assert isinstance(a._graph, dict) and a._graph is not g0, "the graph was not re-captured after the LR change"
+    assert a._graph["sig"][1] == (a.old_lr,)
+    a.ctx.check_pipeline()
+    d = (a.flat - b.flat).abs()
+    assert float(d.max()) < 2.5e-3 and float(d.mean()) < 2e-5, (float(d.max()), float(d.mean()))
+    # step 5 (bias correction ~1): the per-step displacement scales with the learning rate
+    moved = float((a.flat - before).abs().max())
+    assert moved < 3 * 3 * a.old_lr * 1.5, moved
+    # lr -> 0 freezes the weights exactly (4 decays of lr / 4)
+    for _ in range(3):
+        a.update_learning_rate()
+    assert abs(a.old_lr) < 1e-12
+    frozen = a.flat.clone()
+    a.optimize_parameters(**_kw(bt))
+    torch.cuda.synchronize()
+    assert torch.equal(a.flat, frozen)
+
+
+def test_niter_fix_global_param_groups_and_update_fixed_params():
+    """niter_fix_global (:122-130): only 'model{n_local_enhancers}*' parameters train (lr) while the global trunk has
+    lr 0; update_fixed_params (:311-317) then builds a fresh Adam over the whole generator."""
+    opt, model = _mk("bf16x3", netG="local", ngf=4, n_downsample_global=2, n_blocks_global=2, n_local_enhancers=1,
+                     n_blocks_local=2, num_D=2, no_instance=False, niter_fix_global=1)
+    m = model.module
+    lrs = {g["lr"] for g in m.optimizer_G.param_groups}
+    assert lrs == {0.0, opt.lr}
+    for g in m.optimizer_G.param_groups:     # groups partition the flat buffer by the reference's name rule
+        names = [k for k, p in m.fpG.params.items() if any(p is q for q in g["params"])]
+        assert names and all(k.startswith("model1") == (g["lr"] > 0) for k in names), (g["lr"], names[:3])
+    bt = O.synthetic_batch(1, 64, 96, label_nc=opt.label_nc, seed=5)
+    before = {k: p.detach().clone() for k, p in m.fpG.params.items()}
+    for _ in range(3):                       # eager, eager, captured graph
+        m.optimize_parameters(**_kw(bt))
+    torch.cuda.synchronize()
+    for k, p in m.fpG.params.items():
+        same = torch.equal(p.detach(), before[k])
+        if k.startswith("model1"):
+            assert not same or k.endswith("bias"), k    # (biases in front of an InstanceNorm have zero gradient)
+        else:
+            assert same, k
+    m.update_fixed_params()
+    assert len(m.optimizer_G.param_groups) == 1 and m.optimizer_G.param_groups[0]["lr"] == opt.lr
+    assert m.optimizer_G.step_count == 0 and float(m.optimizer_G.m.abs().max()) == 0.0     # fresh Adam state
+    mid = {k: p.detach().clone() for k, p in m.fpG.params.items()}
+    for _ in range(3):
+        m.optimize_parameters(**_kw(bt))
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    moved = [k for k, p in m.fpG.params.items() if k.endswith("weight") and not torch.equal(p.detach(), mid[k])]
+    assert any(k.startswith("model.") for k in moved) and any(k.startswith("model1") for k in moved)
+    assert len(moved) == sum(1 for k in mid if k.endswith("weight"))
+
+
+def test_delete_model_removes_both_checkpoints(tmp_path):
+    opt, model = _mk("bf16x3", checkpoints_dir=str(tmp_path))
+    m = model.module
+    m.save("7")
+    files = [os.path.join(str(tmp_path), "t", "7_net_%s.pth" % x) for x in "GD"]
+    assert all(os.path.isfile(f) for f in files)
+    m.delete_model("7")
+    assert not any(os.path.isfile(f) for f in files)
+    m.delete_model("7")     # deleting a missing epoch is a no-op, as in base_model.py:68-72
+
+
+def test_load_network_falls_back_like_the_reference(tmp_path, capsys):
+    """base_model.py:84-107: a checkpoint with extra entries loads the known ones; one with missing / mis-shaped
+    entries loads what matches, reports the rest, and never leaves a half-copied network behind."""
+    opt, model = _mk("bf16x3", checkpoints_dir=str(tmp_path))
+    m = model.module
+    sd = m.fpG.state_dict()
+    path = os.path.join(str(tmp_path), "t")
+    os.makedirs(path, exist_ok=True)
+    extra = dict(sd); extra["model.99.weight"] = torch.zeros(3)
+    torch.save(extra, os.path.join(path, "x_net_G.pth"))
+    with torch.no_grad():
+        m.fpG.flat.add_(1.0)
+    m.load_network(m.fpG, "G", "x")
+    assert "excessive layers" in capsys.readouterr().out
+    assert all(torch.equal(p.detach().cpu(), sd[k]) for k, p in m.fpG.params.items())
+    bad = dict(sd); bad["model.1.weight"] = torch.zeros(8, 9, 7, 7); del bad["model.4.bias"]
+    torch.save(bad, os.path.join(path, "y_net_G.pth"))
+    with torch.no_grad():
+        m.fpG.flat.add_(1.0)
+    keep = {k: p.detach().cpu().clone() for k, p in m.fpG.params.items()}
+    m.load_network(m.fpG, "G", "y")
+    out = capsys.readouterr().out
+    assert "fewer layers" in out and "model" in out
+    for k, p in m.fpG.params.items():
+        want = keep[k] if k in ("model.1.weight", "model.4.bias") else sd[k]
+        assert torch.equal(p.detach().cpu(), want), k
+    with pytest.raises(RuntimeError):
+        m.load_network(m.fpG, "G", "does_not_exist")
+
+
+def test_weights_init_statistics():
+    """A10 weights_init (layer_util.py:9-16): conv weights ~ N(0, 0.02); biases keep torch's Conv2d default
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in))."""
+    opt, model = _mk("bf16x3", ngf=32, ndf=32)
+    m = model.module
+    allw = torch.cat([p.detach().reshape(-1) for k, p in list(m.fpG.params.items()) + list(m.fpD.params.items())
+                      if k.endswith("weight")]).double().cpu()
+    assert abs(float(allw.mean())) < 2e-4 and abs(float(allw.std()) - 0.02) < 4e-4
+    kurt = float(((allw - allw.mean()) ** 4).mean() / allw.var() ** 2)
+    assert abs(kurt - 3.0) < 0.1, kurt                       # normal, not uniform (1.8)
+    for fp, net in ((m.fpG, m.netG), (m.fpD, m.netD)):
+        for c in net.convs():
+            w, b = c.weight.detach(), c.bias.detach()
+            if w.numel() >= 4096:
+                assert abs(float(w.std()) - 0.02) < 0.002, c.name
+            fan_in = w.shape[1] * c.k * c.k
+            bound = 1.0 / fan_in ** 0.5
+            assert float(b.abs().max()) <= bound * (1 + 1e-6), c.name
+            if b.numel() >= 32:
+                assert float(b.abs().max()) > 0.6 * bound and abs(float(b.mean())) < 0.5 * bound, c.name
 
 
 def test_fused_step_matches_script_sequence():

@@ -16,7 +16,7 @@ from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_bat
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-opt = Options(label_nc=35, no_instance=True, netG="global_twostream", which_encoder="ctx_label", use_skip=True,
+opt = Options(vgg_weights="random", label_nc=35, no_instance=True, netG="global_twostream", which_encoder="ctx_label", use_skip=True,
               use_output_gate=True, no_imgCond=True, mask_gan_input=True, ngf=64, n_downsample_global=4, n_blocks_global=9,
               num_D=2, n_layers_D=3, gpu_ids=[0], precision=prec, name="shipped")
 with contextlib.redirect_stdout(io.StringIO()):

@@ -7,7 +7,7 @@ from oracle import model as O
 import torch.nn.functional as F
 H, W = int(sys.argv[1]), int(sys.argv[2])
 ngf = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-opt = Options(label_nc=35, no_instance=True, netG="global", ngf=ngf, n_downsample_global=2, n_blocks_global=1, num_D=3,
+opt = Options(vgg_weights="random", label_nc=35, no_instance=True, netG="global", ngf=ngf, n_downsample_global=2, n_blocks_global=1, num_D=3,
               gpu_ids=[0], precision="bf16x3", name="fg", checkpoints_dir="/tmp/hm_fg")
 with contextlib.redirect_stdout(io.StringIO()):
     m = create_model(opt).module

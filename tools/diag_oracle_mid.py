@@ -7,7 +7,7 @@ from neurips18_hierchical_image_manipulation_b200.models import Options, create_
 from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_batch
 from oracle import model as O
 H, W = int(sys.argv[1]) if len(sys.argv) > 1 else 128, int(sys.argv[2]) if len(sys.argv) > 2 else 256
-opt = Options(label_nc=35, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9, num_D=3,
+opt = Options(vgg_weights="random", label_nc=35, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9, num_D=3,
               gpu_ids=[0], precision="bf16x3", name="mid", checkpoints_dir="/tmp/hm_mid")
 with contextlib.redirect_stdout(io.StringIO()):
     m = create_model(opt).module

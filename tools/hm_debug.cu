@@ -1,6 +1,7 @@
-// hm_debug.cu -- micro-benchmarks used while tuning the engines (not on the product path).
-#include "hm_ptx.cuh"
-#include "hm_engine2.cuh"
+// hm_debug.cu -- micro-benchmarks used while tuning the engines (NOT part of libhm_b200.so: tools/mma_issue_bench.py
+// compiles this file into tools/libhm_debug.so on demand).
+#include "../neurips18_hierchical_image_manipulation_b200/csrc/hm_ptx.cuh"
+#include "../neurips18_hierchical_image_manipulation_b200/csrc/hm_engine2.cuh"
 
 namespace {
 // one CTA issues `count` back-to-back tcgen05.mma (M=128, N, K=16) on arbitrary smem and reports

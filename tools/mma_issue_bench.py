@@ -1,7 +1,12 @@
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from neurips18_hierchical_image_manipulation_b200 import _lib
-lib = C.CDLL(_lib.LIB_PATH)
+import subprocess
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libhm_debug.so")
+if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(os.path.join(HERE, "hm_debug.cu")):
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
+                           "-Xcompiler", "-fPIC", "-shared", "-o", SO, os.path.join(HERE, "hm_debug.cu"), "-lcudart"])
+lib = C.CDLL(SO)
 lib.hm_debug_mma_issue.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 for n in (16, 64, 256):

@@ -15,7 +15,7 @@ prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 warmup = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 4
-opt = Options(label_nc=35, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9, num_D=3,
+opt = Options(vgg_weights="random", label_nc=35, no_instance=True, netG="global", ngf=64, n_downsample_global=4, n_blocks_global=9, num_D=3,
               gpu_ids=[0], precision=prec, name="prof")
 with contextlib.redirect_stdout(io.StringIO()):
     m = create_model(opt).module
