@@ -52,6 +52,8 @@ class Options(object):
                  vgg_seed=1234,           # seed of that stand-in
                  cuda_graph=True,         # optimize_parameters(): capture the fused step in a CUDA graph after two eager
                                           # steps and replay it (same kernels, no per-launch host work / launch gaps)
+                 data_parallel=True,      # under torch.distributed: allreduce the gradients over all ranks (False: this
+                                          # replica trains on its own -- used by the multi-GPU equivalence check)
                  sn_D=False)              # K13: spectral-norm the PatchGAN convs (models/sn_utils.py SNConv2d); the
                                           # reference's MultiscaleDiscriminator uses plain convs, so default off
         d.update(kw)
@@ -96,6 +98,7 @@ class FusedAdam(object):
         # param_groups: list of dicts with 'lr' and a [begin, end) range of the flat buffer
         self.param_groups = groups if groups is not None else [dict(lr=lr, begin=0, end=fp.total, params=list(fp.params.values()))]
         self.dist_group = dist_group
+        self.data_parallel = True
         self.grads_reduced = False
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=fp.flat.device)  # step count for captured steps
 
@@ -104,6 +107,8 @@ class FusedAdam(object):
         self.grads_reduced = False
 
     def allreduce(self):
+        if not self.data_parallel:
+            return 1.0
         if not self.grads_reduced:
             parallel.allreduce_sum_(self.fp.grad, self.dist_group)
             self.grads_reduced = True
@@ -267,6 +272,7 @@ class Pix2PixHDModel_condImg(object):
                 groups = self.netG.param_groups(opt.lr, opt.n_local_enhancers)
             self.optimizer_G = FusedAdam(self.ctx, self.fpG, opt.lr, (opt.beta1, 0.999), groups=groups)
             self.optimizer_D = FusedAdam(self.ctx, self.fpD, opt.lr, (opt.beta1, 0.999))
+            self.optimizer_G.data_parallel = self.optimizer_D.data_parallel = getattr(opt, "data_parallel", True)
             self.loss_acc = torch.zeros(5, dtype=torch.float64, device=dev)
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._step = None
@@ -425,13 +431,14 @@ class Pix2PixHDModel_condImg(object):
         self._keep_visuals(st)
         self.flat_grad.zero_()
         nG = self.fpG.total
-        scale = 1.0 / parallel.world()[1]
+        dp = getattr(self.opt, "data_parallel", True) and parallel.world()[1] > 1
+        scale = 1.0 / parallel.world()[1] if dp else 1.0
         # the two allreduce segments run on the communicator's stream: G's overlaps the D backward pass, D's overlaps
         # the generator's Adam step (the sum over both is the ONE [G | D] allreduce of SURVEY section 8(e))
         self._backward_G([1.0, 1.0, 1.0])
-        hG = parallel.allreduce_sum_async_(self.flat_grad[:nG])
+        hG = parallel.allreduce_sum_async_(self.flat_grad[:nG]) if dp else None
         self._backward_D([0.5, 0.5])
-        hD = parallel.allreduce_sum_async_(self.flat_grad[nG:])
+        hD = parallel.allreduce_sum_async_(self.flat_grad[nG:]) if dp else None
         if hG is not None:
             hG.wait()
         self.optimizer_G.step(grad_scale=scale, captured=captured)
@@ -575,6 +582,7 @@ class Pix2PixHDModel_condImg(object):
     def update_fixed_params(self):
         """:311-317: after niter_fix_global epochs, train the whole generator (fresh Adam state, as the reference)."""
         self.optimizer_G = FusedAdam(self.ctx, self.fpG, self.opt.lr, (self.opt.beta1, 0.999))
+        self.optimizer_G.data_parallel = getattr(self.opt, "data_parallel", True)
         print("------------ Now also finetuning global generator -----------")
 
     def update_learning_rate(self):
