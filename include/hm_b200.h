@@ -47,6 +47,9 @@ typedef struct hm_operand {
   const void* lo; /* NULL => single bf16 product */
   int n, h, w, c; /* c = valid channels */
   int cs;         /* channel stride in elements, multiple of 8 */
+  int lo_c0;      /* channels [0, lo_c0) are exactly representable in bf16 (their lo plane is all zero, e.g. the one-hot
+                   * label map of pix2pixHD_condImg_model.py:151-152): the engines skip the lo product there.  0 = no
+                   * such guarantee.  Zero padding channels (>= c) are skipped at 16-channel granularity likewise. */
 } hm_operand;
 
 /* destination of an engine epilogue: element (n, y, x, ch) of the logical result is written to

@@ -18,7 +18,7 @@ class HmError(RuntimeError):
 
 class Operand(C.Structure):
     _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int),
-                ("c", C.c_int), ("cs", C.c_int)]
+                ("c", C.c_int), ("cs", C.c_int), ("lo_c0", C.c_int)]
 
 
 class OutF32(C.Structure):

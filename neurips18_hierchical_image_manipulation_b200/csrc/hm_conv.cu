@@ -280,6 +280,8 @@ int run_rows_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int
   }
   p.n_entries = ne;
   p.chunks = k_pad / 64;
+  p.a_c = x->c;
+  p.a_lo_c0 = std::max(0, std::min(x->lo_c0, x->c));
   p.stage_bytes = hm::RCfgCommon::A_PLANE + kw * bn * 128;
   p.n_stages = std::min(hm::RCfgCommon::MAX_STAGES, hm::RCfgCommon::SMEM_BUDGET / p.stage_bytes);
   if (p.n_stages < 2) return HM_ERR_INVALID;
@@ -398,6 +400,9 @@ int run_mnrows(const hm_operand* P, const hm_operand* Q, int KH, int KW, int pad
 bool mnrows_eligible(const hm_operand* P, const hm_operand* Q, int KW, int stride) {
   static const int enabled = env_int("HM_ROWS", 1);
   if (!enabled || stride != 1 || KW < 2 || KW > 8 || Q->w < 96) return false;
+  // wide layers (>= 4 units on both sides: e.g. the stride-1 256 -> 512 PatchGAN layer at full resolution) belong to the
+  // CTA-pair MN-engine: 85 % tensor pipe there against ~40 % for the row-streaming kernel with its 128 x 128 tiles
+  if (round_up(Q->c, 64) / 64 >= 4 && KW * ((P->c + 63) / 64) >= 4) return false;
   const int nb = round_up(Q->c, 64) / 64 >= 2 ? 2 : 1;
   return ((KW + 1) / 2) * nb * 64 <= 512;
 }
@@ -447,6 +452,8 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   }
   p.n_entries = ne;
   p.chunks = k_pad / 64;
+  p.a_c = x->c;
+  p.a_lo_c0 = std::max(0, std::min(x->lo_c0, x->c));
   p.tiles_w = (valid_w + tw - 1) / tw;
   p.tiles_h = (valid_h + th - 1) / th;
   p.n_img = x->n;

@@ -31,6 +31,7 @@ struct __align__(64) RParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB[2];     // 3-D: {k_pad, rows_pad, taps}
   int n_entries, chunks;
+  int a_c, a_lo_c0;       // valid channels of A; channels [0, a_lo_c0) have an all-zero lo plane (hm_operand.lo_c0)
   int kw;                 // taps per filter row (tiles per B box)
   int n_stages;           // pipeline depth (runtime: depends on kw and BN)
   int stage_bytes;        // A_PLANE + kw * BN * 128
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
         uint32_t acc = 0;
         for (int c = 0; c < p.chunks; ++c) {
           for (int e = 0; e < p.n_entries; ++e) {
+            int k0, k1;
+            k_groups(p.a_c, p.a_lo_c0, p.entries[e].a_plane, c, k0, k1);
             mbar_wait(&full[s], ph, ab, 304);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
@@ -142,12 +145,11 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
               for (int j = 0; j < p.kw; ++j) {
                 const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
                 const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
+                for (int k = k0; k < k1; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
               }
               umma_commit(&empty[s]);
             }
-            acc = 1;
+            if (k1 > k0) acc = 1;
             if (++s == nst) { s = 0; ph ^= 1; }
           }
         }
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __gr
       uint32_t acc = 0;
       for (int c = 0; c < p.chunks; ++c) {
         for (int e = 0; e < p.n_entries; ++e) {
+          int k0, k1;
+          k_groups(p.a_c, p.a_lo_c0, p.entries[e].a_plane, c, k0, k1);
           mbar_wait(&bfull[bs], bph, ab, 704);
           const uint32_t b_base = smem_u32(smem_b + bs * b_stage_bytes);
           for (int r = 0; r < MT; ++r) {
@@ -314,8 +318,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __gr
               for (int j = 0; j < p.kw; ++j) {
                 const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
                 const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
+                for (int k = k0; k < k1; ++k) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
               }
               umma_commit(&aempty[as]);
             }
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __gr
           }
           if (elect_one_sync()) umma_commit(&bempty[bs]);
           if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
-          acc = 1;
+          if (k1 > k0) acc = 1;
         }
       }
       if (elect_one_sync()) umma_commit(&tfull[a]);

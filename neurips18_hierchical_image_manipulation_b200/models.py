@@ -321,6 +321,12 @@ class Pix2PixHDModel_condImg(object):
                 d_mask = self._to_device("mask_out", mask_out) if opt.use_soft_mask else mask
         ops.encode_input(ctx, label, inst, image, mask, opt.label_nc, g_in, d_in, v_in,
                          d_no_imgcond=bool(train and opt.no_imgCond), d_mask=d_mask)
+        # the one-hot label map and the 0/1 instance edges are exact in bf16: no lo product over those channels
+        # (a soft D-input mask scales them to arbitrary values, so the guarantee does not hold for d_in then)
+        n_exact = opt.label_nc + (0 if opt.no_instance else 1)
+        g_in.lo_c0 = n_exact
+        if d_in is not None and not (d_mask is not None and opt.use_soft_mask):
+            d_in.lo_c0 = n_exact
         return dict(label=label, inst=inst, image=image, mask=mask, g_in=g_in, d_in=d_in, v_in=v_in, B=B, H=H, W=W,
                     d_mask=d_mask)
 
@@ -368,6 +374,7 @@ class Pix2PixHDModel_condImg(object):
         obj = Operand.__new__(Operand)
         obj.hi, obj.lo, obj.n, obj.h, obj.w, obj.cs, obj.border = g.hi, g.lo, g.n, g.h, g.w, g.cs, g.border
         obj.c = self.netG.input_nc
+        obj.lo_c0 = min(g.lo_c0, obj.c)
         ctx_in = ops.cond_image_operand(self.ctx, st["image"], st["mask"], 3)
         return self.netG.forward(ctx_in, obj, st["mask"])
 

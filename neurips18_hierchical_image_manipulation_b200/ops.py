@@ -53,7 +53,7 @@ class Ctx(object):
 class Operand(object):
     """bf16 (hi, lo) NHWC operand [n, h, w, cs] with c valid channels; h/w include `border`."""
 
-    __slots__ = ("hi", "lo", "n", "h", "w", "c", "cs", "border")
+    __slots__ = ("hi", "lo", "n", "h", "w", "c", "cs", "border", "lo_c0")
 
     def __init__(self, ctx, n, h, w, c, border=0, cs=None, zero=False, grad=False):
         cs = ru(c, 8) if cs is None else cs
@@ -63,13 +63,14 @@ class Operand(object):
         self.hi = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device)
         self.lo = alloc((n, hp, wp, cs), dtype=torch.bfloat16, device=ctx.device) if split else None
         self.n, self.h, self.w, self.c, self.cs, self.border = n, hp, wp, c, cs, border
+        self.lo_c0 = 0   # channels [0, lo_c0) hold values exact in bf16 (one-hot maps): lo plane zero there, engines skip it
 
     def struct(self, n0=0, n=None):
         """hm_operand for images [n0, n0+n)."""
         n = self.n - n0 if n is None else n
         off = n0 * self.h * self.w * self.cs * 2
         return L.Operand(self.hi.data_ptr() + off, (self.lo.data_ptr() + off) if self.lo is not None else None, n,
-                         self.h, self.w, self.c, self.cs)
+                         self.h, self.w, self.c, self.cs, getattr(self, "lo_c0", 0))
 
     @property
     def ih(self):

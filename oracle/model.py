@@ -157,8 +157,10 @@ def nlayer_discriminator_forward(sd, x, scale, n_layers=3):
     taps = []
     h = x
     for j in range(n_layers + 2):
-        w = sd["scale%d_layer%d.0.weight" % (scale, j)]
-        b = sd["scale%d_layer%d.0.bias" % (scale, j)]
+        k = "scale%d_layer%d.0." % (scale, j)
+        if k + "weight" not in sd:   # getIntermFeat=False naming: one flattened Sequential per scale (:28-29,99-106)
+            k = "layer%d.%d." % (scale, 0 if j == 0 else 2 + 3 * (j - 1))
+        w, b = sd[k + "weight"], sd[k + "bias"]
         stride = 2 if j < n_layers else 1
         h = F.conv2d(h, w, b, stride=stride, padding=2)
         if 1 <= j <= n_layers:
