@@ -60,6 +60,15 @@ typedef struct hm_out_bf16 { void* hi; void* lo; int H, W, C, h_off, w_off, c_of
 const char* hm_version(void);
 int hm_last_cuda_error(void); /* cudaError_t of the last failed runtime call on this thread */
 
+/* Optional device scratch for the engines (the library never allocates): hm_scratch_bytes() bytes, 256 B aligned,
+ * owned by the caller and kept alive until it is replaced (ptr == NULL unregisters).  With it the CTA-pair K-engine
+ * balances the last, partly filled wave of output tiles by splitting their contraction range over all SMs
+ * (deterministic two-phase stream-K: partial accumulators go to the scratch and are summed in a fixed order);
+ * without it the engines fall back to whole tiles.  One scratch per process: launches that use it must be ordered on
+ * one stream. */
+size_t hm_scratch_bytes(void);
+int hm_set_scratch(void* ptr, size_t bytes);
+
 /* ---- weight packing --------------------------------------------------------------------------
  * N-tile width the K-engine uses for `rows` output rows, and the padded slab dims. */
 int hm_pick_bn(int rows);

@@ -44,6 +44,8 @@ _P = C.POINTER
 PROTOTYPES = {
     "hm_version": (C.c_char_p, []),
     "hm_last_cuda_error": (_i, []),
+    "hm_scratch_bytes": (_sz, []),
+    "hm_set_scratch": (_i, [_vp, _sz]),
     "hm_pick_bn": (_i, [_i]),
     "hm_rows_pad": (_i, [_i]),
     "hm_k_pad": (_i, [_i]),

@@ -35,6 +35,11 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -107,7 +112,13 @@ int launch_k(const hm::KParams& p, int num_tiles, cudaStream_t st) {
   return HM_OK;
 }
 
-int launch_k2(const hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
+// scratch registered by the caller (hm_set_scratch): stream-K partial accumulators + arrival counters
+void* g_scratch = nullptr;
+size_t g_scratch_bytes = 0;
+constexpr size_t kSkSlotBytes = size_t(256) * 256 * sizeof(float);
+constexpr size_t kSkCounterBytes = 4096;
+
+int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(hm::hm_kgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -116,7 +127,27 @@ int launch_k2(const hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t
     configured = true;
   }
   const int pair_tiles = ((num_m_tiles + 1) / 2) * n_tiles_n;
-  const int clusters = std::min(pair_tiles, sm_count() / 2);
+  const int max_clusters = sm_count() / 2;
+  int clusters = std::min(pair_tiles, max_clusters);
+  // stream-K tail (hm_engine2.cuh): whole waves as tiles, the k-steps of the last partial wave dealt out evenly
+  static const int use_sk = env_int("HM_STREAMK", 1);
+  const int ksteps = p.n_entries * p.chunks;
+  const int waves = pair_tiles / max_clusters;
+  const int rem = pair_tiles - waves * max_clusters;
+  p.sk_full = p.sk_rem = p.sk_per = 0;
+  p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  const size_t need = kSkCounterBytes + size_t(max_clusters) * 2 * kSkSlotBytes;
+  if (use_sk && g_scratch && g_scratch_bytes >= need && rem > 0 && size_t(rem) * 2 * sizeof(int) <= kSkCounterBytes &&
+      rem * 10 <= max_clusters * 9 && (long(rem) * ksteps) / max_clusters >= 24) {
+    clusters = max_clusters;
+    p.sk_full = waves * max_clusters;
+    p.sk_rem = rem;
+    p.sk_per = int((long(rem) * ksteps + clusters - 1) / clusters);
+    p.sk_cnt = static_cast<int*>(g_scratch);
+    p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(g_scratch) + kSkCounterBytes);
+    cudaError_t e = cudaMemsetAsync(p.sk_cnt, 0, size_t(rem) * 2 * sizeof(int), st);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  }
   hm::hm_kgemm2_kernel<256><<<2 * clusters, hm::kEngineThreads, hm::K2Cfg::SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
@@ -208,11 +239,6 @@ int make_tmap_weight3(CUtensorMap* m, const void* base, int taps, int rows_pad, 
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? HM_OK : HM_ERR_TENSORMAP;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
 }
 
 struct Tap { int dw, dh, slab; };
@@ -483,7 +509,15 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
 
 extern "C" {
 
-const char* hm_version(void) { return "hm_b200 0.1 (sm_100a, tcgen05+TMA)"; }
+const char* hm_version(void) { return "hm_b200 0.2 (sm_100a, tcgen05+TMA)"; }
+
+size_t hm_scratch_bytes(void) { return kSkCounterBytes + size_t(sm_count() / 2) * 2 * kSkSlotBytes; }
+int hm_set_scratch(void* ptr, size_t bytes) {
+  if (ptr && (bytes < hm_scratch_bytes() || (reinterpret_cast<uintptr_t>(ptr) & 255))) return HM_ERR_INVALID;
+  g_scratch = ptr;
+  g_scratch_bytes = ptr ? bytes : 0;
+  return HM_OK;
+}
 int hm_last_cuda_error(void) { return g_last_cuda_error; }
 
 int hm_pick_bn(int rows) {

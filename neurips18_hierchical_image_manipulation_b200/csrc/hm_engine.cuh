@@ -45,6 +45,11 @@ struct __align__(64) KParams {
   const float* bias;
   int act; float slope;
   int* err;
+  // stream-K tail of the CTA-pair kernel (hm_engine2.cuh): pair tiles [0, sk_full) are processed whole, the k-steps of
+  // the remaining sk_rem tiles are dealt out evenly, sk_per per cluster (0 = plain persistent tile loop)
+  int sk_full, sk_rem, sk_per;
+  float* sk_ws;           // partial accumulators: [cluster][2 segments][256 rows][256 cols] fp32
+  int* sk_cnt;            // arrival counters [sk_rem][2 CTA ranks], zeroed by the host before the launch
   KEntry entries[kMaxEntries];
 };
 
@@ -240,8 +245,14 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
           const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
           if (elect_one_sync()) {
-            for (int j = j0; j < j1; ++j)  // (K = 16 bf16 = 32 B) groups inside the 128 B swizzle row
-              umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j > j0));
+            if (j0 == 0 && j1 == 4) {      // full chunk: keep the issue path unrolled (it is on the critical path)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
+                umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j != 0));
+            } else {
+              for (int j = j0; j < j1; ++j)
+                umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j > j0));
+            }
             umma_commit(&empty[s]);
           }
           if (j1 > j0) acc = 1;   // warp-uniform: every lane tracks whether the accumulator has been written

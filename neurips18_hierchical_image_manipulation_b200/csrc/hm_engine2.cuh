@@ -84,6 +84,65 @@ struct K2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Deterministic stream-K tail.  A persistent tile loop leaves the last wave partly empty: the residual-block conv
+// (K1: 128 pair tiles on 74 clusters = 1.73 waves) kept the tensor pipe busy for only 78 % of the elapsed cycles.  The
+// host therefore splits the work in two phases: pair tiles [0, sk_full) (whole waves) are processed as before; the
+// k-steps of the remaining sk_rem tiles are dealt out as ONE flattened range, sk_per consecutive k-steps per cluster,
+// so every cluster finishes at the same time.  A cluster's range covers the end of one tile and / or the start of the
+// next; such a SEGMENT's raw fp32 accumulator goes to a workspace slot, an arrival counter per (tile, CTA rank) is
+// bumped, and whoever arrives LAST sums the segments of the tile IN SEGMENT ORDER (not arrival order) and runs the
+// normal epilogue -- the result is bit-identical from run to run, and nobody ever waits for another cluster.
+// ------------------------------------------------------------------------------------------------
+struct SKWork {
+  int tile;         // pair tile
+  int k0, k1;       // k-step range of this work item
+  int partial;      // 1: a segment of a split tile (fix-up path)
+  int seg, nseg;    // position among the tile's segments
+  int slot;         // workspace slot of this segment (cluster * 2 + {0, 1})
+  int r, c_first;   // remainder-tile index and first cluster touching it
+};
+
+struct SKIter {
+  int cid, G, full, ksteps, per, total_k;
+  int t1, kb, ke, nth;
+  __device__ __forceinline__ void init(const KParams& p, int cluster_id, int n_clusters, int num_tiles, int ksteps_) {
+    cid = cluster_id; G = n_clusters; ksteps = ksteps_;
+    if (p.sk_per > 0) { full = p.sk_full; per = p.sk_per; total_k = p.sk_rem * ksteps_; }
+    else { full = num_tiles; per = 0; total_k = 0; }
+    t1 = cid;
+    kb = min(cid * per, total_k); ke = min(kb + per, total_k);
+    nth = 0;
+  }
+  __device__ __forceinline__ bool next(SKWork& w) {
+    if (t1 < full) {
+      w.tile = t1; w.k0 = 0; w.k1 = ksteps; w.partial = 0; w.seg = 0; w.nseg = 1; w.slot = 0; w.r = 0; w.c_first = 0;
+      t1 += G;
+      return true;
+    }
+    if (kb >= ke) return false;
+    const int r = kb / ksteps;
+    const int k0 = kb - r * ksteps;
+    const int len = min(ksteps - k0, ke - kb);
+    const int c_first = (r * ksteps) / per;
+    const int c_last = ((r + 1) * ksteps - 1) / per;
+    w.tile = full + r; w.k0 = k0; w.k1 = k0 + len;
+    w.nseg = c_last - c_first + 1; w.partial = w.nseg > 1; w.seg = cid - c_first;
+    w.slot = cid * 2 + nth; w.r = r; w.c_first = c_first;
+    kb += len; ++nth;
+    return true;
+  }
+};
+
+// workspace slot of segment s of remainder tile r: the cluster's first segment uses slot 0, its second slot 1
+__device__ __forceinline__ int sk_slot_of(int r, int c_first, int s, int per, int ksteps) {
+  const int c = c_first + s;
+  const int first_tile_of_c = (c * per) / ksteps;
+  return c * 2 + (first_tile_of_c == r ? 0 : 1);
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // KParams is reused; tmB must have been encoded with a 128-row box.
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEngineThreads, 1)
@@ -99,6 +158,7 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
   uint64_t* tempty = tfull + C::ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  volatile int* last_flag = abort_flag + 1;
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -122,35 +182,37 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  SKIter it;
+  it.init(p, cluster_id, n_clusters, num_tiles, ksteps);
+  SKWork w;
+
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    {
-      if (elect_one_sync()) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]); }
-      int s = 0; uint32_t ph = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
-        const int nt = tile % p.n_tiles_n;
-        const int mt2 = tile / p.n_tiles_n;
-        int mt = min(mt2 * 2 + int(rank), num_m_tiles - 1);
-        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-        const int thi = mt % p.tiles_h;
-        const int n = mt / p.tiles_h;
-        const int w0 = (twi << p.tw_log2) * p.in_stride;
-        const int h0 = thi * p.th * p.in_stride;
-        for (int e = 0; e < p.n_entries; ++e) {
-          const KEntry en = p.entries[e];
-          for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait(&empty[s], ph ^ 1, ab, 501);
-            uint8_t* sa = smem + s * C::STAGE_BYTES;
-            // only the leader arms its full barrier, for the bytes of BOTH CTAs; the peer's loads cannot run ahead of
-            // it by a phase because they are gated by the leader's multicast commit on empty[s]
-            if (elect_one_sync()) {
-              if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
-              tma_load_4d_2sm(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
-              tma_load_2d_2sm(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
-            }
-            if (++s == C::STAGES) { s = 0; ph ^= 1; }
-          }
+    if (elect_one_sync()) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]); }
+    int s = 0; uint32_t ph = 0;
+    while (it.next(w)) {
+      const int nt = w.tile % p.n_tiles_n;
+      const int mt2 = w.tile / p.n_tiles_n;
+      int mt = min(mt2 * 2 + int(rank), num_m_tiles - 1);
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h;
+      const int n = mt / p.tiles_h;
+      const int w0 = (twi << p.tw_log2) * p.in_stride;
+      const int h0 = thi * p.th * p.in_stride;
+      int e = w.k0 / p.chunks, c = w.k0 - e * p.chunks;
+      for (int k = w.k0; k < w.k1; ++k) {
+        const KEntry en = p.entries[e];
+        mbar_wait(&empty[s], ph ^ 1, ab, 501);
+        uint8_t* sa = smem + s * C::STAGE_BYTES;
+        // only the leader arms its full barrier, for the bytes of BOTH CTAs; the peer's loads cannot run ahead of
+        // it by a phase because they are gated by the leader's multicast commit on empty[s]
+        if (elect_one_sync()) {
+          if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+          tma_load_4d_2sm(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
+          tma_load_2d_2sm(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
         }
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        if (++c == p.chunks) { c = 0; ++e; }
       }
     }
   } else if (warp == 1) {
@@ -158,11 +220,11 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
       int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      while (it.next(w)) {
         mbar_wait(&tempty[a], aph ^ 1, ab, 502);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int k = 0; k < ksteps; ++k) {
+        for (int k = w.k0; k < w.k1; ++k) {
           mbar_wait(&full[s], ph, ab, 503);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
@@ -170,7 +232,8 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
           const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
+            for (int j = 0; j < 4; ++j)
+              umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, uint32_t((k != w.k0) | (j != 0)));
             umma_commit_2sm_mc(&empty[s], 3);
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
@@ -190,9 +253,10 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
                      ((reinterpret_cast<uintptr_t>(p.ohi) & 15) == 0) &&
                      (!p.olo || (reinterpret_cast<uintptr_t>(p.olo) & 15) == 0);
     const bool vb = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
-    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
-      const int nt = tile % p.n_tiles_n;
-      const int mt2 = tile / p.n_tiles_n;
+    constexpr size_t kSlotFloats = size_t(256) * BN;      // one pair-tile accumulator
+    while (it.next(w)) {
+      const int nt = w.tile % p.n_tiles_n;
+      const int mt2 = w.tile / p.n_tiles_n;
       int mt = mt2 * 2 + int(rank);
       const bool tile_ok = mt < num_m_tiles;
       mt = min(mt, num_m_tiles - 1);
@@ -208,19 +272,72 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
       if (p.ohi) off16 = ((size_t(n) * p.o16_H + oh + p.o16_hoff) * p.o16_W + ow + p.o16_woff) * p.o16_C + p.o16_coff;
       mbar_wait(&tfull[a], aph, ab, 504);
       tc_fence_after();
+      if (!w.partial) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + a * BN + c0, raw);
-        tmem_ld_wait();
-        const int cg = nt * BN + c0;
-        if (valid && cg < p.cout) epilogue_chunk<32>(p, raw, cg, v32, v16, vb, off32, off16);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(&tempty[a]);
-        else mbar_arrive_remote(mapa_u32(smem_u32(&tempty[a]), 0));
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + a * BN + c0, raw);
+          tmem_ld_wait();
+          const int cg = nt * BN + c0;
+          if (valid && cg < p.cout) epilogue_chunk<32>(p, raw, cg, v32, v16, vb, off32, off16);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tempty[a]);
+          else mbar_arrive_remote(mapa_u32(smem_u32(&tempty[a]), 0));
+        }
+      } else {
+        // ---- split tile: park the raw accumulator rows of this segment, release TMEM, count the arrival ----
+        float* mine = p.sk_ws + (size_t(w.slot) * 256 + rank * 128 + m) * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + a * BN + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            __stcg(reinterpret_cast<float4*>(mine + c0 + i),
+                   make_float4(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]), __uint_as_float(raw[i + 2]),
+                               __uint_as_float(raw[i + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tempty[a]);
+          else mbar_arrive_remote(mapa_u32(smem_u32(&tempty[a]), 0));
+        }
+        __threadfence();
+        epi_bar_sync();
+        if (m == 0) {
+          const int old = atomicAdd(p.sk_cnt + w.r * 2 + int(rank), 1);
+          *last_flag = (old == w.nseg - 1) ? 1 : 0;
+        }
+        epi_bar_sync();
+        const bool last = *last_flag != 0;
+        epi_bar_sync();            // everybody has read the flag before the next split tile may overwrite it
+        if (last) {
+          __threadfence();
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+            for (int sgm = 0; sgm < w.nseg; ++sgm) {     // fixed order: bit-identical whoever arrives last
+              const float* src = p.sk_ws + (size_t(sk_slot_of(w.r, w.c_first, sgm, it.per, ksteps)) * 256 + rank * 128 + m) * BN + c0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + i));
+                acc[i] += v.x; acc[i + 1] += v.y; acc[i + 2] += v.z; acc[i + 3] += v.w;
+              }
+            }
+            uint32_t raw[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(acc[i]);
+            const int cg = nt * BN + c0;
+            if (valid && cg < p.cout) epilogue_chunk<32>(p, raw, cg, v32, v16, vb, off32, off16);
+          }
+        }
       }
       if (++a == C::ACC) { a = 0; aph ^= 1; }
     }

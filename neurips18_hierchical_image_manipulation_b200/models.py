@@ -406,7 +406,7 @@ class Pix2PixHDModel_condImg(object):
             gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
         dy = Operand(ctx, B, st["H"], st["W"], 3, grad=True)
         rec = w[1] * opt.lambda_rec / st["fake"].numel() if opt.lambda_rec > 0 else 0.0
-        ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.d_img_c0, gV, st["image"], rec, dy,
+        ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.netD.gin_coff, gV, st["image"], rec, dy,
                      d_mask=st["d_mask"])
         self.netG.backward(st["g_tape"], dy_head=dy)
 

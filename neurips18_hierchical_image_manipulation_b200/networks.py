@@ -231,6 +231,21 @@ class ConvP(object):
             ops.conv_dgrad(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, self.stride, zero_pad, x_h, x_w,
                            self.cin, out32=out32)
 
+    def dgrad_rows(self, dy, x_h, x_w, zero_pad, out32, row0, nrows):
+        """dgrad restricted to input channels [row0, row0 + nrows): out32 is [N, x_h, x_w, ld >= nrows].  The generator
+        only needs d(D input)/d(image channels) -- 3 of the 41 input channels of the first PatchGAN layer -- so the
+        gradient GEMM runs with a 16-wide N tile instead of 64 and never produces the label / conditioning columns."""
+        assert not self.transposed and not self.thin_out and not self.thin_in
+        kk = self.k * self.k
+        key = (row0, nrows)
+        if getattr(self, "_pr_key", None) != key:
+            self._pr = PackedWeight(self.ctx, nrows, self.cout, kk, grad=True)
+            self._pr_key, self._vr = key, -1
+        if self._vr != self.fp.version or self.sn_scale is not None:
+            self._pr.pack(self.ctx, self.weight[:, row0:row0 + nrows], kk, self.cin * kk, 1, self.sn_scale)
+            self._vr = self.fp.version
+        ops.conv_dgrad(self.ctx, dy, self._pr, None, self.k, self.k, self.stride, zero_pad, x_h, x_w, nrows, out32=out32)
+
     def _unrolled(self, dy):
         """U[n,h,w',(kw,co)] = dy[n,h,w'-kw,co], w' in [0, W+KW-1): the thin output gradient with its horizontal taps
         folded into channels (shared by dgrad and wgrad of the same dy)."""
@@ -529,7 +544,8 @@ class MultiscaleDiscriminator(object):
 
     def backward(self, tape, nb, mode, w_gan=1.0, w_feat=0.0, w_real=0.5, w_fake=0.5, img_c0=0):
         """mode 'G': d(w_gan*G_GAN + G_GAN_Feat terms)/d(input) for the first nb images (the fake half); returns the
-        fp32 gradient w.r.t. the full-resolution D input (channels [img_c0, img_c0+3) are meaningful).  No weight grads.
+        fp32 gradient w.r.t. the IMAGE channels [img_c0, img_c0+3) of the full-resolution D input as a [nb,H,W,4] tensor
+        (channels 0..2; self.gin_coff = 0).  No weight grads.
         mode 'D': accumulates weight grads of w_fake*D_fake + w_real*D_real over all 2*nb images.
         w_feat is the complete per-tap L1 coefficient numerator (D_weights*feat_weights*lambda_feat)."""
         ctx = self.ctx
@@ -556,6 +572,12 @@ class MultiscaleDiscriminator(object):
                     conv.wgrad(xin, dy, 2, bias_grad=(j == 0 or j == nl - 1))
                     if j == 0:
                         break
+                if j == 0 and mode == "G":
+                    # only the image channels of the D input depend on the generator: 3-row gradient (ld 4, offset 0)
+                    gin = _f32(ctx, nimg, xin.h, xin.w, 4)
+                    conv.dgrad_rows(dy, xin.h, xin.w, 2, gin, img_c0, 3)
+                    gins.append(gin)
+                    break
                 gin = _f32(ctx, nimg, xin.h, xin.w, conv.cin)
                 conv.dgrad(dy, xin.h, xin.w, 2, gin)
                 if j == 0:
@@ -578,9 +600,10 @@ class MultiscaleDiscriminator(object):
             if self._sn is not None:   # dL/dW_bar -> dL/dW through sigma(W) (sn_utils.py:11-25 under autograd)
                 ops.sn_weight_grad(ctx, self._sn["layers"], self._sn["n"], self._sn["max_n"], self._sn["max_m"])
             return None
-        # total gradient at full resolution: g0 + poolT(g1 + poolT(g2 ...))
+        # total gradient at full resolution: g0 + poolT(g1 + poolT(g2 ...)); the tensors hold the 3 image channels only
         for i in range(len(gins) - 1, 0, -1):
-            ops.avgpool3s2_bwd(ctx, gins[i], gins[i - 1], img_c0, img_c0 + 3)
+            ops.avgpool3s2_bwd(ctx, gins[i], gins[i - 1], 0, 3)
+        self.gin_coff = 0      # channel offset of the image gradient inside the returned tensor
         return gins[0]
 
 

@@ -22,12 +22,26 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_SCRATCH = {}   # device index -> the engines' scratch tensor (process lifetime: captured CUDA graphs hold its address)
+
+
+def _register_scratch(lib, device):
+    """One scratch per process / device for the stream-K tail of the CTA-pair engine (include/hm_b200.h:hm_set_scratch)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SCRATCH:
+        t = torch.empty(int(lib.hm_scratch_bytes()), dtype=torch.uint8, device=device)
+        L.check(lib.hm_set_scratch(t.data_ptr(), t.numel()), "hm_set_scratch")
+        _SCRATCH[key] = t
+    return _SCRATCH[key]
+
+
 class Ctx(object):
     """Per-device state shared by all ops: library handle, precision mode, pipeline error flag."""
 
     def __init__(self, device, split=True, split_bwd=None):
         self.lib = L.load()
         self.device = torch.device(device)
+        self.scratch = _register_scratch(self.lib, self.device)
         self.split = bool(split)  # True: bf16x3 (fp32-parity mode); False: plain bf16 products
         # gradient GEMMs (dgrad / wgrad) may run with single bf16 products while the forward stays bf16x3 ("mixed")
         self.split_bwd = self.split if split_bwd is None else bool(split_bwd)

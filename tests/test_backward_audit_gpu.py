@@ -98,7 +98,14 @@ class Recorder(object):
             rec.calls.append(dict(kind="wgrad", conv=self, x=_stored(x, self.cin)[:dy.n], dy=_stored(dy), zero_pad=zero_pad,
                                   bias_grad=bias_grad, dw=(self.weight.grad.detach() - w0).double(),
                                   db=(self.bias.grad.detach() - b0).double()))
+        real_rows = networks.ConvP.dgrad_rows
+
+        def dgrad_rows(self, dy, x_h, x_w, zero_pad, out32, row0, nrows):
+            real_rows(self, dy, x_h, x_w, zero_pad, out32, row0, nrows)
+            rec.calls.append(dict(kind="dgrad", conv=self, dy=_stored(dy), x_hw=(x_h, x_w), zero_pad=zero_pad,
+                                  out=_nchw(out32[..., :nrows]), rows=(row0, nrows)))
         mp.setattr(networks.ConvP, "dgrad", dgrad)
+        mp.setattr(networks.ConvP, "dgrad_rows", dgrad_rows)
         mp.setattr(networks.ConvP, "wgrad", wgrad)
 
 
@@ -118,6 +125,8 @@ def _check_dgrad(c):
     y = _conv_fwd64(conv, x, c["zero_pad"])
     assert y.shape == c["dy"].shape, (conv.name, y.shape, c["dy"].shape)
     ref, = torch.autograd.grad(y, x, c["dy"])
+    if "rows" in c:      # data gradient restricted to a channel range (image channels of the first PatchGAN layer)
+        ref = ref[:, c["rows"][0]:c["rows"][0] + c["rows"][1]]
     return _relmax(c["out"], ref)
 
 

@@ -100,7 +100,7 @@ def run_parity(precision, verbose=False, **kw):
         bad = tot = 0
         err = 0.0
         for k in new:
-            if skip_bias(k, gref[k]):
+            if k not in gref or skip_bias(k, gref[k]):     # (non-trainable state such as spectral-norm u has no gradient)
                 continue
             sel = gref[k].abs() > 1e-3 * gref[k].abs().max()
             dm, dr = (new[k] - before[k])[sel], (ref_after[k] - before[k])[sel]

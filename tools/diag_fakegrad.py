@@ -36,10 +36,10 @@ nc = m.netG_input_nc
 def rel(a, r): return float((a - r).norm() / r.norm())
 g1 = m.netD.backward(st["d_tape"], B, "G", w_gan=1.0, w_feat=0.0, img_c0=nc)
 torch.cuda.synchronize()
-print("D GAN-only  grad err %.3e" % rel(g1[..., nc:nc + 3].cpu().permute(0, 3, 1, 2), gd_gan))
+print("D GAN-only  grad err %.3e" % rel(g1[..., 0:3].cpu().permute(0, 3, 1, 2), gd_gan))
 g2 = m.netD.backward(st["d_tape"], B, "G", w_gan=0.0, w_feat=(1.0 / 3) * 1.0 * 10.0, img_c0=nc)
 torch.cuda.synchronize()
-print("D feat-only grad err %.3e" % rel(g2[..., nc:nc + 3].cpu().permute(0, 3, 1, 2), gd_feat))
+print("D feat-only grad err %.3e" % rel(g2[..., 0:3].cpu().permute(0, 3, 1, 2), gd_feat))
 gV = m.vgg.backward(st["v_tape"], B, [10.0 * w for w in VGG_WEIGHTS])
 torch.cuda.synchronize()
 print("VGG grad err %.3e" % rel(gV.cpu().permute(0, 3, 1, 2), gv_ref))
