@@ -61,7 +61,8 @@ const char* hm_version(void);
 int hm_last_cuda_error(void); /* cudaError_t of the last failed runtime call on this thread */
 
 /* Optional device scratch for the engines (the library never allocates): hm_scratch_bytes() bytes, 256 B aligned,
- * owned by the caller and kept alive until it is replaced (ptr == NULL unregisters).  With it the CTA-pair K-engine
+ * owned by the caller, ZERO-FILLED before registration (its first 4 KB hold self-resetting arrival counters) and kept
+ * alive until it is replaced (ptr == NULL unregisters).  With it the CTA-pair K-engine
  * balances the last, partly filled wave of output tiles by splitting their contraction range over all SMs
  * (deterministic two-phase stream-K: partial accumulators go to the scratch and are summed in a fixed order);
  * without it the engines fall back to whole tiles.  One scratch per process: launches that use it must be ordered on

@@ -145,8 +145,6 @@ int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
     p.sk_per = int((long(rem) * ksteps + clusters - 1) / clusters);
     p.sk_cnt = static_cast<int*>(g_scratch);
     p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(g_scratch) + kSkCounterBytes);
-    cudaError_t e = cudaMemsetAsync(p.sk_cnt, 0, size_t(rem) * 2 * sizeof(int), st);
-    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   }
   hm::hm_kgemm2_kernel<256><<<2 * clusters, hm::kEngineThreads, hm::K2Cfg::SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();

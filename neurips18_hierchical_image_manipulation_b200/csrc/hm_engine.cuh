@@ -49,7 +49,7 @@ struct __align__(64) KParams {
   // the remaining sk_rem tiles are dealt out evenly, sk_per per cluster (0 = plain persistent tile loop)
   int sk_full, sk_rem, sk_per;
   float* sk_ws;           // partial accumulators: [cluster][2 segments][256 rows][256 cols] fp32
-  int* sk_cnt;            // arrival counters [sk_rem][2 CTA ranks], zeroed by the host before the launch
+  int* sk_cnt;            // arrival counters [sk_rem][2 CTA ranks]: zero at registration, reset by the last arriver
   KEntry entries[kMaxEntries];
 };
 

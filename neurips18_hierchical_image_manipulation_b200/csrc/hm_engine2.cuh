@@ -289,7 +289,10 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
         }
       } else {
         // ---- split tile: park the raw accumulator rows of this segment, release TMEM, count the arrival ----
-        float* mine = p.sk_ws + (size_t(w.slot) * 256 + rank * 128 + m) * BN;
+        // slot layout (private to this kernel): float4 index ((c0 / 32) * 8 + i / 4) * 128 + m, i.e. the 128 epilogue
+        // threads of a CTA write / read consecutive 16 B words -> fully coalesced (a row-per-thread layout costs 8x the
+        // L2 transactions and made the tail slower than the wave quantisation it removes)
+        float4* mine = reinterpret_cast<float4*>(p.sk_ws + (size_t(w.slot) * 2 + rank) * 128 * BN) + m;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t raw[32];
@@ -297,7 +300,7 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            __stcg(reinterpret_cast<float4*>(mine + c0 + i),
+            __stcg(mine + ((c0 >> 5) * 8 + (i >> 2)) * 128,
                    make_float4(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]), __uint_as_float(raw[i + 2]),
                                __uint_as_float(raw[i + 3])));
         }
@@ -310,8 +313,11 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
         __threadfence();
         epi_bar_sync();
         if (m == 0) {
-          const int old = atomicAdd(p.sk_cnt + w.r * 2 + int(rank), 1);
-          *last_flag = (old == w.nseg - 1) ? 1 : 0;
+          int* cnt = p.sk_cnt + w.r * 2 + int(rank);
+          const int old = atomicAdd(cnt, 1);
+          const int is_last = (old == w.nseg - 1) ? 1 : 0;
+          if (is_last) *cnt = 0;      // self-resetting: the counters are zero again when the kernel ends (no memset per launch)
+          *last_flag = is_last;
         }
         epi_bar_sync();
         const bool last = *last_flag != 0;
@@ -324,10 +330,11 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = 0.f;
             for (int sgm = 0; sgm < w.nseg; ++sgm) {     // fixed order: bit-identical whoever arrives last
-              const float* src = p.sk_ws + (size_t(sk_slot_of(w.r, w.c_first, sgm, it.per, ksteps)) * 256 + rank * 128 + m) * BN + c0;
+              const float4* src = reinterpret_cast<const float4*>(
+                  p.sk_ws + (size_t(sk_slot_of(w.r, w.c_first, sgm, it.per, ksteps)) * 2 + rank) * 128 * BN) + m;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + i));
+                const float4 v = __ldcg(src + ((c0 >> 5) * 8 + (i >> 2)) * 128);
                 acc[i] += v.x; acc[i + 1] += v.y; acc[i + 2] += v.z; acc[i + 3] += v.w;
               }
             }

