@@ -1,0 +1,132 @@
+"""CPU restatement (torch functional ops) of the reference's box2mask generator -- BASELINE config #5, SURVEY N3.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Follows models/MaskTwoStreamConv_NET.py (the two-stream conv
+auto-encoder), its base class models/MaskContextAE_NET.py, the blocks of models/layer_util.py:136-242
+(ConvResnetBlock / DeconvResnetBlock) and :333-378 (ResnetBlock), and the reconstruction losses of
+models/TwoStreamAE_mask.py:188-203 + models/mask_losses.py:12-27.  Pinned by tests/golden/box2mask_small.npz, which
+oracle/make_golden_box2mask.py produced by running the reference's OWN class (forward, losses, parameter gradients).
+
+Parameters are addressed by the reference's own names: '<params_dict key>.<state_dict key>', e.g.
+'conv_encoder_3.deep.1.weight', 'ctx_conv_decoder_1.shortcut.0.weight', 'latent_encoder.0.conv_block.1.weight'.
+
+Two aliasing effects of the reference code are part of its arithmetic and are restated explicitly:
+  * every Conv/DeconvResnetBlock opens with an IN-PLACE ReLU on its input while `residual = x` aliases that tensor
+    (layer_util.py:156-162, 236-242): the shortcut branch sees relu(x);
+  * the encoder features kept for the skip connections (MaskTwoStreamConv_NET.py:172-173) are rectified in place by
+    the next block before the decoder concatenates them (:161-165).
+"""
+import torch
+import torch.nn.functional as F
+
+IGNORE_INDEX = 255          # models/mask_losses.py:10
+DIM_LIST_TAIL = [96, 128, 256, 512]   # MaskTwoStreamConv_NET.py:25 ("this part is hard-coded")
+
+
+def batch_norm(sd, key, x, eps=1e-5):
+    """nn.BatchNorm2d(affine=True) in TRAINING mode (layer_util.py:19-21 with norm_layer == 'batch'): biased batch
+    statistics over (N, H, W); the running buffers do not enter the result."""
+    mean = x.mean(dim=(0, 2, 3), keepdim=True)
+    var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+    g, b = sd[key + ".weight"].view(1, -1, 1, 1), sd[key + ".bias"].view(1, -1, 1, 1)
+    return (x - mean) / torch.sqrt(var + eps) * g + b
+
+
+def upsample2(x):
+    """nn.Upsample(scale_factor=2, mode='bilinear') as torch >= 0.4 evaluates it (align_corners=False)."""
+    return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+
+
+def conv_resnet_block(sd, p, x, stride=2, k=4):
+    """ConvResnetBlock(in, out, num_layers=1, stride=2, kernel_size=4), layer_util.py:119-162:
+    deep = [ReLU(in place), Conv k x k stride 2 pad (k-1)//2, norm]; shortcut = [Conv 1x1 stride 2, norm]."""
+    xr = F.relu(x)                                   # in place in the reference: BOTH branches see relu(x)
+    pad = (k - 1) // 2
+    deep = batch_norm(sd, p + ".deep.2", F.conv2d(xr, sd[p + ".deep.1.weight"], sd[p + ".deep.1.bias"], stride=stride,
+                                                  padding=pad))
+    short = batch_norm(sd, p + ".shortcut.1", F.conv2d(xr, sd[p + ".shortcut.0.weight"], sd[p + ".shortcut.0.bias"],
+                                                       stride=stride))
+    return deep + short, xr
+
+
+def deconv_resnet_block(sd, p, x, k=4):
+    """DeconvResnetBlock(in, out, num_layers=1, stride=2, kernel_size=4), layer_util.py:164-242 (even kernel ->
+    build_tconv2d_block): deep = [ReLU(in place), ConvTranspose2d k4 s2 p1 output_padding 0, norm];
+    shortcut = [Conv 1x1, norm] (when in != out) + bilinear x2."""
+    xr = F.relu(x)
+    deep = F.conv_transpose2d(xr, sd[p + ".deep.1.weight"], sd[p + ".deep.1.bias"], stride=2, padding=(k - 1) // 2,
+                              output_padding=0)
+    deep = batch_norm(sd, p + ".deep.2", deep)
+    short = xr
+    if p + ".shortcut.0.weight" in sd:
+        short = batch_norm(sd, p + ".shortcut.1", F.conv2d(short, sd[p + ".shortcut.0.weight"], sd[p + ".shortcut.0.bias"]))
+    return deep + upsample2(short)
+
+
+def resnet_block(sd, p, x):
+    """ResnetBlock(dim, 'reflect', norm, ReLU, no dropout), layer_util.py:333-378: x + conv_block(x)."""
+    h = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), sd[p + ".conv_block.1.weight"], sd[p + ".conv_block.1.bias"])
+    h = F.relu(batch_norm(sd, p + ".conv_block.2", h))
+    h = F.conv2d(F.pad(h, (1, 1, 1, 1), mode="reflect"), sd[p + ".conv_block.5.weight"], sd[p + ".conv_block.5.bias"])
+    return x + batch_norm(sd, p + ".conv_block.6", h)
+
+
+def two_stream_forward(sd, cond, num_layers=3, n_blocks=6, conv_size=4):
+    """MaskTwoStreamConv_NET.forward (:159-219), which_stream == 'obj_context'.
+    cond: [B, input_nc, S, S] (cond_in 'ctx_obj': object box mask in its class channel | one-hot context).
+    Returns (comb_logit, comb_logprob, obj_logit, obj_prob)."""
+    # shared encoder (:63-90): Conv 7x7 stride 2 pad 3, norm, ReLU, then num_layers ConvResnetBlocks
+    h = F.conv2d(cond, sd["conv_encoder_0.weight"], sd["conv_encoder_0.bias"], stride=2, padding=3)
+    h = F.relu(batch_norm(sd, "conv_encoder_1", h))
+    enc_features = [h]                                # i == 2 (:172-173)
+    for i in range(num_layers):
+        h, prev_rectified = conv_resnet_block(sd, "conv_encoder_%d" % (3 + i), h, k=conv_size)
+        enc_features[-1] = prev_rectified             # the kept feature was rectified in place by this block
+        if i < num_layers - 1:
+            enc_features.append(h)
+    for j in range(n_blocks // 2):                    # latent encoder (:92-106)
+        h = resnet_block(sd, "latent_encoder.%d" % j, h)
+    latent = h
+
+    def decode(stream, skips):
+        d = latent
+        for j in range((n_blocks + 1) // 2):          # latent decoder (:108-123)
+            d = resnet_block(sd, "%s_latent_decoder.%d" % (stream, j), d)
+        for i in range(num_layers + 1):               # conv decoder (:125-155) + forward_decoder (:157-165)
+            if skips is not None and 1 <= i <= num_layers:
+                d = torch.cat((skips[-1 - (i - 1)], d), 1)
+            d = deconv_resnet_block(sd, "%s_conv_decoder_%d" % (stream, i), d, k=conv_size)
+        k = "%s_conv_decoder_%d" % (stream, num_layers + 1)
+        return F.conv2d(d, sd[k + ".weight"], sd[k + ".bias"], padding=1)
+    ctx_logit = decode("ctx", enc_features)
+    obj_logit = decode("obj", None)
+    obj_prob = torch.sigmoid(obj_logit)
+    # combination (:198-217): the object stream's sigmoid gates between the context logits and its own logit
+    padded_mask = obj_prob.expand_as(ctx_logit)
+    comb_logit = (1 - padded_mask) * ctx_logit + padded_mask * obj_logit
+    return comb_logit, F.log_softmax(comb_logit, dim=1), obj_logit, obj_prob
+
+
+def mask_recon_loss(comb_logprob, label_map, mask_out):
+    """MaskReconLoss (mask_losses.py:12-27): NLL over the pixels INSIDE the box (mask_out >= 0.5); the others get the
+    ignore index 255."""
+    gt = label_map.view(-1, label_map.size(2), label_map.size(3)).long().clone()
+    gt[mask_out[:, 0] < 0.5] = IGNORE_INDEX
+    return F.nll_loss(comb_logprob, gt, ignore_index=IGNORE_INDEX)
+
+
+def obj_recon_loss(obj_prob, mask_out, mask_obj_inst, use_output_gate=True):
+    """TwoStreamAE_mask.forward :199-203 with objReconLoss == 'bce': BCE between the (gated) object mask and the
+    instance mask."""
+    p = obj_prob * mask_out if use_output_gate else obj_prob
+    return F.binary_cross_entropy(p, mask_obj_inst)
+
+
+def encode_input(label_nc, mask_ctx_in, mask_in, cls):
+    """TwoStreamAE_mask.encode_input (:127-151) + construct_input_cond (:331-338) for cond_in == 'ctx_obj'."""
+    B, _, S, S2 = mask_ctx_in.shape
+    ctx = torch.zeros(B, label_nc, S, S2).scatter_(1, mask_ctx_in.long(), 1.0)
+    obj = torch.zeros(B, label_nc, S, S2)
+    for b in range(B):
+        obj[b, int(cls[b, 0])] = mask_in[b, 0]
+    cls_onehot = torch.zeros(B, label_nc).scatter_(1, cls.long(), 1.0)
+    return torch.cat((obj, ctx), 1), cls_onehot

@@ -48,3 +48,19 @@ def random_d_sd(input_nc, ndf, n_layers, num_D, seed=1):
         _conv(sd, "scale%d_layer%d.0" % (s, n_layers), nf, nf_prev, 4, g)
         _conv(sd, "scale%d_layer%d.0" % (s, n_layers + 1), 1, nf, 4, g)
     return sd
+
+
+def named_param(name, shape):
+    """Deterministic parameter values keyed by the parameter's NAME (seed = crc32(name)): conv / linear weights
+    ~ N(0, 0.02) as weights_init leaves them, norm-layer gains ~ N(1, 0.02) (layer_util.py:14), biases / norm shifts
+    ~ U(-0.05, 0.05).  Used where a golden fixture would otherwise have to carry tens of MB of random weights: the
+    generating script loads these values into the reference's modules (as a checkpoint would) and the tests regenerate
+    them from the stored name -> shape manifest."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    shape = tuple(int(v) for v in shape)
+    if name.endswith("weight") and len(shape) >= 2:
+        return torch.randn(shape, generator=g) * 0.02
+    if name.endswith("weight"):
+        return 1.0 + torch.randn(shape, generator=g) * 0.02
+    return (torch.rand(shape, generator=g) * 2 - 1) * 0.05

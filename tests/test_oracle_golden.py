@@ -226,3 +226,51 @@ def test_model_level_forward_against_the_reference_model(golden_dir, name, optkw
             if k.endswith("bias") and float(ref[k].abs().max()) < 1e-3 * float(ref[k[:-4] + "weight"].abs().max()):
                 continue   # bias in front of an InstanceNorm: analytically zero, fp32 noise (1e-8 .. 5e-7) in the reference
             close(gi.float(), ref[k], 1e-4)
+
+
+# ---- N3 box2mask: oracle/box2mask.py against the reference's own MaskTwoStreamConv_NET -------------------------------
+def _box2mask_fixture(golden_dir, dtype):
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_small.npz"))
+    sd = {}
+    for name, shp in zip(z["param_names"], z["param_shapes"]):
+        shape = tuple(int(v) for v in str(shp).split(";"))
+        sd[str(name)] = named_param(str(name), shape).to(dtype).requires_grad_(True)
+    return z, sd
+
+
+def test_box2mask_two_stream_forward_losses_and_gradients_against_the_reference_class(golden_dir):
+    """BASELINE config #5 network (scripts/train_box2mask_city.sh flag set, reduced size): the four outputs of
+    MaskTwoStreamConv_NET.forward, MaskReconLoss + BCE, and the gradient of every one of the 120 parameters."""
+    from oracle import box2mask as B2
+    from oracle.weights import named_param
+    z, sd = _box2mask_fixture(golden_dir, torch.float64)
+    ins = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in::")}
+    cond, cls_onehot = B2.encode_input(6, ins["mask_ctx_in"], ins["mask_in"], ins["cls"])
+    assert torch.equal(cond, torch.from_numpy(z["cond"])) and torch.equal(cls_onehot, torch.from_numpy(z["cls_onehot"]))
+    comb_logit, comb_lp, obj_logit, obj_prob = B2.two_stream_forward(sd, cond.double(), num_layers=3, n_blocks=2)
+    for got, key in ((comb_logit, "comb_logit"), (comb_lp, "comb_prob"), (obj_logit, "obj_logit"), (obj_prob, "obj_prob")):
+        ref = torch.from_numpy(z[key]).double()
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5, key
+    l_comb = B2.mask_recon_loss(comb_lp, ins["label_map"], ins["mask_out"])
+    l_obj = B2.obj_recon_loss(obj_prob, ins["mask_out"].double(), ins["mask_obj_inst"].double())
+    assert abs(float(l_comb) - float(z["loss_comb"])) < 2e-5 * abs(float(z["loss_comb"]))
+    assert abs(float(l_obj) - float(z["loss_obj"])) < 2e-5 * abs(float(z["loss_obj"]))
+    names = list(sd)
+    grads = torch.autograd.grad(l_obj + l_comb, [sd[k] for k in names])
+    n_full = n_proj = 0
+    for k, g in zip(names, grads):
+        if "g::" + k in z.files:
+            ref = torch.from_numpy(z["g::" + k]).double()
+            # (conv biases in front of a BatchNorm have an analytically zero gradient: ~1e-8 fp32 noise in the reference)
+            tol = 2e-3 * float(ref.abs().max()) + 1e-6
+            assert float((g - ref).abs().max()) <= tol, k
+            n_full += 1
+        else:
+            s_, a_, p_ = (float(v) for v in z["gs::" + k])
+            r = named_param("proj::" + k + ".bias", g.shape).double()
+            assert abs(float(g.abs().sum()) - a_) <= 2e-3 * a_ + 1e-5, k
+            assert abs(float(g.sum()) - s_) <= 2e-3 * a_ + 1e-5 and abs(float((g * r).sum()) - p_) <= 2e-3 * a_ * 0.05 + 1e-6, k
+            n_proj += 1
+    assert n_full + n_proj == 120 and n_proj >= 20
