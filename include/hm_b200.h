@@ -62,13 +62,16 @@ int hm_last_cuda_error(void); /* cudaError_t of the last failed runtime call on 
 
 /* Optional device scratch for the engines (the library never allocates): hm_scratch_bytes() bytes, 256 B aligned,
  * owned by the caller, ZERO-FILLED before registration (its first 4 KB hold self-resetting arrival counters) and kept
- * alive until it is replaced (ptr == NULL unregisters).  With it the CTA-pair K-engine
+ * alive until it is replaced (ptr == NULL unregisters).  With it (and hm_set_streamk(1)) the CTA-pair K-engine
  * balances the last, partly filled wave of output tiles by splitting their contraction range over all SMs
  * (deterministic two-phase stream-K: partial accumulators go to the scratch and are summed in a fixed order);
  * without it the engines fall back to whole tiles.  One scratch per process: launches that use it must be ordered on
  * one stream. */
 size_t hm_scratch_bytes(void);
 int hm_set_scratch(void* ptr, size_t bytes);
+/* The stream-K tail is OPT-IN (default off, or HM_STREAMK=1 in the environment): measured on B200 it does not beat the
+ * whole-tile schedule on this path's shapes.  hm_set_streamk(1/0) switches it at run time. */
+int hm_set_streamk(int on);
 
 /* ---- weight packing --------------------------------------------------------------------------
  * N-tile width the K-engine uses for `rows` output rows, and the padded slab dims. */
@@ -251,6 +254,28 @@ int hm_adam_step(float* param, const float* grad, float* m, float* v, long n, fl
  * replays with the right bias corrections. */
 int hm_adam_step_dev(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
                      float eps, const int* step_dev, float grad_scale, void* stream);
+
+/* ---- box2mask generator glue (hm_box2mask.cu; BASELINE config #5) ------------------------------------
+ * hm_box2mask_encode: the generator input of TwoStreamAE_mask (models/TwoStreamAE_mask.py:127-151,331-338, cond_in ==
+ *   'ctx_obj'): operand [B,H,W,o_cs] = cat(object box mask in the object's class channel, one-hot(context labels)).
+ *   mask_ctx_in / mask_in are [B,1,H,W] fp32, cls is [B] fp32 class ids.  All values are 0/1 (exact in bf16).
+ * hm_bn_fold: nn.BatchNorm2d(affine) in training mode (layer_util.py:19-21): batch statistics mean/rstd [C] (from
+ *   hm_in_stats on the tensor viewed as ONE sample of N*H*W pixels) + gamma/beta -> per-(n,c) rows for hm_in_apply:
+ *   rstd' = rstd*gamma, mean' = mean - beta/rstd'.
+ * hm_upsample2_add: out = deep + nn.Upsample(scale_factor=2, mode='bilinear')(small), the DeconvResnetBlock tail
+ *   (layer_util.py:178-179,236-242); fp32 NHWC, small is [N,h,w,C], deep/out are [N,2h,2w,C], C % 4 == 0.
+ * hm_box2mask_head: MaskTwoStreamConv_NET.forward :190-217 -- obj_prob = sigmoid(obj_logit), comb = (1-p)*ctx + p*obj,
+ *   log-softmax over the C classes (outputs in NCHW, any may be NULL) -- and the reconstruction losses of
+ *   TwoStreamAE_mask.forward :188-203: acc[0] += sum of NLL over pixels with mask_out >= 0.5 (mask_losses.py:12-27),
+ *   acc[1] += their count, acc[2] += sum of BCE(obj_prob [* mask_out when use_gate], inst) terms (logs clamped at -100). */
+int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const float* cls, int B, int H, int W, int label_nc,
+                       void* o_hi, void* o_lo, int o_cs, void* stream);
+int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,
+               float* rstd_out, void* stream);
+int hm_upsample2_add(const float* small, const float* deep, int N, int h, int w, int C, float* out, void* stream);
+int hm_box2mask_head(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
+                     const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate, float* comb_logit,
+                     float* comb_logprob, float* obj_prob, double* acc, void* stream);
 
 #ifdef __cplusplus
 }

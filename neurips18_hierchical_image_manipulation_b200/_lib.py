@@ -46,6 +46,7 @@ PROTOTYPES = {
     "hm_last_cuda_error": (_i, []),
     "hm_scratch_bytes": (_sz, []),
     "hm_set_scratch": (_i, [_vp, _sz]),
+    "hm_set_streamk": (_i, [_i]),
     "hm_pick_bn": (_i, [_i]),
     "hm_rows_pad": (_i, [_i]),
     "hm_k_pad": (_i, [_i]),
@@ -89,6 +90,10 @@ PROTOTYPES = {
     "hm_sn_stash_floats": (_sz, [_i, _i]),
     "hm_sn_power_iteration": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hm_sn_weight_grad": (_i, [_vp, _i, _i, _i, _vp]),
+    "hm_box2mask_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "hm_bn_fold": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "hm_upsample2_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "hm_box2mask_head": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hm_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
     "hm_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
 }

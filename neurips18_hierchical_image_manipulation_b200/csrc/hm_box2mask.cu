@@ -1,0 +1,190 @@
+// hm_box2mask.cu -- HBM-bound glue of the box2mask generator (BASELINE config #5; models/MaskTwoStreamConv_NET.py,
+// models/TwoStreamAE_mask.py, models/layer_util.py:119-242): input encoding, BatchNorm folding, the bilinear x2 upsample
+// of the DeconvResnetBlock shortcut fused with the residual add, and the two-stream output head with its losses.
+// Convolutions run on the tcgen05 engines (hm_conv.cu); normalise + activation + operand emission reuse hm_in_apply
+// with the folded statistics.
+#include "../../include/hm_b200.h"
+#include "hm_ptx.cuh"
+
+#include <algorithm>
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int kBlock = 256;
+inline int grid_for(long items, int block = kBlock, int max_blocks = 148 * 32) {
+  long g = (items + block - 1) / block;
+  return int(std::max<long>(1, std::min<long>(g, max_blocks)));
+}
+#define HM_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? HM_OK : HM_ERR_LAUNCH)
+
+// cond = cat(object box mask placed in the object's class channel, one-hot(context label map))
+// (TwoStreamAE_mask.encode_input :127-151 + construct_input_cond :331-338, cond_in == 'ctx_obj').  Every value is 0 or 1,
+// hence exact in bf16: only the hi plane is written (the lo plane, if any, is zeroed).
+__global__ void b2m_encode_kernel(const float* __restrict__ mask_ctx_in, const float* __restrict__ mask_in,
+                                  const float* __restrict__ cls, int B, int H, int W, int label_nc, bf16* o_hi, bf16* o_lo,
+                                  int cs) {
+  const int G = cs >> 3;
+  const long total = long(B) * H * W * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    const long pix = i / G;
+    const int n = int(pix / (long(H) * W));
+    const int c0 = g * 8;
+    const int ctx_cls = int(__ldg(mask_ctx_in + pix));
+    const int obj_cls = int(__ldg(cls + n));
+    const float box = __ldg(mask_in + pix);
+    alignas(16) bf16 h[8];
+    alignas(16) bf16 z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float v = 0.f;
+      if (c < label_nc) v = (c == obj_cls) ? box : 0.f;
+      else if (c < 2 * label_nc) v = (c - label_nc == ctx_cls) ? 1.f : 0.f;
+      h[j] = __float2bfloat16_rn(v);
+      z[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(o_hi + pix * cs + c0) = *reinterpret_cast<const uint4*>(h);
+    if (o_lo) *reinterpret_cast<uint4*>(o_lo + pix * cs + c0) = *reinterpret_cast<const uint4*>(z);
+  }
+}
+
+// BatchNorm2d(affine) in training mode = normalise with the BATCH statistics (mean / rstd over N*H*W, computed by
+// hm_in_stats on the tensor viewed as one sample) then scale and shift:  (x - mean) * rstd * gamma + beta
+//   == (x - mean') * rstd'   with  rstd' = rstd * gamma,  mean' = mean - beta / rstd'   -> per-(n, c) rows for hm_in_apply.
+__global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, int N, int C,
+                               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int c = i % C;
+  const float rs = rstd[c] * (gamma ? gamma[c] : 1.f);
+  const float b = beta ? beta[c] : 0.f;
+  rstd_out[i] = rs;
+  mean_out[i] = (rs != 0.f) ? mean[c] - b / rs : mean[c];
+}
+
+// out = deep + Upsample(scale 2, bilinear, align_corners = False)(small): the tail of DeconvResnetBlock.forward
+// (layer_util.py:236-242, shortcut = [...] + nn.Upsample, :178-179).  One thread per output pixel x 4 channels.
+__global__ void upsample2_add_kernel(const float* __restrict__ small, const float* __restrict__ deep, int N, int h, int w,
+                                     int C, float* __restrict__ out) {
+  const int H = 2 * h, W = 2 * w, G = C >> 2;
+  const long total = long(N) * H * W * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    long r = i / G;
+    const int x = int(r % W); r /= W;
+    const int y = int(r % H);
+    const int n = int(r / H);
+    // source coordinate 0.5 * (dst + 0.5) - 0.5, clamped at 0 (ATen area_pixel_compute_source_index)
+    const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
+    const int y0 = int(sy), x0 = int(sx);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float fy = sy - y0, fx = sx - x0;
+    const float* base = small + size_t(n) * h * w * C + g * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t(y0) * w + x0) * C));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(base + (size_t(y0) * w + x1) * C));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(base + (size_t(y1) * w + x0) * C));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(base + (size_t(y1) * w + x1) * C));
+    const size_t o = ((size_t(n) * H + y) * W + x) * C + g * 4;
+    const float4 e = __ldg(reinterpret_cast<const float4*>(deep + o));
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    float4 v;
+    v.x = e.x + w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+    v.y = e.y + w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+    v.z = e.z + w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z;
+    v.w = e.w + w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w;
+    *reinterpret_cast<float4*>(out + o) = v;
+  }
+}
+
+// Two-stream output head (MaskTwoStreamConv_NET.forward :190-217) + the reconstruction losses of
+// TwoStreamAE_mask.forward :188-203 (MaskReconLoss = NLL over the pixels inside the box, mask_losses.py:12-27;
+// nn.BCELoss on the gated object mask).  One thread per pixel; ctx logits are read twice (second pass from L1/L2).
+//   acc[0] += sum of -log p(label) over box pixels, acc[1] += number of box pixels, acc[2] += sum of BCE terms
+__global__ void b2m_head_kernel(const float* __restrict__ ctx_logit /*[N,H,W,C]*/, const float* __restrict__ obj_logit /*[N,H,W,ldo]*/,
+                                int ldo, const float* __restrict__ label_map, const float* __restrict__ mask_out,
+                                const float* __restrict__ inst, int N, int H, int W, int C, int use_gate,
+                                float* __restrict__ comb_logit /*NCHW*/, float* __restrict__ comb_logprob /*NCHW*/,
+                                float* __restrict__ obj_prob /*[N,1,H,W]*/, double* __restrict__ acc) {
+  const long HW = long(H) * W, total = long(N) * HW;
+  double nll = 0.0, cnt = 0.0, bce = 0.0;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int n = int(i / HW);
+    const long p = i - long(n) * HW;
+    const float o = __ldg(obj_logit + i * ldo);
+    const float pr = 1.f / (1.f + __expf(-o));
+    const float* cl = ctx_logit + i * C;
+    float mx = -3.402823466e38f;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, (1.f - pr) * __ldg(cl + c) + pr * o);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf((1.f - pr) * __ldg(cl + c) + pr * o - mx);
+    const float lse = mx + logf(se);
+    const float mo = mask_out ? __ldg(mask_out + i) : 1.f;
+    const int lab = label_map ? int(__ldg(label_map + i)) : -1;
+    for (int c = 0; c < C; ++c) {
+      const float v = (1.f - pr) * __ldg(cl + c) + pr * o;
+      const size_t oi = (size_t(n) * C + c) * HW + p;
+      if (comb_logit) comb_logit[oi] = v;
+      if (comb_logprob) comb_logprob[oi] = v - lse;
+      if (c == lab && mo >= 0.5f) { nll -= double(v - lse); cnt += 1.0; }
+    }
+    if (obj_prob) obj_prob[i] = pr;
+    if (inst) {
+      const float q = use_gate ? pr * mo : pr;
+      const float t = __ldg(inst + i);
+      const float lq = fmaxf(logf(q), -100.f), l1q = fmaxf(logf(1.f - q), -100.f);   // nn.BCELoss clamps its logs at -100
+      bce -= double(t * lq + (1.f - t) * l1q);
+    }
+  }
+  __shared__ double sh[3][kBlock];
+  sh[0][threadIdx.x] = nll; sh[1][threadIdx.x] = cnt; sh[2][threadIdx.x] = bce;
+  __syncthreads();
+  for (int s = kBlock / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && acc)
+    for (int k = 0; k < 3; ++k) atomicAdd(acc + k, sh[k][0]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const float* cls, int B, int H, int W, int label_nc,
+                       void* o_hi, void* o_lo, int o_cs, void* stream) {
+  if (!mask_ctx_in || !mask_in || !cls || !o_hi || (o_cs & 7) || o_cs < 2 * label_nc) return HM_ERR_INVALID;
+  b2m_encode_kernel<<<grid_for(long(B) * H * W * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      mask_ctx_in, mask_in, cls, B, H, W, label_nc, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,
+               float* rstd_out, void* stream) {
+  if (!mean || !rstd || !mean_out || !rstd_out || N <= 0 || C <= 0) return HM_ERR_INVALID;
+  bn_fold_kernel<<<(N * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, rstd, gamma, beta, N, C,
+                                                                                      mean_out, rstd_out);
+  return HM_LAUNCH_OK();
+}
+
+int hm_upsample2_add(const float* small, const float* deep, int N, int h, int w, int C, float* out, void* stream) {
+  if (!small || !deep || !out || (C & 3)) return HM_ERR_INVALID;
+  upsample2_add_kernel<<<grid_for(long(N) * 4 * h * w * (C >> 2)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      small, deep, N, h, w, C, out);
+  return HM_LAUNCH_OK();
+}
+
+int hm_box2mask_head(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
+                     const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate, float* comb_logit,
+                     float* comb_logprob, float* obj_prob, double* acc, void* stream) {
+  if (!ctx_logit || !obj_logit || C <= 0 || obj_ld <= 0) return HM_ERR_INVALID;
+  b2m_head_kernel<<<grid_for(long(N) * H * W, kBlock, 148 * 8), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      ctx_logit, obj_logit, obj_ld, label_map, mask_out, inst, N, H, W, C, use_gate, comb_logit, comb_logprob, obj_prob,
+      acc);
+  return HM_LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -113,6 +113,7 @@ int launch_k(const hm::KParams& p, int num_tiles, cudaStream_t st) {
 }
 
 // scratch registered by the caller (hm_set_scratch): stream-K partial accumulators + arrival counters
+int g_use_streamk = -1;       // -1: take HM_STREAMK from the environment on first use; hm_set_streamk overrides
 void* g_scratch = nullptr;
 size_t g_scratch_bytes = 0;
 constexpr size_t kSkSlotBytes = size_t(256) * 256 * sizeof(float);
@@ -130,7 +131,11 @@ int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
   const int max_clusters = sm_count() / 2;
   int clusters = std::min(pair_tiles, max_clusters);
   // stream-K tail (hm_engine2.cuh): whole waves as tiles, the k-steps of the last partial wave dealt out evenly
-  static const int use_sk = env_int("HM_STREAMK", 1);
+  // Measured on B200 (tools/bench_k1_variants.py, profiles/r02_k1_streamk_variants.txt): K1 0.294 ms with the tail vs
+  // 0.297 ms with whole tiles in bf16x3, and 3-20 % SLOWER on the other pair-engine shapes and in bf16 -- parking and
+  // re-reading the partial accumulators (2 x 33 MB through L2 for K1) plus the un-overlapped fix-up epilogue cost what the
+  // better balance buys.  Hence opt-in (HM_STREAMK=1); the default stays the whole-tile schedule.
+  const int use_sk = g_use_streamk < 0 ? (g_use_streamk = env_int("HM_STREAMK", 0)) : g_use_streamk;
   const int ksteps = p.n_entries * p.chunks;
   const int waves = pair_tiles / max_clusters;
   const int rem = pair_tiles - waves * max_clusters;
@@ -510,6 +515,7 @@ extern "C" {
 const char* hm_version(void) { return "hm_b200 0.2 (sm_100a, tcgen05+TMA)"; }
 
 size_t hm_scratch_bytes(void) { return kSkCounterBytes + size_t(sm_count() / 2) * 2 * kSkSlotBytes; }
+int hm_set_streamk(int on) { g_use_streamk = on ? 1 : 0; return HM_OK; }
 int hm_set_scratch(void* ptr, size_t bytes) {
   if (ptr && (bytes < hm_scratch_bytes() || (reinterpret_cast<uintptr_t>(ptr) & 255))) return HM_ERR_INVALID;
   g_scratch = ptr;

@@ -245,14 +245,11 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
           const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
           if (elect_one_sync()) {
-            if (j0 == 0 && j1 == 4) {      // full chunk: keep the issue path unrolled (it is on the critical path)
+            // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row; the loop stays unrolled (the issue path is on the
+            // critical path: a run-time trip count cost ~2x per MMA) and unused groups are predicated off
 #pragma unroll
-              for (int j = 0; j < 4; ++j)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
-                umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j != 0));
-            } else {
-              for (int j = j0; j < j1; ++j)
-                umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j > j0));
-            }
+            for (int j = 0; j < 4; ++j)
+              if (j >= j0 && j < j1) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j > j0));
             umma_commit(&empty[s]);
           }
           if (j1 > j0) acc = 1;   // warp-uniform: every lane tracks whether the accumulator has been written

@@ -145,12 +145,9 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
               for (int j = 0; j < p.kw; ++j) {
                 const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
                 const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
-                if (k0 == 0 && k1 == 4) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
-                } else {
-                  for (int k = k0; k < k1; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
-                }
+                for (int k = 0; k < 4; ++k)
+                  if (k >= k0 && k < k1) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
               }
               umma_commit(&empty[s]);
             }
@@ -323,12 +320,9 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __gr
               for (int j = 0; j < p.kw; ++j) {
                 const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
                 const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
-                if (k0 == 0 && k1 == 4) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
-                } else {
-                  for (int k = k0; k < k1; ++k) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
-                }
+                for (int k = 0; k < 4; ++k)
+                  if (k >= k0 && k < k1) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
               }
               umma_commit(&aempty[as]);
             }

@@ -3,6 +3,8 @@
 #include "../../include/hm_b200.h"
 #include "hm_ptx.cuh"
 
+#include <algorithm>
+
 namespace {
 
 // One thread converts TWO adjacent contraction indices (k, k+1) of one row for ALL taps: the fp32 source is read once
@@ -51,6 +53,82 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ G, int taps, int c
   }
 }
 
+// Tiled variants (32 x 32 tile of (row, k) or (q, p), all taps of a chunk staged in shared memory) for the cases where the
+// straightforward kernels above are uncoalesced on one side:
+//  * pack with the ROW index contiguous in the source (the data-gradient role: rows = ci of W[co][ci][t]): the simple
+//    kernel reads 36-byte fragments 36 KB apart (ncu r01: 31 % of the HBM copy bandwidth for the whole pack class);
+//  * unpack, whose source G[(t, p)][q] is contiguous along q while the destination dst[q][p][t] is contiguous along (p, t):
+//    the simple kernel gathers 4-byte words from different sectors (34 %).
+constexpr int kTileTaps = 9;
+
+__global__ void __launch_bounds__(256) pack_weight_rowfast_kernel(const float* __restrict__ src, int rows, int kk, int taps,
+                                                                   long s_row, long s_k, long s_tap, int rows_pad, int k_pad,
+                                                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[kTileTaps][32][33];          // [tap][k][row]
+  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;   // 8 warps
+  const long plane = long(rows_pad) * k_pad;
+  for (int t0 = 0; t0 < taps; t0 += kTileTaps) {
+    const int nt = min(kTileTaps, taps - t0);
+    // load: lanes along rows (contiguous-ish in the source: stride s_row), warps along k
+    for (int kl = wy; kl < 32; kl += 8) {
+      const int r = r0 + lane, k = k0 + kl;
+      const bool ok = r < rows && k < kk;
+      const float* p = src + r * s_row + k * s_k + long(t0) * s_tap;
+      for (int t = 0; t < nt; ++t) tile[t][kl][lane] = ok ? __ldg(p + t * s_tap) : 0.f;
+    }
+    __syncthreads();
+    // store: lanes along k (contiguous in the slab), warps along rows
+    for (int rl = wy; rl < 32; rl += 8) {
+      const int r = r0 + rl, k = k0 + lane;
+      if (r < rows_pad && k < k_pad) {
+        for (int t = 0; t < nt; ++t) {
+          __nv_bfloat16 h, l;
+          hm::split_bf16(tile[t][lane][rl], h, l);
+          const long o = long(t0 + t) * plane + long(r) * k_pad + k;
+          hi[o] = h;
+          if (lo) lo[o] = l;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_unpack_tiled_kernel(const float* __restrict__ G, int taps, int cp, int cq,
+                                                                  int cp_pad, int cq_pad, float* __restrict__ dst,
+                                                                  int accumulate) {
+  __shared__ float tile[kTileTaps][32][33];          // [tap][p][q]
+  const int q0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < taps; t0 += kTileTaps) {
+    const int nt = min(kTileTaps, taps - t0);
+    for (int pl = wy; pl < 32; pl += 8) {              // lanes along q: 128 B runs of G
+      const int p = p0 + pl, q = q0 + lane;
+      const bool ok = p < cp && q < cq;
+      for (int t = 0; t < nt; ++t)
+        tile[t][pl][lane] = ok ? __ldg(G + (long(t0 + t) * cp_pad + p) * cq_pad + q) : 0.f;
+    }
+    __syncthreads();
+    // dst[q][p][t]: for a fixed q the tile covers 32 * taps consecutive floats; lanes walk (p, t) jointly
+    for (int ql = wy; ql < 32; ql += 8) {
+      const int q = q0 + ql;
+      if (q < cq) {
+        for (int e = lane; e < 32 * nt; e += 32) {
+          const int pl = e / nt, t = e - pl * nt;
+          const int p = p0 + pl;
+          if (p < cp) {
+            const long o = (long(q) * cp + p) * taps + t0 + t;
+            const float v = tile[t][pl][ql];
+            dst[o] = accumulate ? dst[o] + v : v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -59,6 +137,13 @@ int hm_pack_weight(const float* src, int rows, int k, int taps, long s_row, long
                    void* dst_lo, void* stream) {
   if (!src || !dst_hi || rows <= 0 || k <= 0 || taps <= 0) return HM_ERR_INVALID;
   const int rows_pad = hm_rows_pad(rows), k_pad = hm_k_pad(k);
+  if (s_row < s_k && rows >= 32 && k >= 32) {     // row index contiguous in the source: transpose through shared memory
+    dim3 grid((rows_pad + 31) / 32, (k_pad + 31) / 32);
+    pack_weight_rowfast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, rows, k, taps, s_row, s_k, s_tap, rows_pad, k_pad, static_cast<__nv_bfloat16*>(dst_hi),
+        static_cast<__nv_bfloat16*>(dst_lo));
+    return cudaGetLastError() == cudaSuccess ? HM_OK : HM_ERR_LAUNCH;
+  }
   const long total = long(rows_pad) * (k_pad / 2);
   const int block = 256;
   const int grid = int(std::min<long>((total + block - 1) / block, 148L * 16));
@@ -72,6 +157,12 @@ int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* ds
   if (!G_ws || !dst) return HM_ERR_INVALID;
   const int taps = KH * KW;
   const int cp_pad = (cp + 63) / 64 * 64, cq_pad = (cq + 63) / 64 * 64;
+  if (cp >= 16 && cq >= 16) {
+    dim3 grid((cq + 31) / 32, (cp + 31) / 32);
+    wgrad_unpack_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(G_ws, taps, cp, cq, cp_pad, cq_pad, dst,
+                                                                                 accumulate);
+    return cudaGetLastError() == cudaSuccess ? HM_OK : HM_ERR_LAUNCH;
+  }
   const long total = long(cq) * cp * taps;
   const int block = 256;
   const int grid = int(std::min<long>((total + block - 1) / block, 148L * 16));

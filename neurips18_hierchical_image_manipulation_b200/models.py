@@ -65,8 +65,11 @@ def create_model(opt, data_size=None):
     """models/models.py:6-24."""
     if opt.model == "pix2pixHD_condImg":
         model = Pix2PixHDModel_condImg(opt)
+    elif opt.model == "AE_maskgen_twostream":      # box2mask (SURVEY N3): forward + reconstruction losses so far
+        from .box2mask import TwoStreamAE_mask
+        model = TwoStreamAE_mask(opt)
     else:
-        # AE_maskgen_twostream / pix2pixHD_condImgColor exist in the reference factory but are outside this path
+        # pix2pixHD_condImgColor exists in the reference factory but is untrainable as shipped (SURVEY D8)
         raise NotImplementedError("the model is not implemented")
     print("model [%s] was created" % (model.name()))
     if opt.isTrain and len(opt.gpu_ids):

@@ -397,3 +397,41 @@ def cond_image_operand(ctx, image_nchw, mask_nchw, border):
                                           _ptr(out.lo), out.cs, border, _stream()), "hm_cond_image_operand")
     ctx.launches += 1
     return out
+
+
+# ---- box2mask generator glue (csrc/hm_box2mask.cu) ---------------------------------------------------------------
+def box2mask_encode(ctx, mask_ctx_in, mask_in, cls, label_nc):
+    """cond operand [B,H,W,2*label_nc]: object box mask in its class channel | one-hot context (exact in bf16: hi only)."""
+    B, _, H, W = mask_ctx_in.shape
+    out = Operand(ctx, B, H, W, 2 * label_nc)
+    L.check(ctx.lib.hm_box2mask_encode(mask_ctx_in.data_ptr(), mask_in.data_ptr(), cls.data_ptr(), B, H, W, label_nc,
+                                       out.hi.data_ptr(), None, out.cs, _stream()), "hm_box2mask_encode")
+    out.lo = None           # every value is 0 or 1: no lo product at all
+    ctx.launches += 1
+    return out
+
+
+def bn_fold(ctx, mean, rstd, gamma, beta, N):
+    Cc = mean.numel()
+    mo = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    ro = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    L.check(ctx.lib.hm_bn_fold(mean.data_ptr(), rstd.data_ptr(), _ptr(gamma), _ptr(beta), N, Cc, mo.data_ptr(),
+                               ro.data_ptr(), _stream()), "hm_bn_fold")
+    ctx.launches += 1
+    return mo, ro
+
+
+def upsample2_add(ctx, small, deep, out):
+    N, h, w, Cc = small.shape
+    assert tuple(deep.shape) == (N, 2 * h, 2 * w, Cc) == tuple(out.shape)
+    L.check(ctx.lib.hm_upsample2_add(small.data_ptr(), deep.data_ptr(), N, h, w, Cc, out.data_ptr(), _stream()),
+            "hm_upsample2_add")
+    ctx.launches += 1
+
+
+def box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, comb_logit, comb_logprob, obj_prob, acc):
+    N, H, W, Cc = ctx_logit.shape
+    L.check(ctx.lib.hm_box2mask_head(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1], _ptr(label_map),
+                                     _ptr(mask_out), _ptr(inst), N, H, W, Cc, 1 if use_gate else 0, _ptr(comb_logit),
+                                     _ptr(comb_logprob), _ptr(obj_prob), _ptr(acc), _stream()), "hm_box2mask_head")
+    ctx.launches += 1

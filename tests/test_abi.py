@@ -111,8 +111,10 @@ def test_model_fails_loudly_without_cuda():
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     with pytest.raises(RuntimeError):
         create_model(Options(ngf=8, n_downsample_global=1, n_blocks_global=1))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):      # box2mask (N3) exists now and, like the rest, refuses to run without CUDA
         create_model(Options(model="AE_maskgen_twostream"))
+    with pytest.raises(NotImplementedError):
+        create_model(Options(model="pix2pixHD_condImgColor"))
 
 
 def test_synthetic_batch_contract_matches_oracle_generator():

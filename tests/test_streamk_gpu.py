@@ -60,6 +60,7 @@ def test_streamk_matches_fp64_is_deterministic_and_agrees_with_whole_tiles(n, h,
         h, w = conv.out_hw(hin, win, pad)
     scratch = ops._SCRATCH[ctx.device.index if ctx.device.index is not None else torch.cuda.current_device()]
     try:
+        assert lib.hm_set_streamk(1) == 0                              # opt-in (off by default: no measured gain)
         y1, o1 = _run(ctx, conv, op, n, h, w, cout, act, out16, kind, ops)
         y2, o2 = _run(ctx, conv, op, n, h, w, cout, act, out16, kind, ops)
         torch.cuda.synchronize()
@@ -68,6 +69,7 @@ def test_streamk_matches_fp64_is_deterministic_and_agrees_with_whole_tiles(n, h,
         torch.cuda.synchronize()
     finally:
         assert lib.hm_set_scratch(scratch.data_ptr(), scratch.numel()) == 0
+        lib.hm_set_streamk(0)
     ctx.check_pipeline()
     assert torch.equal(y1, y2), "stream-K result differs from run to run"
     if out16:

@@ -48,6 +48,7 @@ def time_conv(ctx, split, n, h, w, cin, cout, k, pad, iters=30):
 def main():
     ctx = ops.Ctx("cuda:0", split=True)
     scratch = ops._SCRATCH[0]
+    ctx.lib.hm_set_streamk(1)
     for name, *shape in SHAPES:
         row = []
         for split in (True, False):
