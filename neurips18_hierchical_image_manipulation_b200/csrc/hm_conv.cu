@@ -214,19 +214,26 @@ int launch_rows(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_
   return HM_OK;
 }
 
-template <int BN>
-int launch_rows2(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_t st) {
+template <int BN, bool TRIM>
+int launch_rows2_t(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_t st) {
   static int configured = 0;
   if (configured < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(hm::hm_krows2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_krows2_kernel<BN, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
     if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
     configured = smem_bytes;
   }
   int grid = std::min(num_tiles, sm_count());
-  hm::hm_krows2_kernel<BN><<<grid, hm::kEngineThreads, smem_bytes, st>>>(p);
+  hm::hm_krows2_kernel<BN, TRIM><<<grid, hm::kEngineThreads, smem_bytes, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   return HM_OK;
+}
+// TRIM variant (skips all-zero 16-channel groups) only when the operand has any: partial last chunk or exact low channels
+template <int BN>
+int launch_rows2(const hm::RParams& p, int num_tiles, int smem_bytes, cudaStream_t st) {
+  const bool trim = (p.a_c & 63) != 0 && (((p.a_c & 63) + 15) >> 4) < 4 || p.a_lo_c0 >= 16;
+  return trim ? launch_rows2_t<BN, true>(p, num_tiles, smem_bytes, st) : launch_rows2_t<BN, false>(p, num_tiles, smem_bytes, st);
 }
 
 // packed weights [taps][rows_pad][k_pad] bf16 -> 3-D map, box = 64 (k) x bn rows x kw taps

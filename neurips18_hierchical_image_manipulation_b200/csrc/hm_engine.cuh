@@ -157,9 +157,10 @@ __device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&raw)
 }
 
 // Which 16-channel groups (one K = 16 MMA each) of 64-channel chunk `chunk` carry data: channels >= a_c are zero padding,
-// and the lo plane is all zero below a_lo_c0 (one-hot label channels), so those MMAs are skipped.  The narrow-N layers are
-// bound by the shared-memory reads of the A operand (one 4 KB read per MMA), so skipped MMAs are time saved: the 38-channel
-// stem issues 7 instead of 12 MMAs per tap in bf16x3, the 21-channel head gradient 2 instead of 4.
+// and the lo plane is all zero below a_lo_c0 (one-hot label channels), so those MMAs can be skipped: the 38-channel stem
+// issues 7 instead of 12 MMAs per tap in bf16x3.  Used by the TRIM variant of the multi-row engine only (measured, r02:
+// the generic K-engine's thin layers are bound by L2 -> SM traffic, not by MMA count, and ANY extra work in the single
+// issuing thread's loop slows the full-chunk layers down by 15-50 %, so the other engines keep the plain 4-MMA loop).
 __device__ __forceinline__ void k_groups(int a_c, int a_lo_c0, int a_plane, int chunk, int& j0, int& j1) {
   const int cv = min(64, a_c - chunk * 64);
   j1 = (cv + 15) >> 4;
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int num_m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   const int num_tiles = num_m_tiles * p.n_tiles_n;
+  const int ksteps = p.n_entries * p.chunks;
   AbortCtl ab{abort_flag, p.err};
 
   if (threadIdx.x == 0) {
@@ -233,28 +235,19 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
       mbar_wait(&tempty[a], aph ^ 1, ab, 102);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * BN;
-      uint32_t acc = 0;
-      for (int e = 0; e < p.n_entries; ++e) {
-        const int a_plane = p.entries[e].a_plane;
-        for (int c = 0; c < p.chunks; ++c) {
-          int j0, j1;
-          k_groups(p.a_c, p.a_lo_c0, a_plane, c, j0, j1);
-          mbar_wait(&full[s], ph, ab, 103);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
-          if (elect_one_sync()) {
-            // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row; the loop stays unrolled (the issue path is on the
-            // critical path: a run-time trip count cost ~2x per MMA) and unused groups are predicated off
+      for (int k = 0; k < ksteps; ++k) {
+        mbar_wait(&full[s], ph, ab, 103);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j >= j0 && j < j1) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, acc | uint32_t(j > j0));
-            umma_commit(&empty[s]);
-          }
-          if (j1 > j0) acc = 1;   // warp-uniform: every lane tracks whether the accumulator has been written
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          for (int j = 0; j < 4; ++j)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
+            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
+          umma_commit(&empty[s]);
         }
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
       if (elect_one_sync()) umma_commit(&tfull[a]);
       if (++a == C::ACC) { a = 0; aph ^= 1; }

@@ -134,8 +134,6 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
         uint32_t acc = 0;
         for (int c = 0; c < p.chunks; ++c) {
           for (int e = 0; e < p.n_entries; ++e) {
-            int k0, k1;
-            k_groups(p.a_c, p.a_lo_c0, p.entries[e].a_plane, c, k0, k1);
             mbar_wait(&full[s], ph, ab, 304);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
@@ -146,12 +144,11 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows_kernel(const __gri
                 const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
                 const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k >= k0 && k < k1) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
+                for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
               }
               umma_commit(&empty[s]);
             }
-            if (k1 > k0) acc = 1;
+            acc = 1;
             if (++s == nst) { s = 0; ph ^= 1; }
           }
         }
@@ -223,7 +220,7 @@ struct R2Cfg : RCfgCommon {
   static constexpr int MAX_A_STAGES = 8;
 };
 
-template <int BN>
+template <int BN, bool TRIM>
 __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __grid_constant__ RParams p) {
   using C = R2Cfg<BN>;
   constexpr int MT = C::MT;
@@ -307,8 +304,8 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __gr
       uint32_t acc = 0;
       for (int c = 0; c < p.chunks; ++c) {
         for (int e = 0; e < p.n_entries; ++e) {
-          int k0, k1;
-          k_groups(p.a_c, p.a_lo_c0, p.entries[e].a_plane, c, k0, k1);
+          int k0 = 0, k1 = 4;
+          if constexpr (TRIM) k_groups(p.a_c, p.a_lo_c0, p.entries[e].a_plane, c, k0, k1);
           mbar_wait(&bfull[bs], bph, ab, 704);
           const uint32_t b_base = smem_u32(smem_b + bs * b_stage_bytes);
           for (int r = 0; r < MT; ++r) {
@@ -321,8 +318,13 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_krows2_kernel(const __gr
                 const uint64_t ad = umma_smem_desc(a_base + uint32_t(p.entries[e].a_off[j]) * 128u, 16, 1024);
                 const uint64_t bd = umma_smem_desc(b_base + uint32_t(j) * C::B_TILE, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k >= k0 && k < k1) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
+                for (int k = 0; k < 4; ++k) {
+                  if constexpr (TRIM) {
+                    if (k >= k0 && k < k1) { umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1; }
+                  } else {
+                    umma_bf16(d_tmem + r * BN, ad + 2 * k, bd + 2 * k, idesc, acc_j); acc_j = 1;
+                  }
+                }
               }
               umma_commit(&aempty[as]);
             }

@@ -53,12 +53,11 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ G, int taps, int c
   }
 }
 
-// Tiled variants (32 x 32 tile of (row, k) or (q, p), all taps of a chunk staged in shared memory) for the cases where the
-// straightforward kernels above are uncoalesced on one side:
-//  * pack with the ROW index contiguous in the source (the data-gradient role: rows = ci of W[co][ci][t]): the simple
-//    kernel reads 36-byte fragments 36 KB apart (ncu r01: 31 % of the HBM copy bandwidth for the whole pack class);
-//  * unpack, whose source G[(t, p)][q] is contiguous along q while the destination dst[q][p][t] is contiguous along (p, t):
-//    the simple kernel gathers 4-byte words from different sectors (34 %).
+// Tiled variant (32 x 32 tile of (row, k), all taps of a chunk staged in shared memory) of the pack for sources whose ROW
+// index is the contiguous one (the data-gradient role: rows = ci of W[co][ci][t]): the simple kernel reads 36-byte
+// fragments 36 KB apart (ncu r01: 31 % of the HBM copy bandwidth for the whole pack class; r02: 1.48 -> 1.07 ms per step).
+// (A tiled UNPACK was tried and measured 2.4x slower than the gather above: the workspace G was just written by the
+// weight-gradient engine and is L2 resident, so the 4-byte gathers are cheap.)
 constexpr int kTileTaps = 9;
 
 __global__ void __launch_bounds__(256) pack_weight_rowfast_kernel(const float* __restrict__ src, int rows, int kk, int taps,
@@ -95,40 +94,6 @@ __global__ void __launch_bounds__(256) pack_weight_rowfast_kernel(const float* _
   }
 }
 
-__global__ void __launch_bounds__(256) wgrad_unpack_tiled_kernel(const float* __restrict__ G, int taps, int cp, int cq,
-                                                                  int cp_pad, int cq_pad, float* __restrict__ dst,
-                                                                  int accumulate) {
-  __shared__ float tile[kTileTaps][32][33];          // [tap][p][q]
-  const int q0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  for (int t0 = 0; t0 < taps; t0 += kTileTaps) {
-    const int nt = min(kTileTaps, taps - t0);
-    for (int pl = wy; pl < 32; pl += 8) {              // lanes along q: 128 B runs of G
-      const int p = p0 + pl, q = q0 + lane;
-      const bool ok = p < cp && q < cq;
-      for (int t = 0; t < nt; ++t)
-        tile[t][pl][lane] = ok ? __ldg(G + (long(t0 + t) * cp_pad + p) * cq_pad + q) : 0.f;
-    }
-    __syncthreads();
-    // dst[q][p][t]: for a fixed q the tile covers 32 * taps consecutive floats; lanes walk (p, t) jointly
-    for (int ql = wy; ql < 32; ql += 8) {
-      const int q = q0 + ql;
-      if (q < cq) {
-        for (int e = lane; e < 32 * nt; e += 32) {
-          const int pl = e / nt, t = e - pl * nt;
-          const int p = p0 + pl;
-          if (p < cp) {
-            const long o = (long(q) * cp + p) * taps + t0 + t;
-            const float v = tile[t][pl][ql];
-            dst[o] = accumulate ? dst[o] + v : v;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 }  // namespace
 
 extern "C" {
@@ -157,12 +122,6 @@ int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* ds
   if (!G_ws || !dst) return HM_ERR_INVALID;
   const int taps = KH * KW;
   const int cp_pad = (cp + 63) / 64 * 64, cq_pad = (cq + 63) / 64 * 64;
-  if (cp >= 16 && cq >= 16) {
-    dim3 grid((cq + 31) / 32, (cp + 31) / 32);
-    wgrad_unpack_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(G_ws, taps, cp, cq, cp_pad, cq_pad, dst,
-                                                                                 accumulate);
-    return cudaGetLastError() == cudaSuccess ? HM_OK : HM_ERR_LAUNCH;
-  }
   const long total = long(cq) * cp * taps;
   const int block = 256;
   const int grid = int(std::min<long>((total + block - 1) / block, 148L * 16));

@@ -52,6 +52,9 @@ class Options(object):
                  vgg_seed=1234,           # seed of that stand-in
                  cuda_graph=True,         # optimize_parameters(): capture the fused step in a CUDA graph after two eager
                                           # steps and replay it (same kernels, no per-launch host work / launch gaps)
+                 overlap_streams=True,    # fused step: run the VGG branch / the discriminator's own backward pass on a
+                                          # second CUDA stream so that their HBM-bound kernels overlap the other
+                                          # branch's tensor-core kernels (HM_STREAMS=0 disables)
                  data_parallel=True,      # under torch.distributed: allreduce the gradients over all ranks (False: this
                                           # replica trains on its own -- used by the multi-GPU equivalence check)
                  sn_D=False)              # K13: spectral-norm the PatchGAN convs (models/sn_utils.py SNConv2d); the
@@ -279,6 +282,10 @@ class Pix2PixHDModel_condImg(object):
             self.loss_acc = torch.zeros(5, dtype=torch.float64, device=dev)
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._step = None
+        self._side = None
+        self._after_d_dgrad = None
+        # stream overlap only inside optimize_parameters(); forward() / backward() of the script sequence stay single-stream
+        self._overlap = False
         self._pinned = {}
         self._graph = None          # dict(graph, inputs, losses, st, sig) once the fused step has been captured
         self._eager_steps = 0
@@ -344,10 +351,15 @@ class Pix2PixHDModel_condImg(object):
         ops.finish_fake(ctx, t, st["image"], st["mask"], opt.use_output_gate, fake, st["d_in"], self.d_img_c0, st["v_in"],
                         d_mask=st["d_mask"])
         st.update(t=t, g_tape=g_tape, fake=fake)
-        # D on [fake ; real] (the fake.detach() pass of :218 and the pass of :231 see identical values: computed once)
-        st["d_tape"] = self.netD.forward(st["d_in"])
         acc = self.loss_acc
         acc.zero_()
+        side = self._side_stream() if self.vgg is not None else None
+        if side is not None:                                           # VGG branch (:245-247) on the second stream
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._vgg_forward_losses(st, B, acc)
+        # D on [fake ; real] (the fake.detach() pass of :218 and the pass of :231 see identical values: computed once)
+        st["d_tape"] = self.netD.forward(st["d_in"])
         for lv in st["d_tape"]:
             pred = lv["taps"][-1]
             half = pred.numel() // 2
@@ -358,15 +370,28 @@ class Pix2PixHDModel_condImg(object):
                 cf = (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
                 for tap in lv["taps"][:-1]:
                     ops.l1_sum(ctx, tap[:B], tap[B:], cf / (tap.numel() // 2), acc, 1)
-        if self.vgg is not None:                                      # :245-247
-            st["v_tape"] = self.vgg.forward(st["v_in"])
-            for li, tap in st["v_tape"]["taps"].items():
-                wi = VGG_WEIGHTS[sorted(st["v_tape"]["taps"]).index(li)]
-                ops.l1_sum(ctx, tap[:B], tap[B:], opt.lambda_feat * wi / (tap.numel() // 2), acc, 2)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif self.vgg is not None:                                    # :245-247
+            self._vgg_forward_losses(st, B, acc)
         if opt.lambda_rec > 0:                                        # :249-251
             ops.l1_sum(ctx, fake, st["image"], opt.lambda_rec / fake.numel(), acc, 1)
         st["losses"] = acc.to(torch.float32)
         return st
+
+    def _vgg_forward_losses(self, st, B, acc):
+        st["v_tape"] = self.vgg.forward(st["v_in"])
+        for li, tap in st["v_tape"]["taps"].items():
+            wi = VGG_WEIGHTS[sorted(st["v_tape"]["taps"]).index(li)]
+            ops.l1_sum(self.ctx, tap[:B], tap[B:], self.opt.lambda_feat * wi / (tap.numel() // 2), acc, 2)
+
+    def _side_stream(self):
+        """Second stream of the fused step, or None when overlap is off / we are not inside the fused step."""
+        if not self._overlap:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def _run_generator(self, st):
         """:207-210.  'global' / 'local': netG(cat(label, cond_image)); 'global_twostream': netG(cond_image, label, mask)
@@ -403,14 +428,23 @@ class Pix2PixHDModel_condImg(object):
         st, opt, ctx = self._step, self.opt, self.ctx
         B = st["B"]
         cf = 0.0 if opt.no_ganFeat_loss else w[1] * (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
-        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.d_img_c0)
         gV = None
-        if self.vgg is not None and w[2] != 0.0:
+        side = self._side_stream() if (self.vgg is not None and w[2] != 0.0) else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
+        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.d_img_c0)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif self.vgg is not None and w[2] != 0.0:
             gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
         dy = Operand(ctx, B, st["H"], st["W"], 3, grad=True)
         rec = w[1] * opt.lambda_rec / st["fake"].numel() if opt.lambda_rec > 0 else 0.0
         ops.fake_bwd(ctx, st["t"], st["mask"], opt.use_output_gate, gD, self.netD.gin_coff, gV, st["image"], rec, dy,
                      d_mask=st["d_mask"])
+        if self._after_d_dgrad is not None:      # fused step: the discriminator's own backward pass may start now
+            self._after_d_dgrad()
         self.netG.backward(st["g_tape"], dy_head=dy)
 
     def _backward_D(self, w):
@@ -436,6 +470,13 @@ class Pix2PixHDModel_condImg(object):
                                 mask_out=batch["mask_out"])
 
     def _fused_step(self, label, inst, image, mask_in, captured, mask_out=None):
+        self._overlap = bool(getattr(self.opt, "overlap_streams", True)) and os.environ.get("HM_STREAMS", "1") != "0"
+        try:
+            return self._fused_step_impl(label, inst, image, mask_in, captured, mask_out)
+        finally:
+            self._overlap = False
+
+    def _fused_step_impl(self, label, inst, image, mask_in, captured, mask_out=None):
         st = self._forward_all(label, inst, image, mask_in, mask_out)
         self._step = st
         self._keep_visuals(st)
@@ -445,15 +486,35 @@ class Pix2PixHDModel_condImg(object):
         scale = 1.0 / parallel.world()[1] if dp else 1.0
         # the two allreduce segments run on the communicator's stream: G's overlaps the D backward pass, D's overlaps
         # the generator's Adam step (the sum over both is the ONE [G | D] allreduce of SURVEY section 8(e))
-        self._backward_G([1.0, 1.0, 1.0])
+        side = self._side_stream()
+        hD = [None]
+        if side is not None:
+            # loss_D's graph holds no generator parameter, so its backward pass only needs the D tape: it runs on the
+            # second stream as soon as the generator-side pass through D is enqueued (the packed D weights exist then),
+            # overlapping the long generator backward; its gradient segment is allreduced from that stream.
+            def start_d():
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._backward_D([0.5, 0.5])
+                    hD[0] = parallel.allreduce_sum_async_(self.flat_grad[nG:]) if dp else None
+                    if hD[0] is not None:
+                        hD[0].wait()
+            self._after_d_dgrad = start_d
+        try:
+            self._backward_G([1.0, 1.0, 1.0])
+        finally:
+            self._after_d_dgrad = None
         hG = parallel.allreduce_sum_async_(self.flat_grad[:nG]) if dp else None
-        self._backward_D([0.5, 0.5])
-        hD = parallel.allreduce_sum_async_(self.flat_grad[nG:]) if dp else None
+        if side is None:
+            self._backward_D([0.5, 0.5])
+            hD[0] = parallel.allreduce_sum_async_(self.flat_grad[nG:]) if dp else None
         if hG is not None:
             hG.wait()
         self.optimizer_G.step(grad_scale=scale, captured=captured)
-        if hD is not None:
-            hD.wait()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif hD[0] is not None:
+            hD[0].wait()
         self.optimizer_D.step(grad_scale=scale, captured=captured)
         return st["losses"]
 

@@ -51,8 +51,10 @@ class Ctx(object):
         self.launches = 0  # number of hm kernels enqueued (bench.py reports it)
 
     def ws(self, key, nbytes):
-        """Grow-only scratch buffers keyed by use."""
+        """Grow-only scratch buffers keyed by use AND by the current stream (branches of the fused step that run on
+        different streams must not share scratch)."""
         n = (int(nbytes) + 3) // 4
+        key = (key, torch.cuda.current_stream().cuda_stream)
         t = self._ws.get(key)
         if t is None or t.numel() < n:
             t = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
