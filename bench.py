@@ -372,6 +372,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        from neurips18_hierchical_image_manipulation_b200 import parallel
+        parallel.configure_nccl_env()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_batch

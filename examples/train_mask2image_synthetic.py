@@ -30,6 +30,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from neurips18_hierchical_image_manipulation_b200 import parallel
+        parallel.configure_nccl_env()
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     opt = Options(vgg_weights="random", name="synthetic_city", model="pix2pixHD_condImg", label_nc=35, output_nc=3, no_instance=True,
                   netG="global_twostream", which_encoder="ctx_label", use_skip=True, use_output_gate=True, no_imgCond=True,

@@ -72,6 +72,11 @@ int hm_set_scratch(void* ptr, size_t bytes);
 /* The stream-K tail is OPT-IN (default off, or HM_STREAMK=1 in the environment): measured on B200 it does not beat the
  * whole-tile schedule on this path's shapes.  hm_set_streamk(1/0) switches it at run time. */
 int hm_set_streamk(int on);
+/* Persistent engines launch one CTA (or CTA pair) per SM.  While a collective runs concurrently (the bucketed gradient
+ * allreduce of the data-parallel step, whose NCCL CTAs need SMs of their own), a full-width grid would leave some of its
+ * CTAs waiting for the SMs NCCL holds and double the kernel's time; hm_set_sm_limit(n) makes the engines size their
+ * grids for n SMs (rounded down to even) until it is reset with 0.  Host-side setting, read at launch (or capture) time. */
+int hm_set_sm_limit(int n);
 
 /* ---- weight packing --------------------------------------------------------------------------
  * N-tile width the K-engine uses for `rows` output rows, and the padded slab dims. */

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "hm_scratch_bytes": (_sz, []),
     "hm_set_scratch": (_i, [_vp, _sz]),
     "hm_set_streamk": (_i, [_i]),
+    "hm_set_sm_limit": (_i, [_i]),
     "hm_pick_bn": (_i, [_i]),
     "hm_rows_pad": (_i, [_i]),
     "hm_k_pad": (_i, [_i]),

@@ -74,6 +74,7 @@ int make_tmap_weight(CUtensorMap* m, const void* base, int rows_total, int k_pad
   return r == CUDA_SUCCESS ? HM_OK : HM_ERR_TENSORMAP;
 }
 
+int g_sm_limit = 0;            // hm_set_sm_limit: leave SMs free for a concurrent collective (0 = use all)
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -82,7 +83,7 @@ int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 // choose the th x tw = `pixels` rectangle that wastes the least area on a (vh x vw) tile space
@@ -521,7 +522,14 @@ extern "C" {
 
 const char* hm_version(void) { return "hm_b200 0.2 (sm_100a, tcgen05+TMA)"; }
 
-size_t hm_scratch_bytes(void) { return kSkCounterBytes + size_t(sm_count() / 2) * 2 * kSkSlotBytes; }
+size_t hm_scratch_bytes(void) {
+  const int keep = g_sm_limit;
+  g_sm_limit = 0;
+  const size_t b = kSkCounterBytes + size_t(sm_count() / 2) * 2 * kSkSlotBytes;
+  g_sm_limit = keep;
+  return b;
+}
+int hm_set_sm_limit(int n) { g_sm_limit = n > 0 ? (n & ~1) : 0; return HM_OK; }
 int hm_set_streamk(int on) { g_use_streamk = on ? 1 : 0; return HM_OK; }
 int hm_set_scratch(void* ptr, size_t bytes) {
   if (ptr && (bytes < hm_scratch_bytes() || (reinterpret_cast<uintptr_t>(ptr) & 255))) return HM_ERR_INVALID;

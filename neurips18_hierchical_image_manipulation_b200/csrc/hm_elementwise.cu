@@ -84,101 +84,95 @@ __device__ __forceinline__ float act_grad(float pre_sign_src, int act, float slo
 // K11  encode_input  (models/pix2pixHD_condImg_model.py:144-174, get_edges :285-291)
 // one thread per (padded) generator-input pixel: one-hot(label) | edge(inst) | (1-mask)*image
 // ================================================================================================
-// One thread per (pixel, group of 8 output channels) of one of the three operands, so that the 16 B stores of a warp
-// are contiguous (a thread-per-pixel version wrote 80-96 B apart and ran at 1.4 TB/s); the few scalar inputs of a
-// pixel are re-read by its 5-6 channel-group threads through L1.
-__global__ void encode_kernel(const float* __restrict__ label, const float* __restrict__ inst,
-                              const float* __restrict__ image, const float* __restrict__ mask, int B, int H, int W,
-                              int label_nc, bf16* g_hi, bf16* g_lo, int g_cs, int gb, bf16* d_hi, bf16* d_lo, int d_cs,
-                              bf16* v_hi, bf16* v_lo, int v_cs, int d_no_imgcond, const float* __restrict__ d_mask) {
-  const int Hp = H + 2 * gb, Wp = W + 2 * gb;
-  const int gg = g_cs >> 3, dg = d_hi ? (d_cs >> 3) : 0, vg = v_hi ? (v_cs >> 3) : 0;
-  const long items_g = long(B) * Hp * Wp * gg;
-  const long items_d = long(2) * B * H * W * dg;
-  const long items_v = long(B) * H * W * vg;
-  const long total = items_g + items_d + items_v;
-  const int n_cond = label_nc + (inst ? 1 : 0);
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-    int kind, grp, n, h, w, half = 0;
-    size_t off;
-    if (i < items_g) {
-      kind = 0;
-      grp = int(i % gg);
-      long r = i / gg;
-      const int wp = int(r % Wp); r /= Wp;
-      const int hp = int(r % Hp);
-      n = int(r / Hp);
-      h = reflect_idx(hp - gb, H); w = reflect_idx(wp - gb, W);
-      off = (size_t(n) * Hp * Wp + size_t(hp) * Wp + wp) * g_cs + grp * 8;
-    } else if (i < items_g + items_d) {
-      kind = 1;
-      long r = i - items_g;
-      grp = int(r % dg); r /= dg;
-      w = int(r % W); r /= W;
-      h = int(r % H); r /= H;
-      n = int(r % B);
-      half = int(r / B);   // 0 = fake (image channels filled by hm_finish_fake), 1 = real
-      off = ((size_t(n) + size_t(half) * B) * H * W + size_t(h) * W + w) * d_cs + grp * 8;
-    } else {
-      kind = 2;
-      long r = i - items_g - items_d;
-      grp = int(r % vg); r /= vg;
-      w = int(r % W); r /= W;
-      h = int(r % H);
-      n = int(r / H);
-      off = ((size_t(n) + B) * H * W + size_t(h) * W + w) * v_cs + grp * 8;
-    }
-    const long pix = (long(n) * H + h) * W + w;
-    const int c0 = grp * 8;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    const bool need_img = (kind == 2) ? (c0 < 3) : (c0 + 8 > n_cond);   // (also covers the shifted no_imgCond layout)
-    float img[3] = {0.f, 0.f, 0.f}, cond[3] = {0.f, 0.f, 0.f};
-    if (need_img) {
-      const float m = __ldg(mask + pix);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        img[c] = __ldg(image + (long(n) * 3 + c) * H * W + long(h) * W + w);
-        cond[c] = (1.f - m) * img[c];  // NULLVAL == 0 (:18, :165-166)
-      }
-    }
-    if (kind == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (c0 + j < 3) v[j] = img[c0 + j];
-    } else {
-      if (c0 < label_nc) {
-        const int cls = int(__ldg(label + pix));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (c0 + j < label_nc && c0 + j == cls) v[j] = 1.f;
-      }
-      if (inst && c0 <= label_nc && label_nc < c0 + 8) {  // :285-291: 4-neighbour instance boundary
-        const float t = __ldg(inst + pix);
-        bool e = false;
-        if (w > 0) e |= (t != __ldg(inst + pix - 1));
-        if (w < W - 1) e |= (t != __ldg(inst + pix + 1));
-        if (h > 0) e |= (t != __ldg(inst + pix - W));
-        if (h < H - 1) e |= (t != __ldg(inst + pix + W));
-        v[label_nc - c0] = e ? 1.f : 0.f;
-      }
-      // D operand with no_imgCond (pix2pixHD_condImg_model.py:213-214): [label | edge | image], else [.. | cond | image]
-      const int cimg = (kind == 1 && d_no_imgcond) ? n_cond : n_cond + 3;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        if (!(kind == 1 && d_no_imgcond) && c >= n_cond && c < n_cond + 3) v[j] = cond[c - n_cond];
-        else if (kind == 1 && half == 1 && c >= cimg && c < cimg + 3) v[j] = img[c - cimg];
-      }
-      if (kind == 1 && d_mask) {   // mask_gan_input (:180-181): the whole D input is multiplied by the mask
-        const float dm = __ldg(d_mask + pix);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dm;
-      }
-    }
-    if (kind == 0) store_op8(g_hi, g_lo, off, v);
-    else if (kind == 1) store_op8(d_hi, d_lo, off, v);
-    else store_op8(v_hi, v_lo, off, v);
+// One thread per (pixel, group of 8 output channels) of one of the three operands, groups fastest, so that the 16 B
+// stores of a warp are contiguous (a thread-per-pixel version wrote 80-96 B apart and ran at 1.4 TB/s); the few scalar
+// inputs of a pixel are re-read by its 5-6 channel-group threads through L1.  The grid is (row segment, row, image) per
+// operand kind, so the only index arithmetic left is one division by the group count, done as a float multiply (the
+// flat-index version spent ~4 integer divisions by run-time values per 16 B store and ran at 29 % of the HBM peak).
+struct EncodeArgs {
+  const float* label; const float* inst; const float* image; const float* mask; const float* d_mask;
+  int B, H, W, label_nc, d_no_imgcond;
+  bf16* g_hi; bf16* g_lo; int g_cs, gb;
+  bf16* d_hi; bf16* d_lo; int d_cs;
+  bf16* v_hi; bf16* v_lo; int v_cs;
+};
+
+template <int KIND>   // 0: generator operand (with reflect border), 1: discriminator operand (2B images), 2: VGG operand
+__global__ void __launch_bounds__(kBlock) encode_kernel(EncodeArgs a, int groups, float inv_groups) {
+  const int H = a.H, W = a.W;
+  const int Wrow = KIND == 0 ? W + 2 * a.gb : W;
+  const int t = blockIdx.x * kBlock + threadIdx.x;
+  if (t >= Wrow * groups) return;
+  int wp = __float2int_rd((t + 0.5f) * inv_groups);
+  int grp = t - wp * groups;
+  if (grp < 0) { --wp; grp += groups; } else if (grp >= groups) { ++wp; grp -= groups; }
+  const int hp = blockIdx.y;
+  int n = blockIdx.z, half = 0;
+  int h = hp, w = wp;
+  size_t off;
+  if (KIND == 0) {
+    h = reflect_idx(hp - a.gb, H); w = reflect_idx(wp - a.gb, W);
+    off = ((size_t(n) * (H + 2 * a.gb) + hp) * Wrow + wp) * a.g_cs + grp * 8;
+  } else if (KIND == 1) {
+    half = n >= a.B ? 1 : 0;           // 0 = fake (image channels filled by hm_finish_fake), 1 = real
+    off = ((size_t(n) * H + h) * W + w) * a.d_cs + grp * 8;
+    n -= half * a.B;
+  } else {
+    off = ((size_t(n) + a.B) * H * W + size_t(h) * W + w) * a.v_cs + grp * 8;
   }
+  const int label_nc = a.label_nc;
+  const int n_cond = label_nc + (a.inst ? 1 : 0);
+  const long pix = (long(n) * H + h) * W + w;
+  const int c0 = grp * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  const bool need_img = (KIND == 2) ? (c0 < 3) : (c0 + 8 > n_cond);   // (also covers the shifted no_imgCond layout)
+  float img[3] = {0.f, 0.f, 0.f}, cond[3] = {0.f, 0.f, 0.f};
+  if (need_img) {
+    const float m = __ldg(a.mask + pix);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      img[c] = __ldg(a.image + (long(n) * 3 + c) * H * W + long(h) * W + w);
+      cond[c] = (1.f - m) * img[c];  // NULLVAL == 0 (:18, :165-166)
+    }
+  }
+  if (KIND == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c0 + j < 3) v[j] = img[c0 + j];
+  } else {
+    if (c0 < label_nc) {
+      const int cls = int(__ldg(a.label + pix));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c0 + j < label_nc && c0 + j == cls) v[j] = 1.f;
+    }
+    if (a.inst && c0 <= label_nc && label_nc < c0 + 8) {  // :285-291: 4-neighbour instance boundary
+      const float tt = __ldg(a.inst + pix);
+      bool e = false;
+      if (w > 0) e |= (tt != __ldg(a.inst + pix - 1));
+      if (w < W - 1) e |= (tt != __ldg(a.inst + pix + 1));
+      if (h > 0) e |= (tt != __ldg(a.inst + pix - W));
+      if (h < H - 1) e |= (tt != __ldg(a.inst + pix + W));
+      v[label_nc - c0] = e ? 1.f : 0.f;
+    }
+    // D operand with no_imgCond (pix2pixHD_condImg_model.py:213-214): [label | edge | image], else [.. | cond | image]
+    const bool no_ic = KIND == 1 && a.d_no_imgcond;
+    const int cimg = no_ic ? n_cond : n_cond + 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      if (!no_ic && c >= n_cond && c < n_cond + 3) v[j] = cond[c - n_cond];
+      else if (KIND == 1 && half == 1 && c >= cimg && c < cimg + 3) v[j] = img[c - cimg];
+    }
+    if (KIND == 1 && a.d_mask) {   // mask_gan_input (:180-181): the whole D input is multiplied by the mask
+      const float dm = __ldg(a.d_mask + pix);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= dm;
+    }
+  }
+  if (KIND == 0) store_op8(a.g_hi, a.g_lo, off, v);
+  else if (KIND == 1) store_op8(a.d_hi, a.d_lo, off, v);
+  else store_op8(a.v_hi, a.v_lo, off, v);
 }
 
 // ================================================================================================
@@ -1095,12 +1089,26 @@ int hm_encode_input(const float* label, const float* inst, const float* image, c
     return HM_ERR_INVALID;
   const int cin = label_nc + (inst ? 1 : 0) + 3;
   if (cin > g_cs || (d_hi && cin + (d_no_imgcond ? 0 : 3) > d_cs)) return HM_ERR_INVALID;
-  const long total = long(B) * (H + 2 * g_border) * (W + 2 * g_border) * (g_cs >> 3) +
-                     (d_hi ? long(2) * B * H * W * (d_cs >> 3) : 0) + (v_hi ? long(B) * H * W * (v_cs >> 3) : 0);
-  encode_kernel<<<grid_for(total), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      label, inst, image, mask_in, B, H, W, label_nc, static_cast<bf16*>(g_hi), static_cast<bf16*>(g_lo), g_cs,
-      g_border, static_cast<bf16*>(d_hi), static_cast<bf16*>(d_lo), d_cs, static_cast<bf16*>(v_hi),
-      static_cast<bf16*>(v_lo), v_cs, d_no_imgcond, d_mask);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EncodeArgs a;
+  a.label = label; a.inst = inst; a.image = image; a.mask = mask_in; a.d_mask = d_mask;
+  a.B = B; a.H = H; a.W = W; a.label_nc = label_nc; a.d_no_imgcond = d_no_imgcond;
+  a.g_hi = static_cast<bf16*>(g_hi); a.g_lo = static_cast<bf16*>(g_lo); a.g_cs = g_cs; a.gb = g_border;
+  a.d_hi = static_cast<bf16*>(d_hi); a.d_lo = static_cast<bf16*>(d_lo); a.d_cs = d_cs;
+  a.v_hi = static_cast<bf16*>(v_hi); a.v_lo = static_cast<bf16*>(v_lo); a.v_cs = v_cs;
+  if (H + 2 * g_border > 65535 || 2 * B > 65535) return HM_ERR_INVALID;
+  {
+    const int groups = g_cs >> 3, wrow = W + 2 * g_border;
+    encode_kernel<0><<<dim3((wrow * groups + kBlock - 1) / kBlock, H + 2 * g_border, B), kBlock, 0, st>>>(a, groups, 1.f / groups);
+  }
+  if (d_hi) {
+    const int groups = d_cs >> 3;
+    encode_kernel<1><<<dim3((W * groups + kBlock - 1) / kBlock, H, 2 * B), kBlock, 0, st>>>(a, groups, 1.f / groups);
+  }
+  if (v_hi) {
+    const int groups = v_cs >> 3;
+    encode_kernel<2><<<dim3((W * groups + kBlock - 1) / kBlock, H, B), kBlock, 0, st>>>(a, groups, 1.f / groups);
+  }
   return HM_LAUNCH_OK();
 }
 

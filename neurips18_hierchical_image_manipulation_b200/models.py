@@ -284,6 +284,7 @@ class Pix2PixHDModel_condImg(object):
         self._step = None
         self._side = None
         self._after_d_dgrad = None
+        self._grad_ready = None
         # stream overlap only inside optimize_parameters(); forward() / backward() of the script sequence stay single-stream
         self._overlap = False
         self._pinned = {}
@@ -445,7 +446,10 @@ class Pix2PixHDModel_condImg(object):
                      d_mask=st["d_mask"])
         if self._after_d_dgrad is not None:      # fused step: the discriminator's own backward pass may start now
             self._after_d_dgrad()
-        self.netG.backward(st["g_tape"], dy_head=dy)
+        if self._grad_ready is not None:
+            self.netG.backward(st["g_tape"], dy_head=dy, grad_ready=self._grad_ready)
+        else:
+            self.netG.backward(st["g_tape"], dy_head=dy)
 
     def _backward_D(self, w):
         """d(w0*D_real + w1*D_fake)/d(D params) over the [fake ; real] batch."""
@@ -500,16 +504,43 @@ class Pix2PixHDModel_condImg(object):
                     if hD[0] is not None:
                         hD[0].wait()
             self._after_d_dgrad = start_d
+        # Data parallel: the generator's gradient buffer becomes final from its END towards its start while the backward
+        # pass walks the layers last-to-first, so it is allreduced in buckets as they complete (like DDP) and only the
+        # last small bucket (stem + first down-convs) is exposed.  NCCL's CTAs need SMs of their own: the persistent
+        # engines size their grids for (SMs - comm_sms) while buckets are in flight (hm_set_sm_limit).
+        handles = []
+        bucket = None
+        comm_sms = int(os.environ.get("HM_COMM_SMS", "8"))
+        use_buckets = dp and self.netG_type == "global" and os.environ.get("HM_BUCKETS", "1") != "0"
+        if use_buckets:
+            offs = {name: off for name, _, off in self.fpG.specs}
+            state = dict(hi=nG)
+            min_elems = int(float(os.environ.get("HM_BUCKET_MB", "96")) * (1 << 20) / 4)
+
+            def bucket(conv, flush=False):
+                lo = 0 if flush else offs[conv.name + ".weight"]
+                if state["hi"] - lo >= (1 if flush else min_elems):
+                    if not handles and comm_sms > 0:      # first bucket in flight: leave SMs for NCCL from here on
+                        self.ctx.lib.hm_set_sm_limit(self.ctx.sm_count - comm_sms)
+                    handles.append(parallel.allreduce_sum_async_(self.flat_grad[lo:state["hi"]]))
+                    state["hi"] = lo
+        self._grad_ready = bucket
         try:
             self._backward_G([1.0, 1.0, 1.0])
+            if use_buckets:
+                bucket(None, flush=True)
         finally:
             self._after_d_dgrad = None
-        hG = parallel.allreduce_sum_async_(self.flat_grad[:nG]) if dp else None
+            self._grad_ready = None
+        if dp and not use_buckets:
+            handles.append(parallel.allreduce_sum_async_(self.flat_grad[:nG]))
         if side is None:
             self._backward_D([0.5, 0.5])
             hD[0] = parallel.allreduce_sum_async_(self.flat_grad[nG:]) if dp else None
-        if hG is not None:
-            hG.wait()
+        for h in handles:
+            h.wait()
+        if use_buckets and comm_sms > 0:
+            self.ctx.lib.hm_set_sm_limit(0)
         self.optimizer_G.step(grad_scale=scale, captured=captured)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)

@@ -362,7 +362,8 @@ class GlobalGenerator(object):
             out = o32
         return out, tape
 
-    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False, add_at=None, extra_grad=None):
+    def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False, add_at=None, extra_grad=None,
+                 grad_ready=None):
         """dy_head: Operand gradient w.r.t. the head's pre-tanh output (with_head) or dfeat: dense fp32 gradient
         w.r.t. the trunk feature.  Accumulates parameter gradients; returns d(input operand) (fp32, padded space)
         when need_input_grad.  With add_at, self.add_grad holds the dense gradient w.r.t. the tensor added there.
@@ -414,6 +415,8 @@ class GlobalGenerator(object):
                     ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g1=G1,
                                g1_border=G1_border, g1_ld=G1_ld, g1_coff=G1_coff, out_op=dy)
             conv.wgrad(xin, dy, rec["zero_pad"], bias_grad=(kind == "head"))
+            if grad_ready is not None:       # this conv's .grad is final: stages run last-to-first, so the flat gradient
+                grad_ready(conv)             # buffer is complete from this parameter's offset to its end
             if s == 0 and not need_input_grad:
                 return None
             gin = _f32(ctx, xin.n, xin.h, xin.w, conv.cin)

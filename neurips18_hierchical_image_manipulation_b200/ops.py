@@ -43,6 +43,7 @@ class Ctx(object):
         self.lib = L.load()
         self.device = torch.device(device)
         self.scratch = _register_scratch(self.lib, self.device)
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.split = bool(split)  # True: bf16x3 (fp32-parity mode); False: plain bf16 products
         # gradient GEMMs (dgrad / wgrad) may run with single bf16 products while the forward stays bf16x3 ("mixed")
         self.split_bwd = self.split if split_bwd is None else bool(split_bwd)
@@ -209,7 +210,7 @@ def encode_input(ctx, label, inst, image, mask_in, label_nc, g_op, d_op=None, v_
                                     _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, 1 if d_no_imgcond else 0,
                                     _ptr(d_mask), _stream()),
             "hm_encode_input")
-    ctx.launches += 1
+    ctx.launches += 1 + (1 if d_op else 0) + (1 if v_op else 0)
 
 
 def in_stats(ctx, y, eps=1e-5):

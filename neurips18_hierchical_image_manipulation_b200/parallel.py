@@ -7,6 +7,14 @@ import torch
 import torch.distributed as dist
 
 
+def configure_nccl_env():
+    """Call BEFORE init_process_group.  The fused step overlaps its bucketed gradient allreduce with the backward pass
+    and reserves HM_COMM_SMS (default 8) SMs for it (hm_set_sm_limit); NCCL is told to use at most that many CTAs so it
+    does not take SMs the persistent engines count on.  An explicit NCCL_MAX_CTAS in the environment wins."""
+    import os
+    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("HM_COMM_SMS", "8"))
+
+
 def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

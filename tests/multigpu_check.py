@@ -37,8 +37,9 @@ def main():
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from neurips18_hierchical_image_manipulation_b200 import parallel
+    parallel.configure_nccl_env()
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
     from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_batch
 
@@ -82,7 +83,13 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
             with open(args.out, "w") as fh:
                 json.dump(res, fh)
-    dist.destroy_process_group()
+    # tearing the communicator down while CUDA graphs that captured its kernels are alive can block: drop the models
+    # first and leave without the (optional) destroy
+    del a, b
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
