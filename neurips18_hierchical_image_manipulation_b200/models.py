@@ -283,6 +283,7 @@ class Pix2PixHDModel_condImg(object):
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._step = None
         self._side = None
+        self._side2 = None
         self._after_d_dgrad = None
         self._grad_ready = None
         # stream overlap only inside optimize_parameters(); forward() / backward() of the script sequence stay single-stream
@@ -386,6 +387,14 @@ class Pix2PixHDModel_condImg(object):
             wi = VGG_WEIGHTS[sorted(st["v_tape"]["taps"]).index(li)]
             ops.l1_sum(self.ctx, tap[:B], tap[B:], self.opt.lambda_feat * wi / (tap.numel() // 2), acc, 2)
 
+    def _wgrad_stream(self):
+        """Third stream of the fused step: the generator's weight gradients (None when overlap is off)."""
+        if not self._overlap or os.environ.get("HM_WGRAD_STREAM", "1") == "0":
+            return None
+        if self._side2 is None:
+            self._side2 = torch.cuda.Stream(device=self.device)
+        return self._side2
+
     def _side_stream(self):
         """Second stream of the fused step, or None when overlap is off / we are not inside the fused step."""
         if not self._overlap:
@@ -446,8 +455,8 @@ class Pix2PixHDModel_condImg(object):
                      d_mask=st["d_mask"])
         if self._after_d_dgrad is not None:      # fused step: the discriminator's own backward pass may start now
             self._after_d_dgrad()
-        if self._grad_ready is not None:
-            self.netG.backward(st["g_tape"], dy_head=dy, grad_ready=self._grad_ready)
+        if self.netG_type == "global" and (self._grad_ready is not None or self._overlap):
+            self.netG.backward(st["g_tape"], dy_head=dy, grad_ready=self._grad_ready, wgrad_stream=self._wgrad_stream())
         else:
             self.netG.backward(st["g_tape"], dy_head=dy)
 

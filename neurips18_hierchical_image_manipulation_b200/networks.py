@@ -363,7 +363,7 @@ class GlobalGenerator(object):
         return out, tape
 
     def backward(self, tape, dy_head=None, dfeat=None, need_input_grad=False, add_at=None, extra_grad=None,
-                 grad_ready=None):
+                 grad_ready=None, wgrad_stream=None):
         """dy_head: Operand gradient w.r.t. the head's pre-tanh output (with_head) or dfeat: dense fp32 gradient
         w.r.t. the trunk feature.  Accumulates parameter gradients; returns d(input operand) (fp32, padded space)
         when need_input_grad.  With add_at, self.add_grad holds the dense gradient w.r.t. the tensor added there.
@@ -374,6 +374,12 @@ class GlobalGenerator(object):
         self.add_grad = None
         self.concat_grads = {}
         self.input_T = None
+        # wgrad_stream: the weight gradient of a layer only feeds .grad, so it runs on a second stream while this stream
+        # continues with the data gradient -> InstanceNorm-backward chain of the next layer; the HBM-bound kernels of
+        # the chain then overlap weight-gradient GEMMs and idle SMs of partial waves get filled.  The gradient operands
+        # are kept alive until the streams are joined (they are read by both).
+        keep = []
+        main = torch.cuda.current_stream() if wgrad_stream is not None else None
         G1, G1_border = None, 0   # gradient w.r.t. the current stage's OUTPUT operand (padded space)
         G1_ld, G1_coff = None, 0  # channel stride / offset of G1 when it is a slice of a concatenated input's gradient
         T = dfeat                 # dense gradient w.r.t. the current stage's fp32 output (residual chain)
@@ -414,10 +420,22 @@ class GlobalGenerator(object):
                 else:
                     ops.in_bwd(ctx, rec["shape"], rec["act"], y=rec["y"], mean=rec["mean"], rstd=rec["rstd"], g1=G1,
                                g1_border=G1_border, g1_ld=G1_ld, g1_coff=G1_coff, out_op=dy)
-            conv.wgrad(xin, dy, rec["zero_pad"], bias_grad=(kind == "head"))
-            if grad_ready is not None:       # this conv's .grad is final: stages run last-to-first, so the flat gradient
-                grad_ready(conv)             # buffer is complete from this parameter's offset to its end
+            if wgrad_stream is not None:
+                keep.append(dy)
+                if conv.thin_out:            # the unrolled gradient is shared by wgrad and dgrad: produce it on this stream
+                    conv._unrolled(dy)
+                wgrad_stream.wait_stream(main)
+                with torch.cuda.stream(wgrad_stream):
+                    conv.wgrad(xin, dy, rec["zero_pad"], bias_grad=(kind == "head"))
+                    if grad_ready is not None:
+                        grad_ready(conv)
+            else:
+                conv.wgrad(xin, dy, rec["zero_pad"], bias_grad=(kind == "head"))
+                if grad_ready is not None:   # this conv's .grad is final: stages run last-to-first, so the flat gradient
+                    grad_ready(conv)         # buffer is complete from this parameter's offset to its end
             if s == 0 and not need_input_grad:
+                if wgrad_stream is not None:
+                    main.wait_stream(wgrad_stream)
                 return None
             gin = _f32(ctx, xin.n, xin.h, xin.w, conv.cin)
             conv.dgrad(dy, xin.h, xin.w, rec["zero_pad"], gin)
@@ -434,6 +452,8 @@ class GlobalGenerator(object):
                     self.concat_grads[s] = (gin, conv.cin, 0)
                     G1_ld, G1_coff = conv.cin, cc_
         self.input_T = T
+        if wgrad_stream is not None:
+            main.wait_stream(wgrad_stream)
         return G1
 
 
