@@ -278,6 +278,24 @@ int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const flo
 int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,
                float* rstd_out, void* stream);
 int hm_upsample2_add(const float* small, const float* deep, int N, int h, int w, int C, float* out, void* stream);
+/* Backward halves (training step of TwoStreamAE_mask.forward :233-248 without the GAN terms):
+ * hm_bn_bwd: BatchNorm2d(affine) + activation backward, batch statistics (mean / rstd [C] over N*H*W): the gradient w.r.t.
+ *   the BN OUTPUT is g1 [+ g2] (dense fp32 [N,H,W,C]); the activation mask is the sign of gamma*yhat+beta (or of z /
+ *   mask_hi when given); result = gradient w.r.t. the conv output y as a bf16 operand and / or dense fp32; dgamma / dbeta
+ *   are ACCUMULATED.  ws: hm_in_ws_bytes(1, N*H*W, C).
+ * hm_upsample2_bwd: adjoint of the bilinear x2 upsample of hm_upsample2_add (d_deep is g itself).
+ * hm_box2mask_head_bwd: gradient of  w_obj*loss_obj + w_comb*loss_comb  w.r.t. the context logits (operand [N,H,W,c_cs])
+ *   and the object logit (operand [N,H,W,o_cs], channel 0); acc is the accumulator hm_box2mask_head filled (acc[1] = box
+ *   pixel count). */
+int hm_bn_bwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* z,
+              const void* mask_hi, int mask_cs, const float* g1, const float* g2, int N, int H, int W, int C, int act,
+              float slope, float* ws, void* o_hi, void* o_lo, int o_cs, float* out32, float* dgamma, float* dbeta,
+              void* stream);
+int hm_upsample2_bwd(const float* g, int N, int h, int w, int C, float* dsmall, void* stream);
+int hm_box2mask_head_bwd(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
+                         const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate,
+                         const double* acc, float w_comb, float w_obj, void* c_hi, void* c_lo, int c_cs, void* o_hi,
+                         void* o_lo, int o_cs, void* stream);
 int hm_box2mask_head(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
                      const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate, float* comb_logit,
                      float* comb_logprob, float* obj_prob, double* acc, void* stream);

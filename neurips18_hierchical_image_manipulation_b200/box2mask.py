@@ -1,15 +1,18 @@
-"""box2mask generator executor -- BASELINE config #5 / SURVEY N3 (first slice: the generator's training-mode FORWARD
-and the two reconstruction losses; the backward pass, the GAN terms and the optimizer step of
-models/TwoStreamAE_mask.py:205-248 are not built yet and raise).
+"""box2mask generator and trainer -- BASELINE config #5 / SURVEY N3.
 
   MaskTwoStreamConvNet   <- models/MaskTwoStreamConv_NET.py:13-219 (+ MaskContextAE_NET base, layer_util.py:119-242,333-378)
-  TwoStreamAE_mask       <- models/TwoStreamAE_mask.py (encode_input :127-151, reconstruct :257-300, losses :188-203)
+  TwoStreamAE_mask       <- models/TwoStreamAE_mask.py: encode_input :127-151, reconstruct :257-300, forward :167-255 --
+                            forward pass, the two reconstruction losses, `loss_G.backward()` and the Adam step the
+                            reference runs INSIDE forward (:233-240), for the reference's default `use_gan == False`.
+                            The PatchGAN terms of `--use_gan` (:205-231,243-248), eval-mode BatchNorm and `--no_comb`
+                            (MaskTwoStreamConvSwitch_NET) are not built and raise.
 
 Parameter names are the reference's own ('<params_dict key>.<state_dict key>': conv_encoder_3.deep.1.weight,
 ctx_conv_decoder_1.shortcut.0.weight, latent_encoder.0.conv_block.1.weight, ...), OIHW / IOHW fp32 like the reference, so
 its `save_network_dict` checkpoints map one to one.  Every convolution (7x7 s2, 4x4 s2, 1x1 s2, 3x3 reflect,
-ConvTranspose 4x4 s2, 1x1, 3x3) runs on the tcgen05 engines; BatchNorm (training mode, batch statistics) is
-hm_in_stats over the batch-folded tensor + hm_bn_fold + hm_in_apply; the rest is csrc/hm_box2mask.cu.
+ConvTranspose 4x4 s2, 1x1, 3x3; forward, data gradient, weight gradient) runs on the tcgen05 engines; BatchNorm (training
+mode, batch statistics) is hm_in_stats over the batch-folded tensor + hm_bn_fold + hm_in_apply forward and hm_bn_bwd
+backward; the rest is csrc/hm_box2mask.cu.
 
 Two aliasing effects of the reference are part of its arithmetic (see oracle/box2mask.py): each Conv/DeconvResnetBlock
 rectifies its input IN PLACE, so both of its branches -- and the encoder features kept for the skip connections -- see
@@ -48,10 +51,18 @@ class _BN(object):
         self.fp.version += 1
 
     def apply(self, ctx, y, act, skip=None, out32=None, out_op=None, reflect=True):
+        """Returns the batch statistics (mean, rstd) [1, C] for the backward pass."""
         N, H, W, C = y.shape
         mean, rstd = ops.in_stats(ctx, y.view(1, N * H, W, C))          # statistics over (N, H, W)
         mean_n, rstd_n = ops.bn_fold(ctx, mean, rstd, self.gamma, self.beta, N)
         ops.in_apply(ctx, y, mean_n, rstd_n, act, skip=skip, out32=out32, out_op=out_op, reflect=reflect)
+        return mean, rstd
+
+    def backward(self, ctx, y, stats, act, g1, g2=None, out_op=None, out32=None):
+        """Gradient w.r.t. the BN(+act) output (g1 + g2, dense fp32) -> gradient w.r.t. the conv output y; accumulates
+        d(gamma), d(beta)."""
+        ops.bn_bwd(ctx, y, stats[0], stats[1], self.gamma, self.beta, act, g1, g2=g2, out_op=out_op, out32=out32,
+                   dgamma=self.gamma.grad, dbeta=self.beta.grad)
 
 
 class MaskTwoStreamConvNet(object):
@@ -126,66 +137,73 @@ class MaskTwoStreamConvNet(object):
         for b in self.bns_:
             b.init_reference(gen)
 
-    # ------------------------------------------------------------------------------------------------
-    def _res_block(self, blk, x32, x_op, want_op):
+    # ---- forward --------------------------------------------------------------------------------------
+    def _res_block(self, blk, x32, x_op, want_op, tape):
         """ResnetBlock (layer_util.py:333-378): x + [pad, conv, norm, relu, pad, conv, norm](x)."""
         ctx = self.ctx
         N, H, W, C = x32.shape
         y = _f32(ctx, N, H, W, C)
         blk["c1"].forward(x_op, 0, out32=y)
         mid = Operand(ctx, N, H, W, C, border=1)
-        blk["b1"].apply(ctx, y, ACT_RELU, out_op=mid, reflect=True)
+        st1 = blk["b1"].apply(ctx, y, ACT_RELU, out_op=mid, reflect=True)
         y2 = _f32(ctx, N, H, W, C)
         blk["c2"].forward(mid, 0, out32=y2)
         out32 = _f32(ctx, N, H, W, C)
         out_op = Operand(ctx, N, H, W, C, border=1) if want_op else None
-        blk["b2"].apply(ctx, y2, ACT_NONE, skip=x32, out32=out32, out_op=out_op, reflect=True)
+        st2 = blk["b2"].apply(ctx, y2, ACT_NONE, skip=x32, out32=out32, out_op=out_op, reflect=True)
+        tape.append(dict(blk=blk, x_op=x_op, y1=y, st1=st1, mid=mid, y2=y2, st2=st2))
         return out32, out_op
 
     def _decode(self, latent32, latent_op, res, blocks, final, skips):
         ctx = self.ctx
+        tape = dict(res=[], blocks=[])
         d32, d_op = latent32, latent_op
         for j, blk in enumerate(res):
-            d32, d_op = self._res_block(blk, d32, d_op, want_op=(j + 1 < len(res)))
+            d32, d_op = self._res_block(blk, d32, d_op, want_op=(j + 1 < len(res)), tape=tape["res"])
         N = d32.shape[0]
-        x_op = None
         for i, blk in enumerate(blocks):
             h, w, c = d32.shape[1], d32.shape[2], d32.shape[3]
             xr = Operand(ctx, N, h, w, c)                                  # relu(x): the in-place ReLU of the block
             ops.in_apply(ctx, d32, None, None, ACT_RELU, out_op=xr, reflect=False)
-            x_op = ops.concat_operands(ctx, skips[-1 - (i - 1)], xr) if (skips and 1 <= i <= self.num_layers) else xr
+            skip = skips[-1 - (i - 1)] if (skips and 1 <= i <= self.num_layers) else None
+            x_op = ops.concat_operands(ctx, skip, xr) if skip is not None else xr
             od = blk["out_dim"]
             y = _f32(ctx, N, 2 * h, 2 * w, od)
             blk["deep"].forward(x_op, 0, out32=y)                          # ConvTranspose2d k4 s2 p1
             deep32 = _f32(ctx, N, 2 * h, 2 * w, od)
-            blk["deep_bn"].apply(ctx, y, ACT_NONE, out32=deep32)
+            st_d = blk["deep_bn"].apply(ctx, y, ACT_NONE, out32=deep32)
+            ys = st_s = None
             if blk["short"] is not None:
                 ys = _f32(ctx, N, h, w, od)
                 blk["short"].forward(x_op, 0, out32=ys)
                 s32 = _f32(ctx, N, h, w, od)
-                blk["short_bn"].apply(ctx, ys, ACT_NONE, out32=s32)
+                st_s = blk["short_bn"].apply(ctx, ys, ACT_NONE, out32=s32)
             else:
                 s32 = _f32(ctx, N, h, w, c)
                 ops.in_apply(ctx, d32, None, None, ACT_RELU, out32=s32)
             d32 = _f32(ctx, N, 2 * h, 2 * w, od)
             ops.upsample2_add(ctx, s32, deep32, d32)
+            tape["blocks"].append(dict(blk=blk, xr=xr, x_op=x_op, skip_c=(skip.c if skip is not None else 0), y=y, st_d=st_d,
+                                       ys=ys, st_s=st_s, in_shape=(N, h, w, c)))
         fin = Operand(ctx, N, d32.shape[1], d32.shape[2], d32.shape[3])
         ops.in_apply(ctx, d32, None, None, ACT_NONE, out_op=fin, reflect=False)      # the last conv sees dec_feat as is
         logit = _f32(ctx, N, d32.shape[1], d32.shape[2], final.cout)
         final.forward(fin, 1, out32=logit)
-        return logit
+        tape.update(fin=fin, final=final)
+        return logit, tape
 
     def forward(self, cond_op):
         """cond_op: Operand [B,S,S,input_nc].  Returns the dense fp32 NHWC logits (ctx_logit [B,S,S,output_nc],
-        obj_logit [B,S,S,1]) -- MaskTwoStreamConv_NET.forward :166-196; the head kernel combines them."""
+        obj_logit [B,S,S,1]) -- MaskTwoStreamConv_NET.forward :166-196; the head kernel combines them -- and the tape."""
         ctx = self.ctx
         conv0, bn0 = self.enc0
         N = cond_op.n
         ho, wo = conv0.out_hw(cond_op.h, cond_op.w, 3)
-        y = _f32(ctx, N, ho, wo, conv0.cout)
-        conv0.forward(cond_op, 3, out32=y)
+        y0 = _f32(ctx, N, ho, wo, conv0.cout)
+        conv0.forward(cond_op, 3, out32=y0)
         cur = Operand(ctx, N, ho, wo, conv0.cout)                          # relu(bn(.)) >= 0: in-place ReLU is a no-op
-        bn0.apply(ctx, y, ACT_RELU, out_op=cur, reflect=False)
+        st0 = bn0.apply(ctx, y0, ACT_RELU, out_op=cur, reflect=False)
+        tape = dict(cond=cond_op, y0=y0, st0=st0, enc=[], lat=[])
         skips = [cur]
         h32 = None
         for i, blk in enumerate(self.enc_blocks):                          # ConvResnetBlock (layer_util.py:119-162)
@@ -195,8 +213,9 @@ class MaskTwoStreamConvNet(object):
             blk["deep"].forward(cur, blk["deep"].pad, out32=yd)
             blk["short"].forward(cur, 0, out32=ys)
             tmp, h32 = _f32(ctx, N, ho, wo, c), _f32(ctx, N, ho, wo, c)
-            blk["deep_bn"].apply(ctx, yd, ACT_NONE, out32=tmp)
-            blk["short_bn"].apply(ctx, ys, ACT_NONE, skip=tmp, out32=h32)
+            st_d = blk["deep_bn"].apply(ctx, yd, ACT_NONE, out32=tmp)
+            st_s = blk["short_bn"].apply(ctx, ys, ACT_NONE, skip=tmp, out32=h32)
+            tape["enc"].append(dict(blk=blk, xin=cur, yd=yd, ys=ys, st_d=st_d, st_s=st_s, shape=(N, ho, wo, c)))
             if i + 1 < len(self.enc_blocks):
                 cur = Operand(ctx, N, ho, wo, c)                           # rectified in place by the next block
                 ops.in_apply(ctx, h32, None, None, ACT_RELU, out_op=cur, reflect=False)
@@ -205,17 +224,129 @@ class MaskTwoStreamConvNet(object):
         ops.in_apply(ctx, h32, None, None, ACT_NONE, out_op=lat_op, reflect=True)
         lat32 = h32
         for j, blk in enumerate(self.latent_encoder):
-            lat32, lat_op = self._res_block(blk, lat32, lat_op, want_op=True)
-        ctx_logit = self._decode(lat32, lat_op, self.ctx_latent, self.ctx_dec, self.ctx_final, skips)
-        obj_logit = self._decode(lat32, lat_op, self.obj_latent, self.obj_dec, self.obj_final, None)
-        return ctx_logit, obj_logit
+            lat32, lat_op = self._res_block(blk, lat32, lat_op, want_op=True, tape=tape["lat"])
+        ctx_logit, tape["ctx"] = self._decode(lat32, lat_op, self.ctx_latent, self.ctx_dec, self.ctx_final, skips)
+        obj_logit, tape["obj"] = self._decode(lat32, lat_op, self.obj_latent, self.obj_dec, self.obj_final, None)
+        tape["skips"] = skips
+        return ctx_logit, obj_logit, tape
+
+    # ---- backward -------------------------------------------------------------------------------------
+    def _add(self, a, b):
+        out = torch.empty_like(a)
+        ops.fold_add(self.ctx, a, 0, b, out)
+        return out
+
+    def _res_block_bwd(self, t, g_out):
+        """g_out: dense fp32 gradient w.r.t. the block output -> gradient w.r.t. its input."""
+        ctx, blk = self.ctx, t["blk"]
+        N, H, W, C = g_out.shape
+        dy2 = Operand(ctx, N, H, W, C, grad=True)
+        blk["b2"].backward(ctx, t["y2"], t["st2"], ACT_NONE, g_out, out_op=dy2)
+        blk["c2"].wgrad(t["mid"], dy2, 0, bias_grad=False)
+        gmid_p = _f32(ctx, N, H + 2, W + 2, C)
+        blk["c2"].dgrad(dy2, H + 2, W + 2, 0, gmid_p)
+        gmid = _f32(ctx, N, H, W, C)
+        ops.fold_add(ctx, gmid_p, 1, None, gmid)                          # adjoint of ReflectionPad2d(1)
+        dy1 = Operand(ctx, N, H, W, C, grad=True)
+        blk["b1"].backward(ctx, t["y1"], t["st1"], ACT_RELU, gmid, out_op=dy1)
+        blk["c1"].wgrad(t["x_op"], dy1, 0, bias_grad=False)
+        gx_p = _f32(ctx, N, H + 2, W + 2, C)
+        blk["c1"].dgrad(dy1, H + 2, W + 2, 0, gx_p)
+        gx = _f32(ctx, N, H, W, C)
+        ops.fold_add(ctx, gx_p, 1, g_out, gx)                             # + the identity branch
+        return gx
+
+    def _decode_bwd(self, tape, dlogit, skip_grads):
+        """dlogit: gradient operand w.r.t. the stream's logits.  Returns the dense gradient w.r.t. the latent feature;
+        skip_grads[k] collects (tensor, ld, channels) gradients w.r.t. the encoder skip features."""
+        ctx = self.ctx
+        final, fin = tape["final"], tape["fin"]
+        final.wgrad(fin, dlogit, 1, bias_grad=True)
+        g = _f32(ctx, fin.n, fin.h, fin.w, final.cin)
+        final.dgrad(dlogit, fin.h, fin.w, 1, g)
+        for i in range(len(tape["blocks"]) - 1, -1, -1):
+            t = tape["blocks"][i]
+            blk = t["blk"]
+            N, h, w, c = t["in_shape"]
+            od, x_op = blk["out_dim"], t["x_op"]
+            # deep branch: BN <- ConvTranspose
+            dyd = Operand(ctx, N, 2 * h, 2 * w, od, grad=True)
+            blk["deep_bn"].backward(ctx, t["y"], t["st_d"], ACT_NONE, g, out_op=dyd)
+            blk["deep"].wgrad(x_op, dyd, 0, bias_grad=False)
+            gxa = _f32(ctx, N, h, w, x_op.c)
+            blk["deep"].dgrad(dyd, h, w, 0, gxa)
+            # shortcut branch: bilinear^T <- BN <- Conv 1x1
+            gs = _f32(ctx, N, h, w, od)
+            ops.upsample2_bwd(ctx, g, gs)
+            if blk["short"] is not None:
+                dys = Operand(ctx, N, h, w, od, grad=True)
+                blk["short_bn"].backward(ctx, t["ys"], t["st_s"], ACT_NONE, gs, out_op=dys)
+                blk["short"].wgrad(x_op, dys, 0, bias_grad=False)
+                gxb = _f32(ctx, N, h, w, x_op.c)
+                blk["short"].dgrad(dys, h, w, 0, gxb)
+            else:
+                gxb = gs
+            gx = self._add(gxa, gxb)                                       # w.r.t. cat(skip, relu(d)) or relu(d)
+            sc = t["skip_c"]
+            if sc:
+                skip_grads[len(skip_grads_index(self.num_layers)) - 1 - (i - 1)].append((gx, x_op.c, sc))
+            g = _f32(ctx, N, h, w, c)                                       # through the block's in-place ReLU
+            ops.in_bwd(ctx, (N, h, w, c), ACT_RELU, mask_op=t["xr"], g1=gx, g1_border=0, g1_ld=x_op.c, g1_coff=sc, out32=g)
+        for t in reversed(tape["res"]):
+            g = self._res_block_bwd(t, g)
+        return g
+
+    def backward(self, tape, d_ctx, d_obj):
+        """Accumulates every parameter gradient given the gradient operands w.r.t. the two logit tensors."""
+        ctx = self.ctx
+        skip_grads = [[] for _ in skip_grads_index(self.num_layers)]
+        g_lat = self._add(self._decode_bwd(tape["ctx"], d_ctx, skip_grads), self._decode_bwd(tape["obj"], d_obj, skip_grads))
+        for t in reversed(tape["lat"]):
+            g_lat = self._res_block_bwd(t, g_lat)
+        g_h = g_lat                                                        # w.r.t. the last encoder block's output
+        for i in range(len(tape["enc"]) - 1, -1, -1):
+            t = tape["enc"][i]
+            blk, xin = t["blk"], t["xin"]
+            N, ho, wo, c = t["shape"]
+            dyd, dys = Operand(ctx, N, ho, wo, c, grad=True), Operand(ctx, N, ho, wo, c, grad=True)
+            blk["deep_bn"].backward(ctx, t["yd"], t["st_d"], ACT_NONE, g_h, out_op=dyd)
+            blk["short_bn"].backward(ctx, t["ys"], t["st_s"], ACT_NONE, g_h, out_op=dys)
+            blk["deep"].wgrad(xin, dyd, blk["deep"].pad, bias_grad=False)
+            blk["short"].wgrad(xin, dys, 0, bias_grad=False)
+            ga = _f32(ctx, N, xin.h, xin.w, xin.c)
+            blk["deep"].dgrad(dyd, xin.h, xin.w, blk["deep"].pad, ga)
+            gb = torch.zeros(N, xin.h, xin.w, xin.c, dtype=torch.float32, device=ctx.device)   # 1x1 stride 2: odd pixels get none
+            blk["short"].dgrad(dys, xin.h, xin.w, 0, gb)
+            gsum = self._add(ga, gb)                                       # w.r.t. xin = relu(previous feature)
+            for sg, ld, sc in skip_grads[i]:                               # + the decoder's use of the same rectified feature
+                nxt = _f32(ctx, N, xin.h, xin.w, xin.c)
+                ops.in_bwd(ctx, (N, xin.h, xin.w, xin.c), ACT_NONE, g1=sg, g1_border=0, g1_ld=ld, g1_coff=0, g2=gsum, out32=nxt)
+                gsum = nxt
+            if i > 0:                                                      # through the in-place ReLU onto the previous block's output
+                g_h = _f32(ctx, N, xin.h, xin.w, xin.c)
+                ops.in_bwd(ctx, (N, xin.h, xin.w, xin.c), ACT_RELU, mask_op=xin, g2=gsum, out32=g_h)
+            else:
+                g_h = gsum
+        conv0, bn0 = self.enc0
+        cond = tape["cond"]
+        y0 = tape["y0"]
+        dy0 = Operand(ctx, y0.shape[0], y0.shape[1], y0.shape[2], y0.shape[3], grad=True)
+        bn0.backward(ctx, y0, tape["st0"], ACT_RELU, g_h, out_op=dy0)      # ReLU mask from gamma * xhat + beta
+        conv0.wgrad(cond, dy0, 3, bias_grad=False)
+
+
+def skip_grads_index(num_layers):
+    """Encoder skip features are indexed like enc_features (MaskTwoStreamConv_NET.py:172-173): entry i is the rectified
+    input of encoder block i, used by decoder block num_layers - i."""
+    return list(range(num_layers))
 
 
 class TwoStreamAE_mask(object):
-    """models/TwoStreamAE_mask.py: forward slice.  `forward(...)` returns
-    ([loss_recon_comb, loss_recon_obj], dict(comb_logit, comb_prob (log-softmax), obj_logit, obj_prob)) for a training-mode
-    pass (BatchNorm batch statistics); the reference additionally back-propagates and steps its optimizers inside
-    forward (:237-248) -- not part of this slice."""
+    """models/TwoStreamAE_mask.py.  `forward(...)` in training mode runs the reference's whole iteration for
+    `use_gan == False` (:167-255): forward, loss_recon_comb (MaskReconLoss) and loss_recon_obj (BCE), the backward pass of
+    `loss_recon_obj + rec_weight * loss_recon_comb` and `optimizer.step()` (Adam(lr, beta1, beta2)), and returns
+    ([loss_recon_comb, loss_recon_obj, 0, 0, 0, 0], [comb_recon_label, obj_recon_prob]) like the reference.  With
+    `train=False` it stops after the losses (the parity tests use that to inspect outputs and gradients)."""
 
     def name(self):
         return "TwoStreamAE_mask"
@@ -230,6 +361,10 @@ class TwoStreamAE_mask(object):
         self.ctx = ops.Ctx(dev, split=(prec != "bf16"), split_bwd=(prec == "bf16x3"))
         if getattr(opt, "no_comb", False):
             raise NotImplementedError("--no_comb selects MaskTwoStreamConvSwitch_NET, outside this slice")
+        if getattr(opt, "use_gan", False):
+            raise NotImplementedError("--use_gan (PatchGAN terms of TwoStreamAE_mask.py:205-231) is not built yet")
+        if getattr(opt, "objReconLoss", "bce") != "bce":
+            raise NotImplementedError("objReconLoss: only 'bce' (the shipped setting) is built")
         self.fpG = FlatParams(dev)
         self.netG = MaskTwoStreamConvNet(self.ctx, self.fpG, opt.label_nc, opt.output_nc, opt.conv_dim, opt.num_layers,
                                          opt.conv_size, opt.n_blocks, opt.cond_in, opt.which_stream,
@@ -239,12 +374,17 @@ class TwoStreamAE_mask(object):
         self.netG.init_reference(torch.Generator().manual_seed(getattr(opt, "init_seed", 0)))
         self.loss_names = ["G_Recon_comb", "G_Recon_obj", "KL_loss", "loss_G_GAN", "loss_D_GAN", "loss_G_GAN_Feat"]
         self.acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.rec_weight = float(getattr(opt, "rec_weight", 1.0))
+        self.old_lr = getattr(opt, "lr", 0.0002)
+        from .models import FusedAdam
+        self.optimizer = FusedAdam(self.ctx, self.fpG, self.old_lr, (getattr(opt, "beta1", 0.9), getattr(opt, "beta2", 0.999)))
+        self.optimizer.data_parallel = False
 
     def _dev(self, t):
         return t.to(self.device, torch.float32).contiguous()
 
     def forward(self, label_map, mask_obj_in, mask_ctx_in, mask_obj_out, mask_out, mask_obj_inst, cls, mask_in,
-                eval_mode=False):
+                eval_mode=False, train=True):
         if eval_mode:
             raise NotImplementedError("eval mode uses BatchNorm running statistics, which this slice does not track")
         opt, ctx = self.opt, self.ctx
@@ -253,13 +393,36 @@ class TwoStreamAE_mask(object):
         clsf = self._dev(cls.reshape(-1))
         B, _, H, W = label_map.shape
         cond = ops.box2mask_encode(ctx, mask_ctx_in, mask_in, clsf, opt.label_nc)          # :127-151, :331-338
-        ctx_logit, obj_logit = self.netG.forward(cond)
+        ctx_logit, obj_logit, tape = self.netG.forward(cond)
         C = opt.output_nc
+        gate = bool(getattr(opt, "use_output_gate", False))
         out = dict(comb_logit=torch.empty(B, C, H, W, device=self.device), comb_prob=torch.empty(B, C, H, W, device=self.device),
                    obj_logit=obj_logit[..., :1].permute(0, 3, 1, 2), obj_prob=torch.empty(B, 1, H, W, device=self.device))
         self.acc.zero_()
-        ops.box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, getattr(opt, "use_output_gate", False),
-                          out["comb_logit"], out["comb_prob"], out["obj_prob"], self.acc)
+        ops.box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, gate, out["comb_logit"], out["comb_prob"],
+                          out["obj_prob"], self.acc)
         loss_comb = (self.acc[0] / self.acc[1].clamp_min(1.0)).float()       # NLLLoss2d mean over non-ignored pixels
         loss_obj = (self.acc[2] / float(B * H * W)).float()                  # BCELoss mean
-        return [loss_comb, loss_obj], out
+        self._last = dict(tape=tape, ctx_logit=ctx_logit, obj_logit=obj_logit, label_map=label_map, mask_out=mask_out,
+                          inst=inst, gate=gate)
+        if not train:
+            return [loss_comb, loss_obj], out
+        # ---- :233-240: loss_G = loss_recon_obj + rec_weight * loss_recon_comb; zero_grad, backward, step
+        self.optimizer.zero_grad()
+        self.backward_losses()
+        self.optimizer.step()
+        # :271-275 postprocess_output + argmax (host-side visual output)
+        gt_onehot = torch.zeros_like(out["comb_prob"]).scatter_(1, label_map.long(), 1.0)
+        comb_label = (out["comb_prob"] * mask_out + (1 - mask_out) * gt_onehot).argmax(dim=1, keepdim=True)
+        zero = torch.zeros((), device=self.device)
+        return [loss_comb, loss_obj, zero, zero, zero, zero], [comb_label, out["obj_prob"]]
+
+    def backward_losses(self):
+        """d(loss_recon_obj + rec_weight * loss_recon_comb)/d(parameters), accumulated into the flat .grad buffer."""
+        s, ctx = self._last, self.ctx
+        N, H, W, C = s["ctx_logit"].shape
+        d_ctx = Operand(ctx, N, H, W, C, grad=True)
+        d_obj = Operand(ctx, N, H, W, 1, grad=True)
+        ops.box2mask_head_bwd(ctx, s["ctx_logit"], s["obj_logit"], s["label_map"], s["mask_out"], s["inst"], s["gate"],
+                              self.acc, self.rec_weight, 1.0, d_ctx, d_obj)
+        self.netG.backward(s["tape"], d_ctx, d_obj)

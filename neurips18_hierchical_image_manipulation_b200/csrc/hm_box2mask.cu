@@ -150,9 +150,122 @@ __global__ void b2m_head_kernel(const float* __restrict__ ctx_logit /*[N,H,W,C]*
     for (int k = 0; k < 3; ++k) atomicAdd(acc + k, sh[k][0]);
 }
 
+// Adjoint of the bilinear x2 upsample (align_corners = False): d_small[n, i, j, :] = sum over the output pixels whose
+// interpolation footprint contains (i, j) of weight * g.  Per axis, output 2i-1 ... 2i+2 can touch source i; the weights
+// are recomputed with the forward's own formula so that the clamped borders come out right.
+__device__ __forceinline__ float up2_weight(int dst, int src, int n) {   // weight of source index `src` in output `dst`
+  const float s = fmaxf(0.5f * (dst + 0.5f) - 0.5f, 0.f);
+  const int i0 = int(s), i1 = min(i0 + 1, n - 1);
+  const float f = s - i0;
+  return (src == i0 ? 1.f - f : 0.f) + (src == i1 ? f : 0.f);
+}
+__global__ void upsample2_bwd_kernel(const float* __restrict__ g, int N, int h, int w, int C, float* __restrict__ dsmall) {
+  const int H = 2 * h, W = 2 * w, G = C >> 2;
+  const long total = long(N) * h * w * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int gq = int(i % G);
+    long r = i / G;
+    const int x = int(r % w); r /= w;
+    const int y = int(r % h);
+    const int n = int(r / h);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int Y = max(2 * y - 1, 0); Y <= min(2 * y + 2, H - 1); ++Y) {
+      const float wy = up2_weight(Y, y, h);
+      if (wy == 0.f) continue;
+      for (int X = max(2 * x - 1, 0); X <= min(2 * x + 2, W - 1); ++X) {
+        const float wx = up2_weight(X, x, w);
+        if (wx == 0.f) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g + ((size_t(n) * H + Y) * W + X) * C + gq * 4));
+        const float ww = wy * wx;
+        acc.x += ww * v.x; acc.y += ww * v.y; acc.z += ww * v.z; acc.w += ww * v.w;
+      }
+    }
+    *reinterpret_cast<float4*>(dsmall + ((size_t(n) * h + y) * w + x) * C + gq * 4) = acc;
+  }
+}
+
+// Backward of b2m_head_kernel for  L = w_obj * loss_obj + w_comb * loss_comb  (TwoStreamAE_mask.py:233-235 without the GAN
+// term):  d/d ctx_logit [N,H,W,C]  and  d/d obj_logit [N,H,W,1]  as bf16 gradient operands.
+//   comb_c = (1-p) ctx_c + p o,  lp = log_softmax(comb);  loss_comb = -(1/cnt) sum_{box} lp[label]
+//   q = p * mask_out (gate);     loss_obj = -(1/NHW) sum ( t log q + (1-t) log(1-q) )   (logs clamped at -100: zero slope there)
+__global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const float* __restrict__ obj_logit, int ldo,
+                                    const float* __restrict__ label_map, const float* __restrict__ mask_out,
+                                    const float* __restrict__ inst, int N, int H, int W, int C, int use_gate,
+                                    const double* __restrict__ acc /* acc[1] = number of box pixels */, float w_comb,
+                                    float w_obj, bf16* c_hi, bf16* c_lo, int c_cs, bf16* o_hi, bf16* o_lo, int o_cs) {
+  const long total = long(N) * H * W;
+  const float inv_cnt = acc[1] > 0.5 ? float(1.0 / acc[1]) : 0.f;
+  const float inv_n = 1.f / float(total);
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const float o = __ldg(obj_logit + i * ldo);
+    const float pr = 1.f / (1.f + __expf(-o));
+    const float* cl = ctx_logit + i * C;
+    const float mo = mask_out ? __ldg(mask_out + i) : 1.f;
+    const int lab = int(__ldg(label_map + i));
+    const bool in_box = mo >= 0.5f;
+    float mx = -3.402823466e38f;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, (1.f - pr) * __ldg(cl + c) + pr * o);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf((1.f - pr) * __ldg(cl + c) + pr * o - mx);
+    const float inv_se = 1.f / se;
+    float dp = 0.f, dsum = 0.f;
+    bf16* ch = c_hi + i * c_cs;
+    bf16* clo = c_lo ? c_lo + i * c_cs : nullptr;
+    for (int c = 0; c < c_cs; ++c) {
+      float dctx = 0.f;
+      if (c < C && in_box) {
+        const float x = __ldg(cl + c);
+        const float sm = expf((1.f - pr) * x + pr * o - mx) * inv_se;
+        const float dcomb = w_comb * inv_cnt * (sm - (c == lab ? 1.f : 0.f));
+        dctx = (1.f - pr) * dcomb;
+        dp += dcomb * (o - x);
+        dsum += dcomb;
+      }
+      bf16 hh, ll;
+      hm::split_bf16(dctx, hh, ll);
+      ch[c] = hh;
+      if (clo) clo[c] = ll;
+    }
+    float d_o = pr * dsum;                       // direct path of the object logit into comb
+    {
+      const float q = use_gate ? pr * mo : pr;
+      const float t = __ldg(inst + i);
+      float dq = 0.f;
+      if (logf(q) > -100.f) dq -= t / q;
+      if (logf(1.f - q) > -100.f) dq += (1.f - t) / (1.f - q);
+      dp += w_obj * inv_n * dq * (use_gate ? mo : 1.f);
+    }
+    d_o += dp * pr * (1.f - pr);
+    for (int c = 0; c < o_cs; ++c) {
+      bf16 hh, ll;
+      hm::split_bf16(c == 0 ? d_o : 0.f, hh, ll);
+      o_hi[i * o_cs + c] = hh;
+      if (o_lo) o_lo[i * o_cs + c] = ll;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int hm_upsample2_bwd(const float* g, int N, int h, int w, int C, float* dsmall, void* stream) {
+  if (!g || !dsmall || (C & 3)) return HM_ERR_INVALID;
+  upsample2_bwd_kernel<<<grid_for(long(N) * h * w * (C >> 2)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(g, N, h, w, C,
+                                                                                                               dsmall);
+  return HM_LAUNCH_OK();
+}
+
+int hm_box2mask_head_bwd(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
+                         const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate,
+                         const double* acc, float w_comb, float w_obj, void* c_hi, void* c_lo, int c_cs, void* o_hi,
+                         void* o_lo, int o_cs, void* stream) {
+  if (!ctx_logit || !obj_logit || !label_map || !inst || !acc || !c_hi || !o_hi || c_cs < C || o_cs < 1) return HM_ERR_INVALID;
+  b2m_head_bwd_kernel<<<grid_for(long(N) * H * W, kBlock, 148 * 8), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      ctx_logit, obj_logit, obj_ld, label_map, mask_out, inst, N, H, W, C, use_gate, acc, w_comb, w_obj,
+      static_cast<bf16*>(c_hi), static_cast<bf16*>(c_lo), c_cs, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
 
 int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const float* cls, int B, int H, int W, int label_nc,
                        void* o_hi, void* o_lo, int o_cs, void* stream) {

@@ -585,7 +585,9 @@ int hm_conv_dgrad(const hm_operand* dy, const void* w_hi, const void* w_lo, int 
           taps[nt++] = Tap{(pw + pad - kw) / 2, (ph + pad - kh) / 2, kh * KW + kw};
         }
       }
-      if (nt == 0) return HM_ERR_INVALID;  // every class must be produced (3x3/4x4 stride-2 always have taps)
+      // a class without taps (1x1 stride-2 convolutions: only the even / even positions receive gradient) produces
+      // nothing: the caller passes a zero-filled destination for such kernels
+      if (nt == 0) { if (KH * KW > 1) return HM_ERR_INVALID; continue; }
       const int vh = (Hout - ph + 1) / 2, vw = (Wout - pw + 1) / 2;
       // NOTE: all slabs must be addressable -> rows_total is sized from the largest slab id used by this class;
       // the caller's buffer always holds KH*KW slabs.

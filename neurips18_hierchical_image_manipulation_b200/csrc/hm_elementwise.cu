@@ -316,6 +316,9 @@ struct BwdArgs {
   const float* g2;                                         // dense gradient, same dims as y
   const float* tref; float l1coef;                         // L1 feature-matching term
   int N, H, W, C, act; float slope;
+  // BatchNorm (box2mask, BWD_GENERIC variants only): out = act(gamma * yhat + beta); the activation mask is taken from
+  // gamma * yhat + beta and the result is scaled by gamma:  dy = rstd * gamma * (dact - mean(dact) - yhat * mean(dact * yhat))
+  const float* gamma; const float* beta;
 };
 
 // ---- V-wide (V = 4 or 8 channels per thread) helpers: V = 4 halves the register footprint of the backward kernels
@@ -463,6 +466,11 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
     loadv<V>(a.y + pix * a.C, c, a.C, yh);
 #pragma unroll
     for (int j = 0; j < V; ++j) { yh[j] = (yh[j] - cs.mu[j]) * cs.rs[j]; src[j] = yh[j]; }
+    if ((F & BWD_GENERIC) && a.gamma) {
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (c + j < a.C) src[j] = yh[j] * __ldg(a.gamma + c + j) + (a.beta ? __ldg(a.beta + c + j) : 0.f);
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < V; ++j) yh[j] = 0.f;
@@ -626,6 +634,10 @@ __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_
       if (sums) {
 #pragma unroll
         for (int j = 0; j < V; ++j) dy[j] = (V == 4 || c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
+        if ((F & BWD_GENERIC) && a.gamma) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) if (c + j < a.C) dy[j] *= __ldg(a.gamma + c + j);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) dy[j] = dyh[j];
@@ -1145,10 +1157,21 @@ int hm_in_apply(const float* y, const float* mean, const float* rstd, const floa
   return HM_LAUNCH_OK();
 }
 
-int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float* z, const void* mask_hi, int mask_cs,
-              const float* g1, int g1_border, int g1_ld, int g1_coff, const float* g2, const float* tref, float l1coef,
-              int N, int H, int W, int C, int act, float slope, float* ws, void* o_hi, void* o_lo, int o_cs,
-              float* out32, void* stream) {
+}  // extern "C"
+
+namespace {
+__global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, int C8, float count, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] += sums[c] * count;            // sum of dact
+  if (dgamma) dgamma[c] += sums[C8 + c] * count;     // sum of dact * xhat
+}
+
+int in_bwd_impl(const float* y, const float* mean, const float* rstd, const float* z, const void* mask_hi, int mask_cs,
+                const float* g1, int g1_border, int g1_ld, int g1_coff, const float* g2, const float* tref, float l1coef,
+                int N, int H, int W, int C, int act, float slope, float* ws, void* o_hi, void* o_lo, int o_cs,
+                float* out32, const float* gamma, const float* beta, float** sums_out, void* stream) {
   if ((!o_hi && !out32) || (o_hi && ((o_cs & 7) || o_cs < C))) return HM_ERR_INVALID;
   if (mean && (!y || !ws)) return HM_ERR_INVALID;
   if (g1 && g1_border > 0 && (g1_border >= H || g1_border >= W)) return HM_ERR_INVALID;
@@ -1157,6 +1180,7 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
   a.y = y; a.mean = mean; a.rstd = rstd; a.z = z; a.mask_hi = static_cast<const bf16*>(mask_hi); a.mask_cs = mask_cs;
   a.g1 = g1; a.g1_border = g1_border; a.g1_ld = g1_ld; a.g1_coff = g1_coff; a.g2 = g2; a.tref = tref; a.l1coef = l1coef;
   a.N = N; a.H = H; a.W = W; a.C = C; a.act = act; a.slope = slope;
+  a.gamma = gamma; a.beta = beta;
   const int C8 = (C + 7) & ~7;
   float* sums = nullptr;
   int gx_log2, cgroups;
@@ -1164,8 +1188,10 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
   const bool v4 = ((C & 3) == 0) && (!o_hi || (o_cs & 3) == 0) && (!mask_hi || (mask_cs & 3) == 0) &&
                   (!g1 || (((g1_ld & 3) == 0) && ((g1_coff & 3) == 0)));
   const int V = v4 ? 4 : 8;
-  // presence mask of this call; instantiated combinations run with compile-time flags
-  const int F = (y ? F_IN : 0) | ((g1 && g1_border == 0) ? F_G1D : 0) | ((g1 && g1_border != 0) ? F_G1B : 0) |
+  // presence mask of this call; instantiated combinations run with compile-time flags (the affine / BatchNorm form
+  // always takes the generic kernels: -1 matches no instantiated case)
+  const int F = gamma ? -1 :
+                (y ? F_IN : 0) | ((g1 && g1_border == 0) ? F_G1D : 0) | ((g1 && g1_border != 0) ? F_G1B : 0) |
                 (g2 ? F_G2 : 0) | (z ? F_Z : 0) | (tref ? F_TREF : 0) | ((mask_hi && !y && !z) ? F_MASK : 0);
 #define HM_BWD_CASES(X)                                                                                      \
   X(F_IN | F_G2) X(F_IN | F_G1D) X(F_IN | F_G1B) X(F_IN | F_G1D | F_Z) X(F_IN | F_G1D | F_Z | F_TREF)          \
@@ -1211,6 +1237,37 @@ int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float*
     }
   }
 #undef HM_BWD_CASES
+  if (sums_out) *sums_out = sums;
+  return HM_LAUNCH_OK();
+}
+}  // namespace
+
+extern "C" {
+
+int hm_in_bwd(const float* y, const float* mean, const float* rstd, const float* z, const void* mask_hi, int mask_cs,
+              const float* g1, int g1_border, int g1_ld, int g1_coff, const float* g2, const float* tref, float l1coef,
+              int N, int H, int W, int C, int act, float slope, float* ws, void* o_hi, void* o_lo, int o_cs,
+              float* out32, void* stream) {
+  return in_bwd_impl(y, mean, rstd, z, mask_hi, mask_cs, g1, g1_border, g1_ld, g1_coff, g2, tref, l1coef, N, H, W, C, act,
+                     slope, ws, o_hi, o_lo, o_cs, out32, nullptr, nullptr, nullptr, stream);
+}
+
+/* BatchNorm2d(affine) + activation backward in training mode (box2mask): the tensor is treated as ONE sample of N*H*W
+ * pixels (mean / rstd are the batch statistics [C]); dgamma / dbeta are ACCUMULATED. */
+int hm_bn_bwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* z,
+              const void* mask_hi, int mask_cs, const float* g1, const float* g2, int N, int H, int W, int C, int act,
+              float slope, float* ws, void* o_hi, void* o_lo, int o_cs, float* out32, float* dgamma, float* dbeta,
+              void* stream) {
+  if (!y || !mean || !rstd || !gamma || !ws || long(N) * H > 0x7fffffffL) return HM_ERR_INVALID;
+  float* sums = nullptr;
+  int rc = in_bwd_impl(y, mean, rstd, z, mask_hi, mask_cs, g1, 0, C, 0, g2, nullptr, 0.f, 1, N * H, W, C, act, slope, ws,
+                       o_hi, o_lo, o_cs, out32, gamma, beta, &sums, stream);
+  if (rc != HM_OK) return rc;
+  if (dgamma || dbeta) {
+    const int C8 = (C + 7) & ~7;
+    bn_param_grad_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, C, C8, float(N) * H * W,
+                                                                                         dgamma, dbeta);
+  }
   return HM_LAUNCH_OK();
 }
 

@@ -438,3 +438,32 @@ def box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate
                                      _ptr(mask_out), _ptr(inst), N, H, W, Cc, 1 if use_gate else 0, _ptr(comb_logit),
                                      _ptr(comb_logprob), _ptr(obj_prob), _ptr(acc), _stream()), "hm_box2mask_head")
     ctx.launches += 1
+
+
+def bn_bwd(ctx, y, mean, rstd, gamma, beta, act, g1, g2=None, z=None, mask_op=None, out_op=None, out32=None, dgamma=None,
+           dbeta=None, slope=0.2):
+    """BatchNorm(+act) backward (batch statistics): gradient w.r.t. the BN output g1 (+ g2) -> gradient w.r.t. y."""
+    N, H, W, Cc = y.shape
+    ws = ctx.ws("in", ctx.lib.hm_in_ws_bytes(1, N * H * W, Cc))
+    L.check(ctx.lib.hm_bn_bwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _ptr(beta), _ptr(z),
+                              _ptr(mask_op.hi) if mask_op else None, mask_op.cs if mask_op else 0, _ptr(g1), _ptr(g2), N, H,
+                              W, Cc, act, slope, ws.data_ptr(), _ptr(out_op.hi) if out_op else None,
+                              _ptr(out_op.lo) if out_op else None, out_op.cs if out_op else 0, _ptr(out32), _ptr(dgamma),
+                              _ptr(dbeta), _stream()), "hm_bn_bwd")
+    ctx.launches += 4
+
+
+def upsample2_bwd(ctx, g, dsmall):
+    N, h, w, Cc = dsmall.shape
+    L.check(ctx.lib.hm_upsample2_bwd(g.data_ptr(), N, h, w, Cc, dsmall.data_ptr(), _stream()), "hm_upsample2_bwd")
+    ctx.launches += 1
+
+
+def box2mask_head_bwd(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, acc, w_comb, w_obj, d_ctx, d_obj):
+    N, H, W, Cc = ctx_logit.shape
+    L.check(ctx.lib.hm_box2mask_head_bwd(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1],
+                                         label_map.data_ptr(), _ptr(mask_out), inst.data_ptr(), N, H, W, Cc,
+                                         1 if use_gate else 0, acc.data_ptr(), float(w_comb), float(w_obj),
+                                         d_ctx.hi.data_ptr(), _ptr(d_ctx.lo), d_ctx.cs, d_obj.hi.data_ptr(), _ptr(d_obj.lo),
+                                         d_obj.cs, _stream()), "hm_box2mask_head_bwd")
+    ctx.launches += 1

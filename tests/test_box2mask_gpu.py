@@ -1,7 +1,8 @@
-"""N3 box2mask (BASELINE config #5), forward slice: the B200 executor of MaskTwoStreamConv_NET + the reconstruction
-losses of TwoStreamAE_mask against (a) the golden vectors generated from the reference's OWN class
-(tests/golden/box2mask_small.npz: scripts/train_box2mask_city.sh flag set at label_nc 6, 64x64, batch 3) and (b) the
-oracle at config #5's real geometry (label_nc 35, 256x256, conv_dim 64, n_blocks 6, batch 2).  bf16x3, tolerance 1e-3."""
+"""N3 box2mask (BASELINE config #5): the B200 executor of MaskTwoStreamConv_NET + the reconstruction losses, backward
+pass and Adam step of TwoStreamAE_mask (use_gan off) against (a) the golden vectors generated from the reference's OWN
+class (tests/golden/box2mask_small.npz: scripts/train_box2mask_city.sh flag set at label_nc 6, 64x64, batch 3: outputs,
+losses, the gradients of all 120 parameters) and (b) the oracle at config #5's real geometry (label_nc 35, 256x256,
+conv_dim 64, n_blocks 6, batch 2).  bf16x3; tolerance 1e-3 on outputs and losses, 1e-2 of each tensor's max on gradients."""
 import contextlib
 import io
 import os
@@ -40,7 +41,7 @@ def test_box2mask_forward_and_losses_against_the_reference_class_golden(golden_d
     m.fpG.load_state_dict(sd)
     ins = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in::")}
     losses, out = m.forward(ins["label_map"], None, ins["mask_ctx_in"], None, ins["mask_out"], ins["mask_obj_inst"], ins["cls"],
-                            ins["mask_in"])
+                            ins["mask_in"], train=False)
     torch.cuda.synchronize()
     m.ctx.check_pipeline()
     for k in ("comb_logit", "comb_prob", "obj_logit", "obj_prob"):
@@ -49,6 +50,31 @@ def test_box2mask_forward_and_losses_against_the_reference_class_golden(golden_d
         assert e < 1e-3, (k, e)
     assert abs(float(losses[0]) - float(z["loss_comb"])) < 1e-3 * abs(float(z["loss_comb"]))
     assert abs(float(losses[1]) - float(z["loss_obj"])) < 1e-3 * abs(float(z["loss_obj"]))
+    # ---- backward: d(loss_recon_obj + rec_weight * loss_recon_comb)/d(every parameter) vs the reference's autograd
+    m.optimizer.zero_grad()
+    m.backward_losses()
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    worst, n_full, n_proj = [], 0, 0
+    for k, p in m.fpG.params.items():
+        g = p.grad.detach().double().cpu()
+        if "g::" + k in z.files:
+            ref = torch.from_numpy(z["g::" + k]).double()
+            if k.endswith("bias") and float(ref.abs().max()) < 1e-6:       # conv bias in front of a BatchNorm: exactly 0 here
+                assert float(g.abs().max()) < 1e-6, k
+            else:
+                worst.append((float((g - ref).abs().max() / ref.abs().max()), k))
+            n_full += 1
+        else:
+            s_, a_, p_ = (float(v) for v in z["gs::" + k])
+            r = named_param("proj::" + k + ".bias", g.shape).double()
+            worst.append((abs(float(g.abs().sum()) - a_) / a_, k + " |.|1"))
+            worst.append((abs(float((g * r).sum()) - p_) / (a_ * 0.05), k + " proj"))
+            n_proj += 1
+    worst.sort(reverse=True)
+    print("box2mask gradients vs reference autograd: worst", ["%.1e %s" % w for w in worst[:5]], n_full, n_proj)
+    assert n_full + n_proj == 120
+    assert worst[0][0] < 1e-2, worst[:8]
 
 
 def test_box2mask_forward_at_config5_geometry_against_oracle():
@@ -65,7 +91,7 @@ def test_box2mask_forward_at_config5_geometry_against_oracle():
     m.fpG.load_state_dict(sd)
     d = G.synthetic(dict(label_nc=35, fineSize=256), 2, seed=3)
     losses, out = m.forward(d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"],
-                            d["mask_in"])
+                            d["mask_in"], train=False)
     torch.cuda.synchronize()
     m.ctx.check_pipeline()
     cond, _ = B2.encode_input(35, d["mask_ctx_in"], d["mask_in"], d["cls"])
@@ -79,3 +105,48 @@ def test_box2mask_forward_at_config5_geometry_against_oracle():
                 loss_obj=abs(float(losses[1]) - float(l_obj)) / float(l_obj))
     print("box2mask config #5 geometry:", {k: "%.2e" % v for k, v in errs.items()})
     assert max(errs.values()) < 1e-3, errs
+
+
+def test_box2mask_training_step_against_oracle():
+    """The reference's whole iteration for use_gan == False (TwoStreamAE_mask.forward :167-255: forward, the two losses,
+    loss_G.backward(), optimizer.step() INSIDE forward) against the oracle + oracle Adam: losses, first-step update
+    directions, and two more steps of the loss trajectory."""
+    from oracle import box2mask as B2
+    from oracle import model as O
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import make_golden_box2mask as G
+    lr, beta1 = 2e-4, 0.5
+    m = _model(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2, lr=lr, beta1=beta1, beta2=0.999, rec_weight=1.0)
+    sd = {k: v.detach().cpu().clone() for k, v in m.fpG.params.items()}
+    d = G.synthetic(dict(label_nc=6, fineSize=64), 3, seed=23)
+    cond, _ = B2.encode_input(6, d["mask_ctx_in"], d["mask_in"], d["cls"])
+    ref = {k: v.clone() for k, v in sd.items()}
+    mom = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()}
+    ref_losses, got_losses = [], []
+    for step in range(1, 4):
+        par = {k: v.clone().requires_grad_(True) for k, v in ref.items()}
+        _, lp, _, op_ = B2.two_stream_forward(par, cond, num_layers=3, n_blocks=2)
+        lc = B2.mask_recon_loss(lp, d["label_map"], d["mask_out"])
+        lo = B2.obj_recon_loss(op_, d["mask_out"], d["mask_obj_inst"])
+        grads = torch.autograd.grad(lo + lc, list(par.values()))
+        for (k, v), g in zip(ref.items(), grads):
+            O.adam_step(v, g, mom[k][0], mom[k][1], step, lr, beta1)
+        ref_losses.append((float(lc), float(lo)))
+        ls, _ = m.forward(d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"], d["mask_in"])
+        got_losses.append((float(ls[0]), float(ls[1])))
+        if step == 1:
+            torch.cuda.synchronize()
+            bad = tot = 0
+            for k, p in m.fpG.params.items():
+                g = grads[list(ref).index(k)]
+                sel = g.abs() > 1e-3 * g.abs().max()
+                dm, dr = (p.detach().cpu() - sd[k])[sel], (ref[k] - sd[k])[sel]
+                bad += int((torch.sign(dm) != torch.sign(dr)).sum())
+                tot += int(sel.sum())
+            assert bad / max(tot, 1) < 5e-3, (bad, tot)
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    print("box2mask train steps: oracle", ref_losses, "product", got_losses)
+    for (a, b), (c, e) in zip(ref_losses, got_losses):
+        assert abs(a - c) < 2e-3 * abs(a) and abs(b - e) < 2e-3 * abs(b), (ref_losses, got_losses)
+    assert m.optimizer.step_count == 3
