@@ -41,6 +41,14 @@ CONFIGS = {
               desc="BASELINE config #4: mask2image LocalEnhancer two-scale 1024x2048 (ngf 32, global trunk 4 down / 9 res "
                    "at 512x1024, 1 local enhancer with 3 res-blocks), synthetic labels + instance maps, 2-scale D, VGG19 "
                    "feat-match, full train step, 1 image/GPU (batch 8 on 8 GPUs)"),
+    "5": dict(H=256, W=256, per_gpu_batch=8, metric="box2mask train images/sec @256x256 (TwoStreamAE_mask, use_gan off)",
+              opt=dict(model="AE_maskgen_twostream", label_nc=LABEL_NC, output_nc=LABEL_NC, conv_dim=64, num_layers=3,
+                       conv_size=4, n_blocks=6, which_stream="obj_context", cond_in="ctx_obj", use_output_gate=True,
+                       num_resnetblocks=1, norm_layer="batch", beta1=0.5, beta2=0.999, isTrain=False),
+              desc="BASELINE config #5: box2mask TwoStreamAE_mask (MaskTwoStreamConv_NET, flag set of "
+                   "scripts/train_box2mask_city.sh without --use_gan / --no_comb) 256x256, 35 classes, synthetic bbox + "
+                   "context masks, full training iteration (forward, MaskReconLoss + BCE, backward, Adam), 8 images/GPU "
+                   "(batch 64 on 8 GPUs: per-replica BatchNorm statistics + gradient allreduce, as nn.DataParallel trains it)"),
 }
 H, W, PER_GPU_BATCH = CONFIGS["2"]["H"], CONFIGS["2"]["W"], CONFIGS["2"]["per_gpu_batch"]
 
@@ -335,6 +343,102 @@ def run_mode(model, precision_name, batch_dev, batch_pinned, steps, warmup, worl
                 graph=isinstance(m._graph, dict), peak_mem_gb=torch.cuda.max_memory_allocated(m.device) / 2 ** 30)
 
 
+def box2mask_batch(B, S, label_nc, seed):
+    """Synthetic box2mask sample set (what data/ + TwoStreamAE_mask.encode_input :127-151 consume): a blocky label map, a
+    box (mask_in), its margin-expanded region (mask_out), an elliptical instance mask of class `cls` inside the box and
+    the context map with the region wiped."""
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.randint(1, label_nc, (B, 1, S // 8, S // 8), generator=g).float()
+    label_map = torch.nn.functional.interpolate(lab, size=(S, S), mode="nearest")
+    cls = torch.randint(1, label_nc - 1, (B, 1), generator=g)
+    mask_out, mask_in, inst = torch.zeros(B, 1, S, S), torch.zeros(B, 1, S, S), torch.zeros(B, 1, S, S)
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    for b in range(B):
+        y0, x0 = int(torch.randint(4, S // 4, (1,), generator=g)), int(torch.randint(4, S // 4, (1,), generator=g))
+        h, w = int(torch.randint(S // 4, S // 2, (1,), generator=g)), int(torch.randint(S // 4, S // 2, (1,), generator=g))
+        mask_in[b, :, y0:y0 + h, x0:x0 + w] = 1
+        mask_out[b, :, max(0, y0 - 4):y0 + h + 4, max(0, x0 - 4):x0 + w + 4] = 1
+        ell = (((yy - (y0 + h / 2.0)) / (h / 2.0)) ** 2 + ((xx - (x0 + w / 2.0)) / (w / 2.0)) ** 2) <= 1.0
+        inst[b, 0] = ell.float()
+        label_map[b, 0][ell] = float(cls[b, 0])
+    return dict(label_map=label_map, mask_ctx_in=label_map * (1 - mask_out), mask_out=mask_out, mask_in=mask_in,
+                mask_obj_inst=inst, cls=cls.float())
+
+
+def main_box2mask(args, out_fd):
+    """`--config 5`: one TwoStreamAE_mask training iteration per step (eager launches; no CUDA graph for this model yet)."""
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    cfg = CONFIGS["5"]
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = create_model(Options(gpu_ids=[local], precision=args.precision, name="bench5", **cfg["opt"]))
+    B = cfg["per_gpu_batch"]
+    host = {k: v.pin_memory() for k, v in box2mask_batch(B, cfg["H"], LABEL_NC, 77 + rank).items()}
+    devb = {k: v.to(dev) for k, v in host.items()}
+
+    def step(d):
+        return m.forward(d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"], d["mask_in"])
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+    for _ in range(max(3, args.warmup)):
+        step(devb)
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.reset_peak_memory_stats(dev)
+    l0 = m.ctx.launches
+    ms = timed(lambda: step(devb), args.steps)
+    launches = (m.ctx.launches - l0) // args.steps
+    clocks = sampler.stop()
+    m.ctx.check_pipeline()
+    hl = torch.empty(2, dtype=torch.float32, pin_memory=True)
+
+    def e2e():
+        ls, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        hl.copy_(torch.stack(ls[:2]), non_blocking=False)
+    ms_e2e = timed(e2e, args.steps)
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
+    B = B * world
+    line = dict(metric=cfg["metric"], value=B / (ms / 1e3), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16x3 (fp32-parity mode)" if args.precision == "bf16x3" else args.precision, data="synthetic",
+                config=workload_desc(world, "5"), clocks=clocks,
+                e2e=dict(value=B / (ms_e2e / 1e3), unit="images/sec", ms_per_step=ms_e2e,
+                         h2d_bytes_per_step=sum(v.numel() * 4 for v in host.values()), d2h_bytes_per_step=8),
+                gpu_launches=launches, cuda_graph=False, peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                losses_last_step=[float(x) for x in hl])
+    _emit(line, out_fd)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def _emit(line, fd):
     os.write(fd, (json.dumps(line) + "\n").encode())
 
@@ -351,7 +455,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--config", type=str, default="2", choices=sorted(CONFIGS),
-                    help="BASELINE config: 2 (= 3 per GPU; headline) or 4 (LocalEnhancer 1024x2048, side line)")
+                    help="BASELINE config: 2 (= 3 per GPU; headline), 4 (LocalEnhancer 1024x2048) or 5 (box2mask 256x256): side lines")
     ap.add_argument("--precision", type=str, default="bf16x3", help="primary precision mode (bf16x3 = fp32 parity)")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary precision modes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
@@ -363,6 +467,8 @@ def main():
         return main_torch_gpu(args, out_fd)
     if args.warmup < 3:
         args.warmup = 3
+    if args.config == "5":
+        return main_box2mask(args, out_fd)
     cfg = CONFIGS[args.config]
     headline = args.config == "2"
 

@@ -378,7 +378,10 @@ class TwoStreamAE_mask(object):
         self.old_lr = getattr(opt, "lr", 0.0002)
         from .models import FusedAdam
         self.optimizer = FusedAdam(self.ctx, self.fpG, self.old_lr, (getattr(opt, "beta1", 0.9), getattr(opt, "beta2", 0.999)))
-        self.optimizer.data_parallel = False
+        # data parallel like the reference's nn.DataParallel (models/models.py:21-22): per-replica BatchNorm statistics,
+        # replica losses averaged (train_box2mask.py), i.e. the mean of the shard gradients -- one allreduce of the flat
+        # gradient buffer inside optimizer.step()
+        self.optimizer.data_parallel = bool(getattr(opt, "data_parallel", True))
 
     def _dev(self, t):
         return t.to(self.device, torch.float32).contiguous()
