@@ -12,7 +12,7 @@ def _line(name):
 
 
 def test_bench_line_has_every_contract_key():
-    d = _line("r01_v3_bench_1gpu.json")
+    d = _line("r02_bench_1gpu.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -34,6 +34,31 @@ def test_bench_line_has_every_contract_key():
     for k in ("sm_mhz", "sm_max_mhz", "reasons"):
         assert k in d["clocks"], k
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # round 2: fixed-protocol CPU leg and the stock PyTorch / cuDNN legs travel in the same line
+    assert "1 full 512x1024 image per step" in c["sample"] and "1 warm-up + 2 timed" in c["sample"]
+    t = d["torch_gpu"]
+    for variant in ("tf32", "bf16_channels_last"):
+        assert t[variant]["cudnn_benchmark"] is True and t[variant]["warmup"] >= 5 and t[variant]["steps"] >= 10
+        assert t[variant]["ms_per_step"] > 0
+    assert abs(t["speedup_vs_tf32"] - t["tf32"]["ms_per_step"] / d["ms_per_step"]) < 1e-9
+    assert d["cuda_graph"] is True and d["peak_mem_gb"] > 1
+
+
+def test_side_lines_for_configs_4_and_5():
+    for name, px, batch in (("r02_bench_config4_local_enhancer.json", "1024x2048", 1), ("r02_bench_config5_box2mask.json", "256x256", 8)):
+        d = _line(name)
+        assert px in d["metric"] and d["config"]["per_gpu_batch"] == batch and d["gpu_launches"] > 0
+        assert abs(d["value"] - batch * d["n_gpus"] / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] <= d["value"] * 1.02
+
+
+def test_two_gpu_lines_check_the_replicas():
+    for name in ("r02_bench_2gpu_buckets8.json", "r02_bench_2gpu_single.json"):
+        d = _line(name)
+        assert d["n_gpus"] == 2 and d["replicas_identical"] is True and d["cuda_graph"] is True
+    with open(os.path.join(ROOT, "profiles", "r02_multigpu_check.json")) as fh:
+        c = json.load(fh)
+    assert c["replicas_identical"] is True and c["graph"] is True and c["loss_err"][0] < 1e-5 and max(c["loss_err"]) < 5e-3
 
 
 def test_multi_gpu_lines_report_whole_job_throughput():
