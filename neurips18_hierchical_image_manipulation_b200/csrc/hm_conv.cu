@@ -158,6 +158,32 @@ int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
   return HM_OK;
 }
 
+template <int BN>
+int launch_k3(const hm::KParams& p, int num_tiles, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_kgemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hm::K3Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = true;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_kgemm_kernel<BN, true><<<grid, hm::kEngineThreads, hm::K3Cfg<BN>::SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
+int launch_k3_bn(int bn, const hm::KParams& p, int num_tiles, cudaStream_t st) {
+  switch (bn) {
+    case 16: return launch_k3<16>(p, num_tiles, st);
+    case 32: return launch_k3<32>(p, num_tiles, st);
+    case 64: return launch_k3<64>(p, num_tiles, st);
+    case 128: return launch_k3<128>(p, num_tiles, st);
+  }
+  return HM_ERR_INVALID;
+}
+
 int launch_k_bn(int bn, const hm::KParams& p, int num_tiles, cudaStream_t st) {
   switch (bn) {
     case 16: return launch_k<16>(p, num_tiles, st);
@@ -475,10 +501,13 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   if ((rc = make_tmap_weight(&p.tmB[0], w_hi, rows_total, k_pad, pair ? 128 : bn))) return rc;
   if (b_lo && (rc = make_tmap_weight(&p.tmB[1], w_lo, rows_total, k_pad, pair ? 128 : bn))) return rc;
 
+  // fused-split kernel (one stage = hi + lo boxes of both operands, three products per stage): bf16x3 with N tile <= 128
+  static const int use_fused3 = env_int("HM_FUSED3", 1);
+  const bool fused3 = use_fused3 && a_lo && b_lo && !pair && bn <= 128;
   int ne = 0;
   for (int t = 0; t < n_taps; ++t) {
     const int pa[3] = {0, 1, 0}, pb[3] = {0, 0, 1};
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < (fused3 ? 1 : 3); ++q) {
       if (q == 1 && !a_lo) continue;
       if (q == 2 && !b_lo) continue;
       hm::KEntry& e = p.entries[ne++];
@@ -513,6 +542,7 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   p.bias = bias; p.act = act; p.slope = slope; p.err = err_flag;
   const int num_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
   if (pair) return launch_k2(p, p.tiles_w * p.tiles_h * p.n_img, p.n_tiles_n, st);
+  if (fused3) return launch_k3_bn(bn, p, num_tiles, st);
   return launch_k_bn(bn, p, num_tiles, st);
 }
 

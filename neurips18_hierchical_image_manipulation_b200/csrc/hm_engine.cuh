@@ -82,6 +82,23 @@ struct KCfg {
   static constexpr int CH = (BN >= 32) ? 32 : 16;
 };
 
+// Fused-split variant of the K-engine (bf16x3 only, N tile <= 128): ONE pipeline stage holds the hi AND lo boxes of both
+// operands for a (tap, 64-channel chunk) and the issuer fires all three products (hi*hi, lo*hi, hi*lo) from it.  The
+// per-product stages of the plain kernel load A_hi and B_hi twice: 3 x (A + B) per tap against 2 x (A + B) here.  The
+// narrow-N layers are bound by L2 -> SM delivery (ncu r02: the first PatchGAN layer moves 10.3 GB at the 11 TB/s fabric
+// limit) or by the barrier round trip per 4 MMAs, so a third less traffic and 12 MMAs per wait is time saved.
+template <int BN>
+struct K3Cfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN >= 128) ? 3 : (BN >= 64 ? 4 : (BN >= 32 ? 5 : 6));
+  static constexpr int ACC = 2;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int CH = (BN >= 32) ? 32 : 16;
+};
+
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
@@ -170,9 +187,12 @@ __device__ __forceinline__ void k_groups(int a_c, int a_lo_c0, int a_plane, int 
 // ------------------------------------------------------------------------------------------------
 // K-engine
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <bool B, class T, class F> struct hm_cond { using type = T; };
+template <class T, class F> struct hm_cond<false, T, F> { using type = F; };
+
+template <int BN, bool FUSED3 = false>
 __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __grid_constant__ KParams p) {
-  using C = KCfg<BN>;
+  using C = typename hm_cond<FUSED3, K3Cfg<BN>, KCfg<BN>>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -220,8 +240,15 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
-            tma_load_4d(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
-            tma_load_2d(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN);
+            if constexpr (FUSED3) {     // [A_hi | A_lo | B_hi | B_lo] of this (tap, chunk)
+              tma_load_4d(&p.tmA[0], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
+              tma_load_4d(&p.tmA[1], &full[s], sa + C::A_BYTES, c * 64, w0 + en.dw, h0 + en.dh, n);
+              tma_load_2d(&p.tmB[0], &full[s], sa + 2 * C::A_BYTES, c * 64, en.b_row + nt * BN);
+              tma_load_2d(&p.tmB[1], &full[s], sa + 2 * C::A_BYTES + C::B_BYTES, c * 64, en.b_row + nt * BN);
+            } else {
+              tma_load_4d(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
+              tma_load_2d(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN);
+            }
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
@@ -239,13 +266,28 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_kgemm_kernel(const __gri
         mbar_wait(&full[s], ph, ab, 103);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-        const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
-        if (elect_one_sync()) {
+        if constexpr (FUSED3) {
+          const uint64_t ah = umma_smem_desc(sa, 16, 1024), al = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+          const uint64_t bh = umma_smem_desc(sa + 2 * C::A_BYTES, 16, 1024);
+          const uint64_t bl = umma_smem_desc(sa + 2 * C::A_BYTES + C::B_BYTES, 16, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
-            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
-          umma_commit(&empty[s]);
+            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, ah + 2 * j, bh + 2 * j, idesc, (k | j) != 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, al + 2 * j, bh + 2 * j, idesc, 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, ah + 2 * j, bl + 2 * j, idesc, 1u);
+            umma_commit(&empty[s]);
+          }
+        } else {
+          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row
+              umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0);
+            umma_commit(&empty[s]);
+          }
         }
         if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }

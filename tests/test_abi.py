@@ -140,3 +140,37 @@ def test_visual_conversions_match_the_reference_util(golden_dir):
     for n in (35, 20, 6):
         assert np.array_equal(colorize_labels(z["label_%d" % n], n), z["color_%d" % n]), n
     assert np.array_equal(tensor2im(torch.from_numpy(z["img"])), z["img_u8"])
+
+
+def test_vgg19_weight_loading_remaps_torchvision_keys(tmp_path, capsys):
+    """VGGLoss must be able to use the real ImageNet VGG19 (layer_util.py:384).  A torchvision-style state dict
+    ('features.N.*', classifier entries, deeper convs) is remapped to the reference Vgg19 module tree 'slice{K}.N.*';
+    the seeded random stand-in is only silent when asked for explicitly."""
+    import pytest
+    import torch
+    from neurips18_hierchical_image_manipulation_b200 import models as M
+    from neurips18_hierchical_image_manipulation_b200.networks import VGG19_CONVS, VGG19_SLICE_OF
+    g = torch.Generator().manual_seed(0)
+    tv = {}
+    for idx, cin, cout in VGG19_CONVS + [(30, 512, 512), (32, 512, 512)]:        # features[30:] exist in torchvision's file
+        tv["features.%d.weight" % idx] = torch.randn(cout, cin, 3, 3, generator=g)
+        tv["features.%d.bias" % idx] = torch.randn(cout, generator=g)
+    tv["classifier.0.weight"] = torch.zeros(8, 8)
+    sd = M.remap_torchvision_vgg19(tv)
+    assert list(sd) == [("slice%d.%d.%s" % (VGG19_SLICE_OF[i], i, leaf)) for i, _, _ in VGG19_CONVS for leaf in ("weight", "bias")]
+    assert torch.equal(sd["slice5.28.weight"], tv["features.28.weight"]) and torch.equal(sd["slice1.0.bias"], tv["features.0.bias"])
+    path = str(tmp_path / "vgg19.pth")
+    torch.save(tv, path)
+    got = M.load_vgg19_state_dict(M.Options(vgg_weights=path))
+    assert torch.equal(got["slice3.7.weight"], tv["features.7.weight"])
+    with pytest.raises(FileNotFoundError):
+        M.load_vgg19_state_dict(M.Options(vgg_weights=str(tmp_path / "missing.pth")))
+    bad = dict(tv); del bad["features.19.bias"]
+    with pytest.raises(KeyError):
+        M.remap_torchvision_vgg19(bad)
+    capsys.readouterr()
+    M.load_vgg19_state_dict(M.Options(vgg_weights="random"))
+    assert "WARNING" not in capsys.readouterr().err
+    if not os.path.isfile(os.path.join(torch.hub.get_dir(), "checkpoints", "vgg19-dcbb9e9d.pth")) and not os.environ.get("HM_VGG19_WEIGHTS"):
+        M.load_vgg19_state_dict(M.Options())                                     # implicit fallback: loud
+        assert "SEEDED RANDOM VGG19" in capsys.readouterr().err

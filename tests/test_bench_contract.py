@@ -53,9 +53,11 @@ def test_side_lines_for_configs_4_and_5():
 
 
 def test_two_gpu_lines_check_the_replicas():
-    for name in ("r02_bench_2gpu_buckets8.json", "r02_bench_2gpu_single.json"):
+    for name, n in (("r02_bench_2gpu_buckets8.json", 2), ("r02_bench_2gpu_single.json", 2), ("r02_bench_8gpu_buckets8.json", 8),
+                    ("r02_bench_8gpu_single.json", 8)):
         d = _line(name)
-        assert d["n_gpus"] == 2 and d["replicas_identical"] is True and d["cuda_graph"] is True
+        assert d["n_gpus"] == n and d["replicas_identical"] is True and d["cuda_graph"] is True
+        assert d["config"]["global_batch"] == 4 * n and abs(d["value"] - 4 * n / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
     with open(os.path.join(ROOT, "profiles", "r02_multigpu_check.json")) as fh:
         c = json.load(fh)
     assert c["replicas_identical"] is True and c["graph"] is True and c["loss_err"][0] < 1e-5 and max(c["loss_err"]) < 5e-3

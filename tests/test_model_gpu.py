@@ -374,6 +374,19 @@ def test_weights_init_statistics():
                 assert float(b.abs().max()) > 0.6 * bound and abs(float(b.mean())) < 0.5 * bound, c.name
 
 
+def test_parity_bf16x3_odd_extents_and_unaligned_channels():
+    """(a) H = 72 reaches 9 rows before the fourth VGG pool, so the max-pool adjoint must leave a ZERO last
+    row (it used to be uninitialised memory feeding the generator gradient); (b) ngf = ndf = 12 is not a multiple of 8,
+    so the operand planes have padding channels that the conv epilogue must never leave as NaN bit patterns."""
+    r = run_parity("bf16x3", ngf=12, ndf=12, H=72, W=80)
+    assert r["fake"] < 1e-3, r
+    for k, v in r.items():
+        if k.startswith("loss_"):
+            assert v < 1e-3, (k, r)
+    assert r["gradG"] < 2e-2 and r["gradD"] < 2e-2, r
+    assert r["stepG_sign"] < 1e-2 and r["stepD_sign"] < 1e-2, r
+
+
 def test_fused_step_matches_script_sequence():
     """optimize_parameters() == {forward; G.backward; G.step; D.backward; D.step}."""
     opt, model_a = _mk("bf16x3")
