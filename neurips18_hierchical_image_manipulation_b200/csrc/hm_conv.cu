@@ -211,6 +211,22 @@ int launch_mn(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
   return HM_OK;
 }
 
+template <int NB>
+int launch_mn3(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_mngemm_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         hm::MN3Cfg<NB>::SMEM_BYTES);
+    if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+    configured = true;
+  }
+  int grid = std::min(num_tiles, sm_count());
+  hm::hm_mngemm_kernel<NB, true><<<grid, hm::kEngineThreads, hm::MN3Cfg<NB>::SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
+  return HM_OK;
+}
+
 int launch_mn2(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
@@ -690,6 +706,8 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
   }
   const int num_tiles = base_tiles * splits;
   if (pair) return launch_mn2(p, num_tiles, st);
+  static const int use_fused3 = env_int("HM_FUSED3", 1);
+  if (use_fused3 && P->lo && Q->lo && nb <= 2) return nb == 1 ? launch_mn3<1>(p, num_tiles, st) : launch_mn3<2>(p, num_tiles, st);
   switch (nb) {
     case 1: return launch_mn<1>(p, num_tiles, st);
     case 2: return launch_mn<2>(p, num_tiles, st);

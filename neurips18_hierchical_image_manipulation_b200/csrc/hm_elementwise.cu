@@ -1309,7 +1309,9 @@ int hm_maxpool2(const void* i_hi, const void* i_lo, int N, int H, int W, int cs,
 
 int hm_maxpool2_bwd(const float* g, int N, int H, int W, int C, const void* a_hi, const void* a_lo, int cs, float* dz,
                     void* stream) {
-  if (!g || !a_hi || !dz || (H & 1) || (W & 1)) return HM_ERR_INVALID;
+  // odd extents: the last row / column lies outside every 2x2 window (MaxPool2d floors), its gradient is zero -- the
+  // kernel only writes the windows, so the caller passes a zero-filled dz then
+  if (!g || !a_hi || !dz) return HM_ERR_INVALID;
   maxpool_bwd_kernel<<<grid_for(long(N) * (H / 2) * (W / 2) * ((C + 7) >> 3)), kBlock, 0,
                        static_cast<cudaStream_t>(stream)>>>(g, N, H, W, C, static_cast<const bf16*>(a_hi),
                                                            static_cast<const bf16*>(a_lo), cs, dz);

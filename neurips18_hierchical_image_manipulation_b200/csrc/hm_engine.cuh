@@ -359,9 +359,23 @@ struct MNCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// fused-split variant (see K3Cfg): one stage = hi + lo boxes of both operands, three products per k-tile
 template <int NB>
+struct MN3Cfg {
+  static constexpr int BN = NB * 64;
+  static constexpr int BOX_BYTES = 64 * 128;
+  static constexpr int A_BYTES = 2 * BOX_BYTES;      // per plane
+  static constexpr int B_BYTES = NB * BOX_BYTES;     // per plane
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (NB >= 2) ? 3 : 4;
+  static constexpr int ACC = 2;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int NB, bool FUSED3 = false>
 __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __grid_constant__ MNParams p) {
-  using C = MNCfg<NB>;
+  using C = typename hm_cond<FUSED3, MN3Cfg<NB>, MNCfg<NB>>::type;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -420,7 +434,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
           if (!p.m_tapped) { int t = u / p.upt_n; nc[r] = (u % p.upt_n) * 64; ndw[r] = p.tap_dw[t]; ndh[r] = p.tap_dh[t]; }
           else { nc[r] = u * 64; ndw[r] = p.dwQ0; ndh[r] = p.dhQ0; }
         }
-        for (int pr = 0; pr < p.n_pairs; ++pr) {
+        for (int pr = 0; pr < (FUSED3 ? 1 : p.n_pairs); ++pr) {
           const CUtensorMap* mp = &p.tmP[p.pairP[pr]];
           const CUtensorMap* mq = &p.tmQ[p.pairQ[pr]];
           for (int kt = k0; kt < k1; ++kt) {
@@ -433,13 +447,27 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
             uint8_t* sa = smem + s * C::STAGE_BYTES;
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+              if constexpr (FUSED3) {   // [P_hi | P_lo | Q_hi | Q_lo]
 #pragma unroll
-              for (int r = 0; r < 2; ++r)
-                tma_load_4d(mp, &full[s], sa + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r], h0 * p.sP + mdh[r], n);
+                for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-              for (int r = 0; r < NB; ++r)
-                tma_load_4d(mq, &full[s], sa + C::A_BYTES + r * C::BOX_BYTES, nc[r], w0 * p.sQ + ndw[r],
-                            h0 * p.sQ + ndh[r], n);
+                  for (int r = 0; r < 2; ++r)
+                    tma_load_4d(&p.tmP[pl], &full[s], sa + pl * C::A_BYTES + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r],
+                                h0 * p.sP + mdh[r], n);
+#pragma unroll
+                  for (int r = 0; r < NB; ++r)
+                    tma_load_4d(&p.tmQ[pl], &full[s], sa + 2 * C::A_BYTES + pl * C::B_BYTES + r * C::BOX_BYTES, nc[r],
+                                w0 * p.sQ + ndw[r], h0 * p.sQ + ndh[r], n);
+                }
+              } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                  tma_load_4d(mp, &full[s], sa + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r], h0 * p.sP + mdh[r], n);
+#pragma unroll
+                for (int r = 0; r < NB; ++r)
+                  tma_load_4d(mq, &full[s], sa + C::A_BYTES + r * C::BOX_BYTES, nc[r], w0 * p.sQ + ndw[r],
+                              h0 * p.sQ + ndh[r], n);
+              }
             }
             if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
@@ -453,7 +481,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / (p.n_n_tiles * p.n_m_tiles);
         int k0, k1; k_range(split, k0, k1);
-        const int ksteps = (k1 - k0) * p.n_pairs;
+        const int ksteps = (k1 - k0) * (FUSED3 ? 1 : p.n_pairs);
         mbar_wait(&tempty[a], aph ^ 1, ab, 202);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
@@ -462,13 +490,28 @@ __global__ void __launch_bounds__(kEngineThreads, 1) hm_mngemm_kernel(const __gr
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           // MN-major SW128: LBO = distance between 64-channel groups (one TMA box), SBO = 8 K-rows = 1024 B
-          const uint64_t adesc = umma_smem_desc(sa, C::BOX_BYTES, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, C::BOX_BYTES, 1024);
-          if (elect_one_sync()) {
+          if constexpr (FUSED3) {
+            const uint64_t ph_ = umma_smem_desc(sa, C::BOX_BYTES, 1024), pl_ = umma_smem_desc(sa + C::A_BYTES, C::BOX_BYTES, 1024);
+            const uint64_t qh_ = umma_smem_desc(sa + 2 * C::A_BYTES, C::BOX_BYTES, 1024);
+            const uint64_t ql_ = umma_smem_desc(sa + 2 * C::A_BYTES + C::B_BYTES, C::BOX_BYTES, 1024);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)  // 16 pixels (K) per MMA = 16 rows x 128 B = 2048 B
-              umma_bf16(d_tmem, adesc + j * (2048 >> 4), bdesc + j * (2048 >> 4), idesc, (k | j) != 0);
-            umma_commit(&empty[s]);
+              for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, ph_ + j * (2048 >> 4), qh_ + j * (2048 >> 4), idesc, (k | j) != 0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, pl_ + j * (2048 >> 4), qh_ + j * (2048 >> 4), idesc, 1u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, ph_ + j * (2048 >> 4), ql_ + j * (2048 >> 4), idesc, 1u);
+              umma_commit(&empty[s]);
+            }
+          } else {
+            const uint64_t adesc = umma_smem_desc(sa, C::BOX_BYTES, 1024);
+            const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, C::BOX_BYTES, 1024);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)  // 16 pixels (K) per MMA = 16 rows x 128 B = 2048 B
+                umma_bf16(d_tmem, adesc + j * (2048 >> 4), bdesc + j * (2048 >> 4), idesc, (k | j) != 0);
+              umma_commit(&empty[s]);
+            }
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
