@@ -120,11 +120,14 @@ size_t g_scratch_bytes = 0;
 constexpr size_t kSkSlotBytes = size_t(256) * 256 * sizeof(float);
 constexpr size_t kSkCounterBytes = 4096;
 
-int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
+int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, bool fused3, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(hm::hm_kgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_kgemm2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          hm::K2Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(hm::hm_kgemm2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               hm::K2FCfg::SMEM_BYTES);
     if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
     configured = true;
   }
@@ -152,7 +155,8 @@ int launch_k2(hm::KParams& p, int num_m_tiles, int n_tiles_n, cudaStream_t st) {
     p.sk_cnt = static_cast<int*>(g_scratch);
     p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(g_scratch) + kSkCounterBytes);
   }
-  hm::hm_kgemm2_kernel<256><<<2 * clusters, hm::kEngineThreads, hm::K2Cfg::SMEM_BYTES, st>>>(p);
+  if (fused3) hm::hm_kgemm2_kernel<256, true><<<2 * clusters, hm::kEngineThreads, hm::K2FCfg::SMEM_BYTES, st>>>(p);
+  else hm::hm_kgemm2_kernel<256, false><<<2 * clusters, hm::kEngineThreads, hm::K2Cfg::SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   return HM_OK;
@@ -227,16 +231,20 @@ int launch_mn3(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
   return HM_OK;
 }
 
-int launch_mn2(const hm::MNParams& p, int num_tiles, cudaStream_t st) {
+int launch_mn2(const hm::MNParams& p, int num_tiles, bool fused3, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(hm::hm_mngemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(hm::hm_mngemm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          hm::MN2Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(hm::hm_mngemm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               hm::MN2FCfg::SMEM_BYTES);
     if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
     configured = true;
   }
   const int clusters = std::min(num_tiles, sm_count() / 2);
-  hm::hm_mngemm2_kernel<<<2 * clusters, hm::kEngineThreads, hm::MN2Cfg::SMEM_BYTES, st>>>(p);
+  if (fused3) hm::hm_mngemm2_kernel<true><<<2 * clusters, hm::kEngineThreads, hm::MN2FCfg::SMEM_BYTES, st>>>(p);
+  else hm::hm_mngemm2_kernel<false><<<2 * clusters, hm::kEngineThreads, hm::MN2Cfg::SMEM_BYTES, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   return HM_OK;
@@ -519,7 +527,8 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
 
   // fused-split kernel (one stage = hi + lo boxes of both operands, three products per stage): bf16x3 with N tile <= 128
   static const int use_fused3 = env_int("HM_FUSED3", 1);
-  const bool fused3 = use_fused3 && a_lo && b_lo && !pair && bn <= 128;
+  static const int use_fused3_pair = env_int("HM_FUSED3_PAIR", 1);
+  const bool fused3 = use_fused3 && a_lo && b_lo && (pair ? use_fused3_pair != 0 : bn <= 128);
   int ne = 0;
   for (int t = 0; t < n_taps; ++t) {
     const int pa[3] = {0, 1, 0}, pb[3] = {0, 0, 1};
@@ -557,7 +566,7 @@ int run_k_engine(const hm_operand* x, const void* w_hi, const void* w_lo, int k_
   }
   p.bias = bias; p.act = act; p.slope = slope; p.err = err_flag;
   const int num_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
-  if (pair) return launch_k2(p, p.tiles_w * p.tiles_h * p.n_img, p.n_tiles_n, st);
+  if (pair) return launch_k2(p, p.tiles_w * p.tiles_h * p.n_img, p.n_tiles_n, fused3, st);
   if (fused3) return launch_k3_bn(bn, p, num_tiles, st);
   return launch_k_bn(bn, p, num_tiles, st);
 }
@@ -705,8 +714,9 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
     if (e != cudaSuccess) { g_last_cuda_error = int(e); return HM_ERR_LAUNCH; }
   }
   const int num_tiles = base_tiles * splits;
-  if (pair) return launch_mn2(p, num_tiles, st);
   static const int use_fused3 = env_int("HM_FUSED3", 1);
+  static const int use_fused3_pair = env_int("HM_FUSED3_PAIR", 1);
+  if (pair) return launch_mn2(p, num_tiles, use_fused3 && use_fused3_pair && P->lo && Q->lo, st);
   if (use_fused3 && P->lo && Q->lo && nb <= 2) return nb == 1 ? launch_mn3<1>(p, num_tiles, st) : launch_mn3<2>(p, num_tiles, st);
   switch (nb) {
     case 1: return launch_mn<1>(p, num_tiles, st);

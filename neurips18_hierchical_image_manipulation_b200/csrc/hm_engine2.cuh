@@ -83,6 +83,19 @@ struct K2Cfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
+// fused-split variant (bf16x3): one stage = [A_hi | A_lo | B_hi | B_lo] of a (tap, chunk), three products per stage.  K1
+// moves 3.6 GB from L2 to the SMs per launch in the per-product layout (ncu r02: 11.8 TB/s, the fabric limit) because
+// A_hi and B_hi are staged twice; here a third of that traffic (and of the shared-memory fill) disappears.
+struct K2FCfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = 128 * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int ACC = 2;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
 // ------------------------------------------------------------------------------------------------
 // Deterministic stream-K tail.  A persistent tile loop leaves the last wave partly empty: the residual-block conv
@@ -144,10 +157,10 @@ __device__ __forceinline__ int sk_slot_of(int r, int c_first, int s, int per, in
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // KParams is reused; tmB must have been encoded with a 128-row box.
-template <int BN>
+template <int BN, bool FUSED3 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEngineThreads, 1)
 hm_kgemm2_kernel(const __grid_constant__ KParams p) {
-  using C = K2Cfg;
+  using C = typename hm_cond<FUSED3, K2FCfg, K2Cfg>::type;
   static_assert(BN == C::BN, "the CTA-pair kernel is built for 256-wide N tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -208,8 +221,15 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
         // it by a phase because they are gated by the leader's multicast commit on empty[s]
         if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
-          tma_load_4d_2sm(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
-          tma_load_2d_2sm(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
+          if constexpr (FUSED3) {
+            tma_load_4d_2sm(&p.tmA[0], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
+            tma_load_4d_2sm(&p.tmA[1], &full[s], sa + C::A_BYTES, c * 64, w0 + en.dw, h0 + en.dh, n);
+            tma_load_2d_2sm(&p.tmB[0], &full[s], sa + 2 * C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
+            tma_load_2d_2sm(&p.tmB[1], &full[s], sa + 2 * C::A_BYTES + C::B_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
+          } else {
+            tma_load_4d_2sm(&p.tmA[en.a_plane], &full[s], sa, c * 64, w0 + en.dw, h0 + en.dh, n);
+            tma_load_2d_2sm(&p.tmB[en.b_plane], &full[s], sa + C::A_BYTES, c * 64, en.b_row + nt * BN + int(rank) * 128);
+          }
         }
         if (++s == C::STAGES) { s = 0; ph ^= 1; }
         if (++c == p.chunks) { c = 0; ++e; }
@@ -228,13 +248,28 @@ hm_kgemm2_kernel(const __grid_constant__ KParams p) {
           mbar_wait(&full[s], ph, ab, 503);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
-          if (elect_one_sync()) {
+          if constexpr (FUSED3) {
+            const uint64_t ah = umma_smem_desc(sa, 16, 1024), al = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+            const uint64_t bh = umma_smem_desc(sa + 2 * C::A_BYTES, 16, 1024);
+            const uint64_t bl = umma_smem_desc(sa + 2 * C::A_BYTES + C::B_BYTES, 16, 1024);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, uint32_t((k != w.k0) | (j != 0)));
-            umma_commit_2sm_mc(&empty[s], 3);
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, ah + 2 * j, bh + 2 * j, idesc, uint32_t((k != w.k0) | (j != 0)));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, al + 2 * j, bh + 2 * j, idesc, 1u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, ah + 2 * j, bl + 2 * j, idesc, 1u);
+              umma_commit_2sm_mc(&empty[s], 3);
+            }
+          } else {
+            const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, 16, 1024);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, uint32_t((k != w.k0) | (j != 0)));
+              umma_commit_2sm_mc(&empty[s], 3);
+            }
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }

@@ -24,10 +24,24 @@ struct MN2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// fused-split variant (bf16x3): one stage = [P_hi | P_lo | Q_hi | Q_lo] boxes of a k-tile, three products per stage
+struct MN2FCfg {
+  static constexpr int BN = 256;
+  static constexpr int BOX_BYTES = 64 * 128;
+  static constexpr int A_BYTES = 2 * BOX_BYTES;       // per plane
+  static constexpr int B_BYTES = 2 * BOX_BYTES;       // per plane
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int ACC = 2;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
 // MNParams is reused: n_m_tiles counts 4-unit (256-row) M tiles, n_n_tiles 4-unit (256-column) N tiles.
+template <bool FUSED3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEngineThreads, 1)
 hm_mngemm2_kernel(const __grid_constant__ MNParams p) {
-  using C = MN2Cfg;
+  using C = typename hm_cond<FUSED3, MN2FCfg, MN2Cfg>::type;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,7 +101,7 @@ hm_mngemm2_kernel(const __grid_constant__ MNParams p) {
         if (!p.m_tapped) { const int t = u / p.upt_n; nc[r] = (u % p.upt_n) * 64; ndw[r] = p.tap_dw[t]; ndh[r] = p.tap_dh[t]; }
         else { nc[r] = u * 64; ndw[r] = p.dwQ0; ndh[r] = p.dhQ0; }
       }
-      for (int pr = 0; pr < p.n_pairs; ++pr) {
+      for (int pr = 0; pr < (FUSED3 ? 1 : p.n_pairs); ++pr) {
         const CUtensorMap* mp = &p.tmP[p.pairP[pr]];
         const CUtensorMap* mq = &p.tmQ[p.pairQ[pr]];
         for (int kt = k0; kt < k1; ++kt) {
@@ -100,13 +114,27 @@ hm_mngemm2_kernel(const __grid_constant__ MNParams p) {
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           if (elect_one_sync()) {
             if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            if constexpr (FUSED3) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-              tma_load_4d_2sm(mp, &full[s], sa + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r], h0 * p.sP + mdh[r], n);
+              for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-              tma_load_4d_2sm(mq, &full[s], sa + C::A_BYTES + r * C::BOX_BYTES, nc[r], w0 * p.sQ + ndw[r],
-                              h0 * p.sQ + ndh[r], n);
+                for (int r = 0; r < 2; ++r)
+                  tma_load_4d_2sm(&p.tmP[pl], &full[s], sa + pl * C::A_BYTES + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r],
+                                  h0 * p.sP + mdh[r], n);
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                  tma_load_4d_2sm(&p.tmQ[pl], &full[s], sa + 2 * C::A_BYTES + pl * C::B_BYTES + r * C::BOX_BYTES, nc[r],
+                                  w0 * p.sQ + ndw[r], h0 * p.sQ + ndh[r], n);
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 2; ++r)
+                tma_load_4d_2sm(mp, &full[s], sa + r * C::BOX_BYTES, mc[r], w0 * p.sP + mdw[r], h0 * p.sP + mdh[r], n);
+#pragma unroll
+              for (int r = 0; r < 2; ++r)
+                tma_load_4d_2sm(mq, &full[s], sa + C::A_BYTES + r * C::BOX_BYTES, nc[r], w0 * p.sQ + ndw[r],
+                                h0 * p.sQ + ndh[r], n);
+            }
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
@@ -120,7 +148,7 @@ hm_mngemm2_kernel(const __grid_constant__ MNParams p) {
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int split = tile / (p.n_n_tiles * p.n_m_tiles);
         int k0, k1; k_range(split, k0, k1);
-        const int ksteps = (k1 - k0) * p.n_pairs;
+        const int ksteps = (k1 - k0) * (FUSED3 ? 1 : p.n_pairs);
         mbar_wait(&tempty[a], aph ^ 1, ab, 602);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
@@ -129,6 +157,20 @@ hm_mngemm2_kernel(const __grid_constant__ MNParams p) {
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           // MN-major SW128: LBO = distance between 64-channel groups (one TMA box), SBO = 8 K-rows = 1024 B
+          if constexpr (FUSED3) {
+            const uint64_t ph_ = umma_smem_desc(sa, C::BOX_BYTES, 1024), pl_ = umma_smem_desc(sa + C::A_BYTES, C::BOX_BYTES, 1024);
+            const uint64_t qh_ = umma_smem_desc(sa + 2 * C::A_BYTES, C::BOX_BYTES, 1024);
+            const uint64_t ql_ = umma_smem_desc(sa + 2 * C::A_BYTES + C::B_BYTES, C::BOX_BYTES, 1024);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, ph_ + j * (2048 >> 4), qh_ + j * (2048 >> 4), idesc, (k | j) != 0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, pl_ + j * (2048 >> 4), qh_ + j * (2048 >> 4), idesc, 1u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, ph_ + j * (2048 >> 4), ql_ + j * (2048 >> 4), idesc, 1u);
+              umma_commit_2sm_mc(&empty[s], 3);
+            }
+          } else {
           const uint64_t adesc = umma_smem_desc(sa, C::BOX_BYTES, 1024);
           const uint64_t bdesc = umma_smem_desc(sa + C::A_BYTES, C::BOX_BYTES, 1024);
           if (elect_one_sync()) {
@@ -136,6 +178,7 @@ hm_mngemm2_kernel(const __grid_constant__ MNParams p) {
             for (int j = 0; j < 4; ++j)  // 16 pixels (K) per MMA = 16 rows x 128 B = 2048 B
               umma_bf16_2sm(d_tmem, adesc + j * (2048 >> 4), bdesc + j * (2048 >> 4), idesc, (k | j) != 0);
             umma_commit_2sm_mc(&empty[s], 3);
+          }
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
