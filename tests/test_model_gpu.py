@@ -432,7 +432,10 @@ def test_cuda_graph_replay_matches_eager_steps():
     a.ctx.check_pipeline()
     for k in a.fpG.params:
         d = (a.fpG.params[k] - b.fpG.params[k]).abs()
-        assert float(d.max()) < 2.5e-3 and float(d.mean()) < 2e-5, (k, float(d.max()), float(d.mean()))
+        # split-K weight gradients are summed with fp32 atomics whose order differs between two runs; Adam's first steps
+        # turn the sign of a ~zero gradient element into a +-lr (2e-4) move, so a few percent of the stem's one-hot
+        # weights may differ by that much: max a dozen lr, mean a fraction of lr
+        assert float(d.max()) < 2.5e-3 and float(d.mean()) < 5e-5, (k, float(d.max()), float(d.mean()))
     # host inputs (pinned) go through the same graph
     pinned = {k: v.pin_memory() for k, v in batches[0].items()}
     l1 = a.optimize_parameters(label=pinned["label"], inst=pinned["inst"], image=pinned["image"], feat=None,
