@@ -382,6 +382,8 @@ class TwoStreamAE_mask(object):
         # replica losses averaged (train_box2mask.py), i.e. the mean of the shard gradients -- one allreduce of the flat
         # gradient buffer inside optimizer.step()
         self.optimizer.data_parallel = bool(getattr(opt, "data_parallel", True))
+        self._graph = None           # dict(graph, inputs, outputs) once the training iteration has been captured
+        self._eager_steps = 0
 
     def _dev(self, t):
         return t.to(self.device, torch.float32).contiguous()
@@ -390,10 +392,52 @@ class TwoStreamAE_mask(object):
                 eval_mode=False, train=True):
         if eval_mode:
             raise NotImplementedError("eval mode uses BatchNorm running statistics, which this slice does not track")
+        ins = dict(label_map=label_map, mask_ctx_in=mask_ctx_in, mask_out=mask_out, mask_in=mask_in,
+                   mask_obj_inst=mask_obj_inst, cls=cls.reshape(-1))
+        if train and getattr(self.opt, "cuda_graph", True) and self._graph is not False:
+            # like Pix2PixHDModel_condImg.optimize_parameters: two eager iterations, then the whole iteration (~700 launches)
+            # is captured in a CUDA graph and replayed; a new batch geometry re-captures
+            sig = tuple(tuple(v.shape) for v in ins.values())
+            if self._graph is not None and self._graph["sig"] != sig:
+                self._graph, self._eager_steps = None, 2
+            if self._graph is not None or self._eager_steps >= 2:
+                return self._graph_iteration(ins, sig)
+            self._eager_steps += 1
+        return self._iteration(ins, train, captured=False)
+
+    def _graph_iteration(self, ins, sig):
+        if self._graph is None:
+            try:
+                static = {k: torch.empty(tuple(v.shape), dtype=torch.float32, device=self.device) for k, v in ins.items()}
+                for k, dst in static.items():
+                    dst.copy_(ins[k], non_blocking=True)
+                self.optimizer.step_dev.fill_(self.optimizer.step_count)
+                torch.cuda.synchronize()
+                l0, ver = self.ctx.launches, self.fpG.version
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    outs = self._iteration(static, True, captured=True)
+                launches = self.ctx.launches - l0
+                self.ctx.launches, self.fpG.version = l0, ver
+                self._graph = dict(graph=graph, inputs=static, outputs=outs, sig=sig, launches=launches)
+            except Exception as e:  # noqa: BLE001 -- any capture problem: keep training eagerly
+                print("CUDA-graph capture of the box2mask iteration failed (%s: %s); staying eager" % (type(e).__name__, e))
+                self._graph = False
+                torch.cuda.synchronize()
+                return self._iteration(ins, True, captured=False)
+        g = self._graph
+        for k, dst in g["inputs"].items():
+            dst.copy_(ins[k], non_blocking=True)
+        g["graph"].replay()
+        self.optimizer.step_count += 1
+        self.fpG.version += 1
+        self.ctx.launches += g["launches"]
+        return g["outputs"]
+
+    def _iteration(self, ins, train, captured):
         opt, ctx = self.opt, self.ctx
-        label_map, mask_ctx_in, mask_out, mask_in, inst = (self._dev(t) for t in (label_map, mask_ctx_in, mask_out,
-                                                                                     mask_in, mask_obj_inst))
-        clsf = self._dev(cls.reshape(-1))
+        label_map, mask_ctx_in, mask_out, mask_in, inst, clsf = (self._dev(ins[k]) for k in (
+            "label_map", "mask_ctx_in", "mask_out", "mask_in", "mask_obj_inst", "cls"))
         B, _, H, W = label_map.shape
         cond = ops.box2mask_encode(ctx, mask_ctx_in, mask_in, clsf, opt.label_nc)          # :127-151, :331-338
         ctx_logit, obj_logit, tape = self.netG.forward(cond)
@@ -413,7 +457,7 @@ class TwoStreamAE_mask(object):
         # ---- :233-240: loss_G = loss_recon_obj + rec_weight * loss_recon_comb; zero_grad, backward, step
         self.optimizer.zero_grad()
         self.backward_losses()
-        self.optimizer.step()
+        self.optimizer.step(captured=captured)
         # :271-275 postprocess_output + argmax (host-side visual output)
         gt_onehot = torch.zeros_like(out["comb_prob"]).scatter_(1, label_map.long(), 1.0)
         comb_label = (out["comb_prob"] * mask_out + (1 - mask_out) * gt_onehot).argmax(dim=1, keepdim=True)

@@ -24,3 +24,12 @@ for _ in range(2):
     torch.cuda.synchronize()
 o = out.tolist()
 print("cta_group::2 M=256 N=256: issue %.1f cyc/MMA   complete %.1f cyc/MMA" % (o[0] / 1024, o[1] / 1024))
+
+lib.hm_debug_mma_issue_mn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+for n in (64, 128, 256):
+    for lbo in (8192, 128):     # 8192: separate 64-channel boxes; 128: the "next tap = next pixel row" trick of hm_mnrows
+        for _ in range(2):
+            lib.hm_debug_mma_issue_mn(n, 1024, lbo, out.data_ptr(), None)
+            torch.cuda.synchronize()
+        o = out.tolist()
+        print("MN-major M=128 N=%3d LBO=%4d: issue %.1f cyc/MMA   complete %.1f cyc/MMA" % (n, lbo, o[0] / 1024, o[1] / 1024))
