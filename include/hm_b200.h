@@ -292,10 +292,17 @@ int hm_bn_bwd(const float* y, const float* mean, const float* rstd, const float*
               float slope, float* ws, void* o_hi, void* o_lo, int o_cs, float* out32, float* dgamma, float* dbeta,
               void* stream);
 int hm_upsample2_bwd(const float* g, int N, int h, int w, int C, float* dsmall, void* stream);
+/* g_prob (nullable, fp32 with leading dimension g_ld): gradient w.r.t. channel 0 of the discriminator input of the
+ * --use_gan branch, added to d/d obj_prob (times mask^2 when use_gate). */
 int hm_box2mask_head_bwd(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
                          const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate,
-                         const double* acc, float w_comb, float w_obj, void* c_hi, void* c_lo, int c_cs, void* o_hi,
-                         void* o_lo, int o_cs, void* stream);
+                         const double* acc, float w_comb, float w_obj, const float* g_prob, int g_ld, void* c_hi,
+                         void* c_lo, int c_cs, void* o_hi, void* o_lo, int o_cs, void* stream);
+/* hm_box2mask_d_input: discriminator input of --use_gan (TwoStreamAE_mask.py:153-157,205-213): operand [B,H,W,o_cs] =
+ *   cat(x * mask^x_mask_power, cond * mask) with cond as in hm_box2mask_encode; mask_out == NULL: no gating. */
+int hm_box2mask_d_input(const float* x, const float* mask_ctx_in, const float* mask_in, const float* cls,
+                        const float* mask_out, int x_mask_power, int B, int H, int W, int label_nc, void* o_hi, void* o_lo,
+                        int o_cs, void* stream);
 int hm_box2mask_head(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
                      const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate, float* comb_logit,
                      float* comb_logprob, float* obj_prob, double* acc, void* stream);

@@ -98,8 +98,9 @@ PROTOTYPES = {
     "hm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp,
                        _vp, _vp]),
     "hm_upsample2_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
-    "hm_box2mask_head_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _i,
-                                  _vp]),
+    "hm_box2mask_head_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _f, _vp, _i, _vp, _vp, _i, _vp,
+                                  _vp, _i, _vp]),
+    "hm_box2mask_d_input": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "hm_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
     "hm_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _vp, _f, _vp]),
 }

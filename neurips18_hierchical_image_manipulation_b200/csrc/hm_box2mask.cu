@@ -50,6 +50,43 @@ __global__ void b2m_encode_kernel(const float* __restrict__ mask_ctx_in, const f
   }
 }
 
+// Discriminator input of the --use_gan branch (TwoStreamAE_mask.py:153-157, 205-213): cat(x, cond) with x the object mask
+// (instance mask or generated probability) and cond the generator's own conditioning tensor, everything multiplied by
+// the box mask when use_output_gate is set (the generated mask twice: it is gated once for the loss, once more here).
+__global__ void b2m_d_input_kernel(const float* __restrict__ x, const float* __restrict__ mask_ctx_in,
+                                   const float* __restrict__ mask_in, const float* __restrict__ cls,
+                                   const float* __restrict__ mask_out, int x_mask_power, int B, int H, int W, int label_nc,
+                                   bf16* o_hi, bf16* o_lo, int cs) {
+  const int G = cs >> 3;
+  const long total = long(B) * H * W * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % G);
+    const long pix = i / G;
+    const int n = int(pix / (long(H) * W));
+    const int c0 = g * 8;
+    const int ctx_cls = int(__ldg(mask_ctx_in + pix));
+    const int obj_cls = int(__ldg(cls + n));
+    const float box = __ldg(mask_in + pix);
+    const float m = mask_out ? __ldg(mask_out + pix) : 1.f;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float t = 0.f;
+      if (c == 0) { t = __ldg(x + pix) * m; if (x_mask_power > 1) t *= m; }
+      else if (c <= label_nc) t = ((c - 1 == obj_cls) ? box : 0.f) * m;
+      else if (c <= 2 * label_nc) t = ((c - 1 - label_nc == ctx_cls) ? 1.f : 0.f) * m;
+      v[j] = t;
+    }
+    alignas(16) bf16 h[8];
+    alignas(16) bf16 l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hm::split_bf16(v[j], h[j], l[j]);
+    *reinterpret_cast<uint4*>(o_hi + pix * cs + c0) = *reinterpret_cast<const uint4*>(h);
+    if (o_lo) *reinterpret_cast<uint4*>(o_lo + pix * cs + c0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 // BatchNorm2d(affine) in training mode = normalise with the BATCH statistics (mean / rstd over N*H*W, computed by
 // hm_in_stats on the tensor viewed as one sample) then scale and shift:  (x - mean) * rstd * gamma + beta
 //   == (x - mean') * rstd'   with  rstd' = rstd * gamma,  mean' = mean - beta / rstd'   -> per-(n, c) rows for hm_in_apply.
@@ -192,7 +229,8 @@ __global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const f
                                     const float* __restrict__ label_map, const float* __restrict__ mask_out,
                                     const float* __restrict__ inst, int N, int H, int W, int C, int use_gate,
                                     const double* __restrict__ acc /* acc[1] = number of box pixels */, float w_comb,
-                                    float w_obj, bf16* c_hi, bf16* c_lo, int c_cs, bf16* o_hi, bf16* o_lo, int o_cs) {
+                                    float w_obj, const float* __restrict__ g_prob, int g_ld, bf16* c_hi, bf16* c_lo,
+                                    int c_cs, bf16* o_hi, bf16* o_lo, int o_cs) {
   const long total = long(N) * H * W;
   const float inv_cnt = acc[1] > 0.5 ? float(1.0 / acc[1]) : 0.f;
   const float inv_n = 1.f / float(total);
@@ -235,6 +273,8 @@ __global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const f
       if (logf(1.f - q) > -100.f) dq += (1.f - t) / (1.f - q);
       dp += w_obj * inv_n * dq * (use_gate ? mo : 1.f);
     }
+    // GAN term (--use_gan): g_prob is the gradient w.r.t. channel 0 of the discriminator input = p * mask^2 (gated)
+    if (g_prob) dp += __ldg(g_prob + i * g_ld) * (use_gate ? mo * mo : 1.f);
     d_o += dp * pr * (1.f - pr);
     for (int c = 0; c < o_cs; ++c) {
       bf16 hh, ll;
@@ -258,12 +298,22 @@ int hm_upsample2_bwd(const float* g, int N, int h, int w, int C, float* dsmall, 
 
 int hm_box2mask_head_bwd(const float* ctx_logit, const float* obj_logit, int obj_ld, const float* label_map,
                          const float* mask_out, const float* inst, int N, int H, int W, int C, int use_gate,
-                         const double* acc, float w_comb, float w_obj, void* c_hi, void* c_lo, int c_cs, void* o_hi,
-                         void* o_lo, int o_cs, void* stream) {
+                         const double* acc, float w_comb, float w_obj, const float* g_prob, int g_ld, void* c_hi,
+                         void* c_lo, int c_cs, void* o_hi, void* o_lo, int o_cs, void* stream) {
   if (!ctx_logit || !obj_logit || !label_map || !inst || !acc || !c_hi || !o_hi || c_cs < C || o_cs < 1) return HM_ERR_INVALID;
   b2m_head_bwd_kernel<<<grid_for(long(N) * H * W, kBlock, 148 * 8), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      ctx_logit, obj_logit, obj_ld, label_map, mask_out, inst, N, H, W, C, use_gate, acc, w_comb, w_obj,
+      ctx_logit, obj_logit, obj_ld, label_map, mask_out, inst, N, H, W, C, use_gate, acc, w_comb, w_obj, g_prob, g_ld,
       static_cast<bf16*>(c_hi), static_cast<bf16*>(c_lo), c_cs, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_box2mask_d_input(const float* x, const float* mask_ctx_in, const float* mask_in, const float* cls,
+                        const float* mask_out, int x_mask_power, int B, int H, int W, int label_nc, void* o_hi, void* o_lo,
+                        int o_cs, void* stream) {
+  if (!x || !mask_ctx_in || !mask_in || !cls || !o_hi || (o_cs & 7) || o_cs < 1 + 2 * label_nc) return HM_ERR_INVALID;
+  b2m_d_input_kernel<<<grid_for(long(B) * H * W * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, mask_ctx_in, mask_in, cls, mask_out, x_mask_power, B, H, W, label_nc, static_cast<bf16*>(o_hi),
+      static_cast<bf16*>(o_lo), o_cs);
   return HM_LAUNCH_OK();
 }
 

@@ -459,11 +459,24 @@ def upsample2_bwd(ctx, g, dsmall):
     ctx.launches += 1
 
 
-def box2mask_head_bwd(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, acc, w_comb, w_obj, d_ctx, d_obj):
+def box2mask_head_bwd(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, acc, w_comb, w_obj, d_ctx, d_obj,
+                      g_prob=None):
     N, H, W, Cc = ctx_logit.shape
     L.check(ctx.lib.hm_box2mask_head_bwd(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1],
                                          label_map.data_ptr(), _ptr(mask_out), inst.data_ptr(), N, H, W, Cc,
-                                         1 if use_gate else 0, acc.data_ptr(), float(w_comb), float(w_obj),
-                                         d_ctx.hi.data_ptr(), _ptr(d_ctx.lo), d_ctx.cs, d_obj.hi.data_ptr(), _ptr(d_obj.lo),
-                                         d_obj.cs, _stream()), "hm_box2mask_head_bwd")
+                                         1 if use_gate else 0, acc.data_ptr(), float(w_comb), float(w_obj), _ptr(g_prob),
+                                         g_prob.shape[-1] if g_prob is not None else 0, d_ctx.hi.data_ptr(), _ptr(d_ctx.lo),
+                                         d_ctx.cs, d_obj.hi.data_ptr(), _ptr(d_obj.lo), d_obj.cs, _stream()),
+            "hm_box2mask_head_bwd")
     ctx.launches += 1
+
+
+def box2mask_d_input(ctx, x, mask_ctx_in, mask_in, cls, mask_out, x_mask_power, label_nc):
+    """Discriminator input operand [B,H,W,1 + 2*label_nc] = cat(x, cond) (gated by mask_out when given)."""
+    B, _, H, W = mask_ctx_in.shape
+    out = Operand(ctx, B, H, W, 1 + 2 * label_nc)
+    L.check(ctx.lib.hm_box2mask_d_input(x.data_ptr(), mask_ctx_in.data_ptr(), mask_in.data_ptr(), cls.data_ptr(),
+                                        _ptr(mask_out), x_mask_power, B, H, W, label_nc, out.hi.data_ptr(), _ptr(out.lo),
+                                        out.cs, _stream()), "hm_box2mask_d_input")
+    ctx.launches += 1
+    return out

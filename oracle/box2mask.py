@@ -130,3 +130,66 @@ def encode_input(label_nc, mask_ctx_in, mask_in, cls):
         obj[b, int(cls[b, 0])] = mask_in[b, 0]
     cls_onehot = torch.zeros(B, label_nc).scatter_(1, cls.long(), 1.0)
     return torch.cat((obj, ctx), 1), cls_onehot
+
+
+# --------------------------------------------------------------------------------------------------
+# --use_gan with which_gan == 'patch_multiscale' (TwoStreamAE_mask.py:83-92, 205-248): a 2-scale MultiscaleDiscriminator
+# with BatchNorm (norm_layer == 'batch'), LSGAN, intermediate features kept
+# --------------------------------------------------------------------------------------------------
+def patch_discriminator_bn_forward(sd, x, scale, n_layers=3):
+    """NLayerDiscriminator(getIntermFeat=True) with nn.BatchNorm2d (Discriminator_NET.py:61-118): conv4x4 s2 p2 + LReLU;
+    n_layers-1 x [conv s2, BN, LReLU]; [conv s1, BN, LReLU]; conv s1 -> 1 channel.  Returns the n_layers + 2 taps."""
+    taps, h = [], x
+    for j in range(n_layers + 2):
+        k = "scale%d_layer%d." % (scale, j)
+        h = F.conv2d(h, sd[k + "0.weight"], sd[k + "0.bias"], stride=2 if j < n_layers else 1, padding=2)
+        if 1 <= j <= n_layers:
+            h = batch_norm(sd, k + "1", h)
+        if j <= n_layers:
+            h = F.leaky_relu(h, 0.2)
+        taps.append(h)
+    return taps
+
+
+def multiscale_discriminator_bn_forward(sd, x, num_D=2, n_layers=3):
+    """MultiscaleDiscriminator.forward (Discriminator_NET.py:45-58): scale num_D-1 sees the full resolution."""
+    out, h = [], x
+    for i in range(num_D):
+        out.append(patch_discriminator_bn_forward(sd, h, num_D - 1 - i, n_layers))
+        if i != num_D - 1:
+            h = F.avg_pool2d(h, 3, stride=2, padding=1, count_include_pad=False)
+    return out
+
+
+def lsgan(pred, target_is_real):
+    """GANLoss(use_lsgan=True) on a list of per-scale tap lists (models/losses.py:40-50)."""
+    loss = 0
+    for p in pred:
+        loss = loss + F.mse_loss(p[-1], torch.full_like(p[-1], 1.0 if target_is_real else 0.0))
+    return loss
+
+
+def gan_iteration_losses(sdG, sdD, cond, label_map, mask_out, mask_obj_inst, num_layers=3, n_blocks=6, n_layers_D=3,
+                         use_output_gate=True, rec_weight=1.0, gan_weight=1.0, lambda_feat=1.0, use_ganFeat_loss=True):
+    """TwoStreamAE_mask.forward with use_gan (:188-235).  Returns (loss_G, loss_D, dict of the reported scalars).
+    loss_G = loss_recon_obj + rec_weight * loss_recon_comb + gan_weight * loss_G_GAN   (the feature-matching term is only
+    reported: it is computed on fake.detach() and never enters loss_G, :221-229,233-235)."""
+    _, comb_lp, _, obj_prob = two_stream_forward(sdG, cond, num_layers=num_layers, n_blocks=n_blocks)
+    l_comb = mask_recon_loss(comb_lp, label_map, mask_out)
+    obj_gated = obj_prob * mask_out if use_output_gate else obj_prob           # :200-201
+    l_obj = F.binary_cross_entropy(obj_gated, mask_obj_inst)
+    real, fake, c = mask_obj_inst, obj_gated, cond                               # :208-209 (fake is already gated)
+    if use_output_gate:                                                          # :210-213 ("masking twice")
+        real, fake, c = real * mask_out, fake * mask_out, c * mask_out
+    D = lambda t: multiscale_discriminator_bn_forward(sdD, torch.cat((t, c), 1), 2, n_layers_D)   # noqa: E731  (:153-157)
+    real_d, fake_d = D(real), D(fake.detach())
+    l_d_real, l_d_fake = lsgan(real_d, True), lsgan(fake_d, False)
+    l_feat = torch.zeros(())
+    if use_ganFeat_loss:
+        for i in range(2):
+            for j in range(len(fake_d[i]) - 1):
+                l_feat = l_feat + 0.5 * (4.0 / (n_layers_D + 1)) * F.l1_loss(fake_d[i][j], real_d[i][j].detach()) * lambda_feat
+    l_g_gan = lsgan(D(fake), True)                                              # :231-232
+    loss_G = l_obj + rec_weight * l_comb + gan_weight * l_g_gan
+    loss_D = 0.5 * l_d_real + 0.5 * l_d_fake
+    return loss_G, loss_D, dict(comb=l_comb, obj=l_obj, g_gan=l_g_gan, d=loss_D, feat=l_feat, d_real=l_d_real, d_fake=l_d_fake)

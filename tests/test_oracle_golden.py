@@ -274,3 +274,32 @@ def test_box2mask_two_stream_forward_losses_and_gradients_against_the_reference_
             assert abs(float(g.sum()) - s_) <= 2e-3 * a_ + 1e-5 and abs(float((g * r).sum()) - p_) <= 2e-3 * a_ * 0.05 + 1e-6, k
             n_proj += 1
     assert n_full + n_proj == 120 and n_proj >= 20
+
+
+def test_box2mask_batchnorm_discriminator_against_the_reference_class(golden_dir):
+    """The 2-scale BatchNorm MultiscaleDiscriminator of box2mask's --use_gan branch (TwoStreamAE_mask.py:83-92): taps,
+    LSGAN losses for both targets, parameter gradients of the target-0 loss, input gradient of the target-1 loss."""
+    from oracle import box2mask as B2
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_d_small.npz"))
+    sd = {}
+    for name, shp in zip(z["param_names"], z["param_shapes"]):
+        sd[str(name)] = named_param(str(name), tuple(int(v) for v in str(shp).split(";"))).double().requires_grad_(True)
+    x = torch.from_numpy(z["x"]).double().requires_grad_(True)
+    taps = B2.multiscale_discriminator_bn_forward(sd, x, 2, 3)
+    for i, sc in enumerate(taps):
+        assert len(sc) == 5
+        for j, t in enumerate(sc):
+            ref = torch.from_numpy(z["tap_%d_%d" % (i, j)]).double()
+            assert float((t - ref).abs().max() / ref.abs().max()) < 2e-5, (i, j)
+    l_real, l_fake = B2.lsgan(taps, True), B2.lsgan(taps, False)
+    assert abs(float(l_real) - float(z["loss_real"])) < 2e-5 * float(z["loss_real"])
+    assert abs(float(l_fake) - float(z["loss_fake"])) < 2e-5 * float(z["loss_fake"])
+    names = list(sd)
+    gp = torch.autograd.grad(l_fake, [sd[k] for k in names], retain_graph=True)
+    for k, g in zip(names, gp):
+        ref = torch.from_numpy(z["g::" + k]).double()
+        assert float((g - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-6, k
+    gx, = torch.autograd.grad(l_real, x)
+    ref = torch.from_numpy(z["gx"]).double()
+    assert float((gx - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
