@@ -41,14 +41,18 @@ CONFIGS = {
               desc="BASELINE config #4: mask2image LocalEnhancer two-scale 1024x2048 (ngf 32, global trunk 4 down / 9 res "
                    "at 512x1024, 1 local enhancer with 3 res-blocks), synthetic labels + instance maps, 2-scale D, VGG19 "
                    "feat-match, full train step, 1 image/GPU (batch 8 on 8 GPUs)"),
-    "5": dict(H=256, W=256, per_gpu_batch=8, metric="box2mask train images/sec @256x256 (TwoStreamAE_mask, use_gan off)",
+    "5": dict(H=256, W=256, per_gpu_batch=8, metric="box2mask train images/sec @256x256 (TwoStreamAE_mask, --use_gan)",
               opt=dict(model="AE_maskgen_twostream", label_nc=LABEL_NC, output_nc=LABEL_NC, conv_dim=64, num_layers=3,
                        conv_size=4, n_blocks=6, which_stream="obj_context", cond_in="ctx_obj", use_output_gate=True,
-                       num_resnetblocks=1, norm_layer="batch", beta1=0.5, beta2=0.999, isTrain=False),
-              desc="BASELINE config #5: box2mask TwoStreamAE_mask (MaskTwoStreamConv_NET, flag set of "
-                   "scripts/train_box2mask_city.sh without --use_gan / --no_comb) 256x256, 35 classes, synthetic bbox + "
-                   "context masks, full training iteration (forward, MaskReconLoss + BCE, backward, Adam), 8 images/GPU "
-                   "(batch 64 on 8 GPUs: per-replica BatchNorm statistics + gradient allreduce, as nn.DataParallel trains it)"),
+                       num_resnetblocks=1, norm_layer="batch", beta1=0.5, beta2=0.999, isTrain=False,
+                       use_gan=True, which_gan="patch_multiscale", gan_weight=0.1, num_layers_D=3, ndf=64,
+                       use_ganFeat_loss=True, lambda_feat=1.0),
+              desc="BASELINE config #5: box2mask TwoStreamAE_mask (MaskTwoStreamConv_NET, the flag set of "
+                   "scripts/train_box2mask_city.sh without --no_comb: --use_gan --which_gan patch_multiscale --gan_weight 0.1 "
+                   "--num_layers_D 3 --use_ganFeat_loss) 256x256, 35 classes, synthetic bbox + context masks, full training "
+                   "iteration (forward, MaskReconLoss + BCE, 2-scale BatchNorm PatchGAN on real and generated masks, generator "
+                   "backward + Adam, discriminator backward + Adam), 8 images/GPU (batch 64 on 8 GPUs: per-replica BatchNorm "
+                   "statistics + gradient allreduce, as nn.DataParallel trains it); HM_B2M_GAN=0: the same without --use_gan"),
 }
 H, W, PER_GPU_BATCH = CONFIGS["2"]["H"], CONFIGS["2"]["W"], CONFIGS["2"]["per_gpu_batch"]
 
@@ -378,8 +382,13 @@ def main_box2mask(args, out_fd):
         dist.init_process_group("nccl", device_id=dev)
     import contextlib
     import io
+    opt = dict(cfg["opt"])
+    metric = cfg["metric"]
+    if os.environ.get("HM_B2M_GAN", "1") == "0":
+        opt["use_gan"] = False
+        metric = metric.replace("--use_gan", "use_gan off")
     with contextlib.redirect_stdout(io.StringIO()):
-        m = create_model(Options(gpu_ids=[local], precision=args.precision, name="bench5", **cfg["opt"]))
+        m = create_model(Options(gpu_ids=[local], precision=args.precision, name="bench5", **opt))
     B = cfg["per_gpu_batch"]
     host = {k: v.pin_memory() for k, v in box2mask_batch(B, cfg["H"], LABEL_NC, 77 + rank).items()}
     devb = {k: v.to(dev) for k, v in host.items()}
@@ -413,23 +422,23 @@ def main_box2mask(args, out_fd):
     launches = (m.ctx.launches - l0) // args.steps
     clocks = sampler.stop()
     m.ctx.check_pipeline()
-    hl = torch.empty(2, dtype=torch.float32, pin_memory=True)
+    hl = torch.empty(4, dtype=torch.float32, pin_memory=True)   # loss_recon_comb, loss_recon_obj, loss_G_GAN, loss_D
 
     def e2e():
         ls, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
-        hl.copy_(torch.stack(ls[:2]), non_blocking=False)
+        hl.copy_(torch.stack([ls[0], ls[1], ls[3], ls[4]]), non_blocking=False)
     ms_e2e = timed(e2e, args.steps)
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
         return 0
     B = B * world
-    line = dict(metric=cfg["metric"], value=B / (ms / 1e3), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+    line = dict(metric=metric, value=B / (ms / 1e3), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16x3 (fp32-parity mode)" if args.precision == "bf16x3" else args.precision, data="synthetic",
                 config=workload_desc(world, "5"), clocks=clocks,
                 e2e=dict(value=B / (ms_e2e / 1e3), unit="images/sec", ms_per_step=ms_e2e,
-                         h2d_bytes_per_step=sum(v.numel() * 4 for v in host.values()), d2h_bytes_per_step=8),
+                         h2d_bytes_per_step=sum(v.numel() * 4 for v in host.values()), d2h_bytes_per_step=16),
                 gpu_launches=launches, cuda_graph=isinstance(m._graph, dict), peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                 losses_last_step=[float(x) for x in hl])
     _emit(line, out_fd)

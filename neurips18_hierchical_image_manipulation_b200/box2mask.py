@@ -3,8 +3,10 @@
   MaskTwoStreamConvNet   <- models/MaskTwoStreamConv_NET.py:13-219 (+ MaskContextAE_NET base, layer_util.py:119-242,333-378)
   TwoStreamAE_mask       <- models/TwoStreamAE_mask.py: encode_input :127-151, reconstruct :257-300, forward :167-255 --
                             forward pass, the two reconstruction losses, `loss_G.backward()` and the Adam step the
-                            reference runs INSIDE forward (:233-240), for the reference's default `use_gan == False`.
-                            The PatchGAN terms of `--use_gan` (:205-231,243-248), eval-mode BatchNorm and `--no_comb`
+                            reference runs INSIDE forward (:233-240); with `--use_gan --which_gan patch_multiscale` (the
+                            shipped script) also the PatchGAN terms (:205-231): a 2-scale BatchNorm
+                            MultiscaleDiscriminator, LSGAN losses, the reported feature-matching term, lr_control and
+                            the discriminator's own Adam step (:243-248).  Eval-mode BatchNorm and `--no_comb`
                             (MaskTwoStreamConvSwitch_NET) are not built and raise.
 
 Parameter names are the reference's own ('<params_dict key>.<state_dict key>': conv_encoder_3.deep.1.weight,
@@ -341,12 +343,137 @@ def skip_grads_index(num_layers):
     return list(range(num_layers))
 
 
+class BNMultiscaleDiscriminator(object):
+    """MultiscaleDiscriminator(input_nc, ndf, n_layers, 'batch', use_sigmoid=False, num_D, getIntermFeat=True) as the
+    box2mask trainer builds it for which_gan == 'patch_multiscale' (TwoStreamAE_mask.py:83-92; Discriminator_NET.py:11-118):
+    per scale  conv4x4 s2 p2 + LReLU | (n_layers - 1) x [conv s2, BatchNorm, LReLU] | [conv s1, BatchNorm, LReLU] | conv s1
+    -> 1 channel, on an AvgPool(3, 2, 1, count_include_pad=False) pyramid; level i of the pyramid uses scale{num_D-1-i}.
+    BatchNorm runs in training mode: every pass is normalised with its own batch statistics, which is why the real and
+    the fake batch are evaluated separately (unlike the InstanceNorm discriminator of mask2image)."""
+
+    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=2):
+        self.ctx, self.fp, self.input_nc, self.n_layers, self.num_D = ctx, fp, input_nc, n_layers, num_D
+        self.scales, self.convs_, self.bns_ = [], [], []
+        for s in range(num_D):
+            layers, nf, nf_prev = [], ndf, input_nc
+            for j in range(n_layers + 2):
+                name = "scale%d_layer%d" % (s, j)
+                cout = 1 if j == n_layers + 1 else nf
+                conv = ConvP(ctx, fp, name + ".0", nf_prev, cout, 4, 2 if j < n_layers else 1, 2)
+                bn = _BN(fp, name + ".1", cout) if 1 <= j <= n_layers else None
+                layers.append((conv, bn))
+                self.convs_.append(conv)
+                if bn is not None:
+                    self.bns_.append(bn)
+                nf_prev, nf = nf, min(nf * 2, 512)
+            self.scales.append(layers)
+
+    def init_reference(self, gen):
+        for c in self.convs_:
+            c.init_reference(gen)
+        for b in self.bns_:
+            b.init_reference(gen)
+
+    def forward(self, d_in):
+        """d_in: Operand [N,H,W,input_nc].  Returns one dict per pyramid level: layers, xs (layer inputs), taps (fp32 NHWC
+        layer outputs = the reference's intermediate features), ys / stats (pre-BatchNorm conv outputs, batch statistics)."""
+        ctx = self.ctx
+        tape, x = [], d_in
+        for i in range(self.num_D):
+            layers = self.scales[self.num_D - 1 - i]
+            lv = dict(layers=layers, xs=[], taps=[], ys=[], stats=[])
+            cur = x
+            for j, (conv, bn) in enumerate(layers):
+                ho, wo = conv.out_hw(cur.h, cur.w, 2)
+                lv["xs"].append(cur)
+                tap = _f32(ctx, cur.n, ho, wo, conv.cout)
+                y = st = nxt = None
+                if j == 0:
+                    nxt = Operand(ctx, cur.n, ho, wo, conv.cout, zero=(conv.cout % 8 != 0))
+                    conv.forward(cur, 2, act=ops.ACT_LRELU, slope=0.2, out32=tap, out16=nxt)
+                elif bn is None:
+                    conv.forward(cur, 2, out32=tap)
+                else:
+                    y = _f32(ctx, cur.n, ho, wo, conv.cout)
+                    conv.forward(cur, 2, out32=y)
+                    nxt = Operand(ctx, cur.n, ho, wo, conv.cout, zero=(conv.cout % 8 != 0))
+                    st = bn.apply(ctx, y, ops.ACT_LRELU, out32=tap, out_op=nxt, reflect=False)
+                lv["taps"].append(tap); lv["ys"].append(y); lv["stats"].append(st)
+                cur = nxt
+            tape.append(lv)
+            if i != self.num_D - 1:
+                xn = Operand(ctx, x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, cs=x.cs)
+                if x.lo is None:
+                    xn.lo = None
+                ops.avgpool3s2(ctx, x, xn)
+                x = xn
+        return tape
+
+    def backward(self, tape, target, coef, weight_grads):
+        """Backward pass of  coef * sum_levels mse(pred_level, target)  (GANLoss with LSGAN, models/losses.py:40-50).
+        weight_grads=True: accumulates the gradients of every discriminator parameter (the loss_D pass, :243-248);
+        False: only the data path, and returns the fp32 gradient w.r.t. input channels 0..2 of the full-resolution
+        input as [N,H,W,4] (the generator's loss_G_GAN term, :231-235; channel 0 is the generated mask)."""
+        ctx = self.ctx
+        gins = []
+        for lv in tape:
+            layers = lv["layers"]
+            nl = len(layers)
+            pred = lv["taps"][-1]
+            N = pred.shape[0]
+            dy = Operand(ctx, N, pred.shape[1], pred.shape[2], 1, grad=True)
+            ops.mse_grad(ctx, pred, target, 2.0 * coef / pred.numel(), dy)
+            for j in range(nl - 1, -1, -1):
+                conv, _ = layers[j]
+                xin = lv["xs"][j]
+                if weight_grads:
+                    conv.wgrad(xin, dy, 2, bias_grad=(j == 0 or j == nl - 1))
+                    if j == 0:
+                        break
+                elif j == 0:
+                    gin = _f32(ctx, N, xin.h, xin.w, 4)
+                    conv.dgrad_rows(dy, xin.h, xin.w, 2, gin, 0, 3)
+                    gins.append(gin)
+                    break
+                gin = _f32(ctx, N, xin.h, xin.w, conv.cin)
+                conv.dgrad(dy, xin.h, xin.w, 2, gin)
+                tap = lv["taps"][j - 1]
+                dyn = Operand(ctx, N, tap.shape[1], tap.shape[2], tap.shape[3], grad=True)
+                bn = layers[j - 1][1]
+                if bn is None:       # layer 0: LeakyReLU only
+                    ops.in_bwd(ctx, tuple(tap.shape), ops.ACT_LRELU, 0.2, z=tap, g1=gin, g1_border=0, out_op=dyn)
+                else:
+                    st = lv["stats"][j - 1]
+                    ops.bn_bwd(ctx, lv["ys"][j - 1], st[0], st[1], bn.gamma, bn.beta, ops.ACT_LRELU, gin, out_op=dyn,
+                               dgamma=bn.gamma.grad if weight_grads else None,
+                               dbeta=bn.beta.grad if weight_grads else None, slope=0.2)
+                dy = dyn
+        if weight_grads:
+            return None
+        for i in range(len(gins) - 1, 0, -1):
+            ops.avgpool3s2_bwd(ctx, gins[i], gins[i - 1], 0, 3)
+        return gins[0]
+
+
+def lr_control(loss_G, loss_D_real, loss_D_fake, gan_margin=0.3):
+    """Discriminator_NET.py:190-211: freeze D when it is winning, G when it is losing, never both.  Returns (g_lr, d_lr)."""
+    update_d = not (loss_D_real < gan_margin or loss_D_fake < gan_margin)
+    update_g = not (loss_D_real > 1 - gan_margin or loss_D_fake > 1 - gan_margin)
+    if not (update_d or update_g):
+        update_d = update_g = True
+    what = "Update Both" if (update_g and update_d) else ("Froze Generator" if not update_g else "Froze Discriminator")
+    print("%s\t[G=%.3f],[DR=%.3f],[DF=%.3f]" % (what, loss_G, loss_D_real, loss_D_fake))
+    return float(update_g), float(update_d)
+
+
 class TwoStreamAE_mask(object):
-    """models/TwoStreamAE_mask.py.  `forward(...)` in training mode runs the reference's whole iteration for
-    `use_gan == False` (:167-255): forward, loss_recon_comb (MaskReconLoss) and loss_recon_obj (BCE), the backward pass of
-    `loss_recon_obj + rec_weight * loss_recon_comb` and `optimizer.step()` (Adam(lr, beta1, beta2)), and returns
-    ([loss_recon_comb, loss_recon_obj, 0, 0, 0, 0], [comb_recon_label, obj_recon_prob]) like the reference.  With
-    `train=False` it stops after the losses (the parity tests use that to inspect outputs and gradients)."""
+    """models/TwoStreamAE_mask.py.  `forward(...)` in training mode runs the reference's whole iteration (:167-255):
+    forward, loss_recon_comb (MaskReconLoss) and loss_recon_obj (BCE), with `--use_gan` the discriminator passes and
+    loss_G_GAN / loss_D, the backward pass of `loss_recon_obj + rec_weight * loss_recon_comb + gan_weight * loss_G_GAN`
+    and `optimizer.step()` (Adam(lr, beta1, beta2)), then the discriminator's backward pass and `optimizer_D.step()`, and
+    returns ([loss_recon_comb, loss_recon_obj, 0, loss_G_GAN, loss_D, loss_G_GAN_Feat], [comb_recon_label,
+    obj_recon_prob]) like the reference.  With `train=False` it stops after the losses (the parity tests use that to
+    inspect outputs and gradients)."""
 
     def name(self):
         return "TwoStreamAE_mask"
@@ -361,8 +488,10 @@ class TwoStreamAE_mask(object):
         self.ctx = ops.Ctx(dev, split=(prec != "bf16"), split_bwd=(prec == "bf16x3"))
         if getattr(opt, "no_comb", False):
             raise NotImplementedError("--no_comb selects MaskTwoStreamConvSwitch_NET, outside this slice")
-        if getattr(opt, "use_gan", False):
-            raise NotImplementedError("--use_gan (PatchGAN terms of TwoStreamAE_mask.py:205-231) is not built yet")
+        self.use_gan = bool(getattr(opt, "use_gan", False))
+        if self.use_gan and getattr(opt, "which_gan", "patch") != "patch_multiscale":
+            raise NotImplementedError("--which_gan: only 'patch_multiscale' (the shipped setting, TwoStreamAE_mask.py:83-92) "
+                                      "is built; 'patch' / 'patch_res' use the conditional single-scale discriminators")
         if getattr(opt, "objReconLoss", "bce") != "bce":
             raise NotImplementedError("objReconLoss: only 'bce' (the shipped setting) is built")
         self.fpG = FlatParams(dev)
@@ -373,7 +502,8 @@ class TwoStreamAE_mask(object):
         self.fpG.materialize()
         self.netG.init_reference(torch.Generator().manual_seed(getattr(opt, "init_seed", 0)))
         self.loss_names = ["G_Recon_comb", "G_Recon_obj", "KL_loss", "loss_G_GAN", "loss_D_GAN", "loss_G_GAN_Feat"]
-        self.acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        # slots: 0 NLL sum, 1 box pixels, 2 BCE sum | --use_gan: 3 loss_G_GAN, 4 loss_D_real, 5 loss_D_fake, 6 feature matching
+        self.acc = torch.zeros(8, dtype=torch.float64, device=dev)
         self.rec_weight = float(getattr(opt, "rec_weight", 1.0))
         self.old_lr = getattr(opt, "lr", 0.0002)
         from .models import FusedAdam
@@ -382,7 +512,22 @@ class TwoStreamAE_mask(object):
         # replica losses averaged (train_box2mask.py), i.e. the mean of the shard gradients -- one allreduce of the flat
         # gradient buffer inside optimizer.step()
         self.optimizer.data_parallel = bool(getattr(opt, "data_parallel", True))
-        self._graph = None           # dict(graph, inputs, outputs) once the training iteration has been captured
+        if self.use_gan:                                                   # :64-104
+            cond_nc = opt.label_nc * 2 if opt.cond_in == "ctx_obj" else opt.label_nc
+            if opt.cond_in != "ctx_obj":
+                raise NotImplementedError("--use_gan: the discriminator input kernel is built for cond_in == 'ctx_obj'")
+            self.gan_weight = float(getattr(opt, "gan_weight", 1.0))
+            self.num_layers_D = int(getattr(opt, "num_layers_D", 4))
+            self.fpD = FlatParams(dev)
+            self.netD = BNMultiscaleDiscriminator(self.ctx, self.fpD, 1 + cond_nc, getattr(opt, "ndf", 64),
+                                                  self.num_layers_D, 2)
+            self.fpD.materialize()
+            self.netD.init_reference(torch.Generator().manual_seed(getattr(opt, "init_seed", 0) + 1))
+            self.optimizer_D = FusedAdam(self.ctx, self.fpD, self.old_lr, (getattr(opt, "beta1", 0.9), 0.999))
+            self.optimizer_D.data_parallel = self.optimizer.data_parallel
+        # dict(graph, inputs, outputs) once the training iteration has been captured; False: stay eager -- lr_control
+        # (Discriminator_NET.py:190-211) reads three losses on the host every iteration
+        self._graph = False if (self.use_gan and getattr(opt, "lr_control", False)) else None
         self._eager_steps = 0
 
     def _dev(self, t):
@@ -414,11 +559,17 @@ class TwoStreamAE_mask(object):
                 self.optimizer.step_dev.fill_(self.optimizer.step_count)
                 torch.cuda.synchronize()
                 l0, ver = self.ctx.launches, self.fpG.version
+                ver_d = self.fpD.version if self.use_gan else 0
+                if self.use_gan:
+                    self.optimizer_D.step_dev.fill_(self.optimizer_D.step_count)
+                    torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     outs = self._iteration(static, True, captured=True)
                 launches = self.ctx.launches - l0
                 self.ctx.launches, self.fpG.version = l0, ver
+                if self.use_gan:
+                    self.fpD.version = ver_d
                 self._graph = dict(graph=graph, inputs=static, outputs=outs, sig=sig, launches=launches)
             except Exception as e:  # noqa: BLE001 -- any capture problem: keep training eagerly
                 print("CUDA-graph capture of the box2mask iteration failed (%s: %s); staying eager" % (type(e).__name__, e))
@@ -431,6 +582,9 @@ class TwoStreamAE_mask(object):
         g["graph"].replay()
         self.optimizer.step_count += 1
         self.fpG.version += 1
+        if self.use_gan:
+            self.optimizer_D.step_count += 1
+            self.fpD.version += 1
         self.ctx.launches += g["launches"]
         return g["outputs"]
 
@@ -452,17 +606,53 @@ class TwoStreamAE_mask(object):
         loss_obj = (self.acc[2] / float(B * H * W)).float()                  # BCELoss mean
         self._last = dict(tape=tape, ctx_logit=ctx_logit, obj_logit=obj_logit, label_map=label_map, mask_out=mask_out,
                           inst=inst, gate=gate)
+        zero = torch.zeros((), device=self.device)
+        gan = [zero, zero, zero]
+        if self.use_gan:
+            gan = self._discriminate(out["obj_prob"], inst, mask_ctx_in, mask_in, clsf, mask_out if gate else None)
         if not train:
-            return [loss_comb, loss_obj], out
-        # ---- :233-240: loss_G = loss_recon_obj + rec_weight * loss_recon_comb; zero_grad, backward, step
+            return [loss_comb, loss_obj] + (gan if self.use_gan else []), out
+        g_lr = d_lr = 1.0
+        if self.use_gan and getattr(opt, "lr_control", False):                # :237-239 (host decision, eager only)
+            g_lr, d_lr = lr_control(*[float(v) for v in self.acc[3:6].tolist()])
+        # ---- :233-248: loss_G = loss_recon_obj + rec_weight * loss_recon_comb + gan_weight * loss_G_GAN; zero_grad,
+        # backward, step.  g_lr == 0 zeroes the gradient but Adam still steps on its moments, like the reference's 0 * loss.
         self.optimizer.zero_grad()
-        self.backward_losses()
+        if g_lr != 0.0:
+            self.backward_losses()
         self.optimizer.step(captured=captured)
+        if self.use_gan:                                                      # :243-248: loss_D = d_lr * 0.5 * (real + fake)
+            self.optimizer_D.zero_grad()
+            if d_lr != 0.0:
+                self.netD.backward(self._last["d_real"], 1.0, 0.5, True)
+                self.netD.backward(self._last["d_fake"], 0.0, 0.5, True)
+            self.optimizer_D.step(captured=captured)
         # :271-275 postprocess_output + argmax (host-side visual output)
         gt_onehot = torch.zeros_like(out["comb_prob"]).scatter_(1, label_map.long(), 1.0)
         comb_label = (out["comb_prob"] * mask_out + (1 - mask_out) * gt_onehot).argmax(dim=1, keepdim=True)
-        zero = torch.zeros((), device=self.device)
-        return [loss_comb, loss_obj, zero, zero, zero, zero], [comb_label, out["obj_prob"]]
+        return [loss_comb, loss_obj, zero, gan[0], gan[1], gan[2]], [comb_label, out["obj_prob"]]
+
+    def _discriminate(self, obj_prob, inst, mask_ctx_in, mask_in, clsf, gate_mask):
+        """:203-232.  The three discriminator evaluations of the reference are two here: `discriminate(fake.detach())`
+        and `discriminate(fake)` see the same values and, in training mode, the same batch statistics.  Returns
+        [loss_G_GAN, loss_D, loss_G_GAN_Feat]; the feature-matching term is reported only -- the reference computes it on
+        the detached fake pass and never adds it to loss_G (:221-235)."""
+        ctx, opt = self.ctx, self.opt
+        # fake: the generated mask is gated once for the BCE loss and once more here ("masking twice", :209-212)
+        d_fake = ops.box2mask_d_input(ctx, obj_prob, mask_ctx_in, mask_in, clsf, gate_mask, 2, opt.label_nc)
+        d_real = ops.box2mask_d_input(ctx, inst, mask_ctx_in, mask_in, clsf, gate_mask, 1, opt.label_nc)
+        t_real, t_fake = self.netD.forward(d_real), self.netD.forward(d_fake)
+        for lr_, lf in zip(t_real, t_fake):
+            pr, pf = lr_["taps"][-1], lf["taps"][-1]
+            ops.mse_sum(ctx, pf, 1.0, 1.0 / pf.numel(), self.acc, 3)
+            ops.mse_sum(ctx, pr, 1.0, 1.0 / pr.numel(), self.acc, 4)
+            ops.mse_sum(ctx, pf, 0.0, 1.0 / pf.numel(), self.acc, 5)
+            if getattr(opt, "use_ganFeat_loss", False):
+                cf = 0.5 * (4.0 / (self.num_layers_D + 1)) * float(getattr(opt, "lambda_feat", 1.0))
+                for a, b in zip(lf["taps"][:-1], lr_["taps"][:-1]):
+                    ops.l1_sum(ctx, a, b, cf / a.numel(), self.acc, 6)
+        self._last.update(d_real=t_real, d_fake=t_fake)
+        return [self.acc[3].float(), (0.5 * self.acc[4] + 0.5 * self.acc[5]).float(), self.acc[6].float()]
 
     def backward_losses(self):
         """d(loss_recon_obj + rec_weight * loss_recon_comb)/d(parameters), accumulated into the flat .grad buffer."""
@@ -470,6 +660,9 @@ class TwoStreamAE_mask(object):
         N, H, W, C = s["ctx_logit"].shape
         d_ctx = Operand(ctx, N, H, W, C, grad=True)
         d_obj = Operand(ctx, N, H, W, 1, grad=True)
+        g_prob = None
+        if self.use_gan:    # gan_weight * loss_G_GAN through the discriminator's data path down to the generated mask
+            g_prob = self.netD.backward(s["d_fake"], 1.0, self.gan_weight, False)
         ops.box2mask_head_bwd(ctx, s["ctx_logit"], s["obj_logit"], s["label_map"], s["mask_out"], s["inst"], s["gate"],
-                              self.acc, self.rec_weight, 1.0, d_ctx, d_obj)
+                              self.acc, self.rec_weight, 1.0, d_ctx, d_obj, g_prob=g_prob)
         self.netG.backward(s["tape"], d_ctx, d_obj)

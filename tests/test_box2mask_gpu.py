@@ -150,3 +150,185 @@ def test_box2mask_training_step_against_oracle():
     for (a, b), (c, e) in zip(ref_losses, got_losses):
         assert abs(a - c) < 2e-3 * abs(a) and abs(b - e) < 2e-3 * abs(b), (ref_losses, got_losses)
     assert m.optimizer.step_count == 3
+
+
+def _operand_from(ctx, x_nchw):
+    """Dense fp32 NCHW -> bf16 (hi, lo) NHWC operand (test helper)."""
+    from neurips18_hierchical_image_manipulation_b200.ops import Operand
+    N, C, H, W = x_nchw.shape
+    op = Operand(ctx, N, H, W, C, zero=True)
+    v = x_nchw.permute(0, 2, 3, 1).contiguous().to(ctx.device)
+    hi = v.to(torch.bfloat16)
+    op.hi[..., :C] = hi
+    if op.lo is not None:
+        op.lo[..., :C] = (v - hi.float()).to(torch.bfloat16)
+    return op
+
+
+def test_box2mask_batchnorm_discriminator_against_the_reference_class_golden(golden_dir):
+    """BNMultiscaleDiscriminator (the --use_gan branch) against tests/golden/box2mask_d_small.npz, generated from the
+    reference's own MultiscaleDiscriminator(13, 16, 3, 'batch', False, 2, True): the 10 taps, both LSGAN losses, every
+    parameter gradient of the target-0 loss, the input gradient (channels 0..2) of the target-1 loss."""
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.box2mask import BNMultiscaleDiscriminator
+    from neurips18_hierchical_image_manipulation_b200.networks import FlatParams
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_d_small.npz"))
+    dev = torch.device("cuda", 0)
+    ctx = ops.Ctx(dev, split=True)
+    fp = FlatParams(dev)
+    net = BNMultiscaleDiscriminator(ctx, fp, 13, 16, 3, 2)
+    fp.materialize()
+    sd = {str(n): named_param(str(n), tuple(int(v) for v in str(s).split(";")))
+          for n, s in zip(z["param_names"], z["param_shapes"])}
+    assert set(sd) == set(fp.params), sorted(set(sd) ^ set(fp.params))[:6]
+    fp.load_state_dict(sd)
+    tape = net.forward(_operand_from(ctx, torch.from_numpy(z["x"])))
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    for i, lv in enumerate(tape):
+        assert len(lv["taps"]) == 5
+        for j, t in enumerate(lv["taps"]):
+            e = rel(t.permute(0, 3, 1, 2), z["tap_%d_%d" % (i, j)])
+            assert e < 1e-3, (i, j, e)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    for lv in tape:
+        p = lv["taps"][-1]
+        ops.mse_sum(ctx, p, 1.0, 1.0 / p.numel(), acc, 0)
+        ops.mse_sum(ctx, p, 0.0, 1.0 / p.numel(), acc, 1)
+    assert abs(float(acc[0]) - float(z["loss_real"])) < 1e-3 * float(z["loss_real"])
+    assert abs(float(acc[1]) - float(z["loss_fake"])) < 1e-3 * float(z["loss_fake"])
+    fp.grad.zero_()
+    net.backward(tape, 0.0, 1.0, True)
+    gx = net.backward(tape, 1.0, 1.0, False)
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    worst = []
+    for k, p in fp.params.items():
+        ref = torch.from_numpy(z["g::" + k]).double()
+        g = p.grad.detach().double().cpu()
+        if k.endswith(".0.bias") and float(ref.abs().max()) < 1e-6:      # conv bias in front of a BatchNorm
+            assert float(g.abs().max()) < 1e-6, k
+            continue
+        worst.append((float((g - ref).abs().max() / ref.abs().max()), k))
+    worst.sort(reverse=True)
+    print("box2mask D gradients vs reference autograd: worst", ["%.1e %s" % w for w in worst[:4]])
+    assert worst[0][0] < 1e-2, worst[:6]
+    ref = torch.from_numpy(z["gx"])[:, :3]
+    e = rel(gx[..., :3].permute(0, 3, 1, 2), ref)
+    print("box2mask D input gradient %.2e" % e)
+    assert e < 1e-2, e
+
+
+def test_box2mask_gan_iteration_against_oracle():
+    """TwoStreamAE_mask.forward with --use_gan --which_gan patch_multiscale --use_ganFeat_loss (the shipped flag set):
+    the six reported losses, d(loss_G)/d(generator parameters) incl. the path through the discriminator, d(loss_D)/
+    d(discriminator parameters), then two training iterations (both Adam steps) against the oracle."""
+    from oracle import box2mask as B2
+    from oracle import model as O
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import make_golden_box2mask as G
+    lr, beta1 = 2e-4, 0.5
+    kw = dict(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2, lr=lr, beta1=beta1, beta2=0.999, rec_weight=1.0,
+              use_gan=True, which_gan="patch_multiscale", gan_weight=0.1, num_layers_D=3, ndf=16, use_ganFeat_loss=True,
+              lambda_feat=1.0, cuda_graph=False)
+    m = _model(**kw)
+    sdG = {k: v.detach().cpu().clone() for k, v in m.fpG.params.items()}
+    sdD = {k: v.detach().cpu().clone() for k, v in m.fpD.params.items()}
+    d = G.synthetic(dict(label_nc=6, fineSize=64), 3, seed=29)
+    cond, _ = B2.encode_input(6, d["mask_ctx_in"], d["mask_in"], d["cls"])
+
+    def oracle_losses(pg, pd):
+        return B2.gan_iteration_losses(pg, pd, cond, d["label_map"], d["mask_out"], d["mask_obj_inst"], num_layers=3,
+                                       n_blocks=2, n_layers_D=3, use_output_gate=True, rec_weight=1.0, gan_weight=0.1,
+                                       lambda_feat=1.0, use_ganFeat_loss=True)
+    args = (d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"], d["mask_in"])
+    # ---- losses and gradients at the initial weights
+    pg = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
+    pd = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+    loss_G, loss_D, parts = oracle_losses(pg, pd)
+    gG = torch.autograd.grad(loss_G, list(pg.values()), retain_graph=True)
+    gD = torch.autograd.grad(loss_D, list(pd.values()), allow_unused=True)
+    ls, _ = m.forward(*args, train=False)
+    for got, key in zip(ls, ("comb", "obj", "g_gan", "d", "feat")):
+        r = float(parts[key])
+        assert abs(float(got) - r) < 1e-3 * abs(r), (key, float(got), r)
+    m.optimizer.zero_grad(); m.optimizer_D.zero_grad()
+    m.backward_losses()
+    m.netD.backward(m._last["d_real"], 1.0, 0.5, True)
+    m.netD.backward(m._last["d_fake"], 0.0, 0.5, True)
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    for params, grads, tag in ((m.fpG.params, dict(zip(pg, gG)), "G"), (m.fpD.params, dict(zip(pd, gD)), "D")):
+        worst = []
+        for k, p in params.items():
+            ref = grads[k]
+            g = p.grad.detach().cpu()
+            if ref is None or (k.endswith("bias") and float(ref.abs().max()) < 1e-5):
+                assert float(g.abs().max()) < 1e-5, k      # conv bias in front of a BatchNorm: rounding noise vs exact 0
+                continue
+            worst.append((float((g - ref).abs().max() / ref.abs().max()), k))
+        worst.sort(reverse=True)
+        print("box2mask --use_gan %s gradients vs oracle autograd: worst" % tag, ["%.1e %s" % w for w in worst[:4]])
+        assert worst[0][0] < 1e-2, (tag, worst[:6])
+    # ---- two training iterations
+    refG, refD = {k: v.clone() for k, v in sdG.items()}, {k: v.clone() for k, v in sdD.items()}
+    momG = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sdG.items()}
+    momD = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sdD.items()}
+    for step in (1, 2):
+        pg = {k: v.clone().requires_grad_(True) for k, v in refG.items()}
+        pd = {k: v.clone().requires_grad_(True) for k, v in refD.items()}
+        loss_G, loss_D, parts = oracle_losses(pg, pd)
+        gG = torch.autograd.grad(loss_G, list(pg.values()), retain_graph=True)
+        gD = torch.autograd.grad(loss_D, list(pd.values()), allow_unused=True)
+        for (k, v), g in zip(refG.items(), gG):
+            O.adam_step(v, g, momG[k][0], momG[k][1], step, lr, beta1)
+        for (k, v), g in zip(refD.items(), gD):
+            O.adam_step(v, g if g is not None else torch.zeros_like(v), momD[k][0], momD[k][1], step, lr, beta1)
+        ls, _ = m.forward(*args)
+        got = [float(v) for v in ls]
+        want = [float(parts["comb"]), float(parts["obj"]), 0.0, float(parts["g_gan"]), float(parts["d"]), float(parts["feat"])]
+        print("box2mask --use_gan iteration %d: oracle %s product %s" % (step, want, got))
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 3e-3 * abs(b) + 1e-9, (step, got, want)
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    assert m.optimizer.step_count == 2 and m.optimizer_D.step_count == 2
+    bad = tot = 0
+    for k, p in m.fpD.params.items():       # the discriminator moved the way the oracle's did
+        dm, dr = p.detach().cpu() - sdD[k], refD[k] - sdD[k]
+        sel = dr.abs() > 0.5 * lr
+        bad += int((torch.sign(dm[sel]) != torch.sign(dr[sel])).sum()); tot += int(sel.sum())
+    assert tot > 1000 and bad / tot < 1e-2, (bad, tot)
+
+
+def test_box2mask_gan_cuda_graph_replay_matches_eager_iterations():
+    """--use_gan: iterations 3.. are replays of the captured graph (both Adam steps inside); losses and final weights of
+    five iterations agree with an eager run from the same weights."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import make_golden_box2mask as G
+    kw = dict(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2, lr=2e-4, beta1=0.5, beta2=0.999, use_gan=True,
+              which_gan="patch_multiscale", gan_weight=0.1, num_layers_D=3, ndf=16, use_ganFeat_loss=True, lambda_feat=1.0)
+    d = G.synthetic(dict(label_nc=6, fineSize=64), 3, seed=31)
+    args = (d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"], d["mask_in"])
+    runs = []
+    for graph in (False, True):
+        m = _model(cuda_graph=graph, **kw)
+        losses = []
+        for _ in range(5):
+            ls, _ = m.forward(*args)
+            losses.append([float(v) for v in ls])
+        torch.cuda.synchronize()
+        m.ctx.check_pipeline()
+        assert isinstance(m._graph, dict) == graph
+        runs.append((losses, m.fpG.flat.clone(), m.fpD.flat.clone(), m.optimizer_D.step_count))
+    (l0, g0, d0, s0), (l1, g1, d1, s1) = runs
+    assert s0 == s1 == 5
+    dl = max(abs(a - b) / max(abs(a), 1e-6) for x, y in zip(l0, l1) for a, b in zip(x, y))
+    dg, dd = (g0 - g1).abs(), (d0 - d1).abs()
+    print("box2mask --use_gan graph vs eager: losses %.2e, G weights max %.2e mean %.2e, D weights max %.2e mean %.2e"
+          % (dl, float(dg.max()), float(dg.mean()), float(dd.max()), float(dd.mean())))
+    # same kernels in the same order; the loss reductions use floating-point atomics, so a weight whose gradient is ~0 may
+    # take its +-lr Adam step in the other direction: bound the mean, not the max
+    assert dl < 5e-3, (l0, l1)
+    assert float(dg.mean()) < 0.05 * 2e-4 * 5 and float(dd.mean()) < 0.05 * 2e-4 * 5
