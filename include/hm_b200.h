@@ -266,17 +266,22 @@ int hm_adam_step_dev(float* param, const float* grad, float* m, float* v, long n
  *   mask_ctx_in / mask_in are [B,1,H,W] fp32, cls is [B] fp32 class ids.  All values are 0/1 (exact in bf16).
  * hm_bn_fold: nn.BatchNorm2d(affine) in training mode (layer_util.py:19-21): batch statistics mean/rstd [C] (from
  *   hm_in_stats on the tensor viewed as ONE sample of N*H*W pixels) + gamma/beta -> per-(n,c) rows for hm_in_apply:
- *   rstd' = rstd*gamma, mean' = mean - beta/rstd'.
+ *   rstd' = rstd*gamma, mean' = mean - beta/rstd'.  With running_mean / running_var (both or neither) it also performs the
+ *   module's buffer update: running = (1-momentum)*running + momentum*statistic (variance unbiased by count/(count-1),
+ *   recovered from rstd and eps), `repeat` times, and *num_batches_tracked += repeat (nullable).
  * hm_upsample2_add: out = deep + nn.Upsample(scale_factor=2, mode='bilinear')(small), the DeconvResnetBlock tail
  *   (layer_util.py:178-179,236-242); fp32 NHWC, small is [N,h,w,C], deep/out are [N,2h,2w,C], C % 4 == 0.
  * hm_box2mask_head: MaskTwoStreamConv_NET.forward :190-217 -- obj_prob = sigmoid(obj_logit), comb = (1-p)*ctx + p*obj,
  *   log-softmax over the C classes (outputs in NCHW, any may be NULL) -- and the reconstruction losses of
  *   TwoStreamAE_mask.forward :188-203: acc[0] += sum of NLL over pixels with mask_out >= 0.5 (mask_losses.py:12-27),
- *   acc[1] += their count, acc[2] += sum of BCE(obj_prob [* mask_out when use_gate], inst) terms (logs clamped at -100). */
+ *   acc[1] += their count, acc[2] += sum of BCE(obj_prob [* mask_out when gated], inst) terms (logs clamped at -100).
+ *   `use_gate` is a bit set: bit 0 = --use_output_gate; bit 1 = --no_comb (MaskTwoStreamConvSwitch_NET.forward :208: the
+ *   context logits are returned as they are, comb = ctx), in hm_box2mask_head_bwd too. */
 int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const float* cls, int B, int H, int W, int label_nc,
                        void* o_hi, void* o_lo, int o_cs, void* stream);
 int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,
-               float* rstd_out, void* stream);
+               float* rstd_out, float* running_mean, float* running_var, long long* num_batches_tracked, float count,
+               float momentum, float eps, int repeat, void* stream);
 int hm_upsample2_add(const float* small, const float* deep, int N, int h, int w, int C, float* out, void* stream);
 /* Backward halves (training step of TwoStreamAE_mask.forward :233-248 without the GAN terms):
  * hm_bn_bwd: BatchNorm2d(affine) + activation backward, batch statistics (mean / rstd [C] over N*H*W): the gradient w.r.t.

@@ -20,6 +20,9 @@ Two aliasing effects of the reference are part of its arithmetic (see oracle/box
 rectifies its input IN PLACE, so both of its branches -- and the encoder features kept for the skip connections -- see
 relu(x).
 """
+import os
+from collections import OrderedDict
+
 import torch
 
 from . import ops
@@ -30,12 +33,20 @@ DIM_LIST_TAIL = [96, 128, 256, 512]      # MaskTwoStreamConv_NET.py:25
 
 
 class _BN(object):
-    """nn.BatchNorm2d(C, affine=True) parameters (training mode: the running buffers do not enter the result)."""
+    """nn.BatchNorm2d(C, affine=True): gain / shift parameters and the running_mean / running_var / num_batches_tracked
+    buffers (momentum 0.1, eps 1e-5).  Training mode normalises with the batch statistics and updates the buffers; eval
+    mode (`training = False`) normalises with the buffers."""
+
+    EPS, MOMENTUM = 1e-5, 0.1
 
     def __init__(self, fp, name, c):
         self.fp, self.name, self.c = fp, name, c
+        self.training = True
         fp.declare(name + ".weight", (c,))
         fp.declare(name + ".bias", (c,))
+        fp.buffers[name + ".running_mean"] = torch.zeros(c, dtype=torch.float32, device=fp.device)
+        fp.buffers[name + ".running_var"] = torch.ones(c, dtype=torch.float32, device=fp.device)
+        fp.buffers[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64, device=fp.device)
 
     @property
     def gamma(self):
@@ -45,6 +56,11 @@ class _BN(object):
     def beta(self):
         return self.fp.params[self.name + ".bias"]
 
+    @property
+    def running(self):
+        b = self.fp.buffers
+        return b[self.name + ".running_mean"], b[self.name + ".running_var"], b[self.name + ".num_batches_tracked"]
+
     def init_reference(self, gen):
         """weights_init (layer_util.py:13-15): gain ~ N(1, 0.02), shift 0."""
         with torch.no_grad():
@@ -52,11 +68,18 @@ class _BN(object):
             self.beta.zero_()
         self.fp.version += 1
 
-    def apply(self, ctx, y, act, skip=None, out32=None, out_op=None, reflect=True):
-        """Returns the batch statistics (mean, rstd) [1, C] for the backward pass."""
+    def apply(self, ctx, y, act, skip=None, out32=None, out_op=None, reflect=True, repeat=1):
+        """Returns the statistics (mean, rstd) [1, C] the tensor was normalised with (the backward pass needs the batch
+        statistics).  repeat: how many times the reference evaluates this module on this batch (buffer update count)."""
         N, H, W, C = y.shape
-        mean, rstd = ops.in_stats(ctx, y.view(1, N * H, W, C))          # statistics over (N, H, W)
-        mean_n, rstd_n = ops.bn_fold(ctx, mean, rstd, self.gamma, self.beta, N)
+        if self.training:
+            mean, rstd = ops.in_stats(ctx, y.view(1, N * H, W, C), eps=self.EPS)          # statistics over (N, H, W)
+            mean_n, rstd_n = ops.bn_fold(ctx, mean, rstd, self.gamma, self.beta, N, running=self.running, count=N * H * W,
+                                         repeat=repeat, momentum=self.MOMENTUM, eps=self.EPS)
+        else:
+            rm, rv, _ = self.running
+            mean, rstd = rm.view(1, C), torch.rsqrt(rv + self.EPS).view(1, C)
+            mean_n, rstd_n = ops.bn_fold(ctx, mean, rstd, self.gamma, self.beta, N)
         ops.in_apply(ctx, y, mean_n, rstd_n, act, skip=skip, out32=out32, out_op=out_op, reflect=reflect)
         return mean, rstd
 
@@ -138,6 +161,15 @@ class MaskTwoStreamConvNet(object):
             c.init_reference(gen)
         for b in self.bns_:
             b.init_reference(gen)
+
+    def set_mode(self, eval_mode=False):
+        """MaskContextAE_NET.set_mode: module.eval() / module.train() on every entry of params_dict."""
+        for b in self.bns_:
+            b.training = not eval_mode
+        self.eval_mode = bool(eval_mode)
+
+    def get_mode(self):
+        return getattr(self, "eval_mode", False)
 
     # ---- forward --------------------------------------------------------------------------------------
     def _res_block(self, blk, x32, x_op, want_op, tape):
@@ -374,9 +406,10 @@ class BNMultiscaleDiscriminator(object):
         for b in self.bns_:
             b.init_reference(gen)
 
-    def forward(self, d_in):
+    def forward(self, d_in, repeat=1):
         """d_in: Operand [N,H,W,input_nc].  Returns one dict per pyramid level: layers, xs (layer inputs), taps (fp32 NHWC
-        layer outputs = the reference's intermediate features), ys / stats (pre-BatchNorm conv outputs, batch statistics)."""
+        layer outputs = the reference's intermediate features), ys / stats (pre-BatchNorm conv outputs, batch statistics).
+        repeat: how many evaluations of the reference this pass stands for (BatchNorm buffer updates)."""
         ctx = self.ctx
         tape, x = [], d_in
         for i in range(self.num_D):
@@ -397,7 +430,7 @@ class BNMultiscaleDiscriminator(object):
                     y = _f32(ctx, cur.n, ho, wo, conv.cout)
                     conv.forward(cur, 2, out32=y)
                     nxt = Operand(ctx, cur.n, ho, wo, conv.cout, zero=(conv.cout % 8 != 0))
-                    st = bn.apply(ctx, y, ops.ACT_LRELU, out32=tap, out_op=nxt, reflect=False)
+                    st = bn.apply(ctx, y, ops.ACT_LRELU, out32=tap, out_op=nxt, reflect=False, repeat=repeat)
                 lv["taps"].append(tap); lv["ys"].append(y); lv["stats"].append(st)
                 cur = nxt
             tape.append(lv)
@@ -486,8 +519,14 @@ class TwoStreamAE_mask(object):
         self.device = dev
         prec = getattr(opt, "precision", "bf16x3")
         self.ctx = ops.Ctx(dev, split=(prec != "bf16"), split_bwd=(prec == "bf16x3"))
-        if getattr(opt, "no_comb", False):
-            raise NotImplementedError("--no_comb selects MaskTwoStreamConvSwitch_NET, outside this slice")
+        # --no_comb selects MaskTwoStreamConvSwitch_NET (:29-32): the same network, but its forward returns the context
+        # stream's logits / log-softmax as they are instead of gating them with the object stream (:208 vs :190-217)
+        self.no_comb = bool(getattr(opt, "no_comb", False))
+        if self.no_comb and getattr(opt, "add_dilated_layers", False):
+            raise NotImplementedError("--add_dilated_layers (DilatedResnetBlock, MaskTwoStreamConvSwitch_NET.py:101-104)")
+        self.isTrain = bool(getattr(opt, "isTrain", True))
+        self.gpu_ids = opt.gpu_ids
+        self.save_dir = os.path.join(getattr(opt, "checkpoints_dir", "./checkpoints"), opt.name)
         self.use_gan = bool(getattr(opt, "use_gan", False))
         if self.use_gan and getattr(opt, "which_gan", "patch") != "patch_multiscale":
             raise NotImplementedError("--which_gan: only 'patch_multiscale' (the shipped setting, TwoStreamAE_mask.py:83-92) "
@@ -512,6 +551,7 @@ class TwoStreamAE_mask(object):
         # replica losses averaged (train_box2mask.py), i.e. the mean of the shard gradients -- one allreduce of the flat
         # gradient buffer inside optimizer.step()
         self.optimizer.data_parallel = bool(getattr(opt, "data_parallel", True))
+        self._graph = None
         if self.use_gan:                                                   # :64-104
             cond_nc = opt.label_nc * 2 if opt.cond_in == "ctx_obj" else opt.label_nc
             if opt.cond_in != "ctx_obj":
@@ -525,6 +565,14 @@ class TwoStreamAE_mask(object):
             self.netD.init_reference(torch.Generator().manual_seed(getattr(opt, "init_seed", 0) + 1))
             self.optimizer_D = FusedAdam(self.ctx, self.fpD, self.old_lr, (getattr(opt, "beta1", 0.9), 0.999))
             self.optimizer_D.data_parallel = self.optimizer.data_parallel
+        # :106-118: resume / fine-tune / test-time loading
+        if self.isTrain:
+            if getattr(opt, "continue_train", False) or getattr(opt, "load_pretrain", ""):
+                self.load(getattr(opt, "which_epoch", "latest"), getattr(opt, "load_pretrain", ""))
+        elif os.path.isfile(os.path.join(self.save_dir, "%s_net_G.pth" % getattr(opt, "which_epoch", "latest"))):
+            self.load(getattr(opt, "which_epoch", "latest"))
+        else:   # the reference asserts here; benchmarks and parity tests build test-mode models on initialised weights
+            print("%s not exists yet!" % os.path.join(self.save_dir, "%s_net_G.pth" % getattr(opt, "which_epoch", "latest")))
         # dict(graph, inputs, outputs) once the training iteration has been captured; False: stay eager -- lr_control
         # (Discriminator_NET.py:190-211) reads three losses on the host every iteration
         self._graph = False if (self.use_gan and getattr(opt, "lr_control", False)) else None
@@ -536,7 +584,9 @@ class TwoStreamAE_mask(object):
     def forward(self, label_map, mask_obj_in, mask_ctx_in, mask_obj_out, mask_out, mask_obj_inst, cls, mask_in,
                 eval_mode=False, train=True):
         if eval_mode:
-            raise NotImplementedError("eval mode uses BatchNorm running statistics, which this slice does not track")
+            # the reference's forward(eval_mode=True) ends in `return recon_label`, an undefined name (:254-255): inference
+            # goes through reconstruct(..., eval_mode=True) / generate(), below
+            raise NameError("name 'recon_label' is not defined (TwoStreamAE_mask.py:255); use generate() / reconstruct()")
         ins = dict(label_map=label_map, mask_ctx_in=mask_ctx_in, mask_out=mask_out, mask_in=mask_in,
                    mask_obj_inst=mask_obj_inst, cls=cls.reshape(-1))
         if train and getattr(self.opt, "cuda_graph", True) and self._graph is not False:
@@ -601,7 +651,7 @@ class TwoStreamAE_mask(object):
                    obj_logit=obj_logit[..., :1].permute(0, 3, 1, 2), obj_prob=torch.empty(B, 1, H, W, device=self.device))
         self.acc.zero_()
         ops.box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, gate, out["comb_logit"], out["comb_prob"],
-                          out["obj_prob"], self.acc)
+                          out["obj_prob"], self.acc, no_comb=self.no_comb)
         loss_comb = (self.acc[0] / self.acc[1].clamp_min(1.0)).float()       # NLLLoss2d mean over non-ignored pixels
         loss_obj = (self.acc[2] / float(B * H * W)).float()                  # BCELoss mean
         self._last = dict(tape=tape, ctx_logit=ctx_logit, obj_logit=obj_logit, label_map=label_map, mask_out=mask_out,
@@ -641,7 +691,7 @@ class TwoStreamAE_mask(object):
         # fake: the generated mask is gated once for the BCE loss and once more here ("masking twice", :209-212)
         d_fake = ops.box2mask_d_input(ctx, obj_prob, mask_ctx_in, mask_in, clsf, gate_mask, 2, opt.label_nc)
         d_real = ops.box2mask_d_input(ctx, inst, mask_ctx_in, mask_in, clsf, gate_mask, 1, opt.label_nc)
-        t_real, t_fake = self.netD.forward(d_real), self.netD.forward(d_fake)
+        t_real, t_fake = self.netD.forward(d_real), self.netD.forward(d_fake, repeat=2)
         for lr_, lf in zip(t_real, t_fake):
             pr, pf = lr_["taps"][-1], lf["taps"][-1]
             ops.mse_sum(ctx, pf, 1.0, 1.0 / pf.numel(), self.acc, 3)
@@ -664,5 +714,131 @@ class TwoStreamAE_mask(object):
         if self.use_gan:    # gan_weight * loss_G_GAN through the discriminator's data path down to the generated mask
             g_prob = self.netD.backward(s["d_fake"], 1.0, self.gan_weight, False)
         ops.box2mask_head_bwd(ctx, s["ctx_logit"], s["obj_logit"], s["label_map"], s["mask_out"], s["inst"], s["gate"],
-                              self.acc, self.rec_weight, 1.0, d_ctx, d_obj, g_prob=g_prob)
+                              self.acc, self.rec_weight, 1.0, d_ctx, d_obj, g_prob=g_prob, no_comb=self.no_comb)
         self.netG.backward(s["tape"], d_ctx, d_obj)
+
+    # ---- inference (vis_box2mask.py:36-60, train_box2mask.py:90-100) -------------------------------------------------
+    def reconstruct(self, input_dict, eval_mode=False):
+        """:257-297.  Forward pass only; eval_mode=True normalises with the BatchNorm running statistics and restores
+        the network's mode afterwards.  Returns comb_recon_label [B,1,H,W] (argmax of the generated layout inside the box,
+        ground truth outside, :271-275) and obj_recon_label (the object stream's probability map)."""
+        ctx, opt = self.ctx, self.opt
+        current = self.netG.get_mode()
+        if eval_mode != current:
+            self.netG.set_mode(eval_mode)
+        try:
+            label_map, mask_ctx_in, mask_out, mask_in = (self._dev(input_dict[k]) for k in (
+                "label_map", "mask_ctx_in", "mask_out", "mask_in"))
+            clsf = self._dev(input_dict["cls"].reshape(-1))
+            B, _, H, W = label_map.shape
+            cond = ops.box2mask_encode(ctx, mask_ctx_in, mask_in, clsf, opt.label_nc)
+            ctx_logit, obj_logit, _ = self.netG.forward(cond)
+            C = opt.output_nc
+            out = dict(comb_recon_prob=torch.empty(B, C, H, W, device=self.device),
+                       obj_recon_prob=torch.empty(B, 1, H, W, device=self.device))
+            ops.box2mask_head(ctx, ctx_logit, obj_logit, None, None, None, False, None, out["comb_recon_prob"],
+                              out["obj_recon_prob"], None, no_comb=self.no_comb)
+        finally:
+            if eval_mode != current:
+                self.netG.set_mode(current)
+        gt_onehot = torch.zeros_like(out["comb_recon_prob"]).scatter_(1, label_map.long(), 1.0)
+        comb_label = (out["comb_recon_prob"] * mask_out + (1 - mask_out) * gt_onehot).argmax(dim=1, keepdim=True)
+        res = dict(comb_recon_label=comb_label, obj_recon_label=out["obj_recon_prob"])
+        if not eval_mode:
+            res.update(label_map=label_map, comb_gt_mask=mask_out, comb_recon_prob=out["comb_recon_prob"],
+                       obj_recon_prob=out["obj_recon_prob"])
+        return res
+
+    def generate(self, input_dict):
+        """:299-302."""
+        out = self.reconstruct(input_dict, eval_mode=True)
+        return dict(comb_pred_label=out["comb_recon_label"], obj_pred_label=out["obj_recon_label"])
+
+    # ---- checkpoints (base_model.py:43-64,73-127; TwoStreamAE_mask.py:106-118,359-369) --------------------------------
+    def _network_dict(self):
+        """The generator's state as the reference's save_network_dict writes it: {params_dict key: module.state_dict()}
+        -- a parameter '<key>.<rest>' belongs to module <key>; the parameter-free nn.ReLU at conv_encoder_2 is an empty
+        entry (load_network_dict indexes every params_dict key)."""
+        net = OrderedDict()
+        for k, v in self.fpG.state_dict().items():
+            mk, rest = k.split(".", 1)
+            net.setdefault(mk, OrderedDict())[rest] = v
+        net.setdefault("conv_encoder_2", OrderedDict())
+        return net
+
+    def _adam_state(self, optimizer):
+        """torch.optim.Adam.state_dict() layout, parameters in this implementation's declaration order (the reference's
+        order is the iteration order of a python-2 dict, which no file format pins down)."""
+        fp = optimizer.fp
+        state, off = {}, {n: o for n, _, o in fp.specs}
+        for i, (name, p) in enumerate(fp.params.items()):
+            o, n = off[name], p.numel()
+            state[i] = dict(step=optimizer.step_count, exp_avg=optimizer.m[o:o + n].view(p.shape).cpu().clone(),
+                            exp_avg_sq=optimizer.v[o:o + n].view(p.shape).cpu().clone())
+        g = optimizer.param_groups[0]
+        return dict(state=state, param_groups=[dict(lr=g["lr"], betas=tuple(optimizer.betas), eps=optimizer.eps, weight_decay=0,
+                                                    amsgrad=False, params=list(range(len(fp.params))))])
+
+    def _load_adam_state(self, optimizer, sd):
+        fp = optimizer.fp
+        off = {n: o for n, _, o in fp.specs}
+        for i, (name, p) in enumerate(fp.params.items()):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            o, n = off[name], p.numel()
+            optimizer.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            optimizer.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            optimizer.step_count = int(st["step"])
+        for g, gs in zip(optimizer.param_groups, sd["param_groups"]):
+            g["lr"] = gs["lr"]
+        self._graph = None if self._graph is not False else False       # the captured step count / lr are stale
+
+    def save(self, which_epoch):
+        """:359-363: '<epoch>_net_G.pth' = {'network': {...}, 'optimizer': Adam state}; the discriminator (with --use_gan)
+        as a plain state dict in '<epoch>_net_D.pth'."""
+        os.makedirs(self.save_dir, exist_ok=True)
+        torch.save(dict(network=self._network_dict(), optimizer=self._adam_state(self.optimizer)),
+                   os.path.join(self.save_dir, "%s_net_G.pth" % which_epoch))
+        if self.use_gan:
+            torch.save(self.fpD.state_dict(), os.path.join(self.save_dir, "%s_net_D.pth" % which_epoch))
+
+    def load(self, which_epoch, save_dir=""):
+        """:106-118 (load_network_dict for the generator + its optimizer, load_network for the discriminator)."""
+        path = os.path.join(save_dir or self.save_dir, "%s_net_G.pth" % which_epoch)
+        if not os.path.isfile(path):
+            print("%s not exists yet!" % path)
+            raise AssertionError("Generator must exist!")
+        ck = torch.load(path, map_location="cpu")
+        flat = OrderedDict()
+        for mk, sd in ck["network"].items():
+            for k, v in sd.items():
+                flat[mk + "." + k] = v
+        self.fpG.load_state_dict(flat)
+        if self.isTrain and ck.get("optimizer") is not None and hasattr(self, "optimizer"):
+            self._load_adam_state(self.optimizer, ck["optimizer"])
+        if self.use_gan:
+            pd = os.path.join(save_dir or self.save_dir, "%s_net_D.pth" % which_epoch)
+            if os.path.isfile(pd):
+                self.fpD.load_state_dict(torch.load(pd, map_location="cpu"))
+            else:
+                print("%s not exists yet!" % pd)
+
+    def delete_model(self, which_epoch):
+        """:365-368."""
+        for lbl in ("G", "D") if self.use_gan else ("G",):
+            p = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, lbl))
+            if os.path.isfile(p):
+                os.remove(p)
+
+    def update_learning_rate(self, epoch=0, data_size=0):
+        """:370-383: after opt.niter epochs the rate drops by lr / niter_decay per call, for both optimizers."""
+        if epoch > self.opt.niter:
+            lr = self.old_lr - self.opt.lr / self.opt.niter_decay
+            for o in [self.optimizer] + ([self.optimizer_D] if self.use_gan else []):
+                for g in o.param_groups:
+                    g["lr"] = lr
+            print("update learning rate: %f -> %f" % (self.old_lr, lr))
+            self.old_lr = lr
+            if self._graph is not False:
+                self._graph = None         # the learning rate is baked into the captured Adam launches: re-capture

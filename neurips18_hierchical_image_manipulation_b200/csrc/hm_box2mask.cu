@@ -90,9 +90,14 @@ __global__ void b2m_d_input_kernel(const float* __restrict__ x, const float* __r
 // BatchNorm2d(affine) in training mode = normalise with the BATCH statistics (mean / rstd over N*H*W, computed by
 // hm_in_stats on the tensor viewed as one sample) then scale and shift:  (x - mean) * rstd * gamma + beta
 //   == (x - mean') * rstd'   with  rstd' = rstd * gamma,  mean' = mean - beta / rstd'   -> per-(n, c) rows for hm_in_apply.
+// With running_mean / running_var the kernel also performs BatchNorm's buffer update (momentum 0.1 in the reference's
+// nn.BatchNorm2d defaults): running = (1 - m) * running + m * batch statistic, the variance UNBIASED (x count/(count-1)),
+// `repeat` times (the discriminator evaluates the generated batch twice per iteration), and num_batches_tracked += repeat.
 __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
                                const float* __restrict__ gamma, const float* __restrict__ beta, int N, int C,
-                               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                               float* __restrict__ mean_out, float* __restrict__ rstd_out, float* running_mean,
+                               float* running_var, long long* num_batches_tracked, float count, float momentum, float eps,
+                               int repeat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int c = i % C;
@@ -100,6 +105,19 @@ __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __re
   const float b = beta ? beta[c] : 0.f;
   rstd_out[i] = rs;
   mean_out[i] = (rs != 0.f) ? mean[c] - b / rs : mean[c];
+  if (i < C && running_mean && running_var) {
+    const float r = rstd[c];
+    const float var_b = fmaxf(1.f / (r * r) - eps, 0.f);
+    const float var_u = count > 1.f ? var_b * (count / (count - 1.f)) : var_b;
+    float rm = running_mean[c], rv = running_var[c];
+    for (int k = 0; k < repeat; ++k) {
+      rm = (1.f - momentum) * rm + momentum * mean[c];
+      rv = (1.f - momentum) * rv + momentum * var_u;
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+    if (i == 0 && num_batches_tracked) *num_batches_tracked += repeat;
+  }
 }
 
 // out = deep + Upsample(scale 2, bilinear, align_corners = False)(small): the tail of DeconvResnetBlock.forward
@@ -142,9 +160,10 @@ __global__ void upsample2_add_kernel(const float* __restrict__ small, const floa
 //   acc[0] += sum of -log p(label) over box pixels, acc[1] += number of box pixels, acc[2] += sum of BCE terms
 __global__ void b2m_head_kernel(const float* __restrict__ ctx_logit /*[N,H,W,C]*/, const float* __restrict__ obj_logit /*[N,H,W,ldo]*/,
                                 int ldo, const float* __restrict__ label_map, const float* __restrict__ mask_out,
-                                const float* __restrict__ inst, int N, int H, int W, int C, int use_gate,
+                                const float* __restrict__ inst, int N, int H, int W, int C, int flags,
                                 float* __restrict__ comb_logit /*NCHW*/, float* __restrict__ comb_logprob /*NCHW*/,
                                 float* __restrict__ obj_prob /*[N,1,H,W]*/, double* __restrict__ acc) {
+  const bool use_gate = flags & 1, no_comb = flags & 2;   // bit 0: --use_output_gate, bit 1: --no_comb
   const long HW = long(H) * W, total = long(N) * HW;
   double nll = 0.0, cnt = 0.0, bce = 0.0;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
@@ -154,14 +173,14 @@ __global__ void b2m_head_kernel(const float* __restrict__ ctx_logit /*[N,H,W,C]*
     const float pr = 1.f / (1.f + __expf(-o));
     const float* cl = ctx_logit + i * C;
     float mx = -3.402823466e38f;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, (1.f - pr) * __ldg(cl + c) + pr * o);
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, no_comb ? __ldg(cl + c) : (1.f - pr) * __ldg(cl + c) + pr * o);
     float se = 0.f;
-    for (int c = 0; c < C; ++c) se += expf((1.f - pr) * __ldg(cl + c) + pr * o - mx);
+    for (int c = 0; c < C; ++c) se += expf((no_comb ? __ldg(cl + c) : (1.f - pr) * __ldg(cl + c) + pr * o) - mx);
     const float lse = mx + logf(se);
     const float mo = mask_out ? __ldg(mask_out + i) : 1.f;
     const int lab = label_map ? int(__ldg(label_map + i)) : -1;
     for (int c = 0; c < C; ++c) {
-      const float v = (1.f - pr) * __ldg(cl + c) + pr * o;
+      const float v = no_comb ? __ldg(cl + c) : (1.f - pr) * __ldg(cl + c) + pr * o;
       const size_t oi = (size_t(n) * C + c) * HW + p;
       if (comb_logit) comb_logit[oi] = v;
       if (comb_logprob) comb_logprob[oi] = v - lse;
@@ -227,10 +246,11 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ g, int N, int h, 
 //   q = p * mask_out (gate);     loss_obj = -(1/NHW) sum ( t log q + (1-t) log(1-q) )   (logs clamped at -100: zero slope there)
 __global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const float* __restrict__ obj_logit, int ldo,
                                     const float* __restrict__ label_map, const float* __restrict__ mask_out,
-                                    const float* __restrict__ inst, int N, int H, int W, int C, int use_gate,
+                                    const float* __restrict__ inst, int N, int H, int W, int C, int flags,
                                     const double* __restrict__ acc /* acc[1] = number of box pixels */, float w_comb,
                                     float w_obj, const float* __restrict__ g_prob, int g_ld, bf16* c_hi, bf16* c_lo,
                                     int c_cs, bf16* o_hi, bf16* o_lo, int o_cs) {
+  const bool use_gate = flags & 1, no_comb = flags & 2;   // bit 0: --use_output_gate, bit 1: --no_comb
   const long total = long(N) * H * W;
   const float inv_cnt = acc[1] > 0.5 ? float(1.0 / acc[1]) : 0.f;
   const float inv_n = 1.f / float(total);
@@ -242,9 +262,9 @@ __global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const f
     const int lab = int(__ldg(label_map + i));
     const bool in_box = mo >= 0.5f;
     float mx = -3.402823466e38f;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, (1.f - pr) * __ldg(cl + c) + pr * o);
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, no_comb ? __ldg(cl + c) : (1.f - pr) * __ldg(cl + c) + pr * o);
     float se = 0.f;
-    for (int c = 0; c < C; ++c) se += expf((1.f - pr) * __ldg(cl + c) + pr * o - mx);
+    for (int c = 0; c < C; ++c) se += expf((no_comb ? __ldg(cl + c) : (1.f - pr) * __ldg(cl + c) + pr * o) - mx);
     const float inv_se = 1.f / se;
     float dp = 0.f, dsum = 0.f;
     bf16* ch = c_hi + i * c_cs;
@@ -253,11 +273,10 @@ __global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const f
       float dctx = 0.f;
       if (c < C && in_box) {
         const float x = __ldg(cl + c);
-        const float sm = expf((1.f - pr) * x + pr * o - mx) * inv_se;
+        const float sm = expf((no_comb ? x : (1.f - pr) * x + pr * o) - mx) * inv_se;
         const float dcomb = w_comb * inv_cnt * (sm - (c == lab ? 1.f : 0.f));
-        dctx = (1.f - pr) * dcomb;
-        dp += dcomb * (o - x);
-        dsum += dcomb;
+        dctx = no_comb ? dcomb : (1.f - pr) * dcomb;
+        if (!no_comb) { dp += dcomb * (o - x); dsum += dcomb; }
       }
       bf16 hh, ll;
       hm::split_bf16(dctx, hh, ll);
@@ -326,10 +345,12 @@ int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const flo
 }
 
 int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,
-               float* rstd_out, void* stream) {
-  if (!mean || !rstd || !mean_out || !rstd_out || N <= 0 || C <= 0) return HM_ERR_INVALID;
-  bn_fold_kernel<<<(N * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, rstd, gamma, beta, N, C,
-                                                                                      mean_out, rstd_out);
+               float* rstd_out, float* running_mean, float* running_var, long long* num_batches_tracked, float count,
+               float momentum, float eps, int repeat, void* stream) {
+  if (!mean || !rstd || !mean_out || !rstd_out || N <= 0 || C <= 0 || (!running_mean != !running_var)) return HM_ERR_INVALID;
+  bn_fold_kernel<<<(N * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mean, rstd, gamma, beta, N, C, mean_out, rstd_out, running_mean, running_var, num_batches_tracked, count, momentum, eps,
+      repeat);
   return HM_LAUNCH_OK();
 }
 

@@ -82,7 +82,7 @@ class FlatParams(object):
                     p.copy_(sd[k].to(self.device, torch.float32))
             for k, b in self.buffers.items():
                 if k in sd:
-                    b.copy_(sd[k].to(self.device, torch.float32).view(b.shape))
+                    b.copy_(sd[k].to(self.device).view(b.shape))
         self.version += 1
 
 

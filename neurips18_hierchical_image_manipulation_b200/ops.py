@@ -414,12 +414,15 @@ def box2mask_encode(ctx, mask_ctx_in, mask_in, cls, label_nc):
     return out
 
 
-def bn_fold(ctx, mean, rstd, gamma, beta, N):
+def bn_fold(ctx, mean, rstd, gamma, beta, N, running=None, count=0, repeat=1, momentum=0.1, eps=1e-5):
+    """running = (running_mean, running_var, num_batches_tracked): also perform nn.BatchNorm2d's buffer update."""
     Cc = mean.numel()
     mo = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
     ro = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    rm, rv, nbt = running if running is not None else (None, None, None)
     L.check(ctx.lib.hm_bn_fold(mean.data_ptr(), rstd.data_ptr(), _ptr(gamma), _ptr(beta), N, Cc, mo.data_ptr(),
-                               ro.data_ptr(), _stream()), "hm_bn_fold")
+                               ro.data_ptr(), _ptr(rm), _ptr(rv), _ptr(nbt), float(count), float(momentum), float(eps),
+                               int(repeat), _stream()), "hm_bn_fold")
     ctx.launches += 1
     return mo, ro
 
@@ -432,10 +435,12 @@ def upsample2_add(ctx, small, deep, out):
     ctx.launches += 1
 
 
-def box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, comb_logit, comb_logprob, obj_prob, acc):
+def box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, comb_logit, comb_logprob, obj_prob, acc,
+                  no_comb=False):
     N, H, W, Cc = ctx_logit.shape
     L.check(ctx.lib.hm_box2mask_head(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1], _ptr(label_map),
-                                     _ptr(mask_out), _ptr(inst), N, H, W, Cc, 1 if use_gate else 0, _ptr(comb_logit),
+                                     _ptr(mask_out), _ptr(inst), N, H, W, Cc, (1 if use_gate else 0) | (2 if no_comb else 0),
+                                     _ptr(comb_logit),
                                      _ptr(comb_logprob), _ptr(obj_prob), _ptr(acc), _stream()), "hm_box2mask_head")
     ctx.launches += 1
 
@@ -460,11 +465,12 @@ def upsample2_bwd(ctx, g, dsmall):
 
 
 def box2mask_head_bwd(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, acc, w_comb, w_obj, d_ctx, d_obj,
-                      g_prob=None):
+                      g_prob=None, no_comb=False):
     N, H, W, Cc = ctx_logit.shape
     L.check(ctx.lib.hm_box2mask_head_bwd(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1],
                                          label_map.data_ptr(), _ptr(mask_out), inst.data_ptr(), N, H, W, Cc,
-                                         1 if use_gate else 0, acc.data_ptr(), float(w_comb), float(w_obj), _ptr(g_prob),
+                                         (1 if use_gate else 0) | (2 if no_comb else 0), acc.data_ptr(), float(w_comb),
+                                         float(w_obj), _ptr(g_prob),
                                          g_prob.shape[-1] if g_prob is not None else 0, d_ctx.hi.data_ptr(), _ptr(d_ctx.lo),
                                          d_ctx.cs, d_obj.hi.data_ptr(), _ptr(d_obj.lo), d_obj.cs, _stream()),
             "hm_box2mask_head_bwd")

@@ -25,3 +25,25 @@ def synthetic_batch(B, H, W, label_nc=35, seed=1234):
         dh, dw = int(side_h * 0.15), int(side_w * 0.15)
         mask_out[b, :, max(0, y0 - dh):min(H, y0 + side_h + dh), max(0, x0 - dw):min(W, x0 + side_w + dw)] = 1
     return dict(label=label, inst=inst, image=image, mask_in=mask_in, mask_out=mask_out)
+
+
+def box2mask_batch(B, S, label_nc, seed):
+    """Synthetic box2mask sample set (what data/ + TwoStreamAE_mask.encode_input :127-151 consume): a blocky label map, a
+    box (mask_in), its margin-expanded region (mask_out), an elliptical instance mask of class `cls` inside the box and
+    the context map with the region wiped."""
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.randint(1, label_nc, (B, 1, S // 8, S // 8), generator=g).float()
+    label_map = torch.nn.functional.interpolate(lab, size=(S, S), mode="nearest")
+    cls = torch.randint(1, label_nc - 1, (B, 1), generator=g)
+    mask_out, mask_in, inst = torch.zeros(B, 1, S, S), torch.zeros(B, 1, S, S), torch.zeros(B, 1, S, S)
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    for b in range(B):
+        y0, x0 = int(torch.randint(4, S // 4, (1,), generator=g)), int(torch.randint(4, S // 4, (1,), generator=g))
+        h, w = int(torch.randint(S // 4, S // 2, (1,), generator=g)), int(torch.randint(S // 4, S // 2, (1,), generator=g))
+        mask_in[b, :, y0:y0 + h, x0:x0 + w] = 1
+        mask_out[b, :, max(0, y0 - 4):y0 + h + 4, max(0, x0 - 4):x0 + w + 4] = 1
+        ell = (((yy - (y0 + h / 2.0)) / (h / 2.0)) ** 2 + ((xx - (x0 + w / 2.0)) / (w / 2.0)) ** 2) <= 1.0
+        inst[b, 0] = ell.float()
+        label_map[b, 0][ell] = float(cls[b, 0])
+    return dict(label_map=label_map, mask_ctx_in=label_map * (1 - mask_out), mask_out=mask_out, mask_in=mask_in,
+                mask_obj_inst=inst, cls=cls.float())

@@ -22,12 +22,24 @@ IGNORE_INDEX = 255          # models/mask_losses.py:10
 DIM_LIST_TAIL = [96, 128, 256, 512]   # MaskTwoStreamConv_NET.py:25 ("this part is hard-coded")
 
 
+# BatchNorm mode of the current forward pass: None = training mode (batch statistics); a dict = training mode that also
+# records every module's batch statistics {key: (mean, unbiased var)} (what the running buffers are updated with);
+# "eval" = normalise with sd[key + '.running_mean' / '.running_var'] (nn.BatchNorm2d.eval()).
+_BN_MODE = [None]
+
+
 def batch_norm(sd, key, x, eps=1e-5):
-    """nn.BatchNorm2d(affine=True) in TRAINING mode (layer_util.py:19-21 with norm_layer == 'batch'): biased batch
-    statistics over (N, H, W); the running buffers do not enter the result."""
+    """nn.BatchNorm2d(affine=True) (layer_util.py:19-21 with norm_layer == 'batch').  Training mode: biased batch
+    statistics over (N, H, W); the running buffers (momentum 0.1, unbiased variance) do not enter the result.  Eval mode:
+    the running buffers."""
+    g, b = sd[key + ".weight"].view(1, -1, 1, 1), sd[key + ".bias"].view(1, -1, 1, 1)
+    if _BN_MODE[0] == "eval":
+        mean, var = sd[key + ".running_mean"].view(1, -1, 1, 1), sd[key + ".running_var"].view(1, -1, 1, 1)
+        return (x - mean) / torch.sqrt(var + eps) * g + b
     mean = x.mean(dim=(0, 2, 3), keepdim=True)
     var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
-    g, b = sd[key + ".weight"].view(1, -1, 1, 1), sd[key + ".bias"].view(1, -1, 1, 1)
+    if isinstance(_BN_MODE[0], dict):
+        _BN_MODE[0][key] = (mean.detach().reshape(-1), x.detach().var(dim=(0, 2, 3), unbiased=True))
     return (x - mean) / torch.sqrt(var + eps) * g + b
 
 
@@ -70,10 +82,19 @@ def resnet_block(sd, p, x):
     return x + batch_norm(sd, p + ".conv_block.6", h)
 
 
-def two_stream_forward(sd, cond, num_layers=3, n_blocks=6, conv_size=4):
-    """MaskTwoStreamConv_NET.forward (:159-219), which_stream == 'obj_context'.
+def two_stream_forward(sd, cond, num_layers=3, n_blocks=6, conv_size=4, no_comb=False, bn_mode=None):
+    """MaskTwoStreamConv_NET.forward (:159-219), which_stream == 'obj_context'; no_comb: MaskTwoStreamConvSwitch_NET
+    (--no_comb), the same network whose forward returns the context stream as it is (:208).
     cond: [B, input_nc, S, S] (cond_in 'ctx_obj': object box mask in its class channel | one-hot context).
-    Returns (comb_logit, comb_logprob, obj_logit, obj_prob)."""
+    bn_mode: see _BN_MODE.  Returns (comb_logit, comb_logprob, obj_logit, obj_prob)."""
+    _BN_MODE[0] = bn_mode
+    try:
+        return _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb)
+    finally:
+        _BN_MODE[0] = None
+
+
+def _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb):
     # shared encoder (:63-90): Conv 7x7 stride 2 pad 3, norm, ReLU, then num_layers ConvResnetBlocks
     h = F.conv2d(cond, sd["conv_encoder_0.weight"], sd["conv_encoder_0.bias"], stride=2, padding=3)
     h = F.relu(batch_norm(sd, "conv_encoder_1", h))
@@ -100,6 +121,8 @@ def two_stream_forward(sd, cond, num_layers=3, n_blocks=6, conv_size=4):
     ctx_logit = decode("ctx", enc_features)
     obj_logit = decode("obj", None)
     obj_prob = torch.sigmoid(obj_logit)
+    if no_comb:
+        return ctx_logit, F.log_softmax(ctx_logit, dim=1), obj_logit, obj_prob
     # combination (:198-217): the object stream's sigmoid gates between the context logits and its own logit
     padded_mask = obj_prob.expand_as(ctx_logit)
     comb_logit = (1 - padded_mask) * ctx_logit + padded_mask * obj_logit

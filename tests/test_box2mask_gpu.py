@@ -332,3 +332,75 @@ def test_box2mask_gan_cuda_graph_replay_matches_eager_iterations():
     # take its +-lr Adam step in the other direction: bound the mean, not the max
     assert dl < 5e-3, (l0, l1)
     assert float(dg.mean()) < 0.05 * 2e-4 * 5 and float(dd.mean()) < 0.05 * 2e-4 * 5
+
+
+def test_box2mask_no_comb_running_statistics_eval_mode_and_checkpoint(golden_dir, tmp_path):
+    """--no_comb (MaskTwoStreamConvSwitch_NET, what scripts/train_box2mask_city.sh trains) against the golden generated
+    from the reference's own class: training-mode outputs and losses, the BatchNorm running buffers after that pass, the
+    eval-mode generate() that uses them; then the reference's checkpoint layout (save -> continue_train)."""
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_switch_small.npz"))
+    kw = dict(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2, no_comb=True, checkpoints_dir=str(tmp_path), name="sw",
+              use_gan=True, which_gan="patch_multiscale", num_layers_D=3, ndf=16)
+    m = _model(**kw)
+    sd = {str(n): named_param(str(n), tuple(int(v) for v in str(s).split(";")))
+          for n, s in zip(z["param_names"], z["param_shapes"])}
+    assert set(sd) == set(m.fpG.params)
+    m.fpG.load_state_dict(sd)
+    bufs = {k[5:] for k in z.files if k.startswith("buf::")}
+    assert bufs == set(m.fpG.buffers), sorted(bufs ^ set(m.fpG.buffers))[:6]
+    a = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("a::")}
+    b = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("b::")}
+    losses, out = m.forward(a["label_map"], None, a["mask_ctx_in"], None, a["mask_out"], a["mask_obj_inst"], a["cls"],
+                            a["mask_in"], train=False)
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    for k in ("comb_logit", "comb_prob", "obj_logit", "obj_prob"):
+        e = rel(out[k], z["train_" + k])
+        assert e < 1e-3, (k, e)
+    assert abs(float(losses[0]) - float(z["train_loss_comb"])) < 1e-3 * float(z["train_loss_comb"])
+    assert abs(float(losses[1]) - float(z["train_loss_obj"])) < 1e-3 * float(z["train_loss_obj"])
+    worst = 0.0
+    for k, v in m.fpG.buffers.items():
+        ref = torch.from_numpy(np.asarray(z["buf::" + k]))
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(ref) == 1, k
+        else:
+            worst = max(worst, float((v.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-3)))
+    print("box2mask running statistics vs the reference modules: %.2e" % worst)
+    assert worst < 1e-3
+    gen = m.generate(dict(label_map=b["label_map"], mask_ctx_in=b["mask_ctx_in"], mask_out=b["mask_out"], mask_in=b["mask_in"],
+                          mask_obj_inst=b["mask_obj_inst"], mask_obj_in=None, cls=b["cls"]))
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    e = rel(gen["obj_pred_label"], z["eval_obj_prob"])
+    print("box2mask eval-mode object probability %.2e" % e)
+    assert e < 1e-3, e
+    lp = torch.from_numpy(z["eval_comb_prob"])
+    onehot = torch.zeros_like(lp).scatter_(1, b["label_map"].long(), 1.0)
+    want = (lp * b["mask_out"] + (1 - b["mask_out"]) * onehot).argmax(dim=1, keepdim=True)
+    top2 = lp.topk(2, dim=1).values
+    clear = ((top2[:, :1] - top2[:, 1:2]) > 1e-3) | (b["mask_out"] < 0.5)       # ignore numerically tied pixels
+    agree = (gen["comb_pred_label"].cpu() == want) | ~clear
+    assert bool(agree.all()), int((~agree).sum())
+    assert not m.netG.get_mode() and int(m.fpG.buffers["conv_encoder_1.num_batches_tracked"]) == 1   # mode restored, buffers untouched
+    # ---- checkpoint: {'network': {params_dict key: state_dict}, 'optimizer': Adam state} + plain D state dict
+    m.forward(a["label_map"], None, a["mask_ctx_in"], None, a["mask_out"], a["mask_obj_inst"], a["cls"], a["mask_in"])
+    m.save("latest")
+    ck = torch.load(os.path.join(str(tmp_path), "sw", "latest_net_G.pth"))
+    assert ck["network"]["conv_encoder_2"] == {} and "deep.1.weight" in ck["network"]["conv_encoder_3"]
+    assert "0.conv_block.1.weight" in ck["network"]["latent_encoder"] and "running_var" in ck["network"]["conv_encoder_1"]
+    assert len(ck["optimizer"]["state"]) == 120 and ck["optimizer"]["state"][0]["step"] == 1
+    dsd = torch.load(os.path.join(str(tmp_path), "sw", "latest_net_D.pth"))
+    assert "scale0_layer1.1.running_mean" in dsd and int(dsd["scale0_layer1.1.num_batches_tracked"]) == 6   # 2 forwards x 3 passes
+    m2 = _model(continue_train=True, isTrain=True, gpu_ids=[], **kw)
+    m2 = getattr(m2, "module", m2)
+    assert torch.equal(m2.fpG.flat, m.fpG.flat) and torch.equal(m2.fpD.flat, m.fpD.flat)
+    assert torch.equal(m2.optimizer.m, m.optimizer.m) and m2.optimizer.step_count == 1
+    for k, v in m.fpG.buffers.items():
+        assert torch.equal(v, m2.fpG.buffers[k]), k
+    m.delete_model("latest")
+    assert not os.path.exists(os.path.join(str(tmp_path), "sw", "latest_net_G.pth"))
+    m.opt.niter, m.opt.niter_decay, m.opt.lr = 1, 10, 2e-4
+    m.update_learning_rate(epoch=2)
+    assert abs(m.optimizer.param_groups[0]["lr"] - 1.8e-4) < 1e-12 and abs(m.optimizer_D.param_groups[0]["lr"] - 1.8e-4) < 1e-12

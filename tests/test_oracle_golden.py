@@ -303,3 +303,39 @@ def test_box2mask_batchnorm_discriminator_against_the_reference_class(golden_dir
     gx, = torch.autograd.grad(l_real, x)
     ref = torch.from_numpy(z["gx"]).double()
     assert float((gx - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+def test_box2mask_switch_net_train_and_eval_mode_against_the_reference_class(golden_dir):
+    """--no_comb (MaskTwoStreamConvSwitch_NET) in training mode, the BatchNorm running buffers after that pass, and the
+    eval-mode forward that uses them, against the reference's own class (oracle/make_golden_box2mask_switch.py)."""
+    from oracle import box2mask as B2
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_switch_small.npz"))
+    sd = {str(n): named_param(str(n), tuple(int(v) for v in str(s).split(";"))).double()
+          for n, s in zip(z["param_names"], z["param_shapes"])}
+    a = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("a::")}
+    b = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("b::")}
+    stats = {}
+    cond, _ = B2.encode_input(6, a["mask_ctx_in"], a["mask_in"], a["cls"])
+    with torch.no_grad():
+        outs = B2.two_stream_forward(sd, cond.double(), num_layers=3, n_blocks=2, no_comb=True, bn_mode=stats)
+    for got, k in zip(outs, ("comb_logit", "comb_prob", "obj_logit", "obj_prob")):
+        ref = torch.from_numpy(z["train_" + k]).double()
+        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5, k
+    assert abs(float(B2.mask_recon_loss(outs[1], a["label_map"], a["mask_out"])) - float(z["train_loss_comb"])) < 2e-5
+    assert abs(float(B2.obj_recon_loss(outs[3], a["mask_out"], a["mask_obj_inst"])) - float(z["train_loss_obj"])) < 2e-5
+    n_buf = 0
+    for key, (mean, var_u) in stats.items():      # running = 0.9 * init + 0.1 * batch statistic (unbiased variance)
+        rm, rv = torch.from_numpy(z["buf::" + key + ".running_mean"]).double(), torch.from_numpy(z["buf::" + key + ".running_var"]).double()
+        assert float((0.1 * mean - rm).abs().max()) < 1e-5 * max(1.0, float(rm.abs().max())), key
+        assert float((0.9 + 0.1 * var_u - rv).abs().max()) < 1e-5 * float(rv.abs().max()), key
+        assert int(z["buf::" + key + ".num_batches_tracked"]) == 1
+        sd[key + ".running_mean"], sd[key + ".running_var"] = rm, rv
+        n_buf += 1
+    assert n_buf == 29 == sum(1 for k in z.files if k.endswith("running_mean"))
+    cond, _ = B2.encode_input(6, b["mask_ctx_in"], b["mask_in"], b["cls"])
+    with torch.no_grad():
+        outs = B2.two_stream_forward(sd, cond.double(), num_layers=3, n_blocks=2, no_comb=True, bn_mode="eval")
+    for got, k in zip(outs, ("comb_logit", "comb_prob", "obj_logit", "obj_prob")):
+        ref = torch.from_numpy(z["eval_" + k]).double()
+        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5, k
