@@ -754,6 +754,36 @@ class TwoStreamAE_mask(object):
         out = self.reconstruct(input_dict, eval_mode=True)
         return dict(comb_pred_label=out["comb_recon_label"], obj_pred_label=out["obj_recon_label"])
 
+    def evaluate(self, input_dict, target_size=None):
+        """:304-335, the joint-inference entry point (joint_inference_model.py:61-81): first sample only, eval-mode
+        BatchNorm (left ON, like the reference); the generated maps are resized to `target_size` (bilinear) and pasted
+        into the original-resolution maps; background class (label_nc - 1): arg-max layout inside the box, any other
+        class: the thresholded object mask painted with that class.  Returns comb_recon_label [1,1,H,W] (float)."""
+        ctx, opt = self.ctx, self.opt
+        first = lambda k: self._dev(input_dict[k][0].unsqueeze(0))            # noqa: E731
+        label_map, mask_ctx_in, mask_out, mask_in = first("label_map"), first("mask_ctx_in"), first("mask_out"), first("mask_in")
+        cls = input_dict["cls"][0].reshape(-1)
+        self.netG.set_mode(eval_mode=True)
+        cond = ops.box2mask_encode(ctx, mask_ctx_in, mask_in, self._dev(cls), opt.label_nc)
+        ctx_logit, obj_logit, _ = self.netG.forward(cond)
+        _, _, H, W = label_map.shape
+        comb_prob = torch.empty(1, opt.output_nc, H, W, device=self.device)
+        obj_prob = torch.empty(1, 1, H, W, device=self.device)
+        ops.box2mask_head(ctx, ctx_logit, obj_logit, None, None, None, False, None, comb_prob, obj_prob, None,
+                          no_comb=self.no_comb)
+        if getattr(opt, "use_output_gate", False):
+            obj_prob = obj_prob * mask_out
+        if target_size is not None:
+            label_map, mask_out = first("label_map_orig"), first("mask_out_orig")
+            us = lambda t: torch.nn.functional.interpolate(t, size=target_size, mode="bilinear", align_corners=False)  # noqa: E731
+            comb_prob, obj_prob = us(comb_prob), us(obj_prob)
+        c = int(cls[0])
+        if c == opt.label_nc - 1:
+            gt_onehot = torch.zeros_like(comb_prob).scatter_(1, label_map.long(), 1.0)
+            return (comb_prob * mask_out + (1 - mask_out) * gt_onehot).argmax(dim=1, keepdim=True).float()
+        obj_mask = (obj_prob > 0.5).float()
+        return (1 - obj_mask) * label_map + obj_mask * c
+
     # ---- checkpoints (base_model.py:43-64,73-127; TwoStreamAE_mask.py:106-118,359-369) --------------------------------
     def _network_dict(self):
         """The generator's state as the reference's save_network_dict writes it: {params_dict key: module.state_dict()}

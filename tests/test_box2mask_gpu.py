@@ -404,3 +404,32 @@ def test_box2mask_no_comb_running_statistics_eval_mode_and_checkpoint(golden_dir
     m.opt.niter, m.opt.niter_decay, m.opt.lr = 1, 10, 2e-4
     m.update_learning_rate(epoch=2)
     assert abs(m.optimizer.param_groups[0]["lr"] - 1.8e-4) < 1e-12 and abs(m.optimizer_D.param_groups[0]["lr"] - 1.8e-4) < 1e-12
+
+
+def test_box2mask_evaluate_is_consistent_with_generate():
+    """evaluate() (TwoStreamAE_mask.py:304-335, the joint-inference entry point): first sample, eval-mode BatchNorm;
+    object classes paint the thresholded (gated) object mask, the background class takes the arg-max layout; with
+    target_size the maps are resized before pasting."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import make_golden_box2mask as G
+    m = _model(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2)
+    d = G.synthetic(dict(label_nc=6, fineSize=64), 2, seed=37)
+    d["cls"] = d["cls"].float()
+    m.forward(d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"], d["mask_in"], train=False)
+    full = dict(d, mask_obj_in=None, mask_obj_out=None)
+    gen = m.generate(full)
+    ev = m.evaluate(full)
+    assert m.netG.get_mode() is True                      # the reference leaves the network in eval mode
+    obj = ((gen["obj_pred_label"][:1] * d["mask_out"][:1].cuda()) > 0.5).float()
+    want = (1 - obj) * d["label_map"][:1].cuda() + obj * float(d["cls"][0, 0])
+    assert torch.equal(ev, want)
+    bg = dict(full, cls=torch.full_like(d["cls"], 5.0))
+    gen = m.generate(bg)
+    assert torch.equal(m.evaluate(bg), gen["comb_pred_label"][:1].float())
+    big = dict(full, label_map_orig=torch.nn.functional.interpolate(d["label_map"], scale_factor=2, mode="nearest"),
+               mask_out_orig=torch.nn.functional.interpolate(d["mask_out"], scale_factor=2, mode="nearest"))
+    ev2 = m.evaluate(big, target_size=(128, 128))
+    assert tuple(ev2.shape) == (1, 1, 128, 128)
+    outside = big["mask_out_orig"][:1].cuda() < 0.5
+    assert torch.equal(ev2[outside], big["label_map_orig"][:1].cuda()[outside])      # nothing is painted outside the box
+    m.ctx.check_pipeline()
