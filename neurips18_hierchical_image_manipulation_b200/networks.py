@@ -649,25 +649,37 @@ class Vgg19(object):
             p.grad = None
         self.fp.grad = None
 
-    def forward(self, v_in):
-        """v_in: Operand [N,H,W,8] (3 valid channels).  Returns tape with per-conv input operands / outputs and taps."""
+    def forward(self, v_in, tape=None, n0=0, n=None):
+        """v_in: Operand [N,H,W,8] (3 valid channels).  Returns tape with per-conv input operands / outputs and taps.
+        n0 / n: evaluate images [n0, n0 + n) only, into the full-batch buffers of `tape` (allocated by the first call):
+        the tower has no cross-sample operation, so the real half of the [fake ; real] batch -- which does not depend on
+        the generator -- can run while the generator's forward pass is still in flight."""
         ctx = self.ctx
-        tape = dict(xs=[], outs=[], taps={}, pooled_from={})
+        n = v_in.n - n0 if n is None else n
+        part = (n0, n) != (0, v_in.n)
+        first = tape is None
+        if first:
+            tape = dict(xs=[], outs=[], taps={}, pooled_from={})
+        sl = (lambda op: op.images(n0, n)) if part else (lambda op: op)
         cur = v_in
         for li, (idx, conv) in enumerate(self.convs_):
             if idx in VGG19_POOL_BEFORE:
-                pooled = Operand(ctx, cur.n, cur.h // 2, cur.w // 2, cur.c, cs=cur.cs)
-                ops.maxpool2(ctx, cur, pooled)
-                tape["pooled_from"][li] = cur
+                if first:
+                    pooled = Operand(ctx, cur.n, cur.h // 2, cur.w // 2, cur.c, cs=cur.cs)
+                    tape["pooled_from"][li] = cur
+                else:
+                    pooled = tape["xs"][li]
+                ops.maxpool2(ctx, sl(cur), sl(pooled))
                 cur = pooled
-            tape["xs"].append(cur)
-            out = Operand(ctx, cur.n, cur.h, cur.w, conv.cout, zero=(conv.cout % 8 != 0))
-            tap = None
-            if idx in VGG19_TAP_AFTER:
-                tap = _f32(ctx, cur.n, cur.h, cur.w, conv.cout)
-                tape["taps"][li] = tap
-            conv.forward(cur, 1, act=ACT_RELU, out32=tap, out16=out)
-            tape["outs"].append(out)
+            if first:
+                tape["xs"].append(cur)
+                out = Operand(ctx, cur.n, cur.h, cur.w, conv.cout, zero=(conv.cout % 8 != 0))
+                tape["outs"].append(out)
+                if idx in VGG19_TAP_AFTER:
+                    tape["taps"][li] = _f32(ctx, cur.n, cur.h, cur.w, conv.cout)
+            out = tape["outs"][li]
+            tap = tape["taps"].get(li)
+            conv.forward(sl(cur), 1, act=ACT_RELU, out32=(tap[n0:n0 + n] if (tap is not None and part) else tap), out16=sl(out))
             cur = out
         return tape
 

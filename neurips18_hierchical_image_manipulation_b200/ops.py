@@ -90,6 +90,14 @@ class Operand(object):
         return L.Operand(self.hi.data_ptr() + off, (self.lo.data_ptr() + off) if self.lo is not None else None, n,
                          self.h, self.w, self.c, self.cs, getattr(self, "lo_c0", 0))
 
+    def images(self, n0, n):
+        """View of images [n0, n0 + n): an Operand sharing this one's storage (the batch index is the outermost)."""
+        v = object.__new__(Operand)
+        v.hi = self.hi[n0:n0 + n]
+        v.lo = self.lo[n0:n0 + n] if self.lo is not None else None
+        v.n, v.h, v.w, v.c, v.cs, v.border, v.lo_c0 = n, self.h, self.w, self.c, self.cs, self.border, self.lo_c0
+        return v
+
     @property
     def ih(self):
         return self.h - 2 * self.border
