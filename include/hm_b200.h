@@ -90,6 +90,11 @@ int hm_k_pad(int k);         /* round_up(k, 64) */
  *   ConvTranspose2d W[ci][co][kh][kw] (Pix2Pix_NET.py:89)    fwd   : rows=co, k=ci ; dgrad: rows=ci, k=co */
 int hm_pack_weight(const float* src, int rows, int k, int taps, long s_row, long s_k, long s_tap, void* dst_hi,
                    void* dst_lo, void* stream);
+/* Both roles of one weight tensor in one pass over the fp32 source W[A][B][taps] (Conv2d: A = co, B = ci;
+ * ConvTranspose2d: A = ci, B = co): p1 = slabs with rows = A, k = B; p2 = slabs with rows = B, k = A (each
+ * [taps][hm_rows_pad(rows)][hm_k_pad(k)], lo planes nullable).  Same values as two hm_pack_weight calls. */
+int hm_pack_weight_pair(const float* src, int A, int B, int taps, void* p1_hi, void* p1_lo, void* p2_hi, void* p2_lo,
+                        void* stream);
 
 /* ---- tcgen05 implicit-GEMM convolution engines ----------------------------------------------------
  * hm_conv_fprop: y[n,ho,wo,co] = act(bias[co] + sum_{kh,kw,ci} x[n, ho*stride+kh-pad, wo*stride+kw-pad, ci] * Wp[kh,kw][co][ci])

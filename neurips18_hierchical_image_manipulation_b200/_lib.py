@@ -52,6 +52,7 @@ PROTOTYPES = {
     "hm_rows_pad": (_i, [_i]),
     "hm_k_pad": (_i, [_i]),
     "hm_pack_weight": (_i, [_vp, _i, _i, _i, _l, _l, _l, _vp, _vp, _vp]),
+    "hm_pack_weight_pair": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hm_conv_fprop": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),
                            _P(OutBF16), _vp, _vp]),
     "hm_conv_dgrad": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),

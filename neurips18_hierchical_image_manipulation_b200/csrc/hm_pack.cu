@@ -94,9 +94,90 @@ __global__ void __launch_bounds__(256) pack_weight_rowfast_kernel(const float* _
   }
 }
 
+// Both engine roles of one weight tensor from ONE read of the fp32 source W[A][B][taps] (OIHW: A = co, B = ci; IOHW:
+// A = ci, B = co):  P1[t][a][b] (rows = A, contraction = B) and P2[t][b][a] (rows = B, contraction = A).  A 32 x 32 x taps
+// tile goes through shared memory; every lane converts 8 consecutive contraction indices and writes them with one
+// 16-byte store per plane (the two separate packs read the source twice and store 2-4 bytes per lane: 43 % of the HBM
+// copy bandwidth for the class in round 2).
+__global__ void __launch_bounds__(256) pack_weight_pair_kernel(const float* __restrict__ src, int A, int B, int taps,
+                                                                int rp1, int kp1, int rp2, int kp2,
+                                                                __nv_bfloat16* __restrict__ p1h, __nv_bfloat16* __restrict__ p1l,
+                                                                __nv_bfloat16* __restrict__ p2h, __nv_bfloat16* __restrict__ p2l) {
+  // every element is split ONCE while it is staged; the tile holds (hi | lo << 16) words
+  constexpr int TS = 32 * 33 + 4;                    // tap stride = 4 banks: the staging stores of different taps spread out
+  __shared__ uint32_t tile_[kTileTaps * TS];         // [tap][a][b], rows padded to 33
+#define TILE(t, a, b) tile_[(t) * TS + (a) * 33 + (b)]
+  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;   // 8 warps
+  const long plane1 = long(rp1) * kp1, plane2 = long(rp2) * kp2;
+  for (int t0 = 0; t0 < taps; t0 += kTileTaps) {
+    const int nt = min(kTileTaps, taps - t0);
+    // stage: lanes along b (stride `taps` floats), the tap loop walks the sectors the warp already fetched
+    const bool bok = b0 + lane < B;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int al = wy + 8 * i, a = a0 + al;
+      const float* p = src + (long(a) * B + b0 + lane) * taps + t0;
+      const bool ok = bok && a < A;
+      for (int t = 0; t < nt; ++t) {
+        __nv_bfloat16 h, l;
+        hm::split_bf16(ok ? __ldg(p + t) : 0.f, h, l);
+        TILE(t, al, lane) = uint32_t(__bfloat16_as_ushort(h)) | (uint32_t(__bfloat16_as_ushort(l)) << 16);
+      }
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < nt * 128; w += 256) {
+      const int t = w >> 7, r = (w & 127) >> 2, q = (w & 3) * 8;
+      if (a0 + r < rp1 && b0 + q < kp1) {              // P1: row a0 + r, contraction b0 + q .. +7
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = TILE(t, r, q + j);
+        const long o = long(t0 + t) * plane1 + long(a0 + r) * kp1 + b0 + q;
+        uint4 hh, ll;
+        hh.x = __byte_perm(v[0], v[1], 0x5410); hh.y = __byte_perm(v[2], v[3], 0x5410);
+        hh.z = __byte_perm(v[4], v[5], 0x5410); hh.w = __byte_perm(v[6], v[7], 0x5410);
+        *reinterpret_cast<uint4*>(p1h + o) = hh;
+        if (p1l) {
+          ll.x = __byte_perm(v[0], v[1], 0x7632); ll.y = __byte_perm(v[2], v[3], 0x7632);
+          ll.z = __byte_perm(v[4], v[5], 0x7632); ll.w = __byte_perm(v[6], v[7], 0x7632);
+          *reinterpret_cast<uint4*>(p1l + o) = ll;
+        }
+      }
+      if (b0 + r < rp2 && a0 + q < kp2) {              // P2: row b0 + r, contraction a0 + q .. +7
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = TILE(t, q + j, r);
+        const long o = long(t0 + t) * plane2 + long(b0 + r) * kp2 + a0 + q;
+        uint4 hh, ll;
+        hh.x = __byte_perm(v[0], v[1], 0x5410); hh.y = __byte_perm(v[2], v[3], 0x5410);
+        hh.z = __byte_perm(v[4], v[5], 0x5410); hh.w = __byte_perm(v[6], v[7], 0x5410);
+        *reinterpret_cast<uint4*>(p2h + o) = hh;
+        if (p2l) {
+          ll.x = __byte_perm(v[0], v[1], 0x7632); ll.y = __byte_perm(v[2], v[3], 0x7632);
+          ll.z = __byte_perm(v[4], v[5], 0x7632); ll.w = __byte_perm(v[6], v[7], 0x7632);
+          *reinterpret_cast<uint4*>(p2l + o) = ll;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#undef TILE
+}
+
 }  // namespace
 
 extern "C" {
+
+int hm_pack_weight_pair(const float* src, int A, int B, int taps, void* p1_hi, void* p1_lo, void* p2_hi, void* p2_lo,
+                        void* stream) {
+  if (!src || !p1_hi || !p2_hi || A <= 0 || B <= 0 || taps <= 0) return HM_ERR_INVALID;
+  const int rp1 = hm_rows_pad(A), kp1 = hm_k_pad(B), rp2 = hm_rows_pad(B), kp2 = hm_k_pad(A);
+  dim3 grid((std::max(rp1, kp2) + 31) / 32, (std::max(kp1, rp2) + 31) / 32);
+  pack_weight_pair_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, A, B, taps, rp1, kp1, rp2, kp2, static_cast<__nv_bfloat16*>(p1_hi), static_cast<__nv_bfloat16*>(p1_lo),
+      static_cast<__nv_bfloat16*>(p2_hi), static_cast<__nv_bfloat16*>(p2_lo));
+  return cudaGetLastError() == cudaSuccess ? HM_OK : HM_ERR_LAUNCH;
+}
 
 int hm_pack_weight(const float* src, int rows, int k, int taps, long s_row, long s_k, long s_tap, void* dst_hi,
                    void* dst_lo, void* stream) {

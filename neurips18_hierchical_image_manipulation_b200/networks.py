@@ -14,6 +14,7 @@ from collections import OrderedDict
 
 import torch
 
+from . import _lib as L
 from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, Operand, PackedWeight
 
@@ -25,6 +26,8 @@ VGG19_SLICE_OF = {0: 1, 2: 2, 5: 2, 7: 3, 10: 3, 12: 4, 14: 4, 16: 4, 19: 4, 21:
 
 # HM_THIN=0 disables the tap-unrolled lowering of <= 4-channel convolutions (csrc/hm_thin.cu) for A/B measurements
 THIN = os.environ.get("HM_THIN", "1") != "0"
+# HM_PACK_PAIR=0: pack the forward and data-gradient weight slabs with two separate launches (round-1 behaviour)
+PACK_PAIR = os.environ.get("HM_PACK_PAIR", "1") != "0"
 
 
 class FlatParams(object):
@@ -143,6 +146,8 @@ class ConvP(object):
             return self._pf
         if self._pf is None:
             self._pf = PackedWeight(self.ctx, self.cout, self.cin, self.k * self.k)
+        if self._vf != self.fp.version and self._pack_pair():
+            return self._pf
         if self._vf != self.fp.version:
             if self.transposed:   # W[ci][co][t]
                 self._pf.pack(self.ctx, self.weight, kk, self.cout * kk, 1, self.sn_scale)
@@ -150,6 +155,24 @@ class ConvP(object):
                 self._pf.pack(self.ctx, self.weight, self.cin * kk, kk, 1, self.sn_scale)
             self._vf = self.fp.version
         return self._pf
+
+    def _pack_pair(self):
+        """Training steady state: both roles are stale after every Adam step and both will be used, so they are packed
+        in ONE pass over the fp32 weights (hm_pack_weight_pair).  Only once the data-gradient slab exists (i.e. a backward
+        pass has run), never for spectrally normalised or thin-side convs."""
+        if self._pd is None or self._vd == self.fp.version or self.sn_scale is not None or not PACK_PAIR:
+            return False
+        pf, pd = self._pf, self._pd
+        # W[A][B][taps]: Conv2d A = co, B = ci -> p1 = forward role (rows = co), p2 = data-gradient role (rows = ci);
+        # ConvTranspose2d A = ci, B = co -> p1 = data-gradient role, p2 = forward role
+        p1, p2 = (pd, pf) if self.transposed else (pf, pd)
+        A, Bd = (self.cin, self.cout) if self.transposed else (self.cout, self.cin)
+        L.check(self.ctx.lib.hm_pack_weight_pair(self.weight.data_ptr(), A, Bd, self.k * self.k, p1.hi.data_ptr(),
+                                                 ops._ptr(p1.lo), p2.hi.data_ptr(), ops._ptr(p2.lo), ops._stream()),
+                "hm_pack_weight_pair")
+        self.ctx.launches += 1
+        self._vf = self._vd = self.fp.version
+        return True
 
     def packed_bwd(self):
         """rows = cin, contraction = cout."""
