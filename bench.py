@@ -409,6 +409,13 @@ def main_box2mask(args, out_fd):
         ls, _ = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
         hl.copy_(torch.stack([ls[0], ls[1], ls[3], ls[4]]), non_blocking=False)
     ms_e2e = timed(e2e, args.steps)
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    captured = isinstance(m._graph, dict)
+    # tearing the communicator down while a CUDA graph that captured its kernels is alive can block: drop the graph first
+    m._graph = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
@@ -420,7 +427,7 @@ def main_box2mask(args, out_fd):
                 config=workload_desc(world, "5"), clocks=clocks,
                 e2e=dict(value=B / (ms_e2e / 1e3), unit="images/sec", ms_per_step=ms_e2e,
                          h2d_bytes_per_step=sum(v.numel() * 4 for v in host.values()), d2h_bytes_per_step=16),
-                gpu_launches=launches, cuda_graph=isinstance(m._graph, dict), peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                gpu_launches=launches, cuda_graph=captured, peak_mem_gb=peak_mem,
                 losses_last_step=[float(x) for x in hl])
     _emit(line, out_fd)
     if world > 1:
