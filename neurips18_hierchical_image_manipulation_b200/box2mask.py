@@ -6,8 +6,11 @@
                             reference runs INSIDE forward (:233-240); with `--use_gan --which_gan patch_multiscale` (the
                             shipped script) also the PatchGAN terms (:205-231): a 2-scale BatchNorm
                             MultiscaleDiscriminator, LSGAN losses, the reported feature-matching term, lr_control and
-                            the discriminator's own Adam step (:243-248).  Eval-mode BatchNorm and `--no_comb`
-                            (MaskTwoStreamConvSwitch_NET) are not built and raise.
+                            the discriminator's own Adam step (:243-248); `--no_comb` (MaskTwoStreamConvSwitch_NET,
+                            :29-32); BatchNorm running statistics and the eval-mode `reconstruct` / `generate` /
+                            `evaluate` (:257-335); `save` / `load` / `delete_model` / `update_learning_rate` in the
+                            reference's checkpoint layout (:106-118, 359-383).  `which_gan` 'patch' / 'patch_res',
+                            `--add_dilated_layers`, `--norm_layer instance` and `objReconLoss l1` raise.
 
 Parameter names are the reference's own ('<params_dict key>.<state_dict key>': conv_encoder_3.deep.1.weight,
 ctx_conv_decoder_1.shortcut.0.weight, latent_encoder.0.conv_block.1.weight, ...), OIHW / IOHW fp32 like the reference, so

@@ -68,7 +68,7 @@ def create_model(opt, data_size=None):
     """models/models.py:6-24."""
     if opt.model == "pix2pixHD_condImg":
         model = Pix2PixHDModel_condImg(opt)
-    elif opt.model == "AE_maskgen_twostream":      # box2mask (SURVEY N3): forward + reconstruction losses so far
+    elif opt.model == "AE_maskgen_twostream":      # box2mask (SURVEY N3, BASELINE config #5)
         from .box2mask import TwoStreamAE_mask
         model = TwoStreamAE_mask(opt)
     else:
