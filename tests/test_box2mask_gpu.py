@@ -493,3 +493,27 @@ def test_box2mask_gan_losses_and_discriminator_gradients_at_config5_geometry():
     # pixel moves that channel's weight gradient by ~1e-2.  The 2-norm error, which such isolated flips barely touch, is
     # the tight statement (measured <= 1.8e-3); the small geometry above has too few elements for a flip (2e-5).
     assert worst[0][0] < 3e-2 and max(w[1] for w in worst) < 5e-3, worst[:6]
+
+
+@pytest.mark.parametrize("precision", ["mixed", "bf16"])
+def test_box2mask_alternate_precision_modes_track_the_parity_mode(precision):
+    """The `mixed` (bf16x3 forward, single-product gradient GEMMs) and `bf16` modes run the --use_gan iteration too: first
+    losses within 1e-4 (mixed: identical forward) / 3e-2 (bf16) of the parity mode, three iterations stay finite and close."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import make_golden_box2mask as G
+    kw = dict(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2, lr=2e-4, beta1=0.5, beta2=0.999, use_gan=True,
+              which_gan="patch_multiscale", gan_weight=0.1, num_layers_D=3, ndf=16, use_ganFeat_loss=True, lambda_feat=1.0,
+              cuda_graph=False)
+    d = G.synthetic(dict(label_nc=6, fineSize=64), 3, seed=41)
+    args = (d["label_map"], None, d["mask_ctx_in"], None, d["mask_out"], d["mask_obj_inst"], d["cls"], d["mask_in"])
+    ref, alt = _model(**kw), _model(precision=precision, **kw)
+    tol0 = 1e-4 if precision == "mixed" else 3e-2
+    for it in range(3):
+        a = [float(v) for v in ref.forward(*args)[0]]
+        b = [float(v) for v in alt.forward(*args)[0]]
+        assert all(torch.isfinite(torch.tensor(b)))
+        err = max(abs(x - y) / max(abs(x), 1e-6) for x, y in zip(a, b))
+        print("box2mask %s iteration %d: max loss deviation from bf16x3 %.2e" % (precision, it, err))
+        assert err < (tol0 if it == 0 else 5e-2), (it, a, b)
+    torch.cuda.synchronize()
+    alt.ctx.check_pipeline()
