@@ -160,7 +160,8 @@ int hm_tap_combine(const float* T, int N, int Ht, int Wt, int ldT, int KH, int K
  *   d  : (optional) discriminator input operand [2B,H,W,d_cs]: conditioning channels in both halves, the real
  *        image in channels [cin, cin+3) of the second half (the fake half is filled by hm_finish_fake);
  *   v  : (optional) VGG input operand [2B,H,W,v_cs]: real image in the second half.
- *   d_no_imgcond != 0 (--no_imgCond, :213-214): the D operand is [label | edge | image] without the masked image;
+ *   d_no_imgcond bit 0 (--no_imgCond, :213-214): the D operand is [label | edge | image] without the masked image;
+ *   bit 1 (netG global_twostream with which_encoder 'ctx', :71-72,178-179,227-228): the D operand is the bare [image];
  *   d_mask != NULL (--mask_gan_input, :180-181; mask_in, or mask_out with --use_soft_mask, :217): fp32 [B,1,H,W]
  *   multiplied into every channel of the D operand (here, in hm_finish_fake and, for the gradient, in hm_fake_bwd). */
 int hm_encode_input(const float* label, const float* inst, const float* image, const float* mask_in, int B, int H,

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kBlock) encode_kernel(EncodeArgs a, int groups
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  const bool need_img = (KIND == 2) ? (c0 < 3) : (c0 + 8 > n_cond);   // (also covers the shifted no_imgCond layout)
+  const bool d_img_only = KIND == 1 && (a.d_no_imgcond & 2);          // which_encoder == 'ctx': D sees the bare image
+  const bool need_img = (KIND == 2 || d_img_only) ? (c0 < 3) : (c0 + 8 > n_cond);   // (also covers the shifted no_imgCond layout)
   float img[3] = {0.f, 0.f, 0.f}, cond[3] = {0.f, 0.f, 0.f};
   if (need_img) {
     const float m = __ldg(a.mask + pix);
@@ -140,6 +141,14 @@ __global__ void __launch_bounds__(kBlock) encode_kernel(EncodeArgs a, int groups
   if (KIND == 2) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) if (c0 + j < 3) v[j] = img[c0 + j];
+  } else if (d_img_only) {             // [image] only: real half = the image, fake half filled by hm_finish_fake
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (half == 1 && c0 + j < 3) v[j] = img[c0 + j];
+    if (a.d_mask) {
+      const float dm = __ldg(a.d_mask + pix);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= dm;
+    }
   } else {
     if (c0 < label_nc) {
       const int cls = int(__ldg(a.label + pix));
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(kBlock) encode_kernel(EncodeArgs a, int groups
       v[label_nc - c0] = e ? 1.f : 0.f;
     }
     // D operand with no_imgCond (pix2pixHD_condImg_model.py:213-214): [label | edge | image], else [.. | cond | image]
-    const bool no_ic = KIND == 1 && a.d_no_imgcond;
+    const bool no_ic = KIND == 1 && (a.d_no_imgcond & 1);
     const int cimg = no_ic ? n_cond : n_cond + 3;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1100,7 +1109,7 @@ int hm_encode_input(const float* label, const float* inst, const float* image, c
   if (!label || !image || !mask_in || !g_hi || (g_cs & 7) || (d_hi && (d_cs & 7)) || (v_hi && (v_cs & 7)))
     return HM_ERR_INVALID;
   const int cin = label_nc + (inst ? 1 : 0) + 3;
-  if (cin > g_cs || (d_hi && cin + (d_no_imgcond ? 0 : 3) > d_cs)) return HM_ERR_INVALID;
+  if (cin > g_cs || (d_hi && ((d_no_imgcond & 2) ? 3 : cin + ((d_no_imgcond & 1) ? 0 : 3)) > d_cs)) return HM_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EncodeArgs a;
   a.label = label; a.inst = inst; a.image = image; a.mask = mask_in; a.d_mask = d_mask;

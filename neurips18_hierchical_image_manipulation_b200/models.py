@@ -218,9 +218,6 @@ class Pix2PixHDModel_condImg(object):
             self.netG = GlobalTwoStreamGenerator(self.ctx, self.fpG, netG_input_nc, opt.output_nc, opt.ngf,
                                                  opt.n_downsample_global, opt.n_blocks_global, opt.use_skip,
                                                  opt.which_encoder, opt.use_output_gate, opt.feat_fusion)
-            if opt.which_encoder == "ctx":
-                raise NotImplementedError("which_encoder == 'ctx' changes the discriminator input (:71-72,178-179,227-228)"
-                                          " and is outside this path; use ctx_label or label")
             netG_input_nc += 3    # the encode kernel still lays out [label | edge | cond image] (D conditioning, :216)
         else:
             raise NameError("global generator name is not defined properly: %s" % opt.netG)
@@ -235,6 +232,10 @@ class Pix2PixHDModel_condImg(object):
             # input by mask_in (mask_out with --use_soft_mask)
             n_lab = input_nc + (0 if opt.no_instance else 1)
             netD_input_nc = n_lab + (0 if opt.no_imgCond else 3) + opt.output_nc
+            # :71-72, 178-179, 227-228: the context-only two-stream generator is judged on the bare image
+            self.d_image_only = opt.netG == "global_twostream" and opt.which_encoder == "ctx"
+            if self.d_image_only:
+                netD_input_nc = 3
             self.netD_input_nc = netD_input_nc
             self.d_img_c0 = netD_input_nc - opt.output_nc      # first image channel of the D operand
             self.fpD = FlatParams(dev)
@@ -332,12 +333,13 @@ class Pix2PixHDModel_condImg(object):
             if opt.mask_gan_input:                                   # :217 mask_cond
                 d_mask = self._to_device("mask_out", mask_out) if opt.use_soft_mask else mask
         ops.encode_input(ctx, label, inst, image, mask, opt.label_nc, g_in, d_in, v_in,
-                         d_no_imgcond=bool(train and opt.no_imgCond), d_mask=d_mask)
+                         d_no_imgcond=bool(train and opt.no_imgCond), d_mask=d_mask,
+                         d_image_only=bool(train and getattr(self, "d_image_only", False)))
         # the one-hot label map and the 0/1 instance edges are exact in bf16: no lo product over those channels
         # (a soft D-input mask scales them to arbitrary values, so the guarantee does not hold for d_in then)
         n_exact = opt.label_nc + (0 if opt.no_instance else 1)
         g_in.lo_c0 = n_exact
-        if d_in is not None and not (d_mask is not None and opt.use_soft_mask):
+        if d_in is not None and not (d_mask is not None and opt.use_soft_mask) and not getattr(self, "d_image_only", False):
             d_in.lo_c0 = n_exact
         return dict(label=label, inst=inst, image=image, mask=mask, g_in=g_in, d_in=d_in, v_in=v_in, B=B, H=H, W=W,
                     d_mask=d_mask)

