@@ -10,7 +10,7 @@ train (scripts/train_mask2image_city.sh: --netG global_twostream --which_encoder
 
 Parameter names follow the reference module tree (ctx_inputEmbedder.1, ctx_downsampler.{0,3,..}, obj_*,
 latent_embedder.{i}.conv_block.{1,5}, decoder.{0,3,..}, outputEmbedder.1) so its checkpoints interchange.
-Supported: which_stream in {ctx_label, ctx, label}, feat_fusion = early_add.  Every stage reuses the GlobalGenerator
+Supported: which_stream in {ctx_label, ctx, label}, feat_fusion in {early_add, late_add}.  Every stage reuses the GlobalGenerator
 schedules (networks.py); the glue kernels are csrc/hm_twostream.cu.
 """
 from . import ops
@@ -34,8 +34,12 @@ class GlobalTwoStreamGenerator(object):
                  which_stream="ctx", use_output_gate=False, feat_fusion="early_add"):
         if which_stream not in ("ctx_label", "ctx", "label"):
             raise NotImplementedError("which_encoder must be ctx_label | ctx | label, got %s" % which_stream)
-        if feat_fusion != "early_add":
-            raise NotImplementedError("feat_fusion %s: only early_add is part of this path" % feat_fusion)
+        if feat_fusion not in ("early_add", "late_add"):
+            raise NotImplementedError("feat_fusion %s: early_add and late_add are part of this path (the 'concat' fusions "
+                                      "add a 1x1 fuse conv, layer_util.py:305-327)" % feat_fusion)
+        # Pix2Pix_NET.py:107-108: the late fusions need both streams
+        assert not ("late" in feat_fusion and which_stream != "ctx_label")
+        self.late = "late" in feat_fusion
         if n_blocks < 1:
             raise NotImplementedError("n_blocks_global == 0 is not part of this path")
         self.ctx, self.fp = ctx, fp
@@ -54,10 +58,21 @@ class GlobalTwoStreamGenerator(object):
         # declaration order = the reference's module registration order (state_dict order)
         self.enc_ctx = encoder("ctx", 3) if "ctx" in which_stream else None
         self.enc_obj = encoder("obj", input_nc) if "label" in which_stream else None
-        st = []
-        for i in range(n_blocks):
-            st.append(("resA", ConvP(ctx, fp, "latent_embedder.%d.conv_block.1" % i, self.feat_dim, self.feat_dim, 3, 1, 0)))
-            st.append(("resB", ConvP(ctx, fp, "latent_embedder.%d.conv_block.5" % i, self.feat_dim, self.feat_dim, 3, 1, 0)))
+        def res_blocks(prefix, n):
+            out = []
+            for i in range(n):
+                out.append(("resA", ConvP(ctx, fp, "%s.%d.conv_block.1" % (prefix, i), self.feat_dim, self.feat_dim, 3, 1, 0)))
+                out.append(("resB", ConvP(ctx, fp, "%s.%d.conv_block.5" % (prefix, i), self.feat_dim, self.feat_dim, 3, 1, 0)))
+            return out
+        # feat_fusion 'late_*' (:137-142): floor(n/2) blocks per stream BEFORE the masked fusion, ceil(n/2) after it
+        self.lat_obj = self.lat_ctx = None
+        n_comb = n_blocks
+        if self.late:
+            n_comb = (n_blocks + 1) // 2
+            if n_blocks // 2 > 0:
+                self.lat_obj = _Stages(ctx, fp, res_blocks("obj_latent_embedder", n_blocks // 2), False, ngf)
+                self.lat_ctx = _Stages(ctx, fp, res_blocks("ctx_latent_embedder", n_blocks // 2), False, ngf)
+        st = res_blocks("latent_embedder", n_comb)
         self.first_up = len(st)
         for i in range(n_downsampling):
             m = 2 ** (n_downsampling - i)
@@ -68,7 +83,7 @@ class GlobalTwoStreamGenerator(object):
 
     def convs(self):
         out = []
-        for part in (self.enc_ctx, self.enc_obj, self.trunk):
+        for part in (self.enc_ctx, self.enc_obj, self.lat_obj, self.lat_ctx, self.trunk):
             if part is not None:
                 out += part.convs()
         return out
@@ -84,6 +99,9 @@ class GlobalTwoStreamGenerator(object):
             fa, tape["ctx"] = self.enc_ctx.forward(ctx_in)
         if self.enc_obj is not None:
             fb, tape["obj"] = self.enc_obj.forward(obj_in)
+        if self.lat_ctx is not None:                                                     # :204-206 ('late' fusion)
+            fa, tape["lat_ctx"] = self._embed(self.lat_ctx, fa)
+            fb, tape["lat_obj"] = self._embed(self.lat_obj, fb)
         ref = fa if fa is not None else fb
         N, h, w, C = ref.shape
         m = None
@@ -105,6 +123,14 @@ class GlobalTwoStreamGenerator(object):
         out, tape["trunk"] = self.trunk.forward(comb_op, skip32_init=comb32, concat=concat)
         return out, tape
 
+    def _embed(self, stages, f32):
+        """ResnetBlocks on a dense fp32 feature: materialise its reflect-padded operand, run the block list."""
+        c = self.ctx
+        N, h, w, C = f32.shape
+        op = Operand(c, N, h, w, C, border=1)
+        ops.in_apply(c, f32, None, None, ops.ACT_NONE, out_op=op, reflect=True)
+        return stages.forward(op, skip32_init=f32)
+
     def backward(self, tape, dy_head):
         """dy_head: Operand gradient w.r.t. the head's pre-tanh output.  Accumulates every parameter gradient."""
         c = self.ctx
@@ -122,6 +148,10 @@ class GlobalTwoStreamGenerator(object):
             ops.mask_blend_bwd(c, g, m, da, db)
         else:
             da = db = g
+        if self.lat_ctx is not None:          # through the per-stream ResnetBlocks (their first stage is a block: input_T)
+            self.lat_ctx.backward(tape["lat_ctx"], dfeat=da, need_input_grad=True)
+            self.lat_obj.backward(tape["lat_obj"], dfeat=db, need_input_grad=True)
+            da, db = self.lat_ctx.input_T, self.lat_obj.input_T
         if self.enc_ctx is not None:
             self.enc_ctx.backward(tape["ctx"], dfeat=da, extra_grad=extra)
         if self.enc_obj is not None:

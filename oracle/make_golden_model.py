@@ -124,6 +124,11 @@ def main():
         # (pix2pixHD_condImg_model.py:71-72, 178-179, 227-228)
         _run_case("twostream_ctx", 23, netG="global_twostream", which_encoder="ctx", use_skip=True, use_output_gate=True,
                   mask_gan_input=True, no_instance=True, n_downsample_global=2)
+    if "late" in sys.argv[1:] or len(sys.argv) == 1:
+        # feat_fusion == 'late_add' (Pix2Pix_NET.py:137-142, 203-206): each stream runs floor(n/2) ResnetBlocks of its own
+        # before the masked fusion, ceil(n/2) blocks embed the fused feature
+        _run_case("twostream_late_add", 24, netG="global_twostream", which_encoder="ctx_label", feat_fusion="late_add",
+                  use_skip=True, use_output_gate=True, no_instance=True, n_downsample_global=2, n_blocks_global=3)
 
 
 if __name__ == "__main__":

@@ -69,8 +69,19 @@ def global_generator_forward(sd, x, n_downsampling, n_blocks, mask=None, use_out
 
 
 def global_twostream_forward(sd, img, label, mask, n_downsampling, n_blocks, use_skip=False, which_stream="ctx",
-                             use_output_gate=False):
-    """GlobalTwoStreamGenerator.forward, models/Pix2Pix_NET.py:103-247 (feat_fusion='early_add')."""
+                             use_output_gate=False, feat_fusion="early_add"):
+    """GlobalTwoStreamGenerator.forward, models/Pix2Pix_NET.py:103-247 (feat_fusion 'early_add' or 'late_add')."""
+    def embed(prefix, h, n):                                                   # get_embedder :166-175
+        for i in range(n):
+            k = "%s.%d.conv_block." % (prefix, i)
+            r = F.conv2d(reflect_pad(h, 1), sd[k + "1.weight"], sd[k + "1.bias"])
+            r = F.relu(instance_norm(r))
+            r = F.conv2d(reflect_pad(r, 1), sd[k + "5.weight"], sd[k + "5.bias"])
+            h = h + instance_norm(r)
+        return h
+    late = "late" in feat_fusion
+    if feat_fusion not in ("early_add", "late_add"):
+        raise NotImplementedError(feat_fusion)
     def encode(prefix, x, keep):                                               # forward_encoder :135-142
         h = F.relu(instance_norm(F.conv2d(reflect_pad(x, 3), sd[prefix + "_inputEmbedder.1.weight"],
                                           sd[prefix + "_inputEmbedder.1.bias"])))
@@ -88,17 +99,15 @@ def global_twostream_forward(sd, img, label, mask, n_downsampling, n_blocks, use
     if "label" in which_stream:
         obj_feat, _ = encode("obj", label, False)
     if which_stream == "ctx_label":                                            # :203-209, FeatureFusionBlock 'add'
+        if late:                                                               # :204-206, n_blocks split :138-142
+            ctx_feat = embed("ctx_latent_embedder", ctx_feat, n_blocks // 2)
+            obj_feat = embed("obj_latent_embedder", obj_feat, n_blocks // 2)
         f = 2 ** n_downsampling
         m = F.max_pool2d(mask, f, f)
         h = (1 - m) * ctx_feat + m * obj_feat
     else:
         h = ctx_feat if which_stream == "ctx" else obj_feat
-    for i in range(n_blocks):                                                  # latent_embedder
-        k = "latent_embedder.%d.conv_block." % i
-        r = F.conv2d(reflect_pad(h, 1), sd[k + "1.weight"], sd[k + "1.bias"])
-        r = F.relu(instance_norm(r))
-        r = F.conv2d(reflect_pad(r, 1), sd[k + "5.weight"], sd[k + "5.bias"])
-        h = h + instance_norm(r)
+    h = embed("latent_embedder", h, (n_blocks + 1) // 2 if late else n_blocks)   # latent_embedder
     for s in range(n_downsampling):                                            # forward_decoder :215-223
         if use_skip and len(ctx_feats) > 0 and s > 0:
             h = torch.cat((ctx_feats[-s], h), 1)
@@ -301,7 +310,8 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
     elif opt.netG == "global_twostream":                                       # :209-210
         fake = global_twostream_forward(g_sd, cond, input_mask, mask_in.to(dtype), opt.n_downsample_global,
                                         opt.n_blocks_global, getattr(opt, "use_skip", False),
-                                        getattr(opt, "which_encoder", "ctx"), opt.use_output_gate)
+                                        getattr(opt, "which_encoder", "ctx"), opt.use_output_gate,
+                                        getattr(opt, "feat_fusion", "early_add"))
     else:
         fake = global_generator_forward(g_sd, input_label, opt.n_downsample_global, opt.n_blocks_global,
                                         mask=mask_in.to(dtype), use_output_gate=opt.use_output_gate)   # :208

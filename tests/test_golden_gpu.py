@@ -164,6 +164,10 @@ def test_two_stream_generator_forward_and_parameter_gradients(golden_dir):
     ("model_twostream_ctx.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2,
                                      ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
                                      which_encoder="ctx", use_skip=True, mask_gan_input=True)),
+    # feat_fusion == 'late_add': floor(n/2) ResnetBlocks per stream before the masked fusion, ceil(n/2) after
+    ("model_twostream_late_add.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=3,
+                                          ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
+                                          which_encoder="ctx_label", feat_fusion="late_add", use_skip=True)),
 ])
 def test_training_step_against_the_reference_models_own_forward(golden_dir, name, optkw):
     """The whole forward of the training step (generated image, the five losses) and the gradient directions against

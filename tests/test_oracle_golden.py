@@ -204,6 +204,10 @@ def _model_case(golden_dir, name, **optkw):
     ("model_twostream_ctx.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2,
                                      ndf=8, num_D=2, use_output_gate=True, netG="global_twostream", which_encoder="ctx",
                                      use_skip=True, mask_gan_input=True)),
+    # feat_fusion == 'late_add': per-stream ResnetBlocks before the masked fusion
+    ("model_twostream_late_add.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=3,
+                                          ndf=8, num_D=2, use_output_gate=True, netG="global_twostream",
+                                          which_encoder="ctx_label", feat_fusion="late_add", use_skip=True)),
 ])
 def test_model_level_forward_against_the_reference_model(golden_dir, name, optkw):
     """oracle.model_forward / step_losses against the reference's OWN Pix2PixHDModel_condImg.forward run on CPU
