@@ -331,6 +331,13 @@ def run_mode(model, precision_name, batch_dev, batch_pinned, steps, warmup, worl
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, steps)
+    # BASELINE's second figure, "G-step ms" (SURVEY section 8(d)): the generator half only -- encode, G forward, D / VGG
+    # forward passes, loss_G.backward(), Adam on G -- per iteration at the per-GPU batch, eager launches, same streams
+    for _ in range(2):
+        m.generator_step(**kw_dev)
+    ms_g = timed(lambda: m.generator_step(**kw_dev), steps)
+    m.ctx.check_pipeline()
+
     keys = ["label", "image", "mask_in"] + ([] if m.opt.no_instance else ["inst"])
     h2d = sum(batch_pinned[k].numel() * 4 for k in keys)
     # data-parallel replicas must hold bit-identical weights after the timed steps (each rank saw different data, the
@@ -342,7 +349,7 @@ def run_mode(model, precision_name, batch_dev, batch_pinned, steps, warmup, worl
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         identical = bool((hi - lo).item() == 0)
-    return dict(ms=ms_dev, ms_e2e=ms_e2e, launches=launches, clocks=clocks, h2d=h2d, d2h=20,
+    return dict(ms=ms_dev, ms_e2e=ms_e2e, ms_g=ms_g, launches=launches, clocks=clocks, h2d=h2d, d2h=20,
                 losses=[float(x) for x in host_losses], replicas_identical=identical,
                 graph=isinstance(m._graph, dict), peak_mem_gb=torch.cuda.max_memory_allocated(m.device) / 2 ** 30)
 
@@ -539,7 +546,10 @@ def main():
                     e2e=dict(value=gb / (prim["ms_e2e"] / 1e3), unit="images/sec", h2d_bytes_per_step=prim["h2d"],
                              d2h_bytes_per_step=prim["d2h"], ms_per_step=prim["ms_e2e"]),
                     gpu_launches=prim["launches"], cuda_graph=prim["graph"], peak_mem_gb=prim["peak_mem_gb"],
-                    losses_last_step=prim["losses"])
+                    losses_last_step=prim["losses"],
+                    g_step_ms=dict(value=prim["ms_g"], unit="ms", what="generator half of one iteration (encode, G forward, "
+                                   "D and VGG19 forward passes, loss_G.backward(), Adam on G; train_mask2image.py:58-80) at "
+                                   "the per-GPU batch, device-timed, eager launches, max over ranks"))
         if world > 1:
             line["replicas_identical"] = prim["replicas_identical"]
         if headline:

@@ -497,14 +497,23 @@ class Pix2PixHDModel_condImg(object):
         return self._fused_step(batch["label"], batch["inst"], batch["image"], batch["mask_in"], captured=False,
                                 mask_out=batch["mask_out"])
 
-    def _fused_step(self, label, inst, image, mask_in, captured, mask_out=None):
+    def generator_step(self, label=None, inst=None, image=None, feat=None, mask_in=None, mask_out=None):
+        """The GENERATOR half of one iteration -- BASELINE's "G-step": encode, G forward, the discriminator and VGG19
+        forward passes, `loss_G.backward()` and Adam on G (train_mask2image.py:58-80), with the same stream schedule as
+        the fused step but without loss_D's backward pass and the discriminator's Adam step.  Eager (not graphed);
+        returns the five losses as a device tensor.  bench.py times it for `g_step_ms`."""
+        soft = self.opt.mask_gan_input and self.opt.use_soft_mask
+        return self._fused_step(label, None if self.opt.no_instance else inst, image, mask_in, captured=False,
+                                mask_out=mask_out if soft else None, d_half=False)
+
+    def _fused_step(self, label, inst, image, mask_in, captured, mask_out=None, d_half=True):
         self._overlap = bool(getattr(self.opt, "overlap_streams", True)) and os.environ.get("HM_STREAMS", "1") != "0"
         try:
-            return self._fused_step_impl(label, inst, image, mask_in, captured, mask_out)
+            return self._fused_step_impl(label, inst, image, mask_in, captured, mask_out, d_half)
         finally:
             self._overlap = False
 
-    def _fused_step_impl(self, label, inst, image, mask_in, captured, mask_out=None):
+    def _fused_step_impl(self, label, inst, image, mask_in, captured, mask_out=None, d_half=True):
         st = self._forward_all(label, inst, image, mask_in, mask_out)
         self._step = st
         self._keep_visuals(st)
@@ -516,7 +525,7 @@ class Pix2PixHDModel_condImg(object):
         # the generator's Adam step (the sum over both is the ONE [G | D] allreduce of SURVEY section 8(e))
         side = self._side_stream()
         hD = [None]
-        if side is not None:
+        if side is not None and d_half:
             # loss_D's graph holds no generator parameter, so its backward pass only needs the D tape: it runs on the
             # second stream as soon as the generator-side pass through D is enqueued (the packed D weights exist then),
             # overlapping the long generator backward; its gradient segment is allreduced from that stream.
@@ -558,7 +567,7 @@ class Pix2PixHDModel_condImg(object):
             self._grad_ready = None
         if dp and not use_buckets:
             handles.append(parallel.allreduce_sum_async_(self.flat_grad[:nG]))
-        if side is None:
+        if side is None and d_half:
             self._backward_D([0.5, 0.5])
             hD[0] = parallel.allreduce_sum_async_(self.flat_grad[nG:]) if dp else None
         for h in handles:
@@ -570,7 +579,8 @@ class Pix2PixHDModel_condImg(object):
             torch.cuda.current_stream().wait_stream(side)
         elif hD[0] is not None:
             hD[0].wait()
-        self.optimizer_D.step(grad_scale=scale, captured=captured)
+        if d_half:
+            self.optimizer_D.step(grad_scale=scale, captured=captured)
         return st["losses"]
 
     # ---- CUDA-graph replay of the fused step ------------------------------------------------------------
