@@ -239,6 +239,13 @@ int hm_mask_maxpool(const float* mask, int B, int H, int W, int f, float* out, v
 int hm_mask_blend(const float* a, const float* b, const float* m, int N, int H, int W, int C, float* out32, void* o_hi,
                   void* o_lo, int o_cs, int border, void* stream);
 int hm_mask_blend_bwd(const float* g, const float* m, long P, int C, float* da, float* db, void* stream);
+/* FeatureFusionBlock 'concat' (layer_util.py:305-327; feat_fusion '*_concat' of GlobalTwoStreamGenerator):
+ * hm_mask_concat: operand [P pixels, o_cs >= 2C] = relu(cat((1 - m) * a, m * b)) from dense fp32 a, b [P, C] and m [P];
+ * hm_mask_concat_bwd: g [P, ld >= 2C] = gradient w.r.t. that operand -> da, db [P, C] (through the ReLU and the mask). */
+int hm_mask_concat(const float* a, const float* b, const float* m, long P, int C, void* o_hi, void* o_lo, int o_cs,
+                   void* stream);
+int hm_mask_concat_bwd(const float* g, int ld, const float* m, const float* a, const float* b, long P, int C, float* da,
+                       float* db, void* stream);
 int hm_concat_operands(const void* a_hi, const void* a_lo, int a_cs, int Ca, const void* b_hi, const void* b_lo, int b_cs,
                        int Cb, void* o_hi, void* o_lo, int o_cs, long P, void* stream);
 int hm_cond_image_operand(const float* image, const float* mask, int B, int H, int W, void* o_hi, void* o_lo, int o_cs,

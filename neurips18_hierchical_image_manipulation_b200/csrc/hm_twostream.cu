@@ -94,6 +94,52 @@ __global__ void mask_blend_bwd_kernel(const float* __restrict__ g, const float* 
   }
 }
 
+// FeatureFusionBlock 'concat' (layer_util.py:305-327): operand [N,H,W,2C] = relu(cat((1 - m) * a, m * b)), no border (it
+// feeds the 1x1 fuse convolution).  One thread per (pixel, group of 8 output channels); C % 8 == 0.
+__global__ void mask_concat_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ m,
+                                   long P, int C, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, int o_cs) {
+  const int groups = o_cs >> 3;
+  const long total = P * groups;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int g = int(i % groups);
+    const long pix = i / groups;
+    const float mm = __ldg(m + pix);
+    const int c0 = g * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float x = 0.f;
+      if (c < C) x = (1.f - mm) * __ldg(a + pix * C + c);
+      else if (c < 2 * C) x = mm * __ldg(b + pix * C + c - C);
+      v[j] = fmaxf(x, 0.f);
+    }
+    alignas(16) bf16 hh[8];
+    alignas(16) bf16 ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hm::split_bf16(v[j], hh[j], ll[j]);
+    const size_t off = size_t(pix) * o_cs + c0;
+    *reinterpret_cast<uint4*>(o_hi + off) = *reinterpret_cast<const uint4*>(hh);
+    if (o_lo) *reinterpret_cast<uint4*>(o_lo + off) = *reinterpret_cast<const uint4*>(ll);
+  }
+}
+
+// its adjoint: g [P, ld >= 2C] is the gradient w.r.t. the concatenated operand;
+// da = (1 - m) * g[:, :C] where (1 - m) * a > 0, db = m * g[:, C:2C] where m * b > 0
+__global__ void mask_concat_bwd_kernel(const float* __restrict__ g, int ld, const float* __restrict__ m,
+                                       const float* __restrict__ a, const float* __restrict__ b, long P, int C,
+                                       float* __restrict__ da, float* __restrict__ db) {
+  const long total = P * C;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const long pix = i / C;
+    const int c = int(i - pix * C);
+    const float mm = __ldg(m + pix);
+    const float wa = 1.f - mm;
+    da[i] = (wa * __ldg(a + i) > 0.f) ? wa * __ldg(g + pix * ld + c) : 0.f;
+    db[i] = (mm * __ldg(b + i) > 0.f) ? mm * __ldg(g + pix * ld + C + c) : 0.f;
+  }
+}
+
 // one thread per (pixel, group of 8 output channels); groups never straddle the a / b boundary when Ca % 8 == 0,
 // otherwise elements are gathered one by one
 __global__ void concat_operands_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, int a_cs, int Ca,
@@ -178,6 +224,21 @@ int hm_mask_blend(const float* a, const float* b, const float* m, int N, int H, 
 int hm_mask_blend_bwd(const float* g, const float* m, long P, int C, float* da, float* db, void* stream) {
   if (!g || !m || (!da && !db)) return HM_ERR_INVALID;
   mask_blend_bwd_kernel<<<grid_for(P * C), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(g, m, P, C, da, db);
+  return HM_LAUNCH_OK();
+}
+
+int hm_mask_concat(const float* a, const float* b, const float* m, long P, int C, void* o_hi, void* o_lo, int o_cs,
+                   void* stream) {
+  if (!a || !b || !m || !o_hi || (o_cs & 7) || o_cs < 2 * C || C <= 0) return HM_ERR_INVALID;
+  mask_concat_kernel<<<grid_for(P * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, m, P, C, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_mask_concat_bwd(const float* g, int ld, const float* m, const float* a, const float* b, long P, int C, float* da,
+                       float* db, void* stream) {
+  if (!g || !m || !a || !b || !da || !db || ld < 2 * C) return HM_ERR_INVALID;
+  mask_concat_bwd_kernel<<<grid_for(P * C), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(g, ld, m, a, b, P, C, da, db);
   return HM_LAUNCH_OK();
 }
 

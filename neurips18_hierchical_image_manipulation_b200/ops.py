@@ -390,6 +390,23 @@ def mask_blend_bwd(ctx, g, m, da=None, db=None):
     ctx.launches += 1
 
 
+def mask_concat(ctx, a, b, m):
+    """relu(cat((1 - m) * a, m * b)) as an operand [N,h,w,2C] (FeatureFusionBlock 'concat'); a, b dense fp32 NHWC."""
+    N, h, w, Cc = a.shape
+    out = Operand(ctx, N, h, w, 2 * Cc)
+    L.check(ctx.lib.hm_mask_concat(a.data_ptr(), b.data_ptr(), m.data_ptr(), N * h * w, Cc, out.hi.data_ptr(), _ptr(out.lo),
+                                   out.cs, _stream()), "hm_mask_concat")
+    ctx.launches += 1
+    return out
+
+
+def mask_concat_bwd(ctx, g, m, a, b, da, db):
+    N, h, w, Cc = a.shape
+    L.check(ctx.lib.hm_mask_concat_bwd(g.data_ptr(), g.shape[-1], m.data_ptr(), a.data_ptr(), b.data_ptr(), N * h * w, Cc,
+                                       da.data_ptr(), db.data_ptr(), _stream()), "hm_mask_concat_bwd")
+    ctx.launches += 1
+
+
 def concat_operands(ctx, a, b):
     """torch.cat((a, b), channel) of two border-free operands with equal pixel dims."""
     assert a.border == 0 and b.border == 0 and (a.n, a.h, a.w) == (b.n, b.h, b.w)

@@ -10,7 +10,7 @@ train (scripts/train_mask2image_city.sh: --netG global_twostream --which_encoder
 
 Parameter names follow the reference module tree (ctx_inputEmbedder.1, ctx_downsampler.{0,3,..}, obj_*,
 latent_embedder.{i}.conv_block.{1,5}, decoder.{0,3,..}, outputEmbedder.1) so its checkpoints interchange.
-Supported: which_stream in {ctx_label, ctx, label}, feat_fusion in {early_add, late_add}.  Every stage reuses the GlobalGenerator
+Supported: which_stream in {ctx_label, ctx, label}, feat_fusion in {early_add, late_add, early_concat, late_concat}.  Every stage reuses the GlobalGenerator
 schedules (networks.py); the glue kernels are csrc/hm_twostream.cu.
 """
 from . import ops
@@ -34,12 +34,12 @@ class GlobalTwoStreamGenerator(object):
                  which_stream="ctx", use_output_gate=False, feat_fusion="early_add"):
         if which_stream not in ("ctx_label", "ctx", "label"):
             raise NotImplementedError("which_encoder must be ctx_label | ctx | label, got %s" % which_stream)
-        if feat_fusion not in ("early_add", "late_add"):
-            raise NotImplementedError("feat_fusion %s: early_add and late_add are part of this path (the 'concat' fusions "
-                                      "add a 1x1 fuse conv, layer_util.py:305-327)" % feat_fusion)
+        if feat_fusion not in ("early_add", "late_add", "early_concat", "late_concat"):
+            raise NotImplementedError("feat_fusion %s" % feat_fusion)
         # Pix2Pix_NET.py:107-108: the late fusions need both streams
         assert not ("late" in feat_fusion and which_stream != "ctx_label")
         self.late = "late" in feat_fusion
+        self.concat_fuse = "concat" in feat_fusion and which_stream == "ctx_label"
         if n_blocks < 1:
             raise NotImplementedError("n_blocks_global == 0 is not part of this path")
         self.ctx, self.fp = ctx, fp
@@ -58,6 +58,9 @@ class GlobalTwoStreamGenerator(object):
         # declaration order = the reference's module registration order (state_dict order)
         self.enc_ctx = encoder("ctx", 3) if "ctx" in which_stream else None
         self.enc_obj = encoder("obj", input_nc) if "label" in which_stream else None
+        # FeatureFusionBlock 'concat' (layer_util.py:305-327): cat -> ReLU -> Conv2d(2C, C, 1) -> InstanceNorm
+        self.fuse_conv = ConvP(ctx, fp, "feat_fuser.conv1", 2 * self.feat_dim, self.feat_dim, 1, 1, 0) if self.concat_fuse else None
+
         def res_blocks(prefix, n):
             out = []
             for i in range(n):
@@ -86,6 +89,8 @@ class GlobalTwoStreamGenerator(object):
         for part in (self.enc_ctx, self.enc_obj, self.lat_obj, self.lat_ctx, self.trunk):
             if part is not None:
                 out += part.convs()
+        if self.fuse_conv is not None:
+            out.append(self.fuse_conv)
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -110,7 +115,15 @@ class GlobalTwoStreamGenerator(object):
         first_border = GlobalGenerator.IN_BORDER[self.trunk.stages[0][0]]
         comb32 = _f32(c, N, h, w, C)
         comb_op = Operand(c, N, h, w, C, border=first_border)
-        ops.mask_blend(c, fa, fb, m, out32=comb32, out_op=comb_op)                       # :207-209
+        if self.fuse_conv is not None:                                                   # FeatureFusionBlock 'concat'
+            u = ops.mask_concat(c, fa, fb, m)
+            yf = _f32(c, N, h, w, C)
+            self.fuse_conv.forward(u, 0, out32=yf)
+            mean, rstd = ops.in_stats(c, yf)
+            ops.in_apply(c, yf, mean, rstd, ops.ACT_NONE, out32=comb32, out_op=comb_op, reflect=True)
+            tape["fuse"] = dict(u=u, y=yf, mean=mean, rstd=rstd, fa=fa, fb=fb)
+        else:
+            ops.mask_blend(c, fa, fb, m, out32=comb32, out_op=comb_op)                   # :207-209
         tape["m"] = m
         concat = None
         if self.use_skip:
@@ -143,7 +156,17 @@ class GlobalTwoStreamGenerator(object):
                 k = self.n_down - 1 - s
                 extra[k + 1] = self.trunk.concat_grads[self.first_up + s]   # gradient w.r.t. the output of ctx stage k+1
         m = tape["m"]
-        if m is not None:
+        if self.fuse_conv is not None:
+            t = tape["fuse"]
+            N, h, w, C = g.shape
+            dy = Operand(c, N, h, w, C, grad=True)
+            ops.in_bwd(c, (N, h, w, C), ops.ACT_NONE, y=t["y"], mean=t["mean"], rstd=t["rstd"], g2=g, out_op=dy)
+            self.fuse_conv.wgrad(t["u"], dy, 0, bias_grad=False)          # the bias cancels in the InstanceNorm
+            gu = _f32(c, N, h, w, 2 * C)
+            self.fuse_conv.dgrad(dy, h, w, 0, gu)
+            da, db = _f32(c, N, h, w, C), _f32(c, N, h, w, C)
+            ops.mask_concat_bwd(c, gu, m, t["fa"], t["fb"], da, db)
+        elif m is not None:
             da, db = _f32(c, *g.shape), _f32(c, *g.shape)
             ops.mask_blend_bwd(c, g, m, da, db)
         else:

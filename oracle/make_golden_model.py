@@ -129,6 +129,12 @@ def main():
         # before the masked fusion, ceil(n/2) blocks embed the fused feature
         _run_case("twostream_late_add", 24, netG="global_twostream", which_encoder="ctx_label", feat_fusion="late_add",
                   use_skip=True, use_output_gate=True, no_instance=True, n_downsample_global=2, n_blocks_global=3)
+    if "concat" in sys.argv[1:] or len(sys.argv) == 1:
+        # feat_fusion '*_concat' (layer_util.py:305-327): cat -> ReLU -> 1x1 conv -> norm instead of the sum
+        _run_case("twostream_early_concat", 25, netG="global_twostream", which_encoder="ctx_label", feat_fusion="early_concat",
+                  use_skip=True, use_output_gate=True, no_instance=True, n_downsample_global=2, n_blocks_global=2)
+        _run_case("twostream_late_concat", 26, netG="global_twostream", which_encoder="ctx_label", feat_fusion="late_concat",
+                  use_skip=False, use_output_gate=False, no_instance=False, n_downsample_global=2, n_blocks_global=3)
 
 
 if __name__ == "__main__":

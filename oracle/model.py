@@ -70,7 +70,7 @@ def global_generator_forward(sd, x, n_downsampling, n_blocks, mask=None, use_out
 
 def global_twostream_forward(sd, img, label, mask, n_downsampling, n_blocks, use_skip=False, which_stream="ctx",
                              use_output_gate=False, feat_fusion="early_add"):
-    """GlobalTwoStreamGenerator.forward, models/Pix2Pix_NET.py:103-247 (feat_fusion 'early_add' or 'late_add')."""
+    """GlobalTwoStreamGenerator.forward, models/Pix2Pix_NET.py:103-247 (feat_fusion 'early_add', 'late_add', 'early_concat', 'late_concat')."""
     def embed(prefix, h, n):                                                   # get_embedder :166-175
         for i in range(n):
             k = "%s.%d.conv_block." % (prefix, i)
@@ -80,7 +80,7 @@ def global_twostream_forward(sd, img, label, mask, n_downsampling, n_blocks, use
             h = h + instance_norm(r)
         return h
     late = "late" in feat_fusion
-    if feat_fusion not in ("early_add", "late_add"):
+    if feat_fusion not in ("early_add", "late_add", "early_concat", "late_concat"):
         raise NotImplementedError(feat_fusion)
     def encode(prefix, x, keep):                                               # forward_encoder :135-142
         h = F.relu(instance_norm(F.conv2d(reflect_pad(x, 3), sd[prefix + "_inputEmbedder.1.weight"],
@@ -104,7 +104,11 @@ def global_twostream_forward(sd, img, label, mask, n_downsampling, n_blocks, use
             obj_feat = embed("obj_latent_embedder", obj_feat, n_blocks // 2)
         f = 2 ** n_downsampling
         m = F.max_pool2d(mask, f, f)
-        h = (1 - m) * ctx_feat + m * obj_feat
+        if "concat" in feat_fusion:                                            # FeatureFusionBlock 'concat', layer_util.py:305-327
+            h = F.relu(torch.cat(((1 - m) * ctx_feat, m * obj_feat), 1))
+            h = instance_norm(F.conv2d(h, sd["feat_fuser.conv1.weight"], sd["feat_fuser.conv1.bias"]))
+        else:
+            h = (1 - m) * ctx_feat + m * obj_feat
     else:
         h = ctx_feat if which_stream == "ctx" else obj_feat
     h = embed("latent_embedder", h, (n_blocks + 1) // 2 if late else n_blocks)   # latent_embedder

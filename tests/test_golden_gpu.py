@@ -168,6 +168,13 @@ def test_two_stream_generator_forward_and_parameter_gradients(golden_dir):
     ("model_twostream_late_add.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=3,
                                           ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
                                           which_encoder="ctx_label", feat_fusion="late_add", use_skip=True)),
+    # feat_fusion '*_concat': cat -> ReLU -> 1x1 conv -> InstanceNorm in place of the masked sum
+    ("model_twostream_early_concat.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2,
+                                              ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
+                                              which_encoder="ctx_label", feat_fusion="early_concat", use_skip=True)),
+    ("model_twostream_late_concat.npz", dict(label_nc=6, no_instance=False, ngf=8, n_downsample_global=2, n_blocks_global=3,
+                                             ndf=8, num_D=2, n_layers_D=3, use_output_gate=False, netG="global_twostream",
+                                             which_encoder="ctx_label", feat_fusion="late_concat", use_skip=False)),
 ])
 def test_training_step_against_the_reference_models_own_forward(golden_dir, name, optkw):
     """The whole forward of the training step (generated image, the five losses) and the gradient directions against
