@@ -239,6 +239,13 @@ int hm_mask_maxpool(const float* mask, int B, int H, int W, int f, float* out, v
 int hm_mask_blend(const float* a, const float* b, const float* m, int N, int H, int W, int C, float* out32, void* o_hi,
                   void* o_lo, int o_cs, int border, void* stream);
 int hm_mask_blend_bwd(const float* g, const float* m, long P, int C, float* da, float* db, void* stream);
+/* hm_pool_exchange: ImagePool.query (util/image_pool.py:11-31, --pool_size > 0; discriminate(..., use_pool=True),
+ * pix2pixHD_condImg_model.py:182-184) for image b of a batch of bf16 operands with elems_per_image elements each (% 8 == 0).
+ * The decisions are drawn on the host and read from DEVICE memory (int32 dec[2b] = action, dec[2b+1] = pool slot):
+ * 0 out = cur; 1 pool[slot] = cur, out = cur (pool filling); 2 out = pool[slot], pool[slot] = cur (exchange).  Images of
+ * one batch must be processed in order (one launch per image). */
+int hm_pool_exchange(const void* cur_hi, const void* cur_lo, void* pool_hi, void* pool_lo, void* out_hi, void* out_lo,
+                     const int* dec, int b, long elems_per_image, void* stream);
 /* FeatureFusionBlock 'concat' (layer_util.py:305-327; feat_fusion '*_concat' of GlobalTwoStreamGenerator):
  * hm_mask_concat: operand [P pixels, o_cs >= 2C] = relu(cat((1 - m) * a, m * b)) from dense fp32 a, b [P, C] and m [P];
  * hm_mask_concat_bwd: g [P, ld >= 2C] = gradient w.r.t. that operand -> da, db [P, C] (through the ReLU and the mask). */

@@ -87,6 +87,7 @@ PROTOTYPES = {
     "hm_mask_maxpool": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "hm_mask_blend": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "hm_mask_blend_bwd": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp]),
+    "hm_pool_exchange": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _l, _vp]),
     "hm_mask_concat": (_i, [_vp, _vp, _vp, _l, _i, _vp, _vp, _i, _vp]),
     "hm_mask_concat_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _l, _i, _vp, _vp, _vp]),
     "hm_concat_operands": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _l, _vp]),

@@ -140,6 +140,33 @@ __global__ void mask_concat_bwd_kernel(const float* __restrict__ g, int ld, cons
   }
 }
 
+// ImagePool.query for ONE image (util/image_pool.py:11-31): `dec` holds the host-drawn decision of every image of the batch
+// in device memory (so that the launch can sit in a CUDA graph): dec[2b] = 0 pass through, 1 store in slot dec[2b+1] and
+// pass through (pool still filling), 2 exchange with slot dec[2b+1] (return the stored image, keep the new one).
+__global__ void pool_exchange_kernel(const uint4* __restrict__ cur_hi, const uint4* __restrict__ cur_lo, uint4* __restrict__ pool_hi,
+                                     uint4* __restrict__ pool_lo, uint4* __restrict__ out_hi, uint4* __restrict__ out_lo,
+                                     const int* __restrict__ dec, int b, long vecs) {
+  const int action = dec[2 * b];
+  const long slot = dec[2 * b + 1];
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < vecs; i += long(gridDim.x) * blockDim.x) {
+    const long ci = long(b) * vecs + i, pi = slot * vecs + i;
+    const uint4 ch = cur_hi[ci];
+    uint4 cl = make_uint4(0, 0, 0, 0);
+    if (cur_lo) cl = cur_lo[ci];
+    uint4 oh = ch, ol = cl;
+    if (action == 2) {
+      oh = pool_hi[pi];
+      if (pool_lo) ol = pool_lo[pi];
+    }
+    if (action != 0) {
+      pool_hi[pi] = ch;
+      if (pool_lo) pool_lo[pi] = cl;
+    }
+    out_hi[ci] = oh;
+    if (out_lo) out_lo[ci] = ol;
+  }
+}
+
 // one thread per (pixel, group of 8 output channels); groups never straddle the a / b boundary when Ca % 8 == 0,
 // otherwise elements are gathered one by one
 __global__ void concat_operands_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, int a_cs, int Ca,
@@ -224,6 +251,16 @@ int hm_mask_blend(const float* a, const float* b, const float* m, int N, int H, 
 int hm_mask_blend_bwd(const float* g, const float* m, long P, int C, float* da, float* db, void* stream) {
   if (!g || !m || (!da && !db)) return HM_ERR_INVALID;
   mask_blend_bwd_kernel<<<grid_for(P * C), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(g, m, P, C, da, db);
+  return HM_LAUNCH_OK();
+}
+
+int hm_pool_exchange(const void* cur_hi, const void* cur_lo, void* pool_hi, void* pool_lo, void* out_hi, void* out_lo,
+                     const int* dec, int b, long elems_per_image, void* stream) {
+  if (!cur_hi || !pool_hi || !out_hi || !dec || b < 0 || elems_per_image <= 0 || (elems_per_image & 7)) return HM_ERR_INVALID;
+  const long vecs = elems_per_image >> 3;
+  pool_exchange_kernel<<<grid_for(vecs), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(cur_hi), static_cast<const uint4*>(cur_lo), static_cast<uint4*>(pool_hi),
+      static_cast<uint4*>(pool_lo), static_cast<uint4*>(out_hi), static_cast<uint4*>(out_lo), dec, b, vecs);
   return HM_LAUNCH_OK();
 }
 

@@ -264,10 +264,12 @@ class Pix2PixHDModel_condImg(object):
                 self.load_network(self.fpD, "D", opt.which_epoch, pretrained_path)
         # ---- losses and optimizers (:103-139)
         if self.isTrain:
-            if opt.pool_size > 0 and len(self.gpu_ids) > 1:
+            # :105-107 ImagePool(opt.pool_size): a history of discriminator inputs for the fake pass of loss_D.  One process
+            # per GPU here, so the reference's multi-GPU ban applies to a multi-rank job
+            if opt.pool_size > 0 and (len(self.gpu_ids) > 1 or parallel.world()[1] > 1):
                 raise NotImplementedError("Fake Pool Not Implemented for MultiGPU")
-            if opt.pool_size > 0:
-                raise NotImplementedError("image pool (pool_size > 0) is outside this path; the default is 0")
+            self.pool_size = int(opt.pool_size)
+            self._pool = None          # dict(op=Operand [pool_size, H, W, cs], num=stored images, dec=int32 [B, 2] on the device)
             self.old_lr = opt.lr
             self.vgg = None
             if not opt.no_vgg_loss:
@@ -327,7 +329,7 @@ class Pix2PixHDModel_condImg(object):
         g_in = Operand(ctx, B, H, W, self.netG_input_nc, border=3)
         d_in = v_in = d_mask = None
         if train:
-            d_in = Operand(ctx, 2 * B, H, W, self.netD_input_nc)
+            d_in = Operand(ctx, self._d_segments() * B, H, W, self.netD_input_nc)   # [fake ; real (; pooled fakes)]
             if self.vgg is not None:
                 v_in = Operand(ctx, 2 * B, H, W, 3)
             if opt.mask_gan_input:                                   # :217 mask_cond
@@ -365,6 +367,11 @@ class Pix2PixHDModel_condImg(object):
         ops.finish_fake(ctx, t, st["image"], st["mask"], opt.use_output_gate, fake, st["d_in"], self.d_img_c0, st["v_in"],
                         d_mask=st["d_mask"])
         st.update(t=t, g_tape=g_tape, fake=fake)
+        if self._d_segments() == 3:           # discriminate(..., use_pool=True), :182-184: third segment = pool.query(fake half)
+            pool, d_in = self._pool, st["d_in"]
+            cur, out = d_in.images(0, B), d_in.images(2 * B, B)
+            for b in range(B):
+                ops.pool_exchange(ctx, cur, pool["op"], out, pool["dec"], b)
         acc = self.loss_acc
         acc.zero_()
         side = self._side_stream() if self.vgg is not None else None
@@ -376,14 +383,15 @@ class Pix2PixHDModel_condImg(object):
         st["d_tape"] = self.netD.forward(st["d_in"])
         for lv in st["d_tape"]:
             pred = lv["taps"][-1]
-            half = pred.numel() // 2
+            nseg = self._d_segments()
+            half = pred.numel() // nseg
             ops.mse_sum(ctx, pred[:B], 1.0, 1.0 / half, acc, 0)      # G_GAN  (:232)
-            ops.mse_sum(ctx, pred[B:], 1.0, 1.0 / half, acc, 3)      # D_real (:223)
-            ops.mse_sum(ctx, pred[:B], 0.0, 1.0 / half, acc, 4)      # D_fake (:219)
+            ops.mse_sum(ctx, pred[B:2 * B], 1.0, 1.0 / half, acc, 3)  # D_real (:223)
+            ops.mse_sum(ctx, pred[2 * B:] if nseg == 3 else pred[:B], 0.0, 1.0 / half, acc, 4)   # D_fake (:219; pool :182-184)
             if not opt.no_ganFeat_loss:                               # :235-242
                 cf = (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
                 for tap in lv["taps"][:-1]:
-                    ops.l1_sum(ctx, tap[:B], tap[B:], cf / (tap.numel() // 2), acc, 1)
+                    ops.l1_sum(ctx, tap[:B], tap[B:2 * B], cf / (tap.numel() // nseg), acc, 1)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         elif self.vgg is not None:                                    # :245-247
@@ -434,6 +442,8 @@ class Pix2PixHDModel_condImg(object):
     def forward(self, label, inst, image, feat, mask_in, mask_out, infer=False):
         """pix2pixHD_condImg_model.py:198-259.  Inputs are the reference's CPU NCHW tensors; returns
         [[G_GAN, G_GAN_Feat, G_VGG, D_real, D_fake], fake_image | None] with differentiable scalar losses."""
+        if self.isTrain:
+            self._pool_decide(label)
         st = self._forward_all(label, inst, image, mask_in, mask_out)
         self._step = st
         lg = _LossFn.apply(self._anchor, self, "G", st["losses"][:3])
@@ -459,7 +469,7 @@ class Pix2PixHDModel_condImg(object):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 gV = self.vgg.backward(st["v_tape"], B, [w[2] * opt.lambda_feat * wi for wi in VGG_WEIGHTS])
-        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.d_img_c0)
+        gD = self.netD.backward(st["d_tape"], B, "G", w_gan=w[0], w_feat=cf, img_c0=self.d_img_c0, nseg=self._d_segments())
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         elif self.vgg is not None and w[2] != 0.0:
@@ -478,7 +488,39 @@ class Pix2PixHDModel_condImg(object):
     def _backward_D(self, w):
         """d(w0*D_real + w1*D_fake)/d(D params) over the [fake ; real] batch."""
         st = self._step
-        self.netD.backward(st["d_tape"], st["B"], "D", w_real=w[0], w_fake=w[1])
+        self.netD.backward(st["d_tape"], st["B"], "D", w_real=w[0], w_fake=w[1], nseg=self._d_segments())
+
+    # ---- image pool (util/image_pool.py; --pool_size > 0) ---------------------------------------------------------------
+    def _d_segments(self):
+        """Images per sample the discriminator evaluates in training: [fake ; real], plus the pool's answer when it is on."""
+        return 3 if (self.isTrain and getattr(self, "pool_size", 0) > 0) else 2
+
+    def _pool_decide(self, label):
+        """ImagePool.query's host half, called once per forward BEFORE anything is enqueued (so it also works when the
+        step is a CUDA-graph replay): draws the reference's decisions in the reference's order from python's `random`
+        -- store while the pool fills, then per image uniform(0, 1) > 0.5 ? exchange with slot randint(0, size - 1) :
+        pass -- and ships them to the device tensor the hm_pool_exchange launches read."""
+        if self._d_segments() != 3:
+            return
+        import random
+        B, _, H, W = label.shape
+        p = self._pool
+        if p is None or p["sig"] != (B, H, W):
+            op = Operand(self.ctx, self.pool_size, H, W, self.netD_input_nc, zero=True)
+            p = self._pool = dict(op=op, num=0, sig=(B, H, W), dec=torch.zeros(B, 2, dtype=torch.int32, device=self.device),
+                                  host=[torch.zeros(B, 2, dtype=torch.int32).pin_memory() for _ in range(8)], turn=0)
+        # the H2D copy below is asynchronous: rotate the pinned staging buffers so that a queued copy is never overwritten
+        host = p["host"][p["turn"] % len(p["host"])]
+        p["turn"] += 1
+        for b in range(B):
+            if p["num"] < self.pool_size:
+                host[b, 0], host[b, 1] = 1, p["num"]
+                p["num"] += 1
+            elif random.uniform(0, 1) > 0.5:
+                host[b, 0], host[b, 1] = 2, random.randint(0, self.pool_size - 1)
+            else:
+                host[b, 0], host[b, 1] = 0, 0
+        p["dec"].copy_(host, non_blocking=True)
 
     def optimize_parameters(self, label=None, inst=None, image=None, feat=None, mask_in=None, mask_out=None):
         """Fused step: forward, G backward, D backward, one allreduce of [G | D] grads, Adam x2.
@@ -491,6 +533,7 @@ class Pix2PixHDModel_condImg(object):
         soft = self.opt.mask_gan_input and self.opt.use_soft_mask
         batch = dict(label=label, inst=None if self.opt.no_instance else inst, image=image, mask_in=mask_in,
                      mask_out=mask_out if soft else None)
+        self._pool_decide(label)
         if self._use_graph(batch):
             return self._graph_step(batch)
         self._eager_steps += 1
@@ -503,6 +546,7 @@ class Pix2PixHDModel_condImg(object):
         the fused step but without loss_D's backward pass and the discriminator's Adam step.  Eager (not graphed);
         returns the five losses as a device tensor.  bench.py times it for `g_step_ms`."""
         soft = self.opt.mask_gan_input and self.opt.use_soft_mask
+        self._pool_decide(label)
         return self._fused_step(label, None if self.opt.no_instance else inst, image, mask_in, captured=False,
                                 mask_out=mask_out if soft else None, d_half=False)
 

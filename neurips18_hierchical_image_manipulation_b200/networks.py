@@ -588,7 +588,7 @@ class MultiscaleDiscriminator(object):
                 x = xn
         return tape
 
-    def backward(self, tape, nb, mode, w_gan=1.0, w_feat=0.0, w_real=0.5, w_fake=0.5, img_c0=0):
+    def backward(self, tape, nb, mode, w_gan=1.0, w_feat=0.0, w_real=0.5, w_fake=0.5, img_c0=0, nseg=2):
         """mode 'G': d(w_gan*G_GAN + G_GAN_Feat terms)/d(input) for the first nb images (the fake half); returns the
         fp32 gradient w.r.t. the IMAGE channels [img_c0, img_c0+3) of the full-resolution D input as a [nb,H,W,4] tensor
         (channels 0..2; self.gin_coff = 0).  No weight grads.
@@ -601,7 +601,7 @@ class MultiscaleDiscriminator(object):
             nl = len(layers)
             pred = lv["taps"][-1]
             N = pred.shape[0]
-            half_numel = pred.numel() // 2
+            half_numel = pred.numel() // nseg          # nseg == 3: [fake ; real ; pooled fakes] (--pool_size > 0)
             if mode == "G":
                 nimg = nb
                 dy = Operand(ctx, nimg, pred.shape[1], pred.shape[2], 1, grad=True)
@@ -609,8 +609,12 @@ class MultiscaleDiscriminator(object):
             else:
                 nimg = N
                 dy = Operand(ctx, N, pred.shape[1], pred.shape[2], 1, grad=True)
-                ops.mse_grad(ctx, pred[:nb], 0.0, 2.0 * w_fake / half_numel, dy, 0)   # fake half: target 0
-                ops.mse_grad(ctx, pred[nb:], 1.0, 2.0 * w_real / half_numel, dy, nb)  # real half: target 1
+                if nseg == 2:
+                    ops.mse_grad(ctx, pred[:nb], 0.0, 2.0 * w_fake / half_numel, dy, 0)   # fake half: target 0
+                else:   # loss_D_fake is taken on the image pool's history (third segment); the current fakes carry none
+                    ops.mse_grad(ctx, pred[:nb], 0.0, 0.0, dy, 0)
+                    ops.mse_grad(ctx, pred[2 * nb:], 0.0, 2.0 * w_fake / half_numel, dy, 2 * nb)
+                ops.mse_grad(ctx, pred[nb:2 * nb], 1.0, 2.0 * w_real / half_numel, dy, nb)  # real half: target 1
             for j in range(nl - 1, -1, -1):
                 conv = layers[j]
                 xin = lv["xs"][j]
@@ -635,8 +639,8 @@ class MultiscaleDiscriminator(object):
                 dyn = Operand(ctx, nimg, tap.shape[1], tap.shape[2], tap.shape[3], grad=True)
                 tref, l1 = None, 0.0
                 if mode == "G" and w_feat != 0.0:
-                    tref = tap[nb:]
-                    l1 = w_feat / (tap.numel() // 2)
+                    tref = tap[nb:2 * nb]
+                    l1 = w_feat / (tap.numel() // nseg)
                 y, mean, rstd = lv["ys"][j - 1], lv["means"][j - 1], lv["rstds"][j - 1]
                 ops.in_bwd(ctx, shape, ACT_LRELU, 0.2, y=y[:nimg] if y is not None else None,
                            mean=mean[:nimg] if mean is not None else None, rstd=rstd[:nimg] if rstd is not None else None,

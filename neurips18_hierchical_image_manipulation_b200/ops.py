@@ -390,6 +390,15 @@ def mask_blend_bwd(ctx, g, m, da=None, db=None):
     ctx.launches += 1
 
 
+def pool_exchange(ctx, cur, pool, out, dec, b):
+    """ImagePool.query for image b: cur / out are operands of the batch, pool the stored history, dec int32 [B, 2] on the
+    device (action, slot)."""
+    e = cur.h * cur.w * cur.cs
+    L.check(ctx.lib.hm_pool_exchange(cur.hi.data_ptr(), _ptr(cur.lo), pool.hi.data_ptr(), _ptr(pool.lo), out.hi.data_ptr(),
+                                     _ptr(out.lo), dec.data_ptr(), b, e, _stream()), "hm_pool_exchange")
+    ctx.launches += 1
+
+
 def mask_concat(ctx, a, b, m):
     """relu(cat((1 - m) * a, m * b)) as an operand [N,h,w,2C] (FeatureFusionBlock 'concat'); a, b dense fp32 NHWC."""
     N, h, w, Cc = a.shape

@@ -112,6 +112,36 @@ def _run_case(name, seed, **kw):
     print(name, os.path.getsize(path), [round(float(x), 5) for x in losses])
 
 
+def _run_pool_case(name, seed, iters=4, **kw):
+    """--pool_size > 0 (util/image_pool.py:4-31 through discriminate(..., use_pool=True), :176-186,218): the discriminator's
+    fake pass sees a history of generated inputs.  `iters` forwards on DIFFERENT batches with constant weights; python's
+    `random` (which the pool draws from) is seeded with 100 + it before each forward.  Stored: the five losses of every
+    forward and the discriminator gradients of the last one (its loss_D_fake is evaluated on pooled images)."""
+    import random
+    from models.pix2pixHD_condImg_model import Pix2PixHDModel_condImg
+    torch.manual_seed(seed)
+    opt = _opt(**kw)
+    model = Pix2PixHDModel_condImg(opt)
+    out = dict(iters=np.array(iters))
+    for it in range(iters):
+        batch = _batch(2, 64, 96, opt.label_nc, seed + 100 + it)
+        random.seed(100 + it)
+        losses, _ = model.forward(batch["label"], batch["inst"], batch["image"], None, batch["mask_in"], batch["mask_out"],
+                                  infer=False)
+        losses = [torch.mean(x) if not isinstance(x, (int, float)) else torch.tensor(float(x)) for x in losses]
+        out["losses_%d" % it] = np.array([float(x) for x in losses], dtype=np.float64)
+        out.update({"in%d::%s" % (it, k): v.numpy() for k, v in batch.items()})
+    ld = dict(zip(model.loss_names, losses))
+    model.optimizer_D.zero_grad()
+    ((ld["D_fake"] + ld["D_real"]) * 0.5).backward()
+    out.update({"gD::" + k: p.grad.detach().numpy().copy() for k, p in model.netD.named_parameters()})
+    out.update({"wG::" + k: v.detach().numpy() for k, v in model.netG.state_dict().items()})
+    out.update({"wD::" + k: v.detach().numpy() for k, v in model.netD.state_dict().items()})
+    path = os.path.join(OUT, "model_%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path), [[round(float(x), 5) for x in out["losses_%d" % it]] for it in range(iters)])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -129,6 +159,8 @@ def main():
         # before the masked fusion, ceil(n/2) blocks embed the fused feature
         _run_case("twostream_late_add", 24, netG="global_twostream", which_encoder="ctx_label", feat_fusion="late_add",
                   use_skip=True, use_output_gate=True, no_instance=True, n_downsample_global=2, n_blocks_global=3)
+    if "pool" in sys.argv[1:] or len(sys.argv) == 1:
+        _run_pool_case("global_pool", 27, netG="global", use_output_gate=True, no_instance=True, pool_size=3)
     if "concat" in sys.argv[1:] or len(sys.argv) == 1:
         # feat_fusion '*_concat' (layer_util.py:305-327): cat -> ReLU -> 1x1 conv -> norm instead of the sum
         _run_case("twostream_early_concat", 25, netG="global_twostream", which_encoder="ctx_label", feat_fusion="early_concat",

@@ -302,7 +302,34 @@ class Opt(object):
             setattr(self, k, v)
 
 
-def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=torch.float32, mask_out=None):
+class ImagePool(object):
+    """util/image_pool.py:4-31: history of discriminator inputs.  While the pool is filling, images are stored and returned;
+    afterwards each image is, with probability 1/2 (python's `random`, one uniform(0, 1) draw per image and one randint
+    per swap), exchanged with a random stored one."""
+
+    def __init__(self, pool_size):
+        self.pool_size, self.images = pool_size, []
+
+    def query(self, images):
+        import random
+        if self.pool_size == 0:
+            return images
+        out = []
+        for i in range(images.shape[0]):
+            img = images[i:i + 1].detach()
+            if len(self.images) < self.pool_size:
+                self.images.append(img)
+                out.append(img)
+            elif random.uniform(0, 1) > 0.5:
+                k = random.randint(0, self.pool_size - 1)
+                out.append(self.images[k].clone())
+                self.images[k] = img
+            else:
+                out.append(img)
+        return torch.cat(out, 0)
+
+
+def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=torch.float32, mask_out=None, pool=None):
     """Pix2PixHDModel_condImg.forward, models/pix2pixHD_condImg_model.py:198-259 (netG == 'global' or 'local',
     no_imgCond / mask_gan_input / use_soft_mask off, pool_size 0).
     Returns ([G_GAN, G_GAN_Feat, G_VGG, D_real, D_fake], fake_image, extras)."""
@@ -327,12 +354,14 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
 
     image_only = opt.netG == "global_twostream" and getattr(opt, "which_encoder", "ctx") == "ctx"   # :71-72,178-179,227-228
 
-    def D(test_image):                                                         # discriminate :176-186 / :226-231
+    def D(test_image, use_pool=False):                                         # discriminate :176-186 / :226-231
         x = test_image if image_only else torch.cat((netD_cond, test_image), 1)
         if getattr(opt, "mask_gan_input", False):
             x = x * mask_cond.repeat(1, x.shape[1], 1, 1)
+        if use_pool and pool is not None:                                      # :182-184
+            x = pool.query(x)
         return multiscale_discriminator_forward(d_sd, x, opt.num_D, opt.n_layers_D)
-    pred_fake_pool = D(fake.detach())                                          # :218
+    pred_fake_pool = D(fake.detach(), use_pool=True)                           # :218
     loss_D_fake = gan_loss(pred_fake_pool, False)                              # :219
     pred_real = D(real)                                                        # :222
     loss_D_real = gan_loss(pred_real, True)                                    # :223

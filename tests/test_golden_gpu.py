@@ -213,3 +213,63 @@ def test_training_step_against_the_reference_models_own_forward(golden_dir, name
         return float((a @ r) / (a.norm() * r.norm()))
     assert cosine(gG, part("gG::")) > 0.99
     assert cosine(gD, part("gD::")) > 0.95
+
+
+def test_image_pool_against_the_reference_models_own_forward(golden_dir):
+    """--pool_size 3 (util/image_pool.py through discriminate(..., use_pool=True)): four forwards on different batches with
+    constant weights, python's `random` seeded like the golden run (oracle/make_golden_model.py::_run_pool_case); the five
+    losses of every forward -- loss_D_fake is evaluated on the pool's answer -- and the discriminator gradient direction
+    of the last one."""
+    import random
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    z = np.load(os.path.join(golden_dir, "model_global_pool.npz"))
+    part = lambda p: {k[len(p):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(p)}  # noqa: E731
+    opt = Options(precision="bf16x3", gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="golden_pool", vgg_weights="random",
+                  label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2, ndf=8, num_D=2, n_layers_D=3,
+                  use_output_gate=True, pool_size=3)
+    model = create_model(opt)
+    m = model.module
+    m.fpG.load_state_dict(part("wG::"))
+    m.fpD.load_state_dict(part("wD::"))
+    for it in range(int(z["iters"])):
+        b = part("in%d::" % it)
+        random.seed(100 + it)
+        losses, _ = model(label=b["label"], inst=b["inst"], image=b["image"], feat=None, mask_in=b["mask_in"],
+                          mask_out=b["mask_out"], infer=False)
+        for n_, a, r in zip(m.loss_names, losses, z["losses_%d" % it]):
+            assert abs(float(a) - float(r)) <= 1e-3 * abs(float(r)), (it, n_, float(a), float(r))
+    ld = dict(zip(m.loss_names, [torch.mean(x) for x in losses]))
+    m.optimizer_D.zero_grad()
+    ((ld["D_fake"] + ld["D_real"]) * 0.5).backward()
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    ref = part("gD::")
+    keys = [k for k in ref if k.endswith("weight")]
+    a = torch.cat([m.fpD.params[k].grad.detach().cpu().reshape(-1) for k in keys]).double()
+    r = torch.cat([ref[k].reshape(-1) for k in keys]).double()
+    assert float((a @ r) / (a.norm() * r.norm())) > 0.95
+
+
+def test_image_pool_fused_step_graph_replay_matches_eager():
+    """The pool inside the fused step: its exchanges are kernel launches driven by a device-resident decision tensor, so
+    the CUDA-graph replay and the eager step see the same history (same python `random` seed): losses agree."""
+    import random
+    from neurips18_hierchical_image_manipulation_b200.models import Options, create_model
+    from neurips18_hierchical_image_manipulation_b200.synthetic import synthetic_batch
+    runs = []
+    for graph in (False, True):
+        opt = Options(precision="bf16x3", gpu_ids=[0], checkpoints_dir="/tmp/hm_ckpt", name="pool_graph", vgg_weights="random",
+                      label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2, ndf=8, num_D=2,
+                      n_layers_D=3, use_output_gate=True, pool_size=3, cuda_graph=graph)
+        m = create_model(opt).module
+        random.seed(7)
+        ls = []
+        for i in range(6):
+            d = synthetic_batch(2, 64, 96, 6, seed=50 + i)
+            ls.append(m.optimize_parameters(label=d["label"], inst=d["inst"], image=d["image"], feat=None, mask_in=d["mask_in"],
+                                            mask_out=d["mask_out"]).clone())
+        torch.cuda.synchronize()
+        m.ctx.check_pipeline()
+        assert isinstance(m._graph, dict) == graph and m._pool["num"] == 3
+        runs.append(torch.stack(ls).cpu())
+    assert torch.allclose(runs[0], runs[1], rtol=5e-3, atol=1e-5), (runs[0], runs[1])

@@ -354,3 +354,31 @@ def test_box2mask_switch_net_train_and_eval_mode_against_the_reference_class(gol
     for got, k in zip(outs, ("comb_logit", "comb_prob", "obj_logit", "obj_prob")):
         ref = torch.from_numpy(z["eval_" + k]).double()
         assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5, k
+
+
+def test_image_pool_against_the_reference_model(golden_dir):
+    """--pool_size 3 over four forwards on different batches (oracle/make_golden_model.py::_run_pool_case): the five losses
+    of every forward (loss_D_fake is evaluated on the pool's history) and the discriminator gradients of the last one."""
+    import random
+    z = np.load(os.path.join(golden_dir, "model_global_pool.npz"))
+    part = lambda p: OrderedDict((k[len(p):], torch.from_numpy(z[k])) for k in z.files if k.startswith(p))  # noqa: E731
+    opt = O.Opt(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2, ndf=8, num_D=2,
+                use_output_gate=True, pool_size=3)
+    dt = torch.float64
+    g_par = OrderedDict((k, v.to(dt)) for k, v in part("wG::").items())
+    d_par = OrderedDict((k, v.clone().to(dt).requires_grad_(True)) for k, v in part("wD::").items())
+    vgg = OrderedDict((k, v.to(dt)) for k, v in O.vgg19_random_state_dict().items())
+    pool = O.ImagePool(3)
+    for it in range(int(z["iters"])):
+        b = part("in%d::" % it)
+        random.seed(100 + it)
+        losses, _, _ = O.model_forward(opt, g_par, d_par, vgg, b["label"], b["inst"], b["image"], b["mask_in"], dtype=dt,
+                                       mask_out=b["mask_out"], pool=pool)
+        for a, r in zip(losses, z["losses_%d" % it]):
+            assert abs(float(a) - float(r)) <= 2e-5 * abs(float(r)), (it, float(a), float(r))
+    _, loss_D = O.step_losses(losses)
+    gD = part("gD::")
+    for (k, _), gi in zip(d_par.items(), torch.autograd.grad(loss_D, list(d_par.values()))):
+        if k.endswith("bias") and float(gD[k].abs().max()) < 1e-3 * float(gD[k[:-4] + "weight"].abs().max()):
+            continue
+        close(gi.float(), gD[k], 2e-4)
