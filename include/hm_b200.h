@@ -208,6 +208,11 @@ int hm_maxpool2_bwd(const float* g, int N, int H, int W, int C, const void* a_hi
 int hm_l1_sum(const float* a, const float* b, long n, double coef, double* acc, void* stream);
 int hm_mse_sum(const float* a, long n, float target, double coef, double* acc, void* stream);
 int hm_mse_grad(const float* y, long P, int C, float target, float scale, void* o_hi, void* o_lo, int o_cs, void* stream);
+/* Vanilla GAN (--no_lsgan: GANLoss with nn.BCELoss, models/losses.py:17-20) on the discriminator's raw last-layer output:
+ * hm_bce_sum: *acc += coef * sum BCE(sigmoid(x), target) (logs clamped at -100 like nn.BCELoss);
+ * hm_bce_grad: operand = scale * d/dx BCE(sigmoid(x), target), same conventions as hm_mse_grad. */
+int hm_bce_sum(const float* x, long n, float target, double coef, double* acc, void* stream);
+int hm_bce_grad(const float* x, long P, int C, float target, float scale, void* o_hi, void* o_lo, int o_cs, void* stream);
 
 /* K12. generator head epilogue: output gate (Pix2Pix_NET.py:96-99), NCHW fp32 copy for the caller, fake image into
  * channels [d_coff, d_coff+3) of the first half of the D operand and into the first half of the VGG operand;

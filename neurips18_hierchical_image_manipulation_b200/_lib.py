@@ -79,6 +79,8 @@ PROTOTYPES = {
     "hm_l1_sum": (_i, [_vp, _vp, _l, C.c_double, _vp, _vp]),
     "hm_mse_sum": (_i, [_vp, _l, _f, C.c_double, _vp, _vp]),
     "hm_mse_grad": (_i, [_vp, _l, _i, _f, _f, _vp, _vp, _i, _vp]),
+    "hm_bce_sum": (_i, [_vp, _l, _f, C.c_double, _vp, _vp]),
+    "hm_bce_grad": (_i, [_vp, _l, _i, _f, _f, _vp, _vp, _i, _vp]),
     "hm_finish_fake": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "hm_fake_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _f, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "hm_f32_to_operand": (_i, [_vp, _l, _i, _i, _i, _f, _vp, _vp, _i, _vp]),

@@ -838,6 +838,50 @@ __global__ void mse_grad_kernel(const float* __restrict__ y, long P, int C, floa
   }
 }
 
+// Vanilla GAN (--no_lsgan; GANLoss with nn.BCELoss, models/losses.py:17-20) on the discriminator's raw last-layer output x:
+// p = sigmoid(x) is the nn.Sigmoid the reference appends (Discriminator_NET.py:95-96); BCELoss clamps its logs at -100.
+__global__ void bce_sum_kernel(const float* __restrict__ x, long n, float target, double coef, double* acc) {
+  double sd = 0.0;
+  float s = 0.f;
+  int k = 0;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
+    const float p = 1.f / (1.f + expf(-__ldg(x + i)));
+    s -= target * fmaxf(logf(p), -100.f) + (1.f - target) * fmaxf(logf(1.f - p), -100.f);
+    if (++k == 64) { sd += s; s = 0.f; k = 0; }
+  }
+  sd += s;
+  __shared__ double sm[kBlock];
+  sm[threadIdx.x] = sd;
+  __syncthreads();
+  for (int st = kBlock / 2; st >= 1; st >>= 1) {
+    if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(acc, sm[0] * coef);
+}
+// d/dx of scale * sum BCE(sigmoid(x), t) as a bf16 operand: torch's BCELoss backward (p - t) / max(p (1 - p), 1e-12) times
+// the sigmoid's p (1 - p)
+__global__ void bce_grad_kernel(const float* __restrict__ x, long P, int C, float target, float scale, bf16* o_hi,
+                                bf16* o_lo, int cs) {
+  const int G = cs >> 3;
+  const long total = P * G;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int c = int(i % G) * 8;
+    const long p = i / G;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C) {
+      load8(x + p * C, c, C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pr = 1.f / (1.f + expf(-v[j]));
+        const float q = pr * (1.f - pr);
+        v[j] = (c + j < C) ? scale * (pr - target) * (q / fmaxf(q, 1e-12f)) : 0.f;
+      }
+    }
+    store_op8(o_hi, o_lo, size_t(p) * cs + c, v);
+  }
+}
+
 // ================================================================================================
 // K12  generator output: gate (Pix2Pix_NET.py:96-99), NCHW copy for the caller, D / VGG operand slots
 // ================================================================================================
@@ -1341,6 +1385,18 @@ int hm_mse_grad(const float* y, long P, int C, float target, float scale, void* 
   if (!y || !o_hi || (o_cs & 7) || o_cs < C) return HM_ERR_INVALID;
   mse_grad_kernel<<<grid_for(P * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       y, P, C, target, scale, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
+  return HM_LAUNCH_OK();
+}
+
+int hm_bce_sum(const float* x, long n, float target, double coef, double* acc, void* stream) {
+  if (!x || !acc) return HM_ERR_INVALID;
+  bce_sum_kernel<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(x, n, target, coef, acc);
+  return HM_LAUNCH_OK();
+}
+int hm_bce_grad(const float* x, long P, int C, float target, float scale, void* o_hi, void* o_lo, int o_cs, void* stream) {
+  if (!x || !o_hi || (o_cs & 7) || o_cs < C) return HM_ERR_INVALID;
+  bce_grad_kernel<<<grid_for(P * (o_cs >> 3)), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, P, C, target, scale, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo), o_cs);
   return HM_LAUNCH_OK();
 }
 

@@ -226,8 +226,11 @@ class Pix2PixHDModel_condImg(object):
         # ---- discriminator (:59-81)
         self.netD = None
         if self.isTrain:
-            if opt.no_lsgan:
-                raise NotImplementedError("no_lsgan (vanilla GAN loss) is outside this path")
+            if opt.no_lsgan and not opt.no_ganFeat_loss:
+                # the reference's feature-matching discriminator never applies the Sigmoid it appends
+                # (Discriminator_NET.py:111-114 loops over n_layers + 2 sub-models), so nn.BCELoss would see raw logits
+                raise NotImplementedError("--no_lsgan is only defined together with --no_ganFeat_loss (the reference's "
+                                          "getIntermFeat discriminator skips its Sigmoid, Discriminator_NET.py:111-114)")
             # :61-70  --no_imgCond drops the masked image from the D conditioning, --mask_gan_input multiplies the D
             # input by mask_in (mask_out with --use_soft_mask)
             n_lab = input_nc + (0 if opt.no_instance else 1)
@@ -241,7 +244,8 @@ class Pix2PixHDModel_condImg(object):
             self.fpD = FlatParams(dev)
             self.netD = MultiscaleDiscriminator(self.ctx, self.fpD, netD_input_nc, opt.ndf, opt.n_layers_D, opt.num_D,
                                                 spectral_norm=getattr(opt, "sn_D", False),
-                                                getIntermFeat=not opt.no_ganFeat_loss)   # :75 (state-dict key names)
+                                                getIntermFeat=not opt.no_ganFeat_loss,   # :75 (state-dict key names)
+                                                use_sigmoid=opt.no_lsgan)                # :64
         # one flat buffer [G | D] so data parallelism is a single allreduce
         total = self.fpG.total + (self.fpD.total if self.isTrain else 0)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -385,9 +389,10 @@ class Pix2PixHDModel_condImg(object):
             pred = lv["taps"][-1]
             nseg = self._d_segments()
             half = pred.numel() // nseg
-            ops.mse_sum(ctx, pred[:B], 1.0, 1.0 / half, acc, 0)      # G_GAN  (:232)
-            ops.mse_sum(ctx, pred[B:2 * B], 1.0, 1.0 / half, acc, 3)  # D_real (:223)
-            ops.mse_sum(ctx, pred[2 * B:] if nseg == 3 else pred[:B], 0.0, 1.0 / half, acc, 4)   # D_fake (:219; pool :182-184)
+            bce = bool(opt.no_lsgan)                                    # GANLoss: MSE (LSGAN) or BCE on sigmoid(pred), losses.py:17-20
+            ops.mse_sum(ctx, pred[:B], 1.0, 1.0 / half, acc, 0, bce=bce)      # G_GAN  (:232)
+            ops.mse_sum(ctx, pred[B:2 * B], 1.0, 1.0 / half, acc, 3, bce=bce)  # D_real (:223)
+            ops.mse_sum(ctx, pred[2 * B:] if nseg == 3 else pred[:B], 0.0, 1.0 / half, acc, 4, bce=bce)   # D_fake (:219; pool :182-184)
             if not opt.no_ganFeat_loss:                               # :235-242
                 cf = (1.0 / opt.num_D) * (4.0 / (opt.n_layers_D + 1)) * opt.lambda_feat
                 for tap in lv["taps"][:-1]:

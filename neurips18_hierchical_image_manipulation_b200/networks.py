@@ -486,8 +486,12 @@ class GlobalGenerator(object):
 class MultiscaleDiscriminator(object):
     """models/Discriminator_NET.py:11-118: num_D PatchGANs on an AvgPool(3,2,1) pyramid, every layer output kept."""
 
-    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3, spectral_norm=False, getIntermFeat=True):
+    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=3, spectral_norm=False, getIntermFeat=True,
+                 use_sigmoid=False):
         self.ctx, self.fp = ctx, fp
+        # use_sigmoid (--no_lsgan): the nn.Sigmoid the reference appends (Discriminator_NET.py:95-96) is folded into the
+        # BCE loss / gradient kernels (hm_bce_sum / hm_bce_grad); the last tap stays the raw logit
+        self.use_sigmoid = bool(use_sigmoid)
         self.input_nc, self.n_layers, self.num_D = input_nc, n_layers, num_D
         self.spectral_norm = bool(spectral_norm)
         self._sn = None
@@ -605,16 +609,16 @@ class MultiscaleDiscriminator(object):
             if mode == "G":
                 nimg = nb
                 dy = Operand(ctx, nimg, pred.shape[1], pred.shape[2], 1, grad=True)
-                ops.mse_grad(ctx, pred[:nb], 1.0, 2.0 * w_gan / half_numel, dy)
+                ops.mse_grad(ctx, pred[:nb], 1.0, 2.0 * w_gan / half_numel, dy, bce=self.use_sigmoid)
             else:
                 nimg = N
                 dy = Operand(ctx, N, pred.shape[1], pred.shape[2], 1, grad=True)
                 if nseg == 2:
-                    ops.mse_grad(ctx, pred[:nb], 0.0, 2.0 * w_fake / half_numel, dy, 0)   # fake half: target 0
+                    ops.mse_grad(ctx, pred[:nb], 0.0, 2.0 * w_fake / half_numel, dy, 0, bce=self.use_sigmoid)   # fake half: target 0
                 else:   # loss_D_fake is taken on the image pool's history (third segment); the current fakes carry none
                     ops.mse_grad(ctx, pred[:nb], 0.0, 0.0, dy, 0)
-                    ops.mse_grad(ctx, pred[2 * nb:], 0.0, 2.0 * w_fake / half_numel, dy, 2 * nb)
-                ops.mse_grad(ctx, pred[nb:2 * nb], 1.0, 2.0 * w_real / half_numel, dy, nb)  # real half: target 1
+                    ops.mse_grad(ctx, pred[2 * nb:], 0.0, 2.0 * w_fake / half_numel, dy, 2 * nb, bce=self.use_sigmoid)
+                ops.mse_grad(ctx, pred[nb:2 * nb], 1.0, 2.0 * w_real / half_numel, dy, nb, bce=self.use_sigmoid)  # real half: target 1
             for j in range(nl - 1, -1, -1):
                 conv = layers[j]
                 xin = lv["xs"][j]

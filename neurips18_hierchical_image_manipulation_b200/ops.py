@@ -295,16 +295,25 @@ def l1_sum(ctx, a, b, coef, acc, slot):
     ctx.launches += 1
 
 
-def mse_sum(ctx, a, target, coef, acc, slot):
-    L.check(ctx.lib.hm_mse_sum(a.data_ptr(), a.numel(), float(target), float(coef), acc.data_ptr() + 8 * slot, _stream()),
-            "hm_mse_sum")
+def mse_sum(ctx, a, target, coef, acc, slot, bce=False):
+    """bce=True: BCE(sigmoid(a), target) instead of (a - target)^2 (vanilla GAN, --no_lsgan)."""
+    fn = ctx.lib.hm_bce_sum if bce else ctx.lib.hm_mse_sum
+    L.check(fn(a.data_ptr(), a.numel(), float(target), float(coef), acc.data_ptr() + 8 * slot, _stream()),
+            "hm_bce_sum" if bce else "hm_mse_sum")
     ctx.launches += 1
 
 
-def mse_grad(ctx, y, target, scale, out_op, op_n0=0):
-    """out_op[op_n0 : op_n0 + y.shape[0]] = scale * (y - target)"""
+def mse_grad(ctx, y, target, scale, out_op, op_n0=0, bce=False):
+    """out_op[op_n0 : op_n0 + y.shape[0]] = scale * (y - target); bce=True: scale/2 * d BCE(sigmoid(y), target)/dy (the
+    callers pass 2 * weight / numel, the factor 2 being the square's derivative)."""
     P = y.numel() // y.shape[-1]
     off = op_n0 * out_op.h * out_op.w * out_op.cs * 2
+    if bce:
+        L.check(ctx.lib.hm_bce_grad(y.data_ptr(), P, y.shape[-1], float(target), 0.5 * float(scale), out_op.hi.data_ptr() + off,
+                                    (out_op.lo.data_ptr() + off) if out_op.lo is not None else None, out_op.cs, _stream()),
+                "hm_bce_grad")
+        ctx.launches += 1
+        return
     L.check(ctx.lib.hm_mse_grad(y.data_ptr(), P, y.shape[-1], float(target), float(scale), out_op.hi.data_ptr() + off,
                                 (out_op.lo.data_ptr() + off) if out_op.lo is not None else None, out_op.cs, _stream()),
             "hm_mse_grad")

@@ -159,6 +159,12 @@ def main():
         # before the masked fusion, ceil(n/2) blocks embed the fused feature
         _run_case("twostream_late_add", 24, netG="global_twostream", which_encoder="ctx_label", feat_fusion="late_add",
                   use_skip=True, use_output_gate=True, no_instance=True, n_downsample_global=2, n_blocks_global=3)
+    if "vanilla" in sys.argv[1:] or len(sys.argv) == 1:
+        # --no_lsgan (GANLoss with nn.BCELoss, losses.py:8-20) is only well defined together with --no_ganFeat_loss: the
+        # Sigmoid the discriminator appends (Discriminator_NET.py:95-96) is never applied by its getIntermFeat branch
+        # (:111-114 loops over n_layers + 2 sub-models)
+        _run_case("global_vanilla_gan", 28, netG="global", use_output_gate=True, no_instance=True, no_lsgan=True,
+                  no_ganFeat_loss=True)
     if "pool" in sys.argv[1:] or len(sys.argv) == 1:
         _run_pool_case("global_pool", 27, netG="global", use_output_gate=True, no_instance=True, pool_size=3)
     if "concat" in sys.argv[1:] or len(sys.argv) == 1:

@@ -234,12 +234,17 @@ def vgg_loss(vgg_sd, x, y):
     return loss
 
 
-def gan_loss(pred, target_is_real):
-    """GANLoss.__call__ with use_lsgan=True, models/losses.py:40-50: sum over scales of MSE(last tap, 1|0)."""
+def gan_loss(pred, target_is_real, use_lsgan=True):
+    """GANLoss.__call__, models/losses.py:40-50: sum over scales of MSE(last tap, 1|0) (LSGAN) or, with --no_lsgan,
+    BCE(sigmoid(last tap), 1|0) (:17-20; the Sigmoid is the discriminator's last module, Discriminator_NET.py:95-96 --
+    only applied on its getIntermFeat=False path, i.e. together with --no_ganFeat_loss)."""
     loss = 0
     for p in pred:
         last = p[-1]
         t = torch.full_like(last, 1.0 if target_is_real else 0.0)
+        if not use_lsgan:
+            loss = loss + F.binary_cross_entropy(torch.sigmoid(last), t)
+            continue
         loss = loss + F.mse_loss(last, t)
     return loss
 
@@ -362,11 +367,12 @@ def model_forward(opt, g_sd, d_sd, vgg_sd, label, inst, image, mask_in, dtype=to
             x = pool.query(x)
         return multiscale_discriminator_forward(d_sd, x, opt.num_D, opt.n_layers_D)
     pred_fake_pool = D(fake.detach(), use_pool=True)                           # :218
-    loss_D_fake = gan_loss(pred_fake_pool, False)                              # :219
+    lsgan = not getattr(opt, "no_lsgan", False)
+    loss_D_fake = gan_loss(pred_fake_pool, False, lsgan)                       # :219
     pred_real = D(real)                                                        # :222
-    loss_D_real = gan_loss(pred_real, True)                                    # :223
+    loss_D_real = gan_loss(pred_real, True, lsgan)                             # :223
     pred_fake = D(fake)                                                        # :226-231
-    loss_G_GAN = gan_loss(pred_fake, True)                                     # :232
+    loss_G_GAN = gan_loss(pred_fake, True, lsgan)                              # :232
     loss_G_GAN_Feat = torch.zeros((), dtype=dtype)
     if not opt.no_ganFeat_loss:                                                # :235-242
         feat_weights = 4.0 / (opt.n_layers_D + 1)

@@ -160,6 +160,10 @@ def test_two_stream_generator_forward_and_parameter_gradients(golden_dir):
     ("model_shipped_twostream.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=3, n_blocks_global=2,
                                          ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
                                          which_encoder="ctx_label", use_skip=True, no_imgCond=True, mask_gan_input=True)),
+    # --no_lsgan --no_ganFeat_loss: vanilla GAN (Sigmoid + BCE folded into hm_bce_sum / hm_bce_grad)
+    ("model_global_vanilla_gan.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2,
+                                          ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, no_lsgan=True,
+                                          no_ganFeat_loss=True)),
     # which_encoder == 'ctx' (the option's default): context stream only, the discriminator is fed the bare image
     ("model_twostream_ctx.npz", dict(label_nc=6, no_instance=True, ngf=8, n_downsample_global=2, n_blocks_global=2,
                                      ndf=8, num_D=2, n_layers_D=3, use_output_gate=True, netG="global_twostream",
