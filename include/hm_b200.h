@@ -123,6 +123,18 @@ int hm_conv_dgrad(const hm_operand* dy, const void* w_hi, const void* w_lo, int 
 size_t hm_wgrad_ws_bytes(int KH, int KW, int cp, int cq);
 int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int stride, int pad, float* G_ws,
                   int* err_flag, void* stream);
+/* Dilated variants (nn.Conv2d(..., dilation=d, padding=d): DilatedResnetBlock, models/layer_util.py:255-293, the
+ * --add_dilated_layers latent blocks of MaskTwoStreamConvSwitch_NET.py:101-104): tap (kh, kw) reads x[h + kh*d - pad,
+ * w + kw*d - pad]; dilation == 1 is hm_conv_fprop / hm_conv_dgrad / hm_conv_wgrad exactly.  dilation > 1 needs stride 1 for
+ * the gradients and runs on the generic / CTA-pair engines (the row-streaming engines need adjacent horizontal taps). */
+int hm_conv_fprop_dil(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
+                      const float* bias, int KH, int KW, int stride, int pad, int dilation, int Hout, int Wout, int Cout,
+                      int act, float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream);
+int hm_conv_dgrad_dil(const hm_operand* dy, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
+                      const float* bias, int KH, int KW, int stride, int pad, int dilation, int Hout, int Wout, int Cout,
+                      int act, float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream);
+int hm_conv_wgrad_dil(const hm_operand* P, const hm_operand* Q, int KH, int KW, int stride, int pad, int dilation, float* G_ws,
+                      int* err_flag, void* stream);
 int hm_wgrad_unpack(const float* G_ws, int KH, int KW, int cp, int cq, float* dst, int accumulate, void* stream);
 
 /* ---- tap-unrolled lowering of thin (<= 4 channel) convolutions (hm_thin.cu) ---------------------------------

@@ -57,6 +57,11 @@ PROTOTYPES = {
                            _P(OutBF16), _vp, _vp]),
     "hm_conv_dgrad": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),
                            _P(OutBF16), _vp, _vp]),
+    "hm_conv_fprop_dil": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),
+                               _P(OutBF16), _vp, _vp]),
+    "hm_conv_dgrad_dil": (_i, [_P(Operand), _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _P(OutF32),
+                               _P(OutBF16), _vp, _vp]),
+    "hm_conv_wgrad_dil": (_i, [_P(Operand), _P(Operand), _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hm_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "hm_conv_wgrad": (_i, [_P(Operand), _P(Operand), _i, _i, _i, _i, _vp, _vp, _vp]),
     "hm_wgrad_unpack": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -305,8 +305,13 @@ int make_tmap_weight3(CUtensorMap* m, const void* base, int taps, int rows_pad, 
 struct Tap { int dw, dh, slab; };
 
 // Row-streaming engine (hm_engine_rows.cuh): stride-1 tap grids on wide images with a narrow N tile.
+// Dilated convolutions (hm_conv_*_dil with dilation > 1) have gaps between their horizontal taps: the row-streaming
+// engines, which read all taps of a filter row out of one contiguous row box, are not eligible for them.
+thread_local bool g_dilated = false;
+
 bool rows_eligible(const Tap* taps, int n_taps, int in_stride, int out_sh, int out_sw, int valid_w, int bn) {
   static const int enabled = env_int("HM_ROWS", 1);
+  if (g_dilated) return false;
   if (!enabled || in_stride != 1 || out_sh != 1 || out_sw != 1 || bn > 128 || valid_w < 96 || n_taps > 64) return false;
   int dw_min = taps[0].dw, dw_max = taps[0].dw;
   for (int t = 0; t < n_taps; ++t) { dw_min = std::min(dw_min, taps[t].dw); dw_max = std::max(dw_max, taps[t].dw); }
@@ -486,6 +491,7 @@ int run_mnrows(const hm_operand* P, const hm_operand* Q, int KH, int KW, int pad
 
 bool mnrows_eligible(const hm_operand* P, const hm_operand* Q, int KW, int stride) {
   static const int enabled = env_int("HM_ROWS", 1);
+  if (g_dilated) return false;
   if (!enabled || stride != 1 || KW < 2 || KW > 8 || Q->w < 96) return false;
   // wide layers (>= 4 units on both sides: e.g. the stride-1 256 -> 512 PatchGAN layer at full resolution) belong to the
   // CTA-pair MN-engine: 85 % tensor pipe there against ~40 % for the row-streaming kernel with its 128 x 128 tiles
@@ -607,27 +613,48 @@ int hm_k_pad(int k) { return round_up(k, 64); }
 int hm_conv_fprop(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
                   const float* bias, int KH, int KW, int stride, int pad, int Hout, int Wout, int Cout, int act,
                   float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream) {
-  if (!x || !x->hi || !w_hi || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
+  return hm_conv_fprop_dil(x, w_hi, w_lo, k_pad, rows_pad, bias, KH, KW, stride, pad, 1, Hout, Wout, Cout, act, slope, out32,
+                           out16, err_flag, stream);
+}
+
+int hm_conv_fprop_dil(const hm_operand* x, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
+                      const float* bias, int KH, int KW, int stride, int pad, int dilation, int Hout, int Wout, int Cout,
+                      int act, float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream) {
+  if (!x || !x->hi || !w_hi || KH * KW > 64 || (stride != 1 && stride != 2) || dilation < 1) return HM_ERR_INVALID;
   Tap taps[64];
   int nt = 0;
   for (int kh = 0; kh < KH; ++kh)
-    for (int kw = 0; kw < KW; ++kw) taps[nt++] = Tap{kw - pad, kh - pad, kh * KW + kw};
-  return run_k_engine(x, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, stride, Hout, Wout, 1, 1, 0, 0, Cout, act, slope,
-                      out32, out16, err_flag, static_cast<cudaStream_t>(stream));
+    for (int kw = 0; kw < KW; ++kw) taps[nt++] = Tap{kw * dilation - pad, kh * dilation - pad, kh * KW + kw};
+  g_dilated = dilation > 1;
+  const int rc = run_k_engine(x, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, stride, Hout, Wout, 1, 1, 0, 0, Cout, act,
+                              slope, out32, out16, err_flag, static_cast<cudaStream_t>(stream));
+  g_dilated = false;
+  return rc;
 }
 
 int hm_conv_dgrad(const hm_operand* dy, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
                   const float* bias, int KH, int KW, int stride, int pad, int Hout, int Wout, int Cout, int act,
                   float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream) {
-  if (!dy || !dy->hi || !w_hi || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
+  return hm_conv_dgrad_dil(dy, w_hi, w_lo, k_pad, rows_pad, bias, KH, KW, stride, pad, 1, Hout, Wout, Cout, act, slope, out32,
+                           out16, err_flag, stream);
+}
+
+int hm_conv_dgrad_dil(const hm_operand* dy, const void* w_hi, const void* w_lo, int k_pad, int rows_pad,
+                      const float* bias, int KH, int KW, int stride, int pad, int dilation, int Hout, int Wout, int Cout,
+                      int act, float slope, const hm_out_f32* out32, const hm_out_bf16* out16, int* err_flag, void* stream) {
+  if (!dy || !dy->hi || !w_hi || KH * KW > 64 || (stride != 1 && stride != 2) || dilation < 1 || (dilation > 1 && stride != 1))
+    return HM_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Tap taps[64];
   if (stride == 1) {
     int nt = 0;
     for (int kh = 0; kh < KH; ++kh)
-      for (int kw = 0; kw < KW; ++kw) taps[nt++] = Tap{pad - kw, pad - kh, kh * KW + kw};
-    return run_k_engine(dy, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, 1, Hout, Wout, 1, 1, 0, 0, Cout, act, slope,
-                        out32, out16, err_flag, st);
+      for (int kw = 0; kw < KW; ++kw) taps[nt++] = Tap{pad - kw * dilation, pad - kh * dilation, kh * KW + kw};
+    g_dilated = dilation > 1;
+    const int rc = run_k_engine(dy, w_hi, w_lo, k_pad, rows_pad, bias, taps, nt, 1, Hout, Wout, 1, 1, 0, 0, Cout, act, slope,
+                                out32, out16, err_flag, st);
+    g_dilated = false;
+    return rc;
   }
   // stride 2: four output parity classes, each a dense unit-stride tap-GEMM over its own tap subset
   for (int ph = 0; ph < 2; ++ph)
@@ -659,10 +686,20 @@ size_t hm_wgrad_ws_bytes(int KH, int KW, int cp, int cq) {
 
 int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int stride, int pad, float* G_ws,
                   int* err_flag, void* stream) {
-  if (!P || !Q || !P->hi || !Q->hi || !G_ws || KH * KW > 64 || (stride != 1 && stride != 2)) return HM_ERR_INVALID;
+  return hm_conv_wgrad_dil(P, Q, KH, KW, stride, pad, 1, G_ws, err_flag, stream);
+}
+
+int hm_conv_wgrad_dil(const hm_operand* P, const hm_operand* Q, int KH, int KW, int stride, int pad, int dilation, float* G_ws,
+                      int* err_flag, void* stream) {
+  if (!P || !Q || !P->hi || !Q->hi || !G_ws || KH * KW > 64 || (stride != 1 && stride != 2) || dilation < 1 ||
+      (dilation > 1 && stride != 1))
+    return HM_ERR_INVALID;
   if (P->n != Q->n) return HM_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mnrows_eligible(P, Q, KW, stride)) return run_mnrows(P, Q, KH, KW, pad, G_ws, err_flag, st);
+  g_dilated = dilation > 1;
+  const bool rows = mnrows_eligible(P, Q, KW, stride);
+  g_dilated = false;
+  if (rows) return run_mnrows(P, Q, KH, KW, pad, G_ws, err_flag, st);
   hm::MNParams p;
   std::memset(&p, 0, sizeof(p));
   int tw = 64, th = 1;
@@ -704,7 +741,10 @@ int hm_conv_wgrad(const hm_operand* P, const hm_operand* Q, int KH, int KW, int 
   p.splits = splits;
   p.dwP0 = p.dhP0 = p.dwQ0 = p.dhQ0 = 0;
   for (int kh = 0; kh < KH; ++kh)
-    for (int kw = 0; kw < KW; ++kw) { p.tap_dw[kh * KW + kw] = int16_t(kw - pad); p.tap_dh[kh * KW + kw] = int16_t(kh - pad); }
+    for (int kw = 0; kw < KW; ++kw) {
+      p.tap_dw[kh * KW + kw] = int16_t(kw * dilation - pad);
+      p.tap_dh[kh * KW + kw] = int16_t(kh * dilation - pad);
+    }
   p.G = G_ws;
   p.ldG = p.n_units * 64;
   p.use_atomic = splits > 1;

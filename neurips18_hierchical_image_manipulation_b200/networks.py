@@ -92,16 +92,20 @@ class FlatParams(object):
 class ConvP(object):
     """One Conv2d / ConvTranspose2d: parameter views + lazily packed bf16 weight slabs for the three engine roles."""
 
-    def __init__(self, ctx, fp, name, cin, cout, k, stride, pad, transposed=False):
+    def __init__(self, ctx, fp, name, cin, cout, k, stride, pad, transposed=False, dilation=1, bias=True):
         self.ctx, self.fp, self.name = ctx, fp, name
         self.cin, self.cout, self.k, self.stride, self.pad, self.transposed = cin, cout, k, stride, pad, transposed
+        # dilation > 1: nn.Conv2d(..., dilation=d) of DilatedResnetBlock (layer_util.py:255-293); bias=False: its conv3x3
+        self.dilation, self.has_bias = int(dilation), bool(bias)
+        assert self.dilation == 1 or (stride == 1 and not transposed)
         shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
         fp.declare(name + ".weight", shape)
-        fp.declare(name + ".bias", (cout,))
+        if self.has_bias:
+            fp.declare(name + ".bias", (cout,))
         self._pf = self._pd = None
         self._vf = self._vd = -1
         # thin sides (csrc/hm_thin.cu): generator head / PatchGAN output (cout <= 4), VGG conv1_1 (cin <= 4)
-        plain = THIN and not transposed and stride == 1 and k >= 2
+        plain = THIN and not transposed and stride == 1 and k >= 2 and self.dilation == 1
         self.thin_out = plain and cout <= 4
         self.thin_in = plain and not self.thin_out and cin <= 4 and k * k * cin <= 64
         self._u = None  # (dy, unrolled dy) of the last thin-output gradient call
@@ -114,7 +118,7 @@ class ConvP(object):
 
     @property
     def bias(self):
-        return self.fp.params[self.name + ".bias"]
+        return self.fp.params[self.name + ".bias"] if self.has_bias else None
 
     def init_reference(self, gen):
         """weights_init (models/layer_util.py:9-16): N(0, 0.02) conv weights, torch-default uniform biases."""
@@ -123,7 +127,8 @@ class ConvP(object):
             w.copy_((torch.randn(w.shape, generator=gen) * 0.02).to(w.device))
             fan_in = w.shape[1] * self.k * self.k
             bound = 1.0 / fan_in ** 0.5
-            self.bias.copy_(((torch.rand(self.cout, generator=gen) * 2 - 1) * bound).to(w.device))
+            if self.has_bias:
+                self.bias.copy_(((torch.rand(self.cout, generator=gen) * 2 - 1) * bound).to(w.device))
         self.fp.version += 1
 
     # packed slabs ---------------------------------------------------------------------------------
@@ -206,7 +211,8 @@ class ConvP(object):
         """h, w: stored input dims (incl. any materialised border)."""
         if self.transposed:
             return 2 * h, 2 * w
-        return (h + 2 * zero_pad - self.k) // self.stride + 1, (w + 2 * zero_pad - self.k) // self.stride + 1
+        ke = self.dilation * (self.k - 1) + 1
+        return (h + 2 * zero_pad - ke) // self.stride + 1, (w + 2 * zero_pad - ke) // self.stride + 1
 
     # engine calls -----------------------------------------------------------------------------------
     def forward(self, x, zero_pad, act=ACT_NONE, slope=0.2, out32=None, out16=None, use_bias=True):
@@ -232,7 +238,7 @@ class ConvP(object):
                            out32, out16)
         else:
             ops.conv_fprop(self.ctx, x, self.packed_fwd(), b, self.k, self.k, self.stride, zero_pad, ho, wo, self.cout,
-                           act, slope, out32, out16)
+                           act, slope, out32, out16, dilation=self.dilation)
         return ho, wo
 
     def dgrad(self, dy, x_h, x_w, zero_pad, out32):
@@ -252,7 +258,7 @@ class ConvP(object):
                            out32=out32)
         else:
             ops.conv_dgrad(self.ctx, dy, self.packed_bwd(), None, self.k, self.k, self.stride, zero_pad, x_h, x_w,
-                           self.cin, out32=out32)
+                           self.cin, out32=out32, dilation=self.dilation)
 
     def dgrad_rows(self, dy, x_h, x_w, zero_pad, out32, row0, nrows):
         """dgrad restricted to input channels [row0, row0 + nrows): out32 is [N, x_h, x_w, ld >= nrows].  The generator
@@ -291,8 +297,9 @@ class ConvP(object):
         elif self.transposed:
             ops.conv_wgrad(self.ctx, dy, x, self.k, self.k, 2, self.pad, self.weight.grad, accumulate=True)
         else:
-            ops.conv_wgrad(self.ctx, x, dy, self.k, self.k, self.stride, zero_pad, self.weight.grad, accumulate=True)
-        if bias_grad:
+            ops.conv_wgrad(self.ctx, x, dy, self.k, self.k, self.stride, zero_pad, self.weight.grad, accumulate=True,
+                           dilation=self.dilation)
+        if bias_grad and self.has_bias:
             ops.colsum_operand(self.ctx, dy, self.bias.grad, accumulate=True)
 
 

@@ -145,7 +145,7 @@ class PackedWeight(object):
 
 
 def conv_fprop(ctx, x, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT_NONE, slope=0.2, out32=None,
-               out16=None, out16_coff=0, n0=0, n=None):
+               out16=None, out16_coff=0, n0=0, n=None, dilation=1):
     """x: Operand (stored, incl. border); out32: fp32 [N,hout,wout,cout]; out16: Operand (written at its interior)."""
     xs = x.struct(n0, n)
     o32 = L.OutF32(out32.data_ptr(), hout, wout, out32.shape[-1], 0, 0, 0) if out32 is not None else None
@@ -153,26 +153,26 @@ def conv_fprop(ctx, x, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT_
     if out16 is not None:
         o16 = L.OutBF16(out16.hi.data_ptr(), _ptr(out16.lo), out16.h, out16.w, out16.cs, out16.border, out16.border,
                         out16_coff)
-    L.check(ctx.lib.hm_conv_fprop(C.byref(xs), pw.hi.data_ptr(), _ptr(pw.lo), pw.k_pad, pw.rows_pad, _ptr(bias), kh, kw,
-                                  stride, pad, hout, wout, cout, act, slope, C.byref(o32) if o32 else None,
-                                  C.byref(o16) if o16 else None, ctx.err.data_ptr(), _stream()), "hm_conv_fprop")
+    L.check(ctx.lib.hm_conv_fprop_dil(C.byref(xs), pw.hi.data_ptr(), _ptr(pw.lo), pw.k_pad, pw.rows_pad, _ptr(bias), kh, kw,
+                                      stride, pad, dilation, hout, wout, cout, act, slope, C.byref(o32) if o32 else None,
+                                      C.byref(o16) if o16 else None, ctx.err.data_ptr(), _stream()), "hm_conv_fprop")
     ctx.launches += 1
 
 
 def conv_dgrad(ctx, dy, pw, bias, kh, kw, stride, pad, hout, wout, cout, act=ACT_NONE, slope=0.2, out32=None,
-               out16=None):
+               out16=None, dilation=1):
     ds = dy.struct()
     o32 = L.OutF32(out32.data_ptr(), hout, wout, out32.shape[-1], 0, 0, 0) if out32 is not None else None
     o16 = None
     if out16 is not None:
         o16 = L.OutBF16(out16.hi.data_ptr(), _ptr(out16.lo), out16.h, out16.w, out16.cs, out16.border, out16.border, 0)
-    L.check(ctx.lib.hm_conv_dgrad(C.byref(ds), pw.hi.data_ptr(), _ptr(pw.lo), pw.k_pad, pw.rows_pad, _ptr(bias), kh, kw,
-                                  stride, pad, hout, wout, cout, act, slope, C.byref(o32) if o32 else None,
-                                  C.byref(o16) if o16 else None, ctx.err.data_ptr(), _stream()), "hm_conv_dgrad")
+    L.check(ctx.lib.hm_conv_dgrad_dil(C.byref(ds), pw.hi.data_ptr(), _ptr(pw.lo), pw.k_pad, pw.rows_pad, _ptr(bias), kh, kw,
+                                      stride, pad, dilation, hout, wout, cout, act, slope, C.byref(o32) if o32 else None,
+                                      C.byref(o16) if o16 else None, ctx.err.data_ptr(), _stream()), "hm_conv_dgrad")
     ctx.launches += 4 if stride == 2 else 1
 
 
-def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=0, n=None, unpack_cols=None):
+def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=0, n=None, unpack_cols=None, dilation=1):
     """dst[cq][cp][kh][kw] (+)= sum_pixels P[., y*stride+kh-pad, ., cp] * Q[., y, ., cq].
     unpack_cols=(KW, cq): Q is a tap-unrolled operand with channels (kw, cq) and kw == 1 here; dst is [cq][cp][kh][KW]."""
     ps, qs = P.struct(n0P, n), Q.struct(n0Q, n)
@@ -180,8 +180,8 @@ def conv_wgrad(ctx, P, Q, kh, kw, stride, pad, dst, accumulate=True, n0P=0, n0Q=
         ps.lo = None
         qs.lo = None
     ws = ctx.ws("wgrad", ctx.lib.hm_wgrad_ws_bytes(kh, kw, P.c, Q.c))
-    L.check(ctx.lib.hm_conv_wgrad(C.byref(ps), C.byref(qs), kh, kw, stride, pad, ws.data_ptr(), ctx.err.data_ptr(),
-                                  _stream()), "hm_conv_wgrad")
+    L.check(ctx.lib.hm_conv_wgrad_dil(C.byref(ps), C.byref(qs), kh, kw, stride, pad, dilation, ws.data_ptr(),
+                                      ctx.err.data_ptr(), _stream()), "hm_conv_wgrad")
     if unpack_cols is not None:
         L.check(ctx.lib.hm_wgrad_unpack_cols(ws.data_ptr(), kh, unpack_cols[0], P.c, unpack_cols[1], dst.data_ptr(),
                                              1 if accumulate else 0, _stream()), "hm_wgrad_unpack_cols")

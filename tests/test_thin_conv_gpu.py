@@ -144,3 +144,42 @@ def test_tap_unroll_and_combine_kernels():
     torch.cuda.synchronize()
     ref = bias.view(1, 1, 1, 3) + sum(T[:, :, i:i + 21, i * 3:(i + 1) * 3] for i in range(5))
     assert float((out.cpu() - ref).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("split", [True, False], ids=["x3", "x1"])
+@pytest.mark.parametrize("cin,cout,d,h,w", [(48, 64, 2, 16, 16), (256, 256, 4, 16, 16), (40, 72, 2, 19, 131), (64, 32, 4, 12, 200)])
+def test_dilated_conv3x3_forward_and_gradients(cin, cout, d, h, w, split):
+    """nn.Conv2d(cin, cout, 3, padding=d, dilation=d, bias=False) -- DilatedResnetBlock's conv3x3 (layer_util.py:255-293) --
+    through hm_conv_fprop_dil / hm_conv_dgrad_dil / hm_conv_wgrad_dil against torch CPU fp64; wide rows included (the
+    row-streaming engines must NOT pick these up: their taps are not adjacent)."""
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.networks import ConvP, FlatParams
+    tol = 1e-4 if split else 3e-2
+    ctx = ops.Ctx("cuda:0", split=split)
+    fp = FlatParams(ctx.device)
+    conv = ConvP(ctx, fp, "c", cin, cout, 3, 1, d, dilation=d, bias=False)
+    fp.materialize()
+    conv.init_reference(torch.Generator().manual_seed(4))
+    assert set(fp.params) == {"c.weight"}
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, cin, h, w, generator=g)
+    xin = _operand(ctx, x, 0, reflect=False)
+    assert conv.out_hw(h, w, d) == (h, w)
+    y = torch.full((2, h, w, cout), float("nan"), device="cuda")
+    conv.forward(xin, d, out32=y)
+    xd = x.double().requires_grad_(True)
+    wd = conv.weight.detach().cpu().double().requires_grad_(True)
+    ref = F.conv2d(xd, wd, None, padding=d, dilation=d)
+    torch.cuda.synchronize()
+    assert rel(y.cpu().permute(0, 3, 1, 2).double(), ref.detach()) < tol
+    dy = torch.randn(2, cout, h, w, generator=g)
+    ref.backward(dy.double())
+    dyo = _operand(ctx, dy, 0, reflect=False, grad=True)
+    fp.grad.zero_()
+    conv.wgrad(xin, dyo, d, bias_grad=False)
+    gin = torch.full((2, h, w, cin), float("nan"), device="cuda")
+    conv.dgrad(dyo, h, w, d, gin)
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    assert rel(gin.cpu().permute(0, 3, 1, 2).double(), xd.grad) < tol
+    assert rel(conv.weight.grad.cpu().double(), wd.grad) < tol
