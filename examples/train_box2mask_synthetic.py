@@ -4,6 +4,8 @@ scripts/train_box2mask_city.sh (--use_gan --which_gan patch_multiscale --gan_wei
 The only changed line is the import of create_model.
 
     python examples/train_box2mask_synthetic.py [--iters 20] [--batchSize 16] [--comb]     (--comb: omit --no_comb)
+    python examples/train_box2mask_synthetic.py --ade      (scripts/train_box2mask_ade.sh: 49 classes, --norm_layer instance,
+                                                            --add_dilated_layers, --lr_control, batch 8)
 """
 import argparse
 import os
@@ -24,14 +26,20 @@ def main():
     ap.add_argument("--fineSize", type=int, default=256)
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--comb", action="store_true")
+    ap.add_argument("--ade", action="store_true")
     args = ap.parse_args()
+    extra = dict(label_nc=35, output_nc=35)
+    if args.ade:
+        args.batchSize = min(args.batchSize, 8)
+        extra = dict(label_nc=49, output_nc=49, norm_layer="instance", add_dilated_layers=True, lr_control=True)
     torch.cuda.set_device(0)
-    opt = Options(model="AE_maskgen_twostream", name="synthetic_box2mask", isTrain=True, gpu_ids=[0], label_nc=35, output_nc=35,
+    opt = Options(model="AE_maskgen_twostream", name="synthetic_box2mask", isTrain=True, gpu_ids=[0],
                   use_gan=True, which_gan="patch_multiscale", gan_weight=0.1, num_layers_D=3, ndf=64, use_ganFeat_loss=True,
                   lambda_feat=1.0, which_stream="obj_context", cond_in="ctx_obj", conv_dim=64, conv_size=4, num_layers=3,
-                  num_resnetblocks=1, n_blocks=6, norm_layer="batch", use_output_gate=True, no_comb=not args.comb,
+                  num_resnetblocks=1, n_blocks=6, use_output_gate=True, no_comb=not args.comb,
                   objReconLoss="bce", beta1=0.5, beta2=0.999, lr=0.0002, niter=400, niter_decay=100,
-                  batchSize=args.batchSize, precision=args.precision, checkpoints_dir="./checkpoints")
+                  batchSize=args.batchSize, precision=args.precision, checkpoints_dir="./checkpoints",
+                  **dict(dict(norm_layer="batch"), **extra))
     model = create_model(opt)                                                       # train_box2mask.py:45
     t0 = time.time()
     for i in range(args.iters):

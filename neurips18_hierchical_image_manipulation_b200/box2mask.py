@@ -9,8 +9,9 @@
                             the discriminator's own Adam step (:243-248); `--no_comb` (MaskTwoStreamConvSwitch_NET,
                             :29-32); BatchNorm running statistics and the eval-mode `reconstruct` / `generate` /
                             `evaluate` (:257-335); `save` / `load` / `delete_model` / `update_learning_rate` in the
-                            reference's checkpoint layout (:106-118, 359-383).  `which_gan` 'patch' / 'patch_res',
-                            `--add_dilated_layers`, `--norm_layer instance` and `objReconLoss l1` raise.
+                            reference's checkpoint layout (:106-118, 359-383); `--norm_layer instance` and
+                            `--add_dilated_layers` (what scripts/train_box2mask_ade.sh adds).  `which_gan` 'patch' /
+                            'patch_res' and `objReconLoss l1` raise.
 
 Parameter names are the reference's own ('<params_dict key>.<state_dict key>': conv_encoder_3.deep.1.weight,
 ctx_conv_decoder_1.shortcut.0.weight, latent_encoder.0.conv_block.1.weight, ...), OIHW / IOHW fp32 like the reference, so
@@ -93,12 +94,34 @@ class _BN(object):
                    dgamma=self.gamma.grad, dbeta=self.beta.grad)
 
 
+class _IN(object):
+    """nn.InstanceNorm2d(C, affine=False) (--norm_layer instance, layer_util.py:22-23) with _BN's interface: no
+    parameters, no buffers, the same arithmetic in training and in eval mode."""
+
+    def __init__(self, fp, name, c):
+        self.fp, self.name, self.c = fp, name, c
+        self.training = True
+
+    def init_reference(self, gen):
+        pass
+
+    def apply(self, ctx, y, act, skip=None, out32=None, out_op=None, reflect=True, repeat=1):
+        mean, rstd = ops.in_stats(ctx, y)
+        ops.in_apply(ctx, y, mean, rstd, act, skip=skip, out32=out32, out_op=out_op, reflect=reflect)
+        return mean, rstd
+
+    def backward(self, ctx, y, stats, act, g1, g2=None, out_op=None, out32=None):
+        ops.in_bwd(ctx, tuple(y.shape), act, 0.2, y=y, mean=stats[0], rstd=stats[1], g1=g1, g1_border=0, g2=g2,
+                   out_op=out_op, out32=out32)
+
+
 class MaskTwoStreamConvNet(object):
     def __init__(self, ctx, fp, label_nc, output_nc, conv_dim=64, num_layers=3, conv_size=4, n_blocks=6,
-                 cond_in="ctx_obj", which_stream="obj_context", num_resnetblocks=1, norm_layer="batch", use_simpleRes=False):
-        if which_stream != "obj_context" or num_resnetblocks != 1 or norm_layer != "batch" or use_simpleRes:
-            raise NotImplementedError("box2mask: only the shipped configuration (which_stream obj_context, one conv per "
-                                      "block, batch norm, ConvResnetBlock) is part of this slice")
+                 cond_in="ctx_obj", which_stream="obj_context", num_resnetblocks=1, norm_layer="batch", use_simpleRes=False,
+                 add_dilated_layers=False):
+        if which_stream != "obj_context" or num_resnetblocks != 1 or norm_layer not in ("batch", "instance") or use_simpleRes:
+            raise NotImplementedError("box2mask: only the shipped configurations (which_stream obj_context, one conv per "
+                                      "block, batch or instance norm, ConvResnetBlock) are part of this slice")
         if conv_size % 2 != 0:
             raise NotImplementedError("box2mask: odd conv_size selects the upsample+conv decoder (layer_util.py:196-209)")
         self.ctx, self.fp = ctx, fp
@@ -114,7 +137,7 @@ class MaskTwoStreamConvNet(object):
             return c
 
         def bn(name, c):
-            b = _BN(fp, name, c)
+            b = (_BN if norm_layer == "batch" else _IN)(fp, name, c)
             self.bns_.append(b)
             return b
         # shared encoder (:63-90)
@@ -128,14 +151,24 @@ class MaskTwoStreamConvNet(object):
                                         short_bn=bn(p + ".shortcut.1", dims[i + 1])))
         self.latent_dim = dims[num_layers]
 
-        def res_blocks(prefix, n):
+        def res_blocks(prefix, n, first=0):
             out = []
-            for j in range(n):
+            for j in range(first, first + n):
                 p = "%s.%d.conv_block" % (prefix, j)
                 out.append(dict(c1=conv(p + ".1", self.latent_dim, self.latent_dim, 3, 1, 0), b1=bn(p + ".2", self.latent_dim),
                                 c2=conv(p + ".5", self.latent_dim, self.latent_dim, 3, 1, 0), b2=bn(p + ".6", self.latent_dim)))
             return out
-        self.latent_encoder = res_blocks("latent_encoder", n_blocks // 2)               # :92-106
+        # --add_dilated_layers (MaskTwoStreamConvSwitch_NET.py:101-104): two DilatedResnetBlocks (dilation 2 and 4, conv3x3
+        # without bias, layer_util.py:255-293) in front of the latent encoder's ResnetBlocks
+        self.dilated = []
+        if add_dilated_layers:
+            for j, d in enumerate((2, 4)):
+                p = "latent_encoder.%d" % j
+                self.dilated.append(dict(d=d, c1=conv(p + ".conv1", self.latent_dim, self.latent_dim, 3, 1, d, dilation=d, bias=False),
+                                         b1=bn(p + ".bn1", self.latent_dim),
+                                         c2=conv(p + ".conv2", self.latent_dim, self.latent_dim, 3, 1, d, dilation=d, bias=False),
+                                         b2=bn(p + ".bn2", self.latent_dim)))
+        self.latent_encoder = res_blocks("latent_encoder", n_blocks // 2, first=len(self.dilated))      # :92-106
 
         def decoder(stream, out_nc, skips):                                               # :108-155
             blocks, out_dim = [], self.latent_dim
@@ -190,6 +223,42 @@ class MaskTwoStreamConvNet(object):
         st2 = blk["b2"].apply(ctx, y2, ACT_NONE, skip=x32, out32=out32, out_op=out_op, reflect=True)
         tape.append(dict(blk=blk, x_op=x_op, y1=y, st1=st1, mid=mid, y2=y2, st2=st2))
         return out32, out_op
+
+    def _dilated_block(self, blk, x32, tape):
+        """DilatedResnetBlock (layer_util.py:277-293): relu(norm(conv_d(relu(norm(conv_d(x))))) + x), zero padding = dilation."""
+        ctx, d = self.ctx, blk["d"]
+        N, H, W, C = x32.shape
+        x_op = Operand(ctx, N, H, W, C)
+        ops.in_apply(ctx, x32, None, None, ACT_NONE, out_op=x_op, reflect=False)
+        y1 = _f32(ctx, N, H, W, C)
+        blk["c1"].forward(x_op, d, out32=y1)
+        mid = Operand(ctx, N, H, W, C)
+        st1 = blk["b1"].apply(ctx, y1, ACT_RELU, out_op=mid, reflect=False)
+        y2 = _f32(ctx, N, H, W, C)
+        blk["c2"].forward(mid, d, out32=y2)
+        pre = _f32(ctx, N, H, W, C)
+        st2 = blk["b2"].apply(ctx, y2, ACT_NONE, skip=x32, out32=pre, reflect=False)
+        out32 = _f32(ctx, N, H, W, C)
+        ops.in_apply(ctx, pre, None, None, ACT_RELU, out32=out32, reflect=False)        # the block's trailing ReLU
+        tape.append(dict(blk=blk, x_op=x_op, y1=y1, st1=st1, mid=mid, y2=y2, st2=st2, out=out32))
+        return out32
+
+    def _dilated_block_bwd(self, t, g_out):
+        ctx, blk, d = self.ctx, t["blk"], t["blk"]["d"]
+        N, H, W, C = g_out.shape
+        g_pre = _f32(ctx, N, H, W, C)
+        ops.in_bwd(ctx, (N, H, W, C), ACT_RELU, z=t["out"], g2=g_out, out32=g_pre)      # through the trailing ReLU
+        dy2 = Operand(ctx, N, H, W, C, grad=True)
+        blk["b2"].backward(ctx, t["y2"], t["st2"], ACT_NONE, g_pre, out_op=dy2)
+        blk["c2"].wgrad(t["mid"], dy2, d, bias_grad=False)
+        gmid = _f32(ctx, N, H, W, C)
+        blk["c2"].dgrad(dy2, H, W, d, gmid)
+        dy1 = Operand(ctx, N, H, W, C, grad=True)
+        blk["b1"].backward(ctx, t["y1"], t["st1"], ACT_RELU, gmid, out_op=dy1)
+        blk["c1"].wgrad(t["x_op"], dy1, d, bias_grad=False)
+        gx = _f32(ctx, N, H, W, C)
+        blk["c1"].dgrad(dy1, H, W, d, gx)
+        return self._add(gx, g_pre)                                                     # + the identity branch
 
     def _decode(self, latent32, latent_op, res, blocks, final, skips):
         ctx = self.ctx
@@ -257,6 +326,9 @@ class MaskTwoStreamConvNet(object):
                 cur = Operand(ctx, N, ho, wo, c)                           # rectified in place by the next block
                 ops.in_apply(ctx, h32, None, None, ACT_RELU, out_op=cur, reflect=False)
                 skips.append(cur)
+        tape["dil"] = []
+        for blk in self.dilated:
+            h32 = self._dilated_block(blk, h32, tape["dil"])
         lat_op = Operand(ctx, N, h32.shape[1], h32.shape[2], h32.shape[3], border=1)
         ops.in_apply(ctx, h32, None, None, ACT_NONE, out_op=lat_op, reflect=True)
         lat32 = h32
@@ -340,6 +412,8 @@ class MaskTwoStreamConvNet(object):
         g_lat = self._add(self._decode_bwd(tape["ctx"], d_ctx, skip_grads), self._decode_bwd(tape["obj"], d_obj, skip_grads))
         for t in reversed(tape["lat"]):
             g_lat = self._res_block_bwd(t, g_lat)
+        for t in reversed(tape["dil"]):
+            g_lat = self._dilated_block_bwd(t, g_lat)
         g_h = g_lat                                                        # w.r.t. the last encoder block's output
         for i in range(len(tape["enc"]) - 1, -1, -1):
             t = tape["enc"][i]
@@ -386,8 +460,9 @@ class BNMultiscaleDiscriminator(object):
     BatchNorm runs in training mode: every pass is normalised with its own batch statistics, which is why the real and
     the fake batch are evaluated separately (unlike the InstanceNorm discriminator of mask2image)."""
 
-    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=2):
+    def __init__(self, ctx, fp, input_nc, ndf=64, n_layers=3, num_D=2, norm_layer="batch"):
         self.ctx, self.fp, self.input_nc, self.n_layers, self.num_D = ctx, fp, input_nc, n_layers, num_D
+        norm = _BN if norm_layer == "batch" else _IN      # --norm_layer instance: InstanceNorm2d(affine=False), no parameters
         self.scales, self.convs_, self.bns_ = [], [], []
         for s in range(num_D):
             layers, nf, nf_prev = [], ndf, input_nc
@@ -395,7 +470,7 @@ class BNMultiscaleDiscriminator(object):
                 name = "scale%d_layer%d" % (s, j)
                 cout = 1 if j == n_layers + 1 else nf
                 conv = ConvP(ctx, fp, name + ".0", nf_prev, cout, 4, 2 if j < n_layers else 1, 2)
-                bn = _BN(fp, name + ".1", cout) if 1 <= j <= n_layers else None
+                bn = norm(fp, name + ".1", cout) if 1 <= j <= n_layers else None
                 layers.append((conv, bn))
                 self.convs_.append(conv)
                 if bn is not None:
@@ -480,9 +555,13 @@ class BNMultiscaleDiscriminator(object):
                     ops.in_bwd(ctx, tuple(tap.shape), ops.ACT_LRELU, 0.2, z=tap, g1=gin, g1_border=0, out_op=dyn)
                 else:
                     st = lv["stats"][j - 1]
-                    ops.bn_bwd(ctx, lv["ys"][j - 1], st[0], st[1], bn.gamma, bn.beta, ops.ACT_LRELU, gin, out_op=dyn,
-                               dgamma=bn.gamma.grad if weight_grads else None,
-                               dbeta=bn.beta.grad if weight_grads else None, slope=0.2)
+                    if isinstance(bn, _IN):
+                        ops.in_bwd(ctx, tuple(tap.shape), ops.ACT_LRELU, 0.2, y=lv["ys"][j - 1], mean=st[0], rstd=st[1], g1=gin,
+                                   g1_border=0, out_op=dyn)
+                    else:
+                        ops.bn_bwd(ctx, lv["ys"][j - 1], st[0], st[1], bn.gamma, bn.beta, ops.ACT_LRELU, gin, out_op=dyn,
+                                   dgamma=bn.gamma.grad if weight_grads else None,
+                                   dbeta=bn.beta.grad if weight_grads else None, slope=0.2)
                 dy = dyn
         if weight_grads:
             return None
@@ -525,8 +604,8 @@ class TwoStreamAE_mask(object):
         # --no_comb selects MaskTwoStreamConvSwitch_NET (:29-32): the same network, but its forward returns the context
         # stream's logits / log-softmax as they are instead of gating them with the object stream (:208 vs :190-217)
         self.no_comb = bool(getattr(opt, "no_comb", False))
-        if self.no_comb and getattr(opt, "add_dilated_layers", False):
-            raise NotImplementedError("--add_dilated_layers (DilatedResnetBlock, MaskTwoStreamConvSwitch_NET.py:101-104)")
+        # --add_dilated_layers only exists in the Switch network (MaskTwoStreamConvSwitch_NET.py:29,101-104)
+        dilated = bool(getattr(opt, "add_dilated_layers", False)) and self.no_comb
         self.isTrain = bool(getattr(opt, "isTrain", True))
         self.gpu_ids = opt.gpu_ids
         self.save_dir = os.path.join(getattr(opt, "checkpoints_dir", "./checkpoints"), opt.name)
@@ -540,7 +619,7 @@ class TwoStreamAE_mask(object):
         self.netG = MaskTwoStreamConvNet(self.ctx, self.fpG, opt.label_nc, opt.output_nc, opt.conv_dim, opt.num_layers,
                                          opt.conv_size, opt.n_blocks, opt.cond_in, opt.which_stream,
                                          getattr(opt, "num_resnetblocks", 1), getattr(opt, "norm_layer", "batch"),
-                                         getattr(opt, "use_simpleRes", False))
+                                         getattr(opt, "use_simpleRes", False), add_dilated_layers=dilated)
         self.fpG.materialize()
         self.netG.init_reference(torch.Generator().manual_seed(getattr(opt, "init_seed", 0)))
         self.loss_names = ["G_Recon_comb", "G_Recon_obj", "KL_loss", "loss_G_GAN", "loss_D_GAN", "loss_G_GAN_Feat"]
@@ -563,7 +642,7 @@ class TwoStreamAE_mask(object):
             self.num_layers_D = int(getattr(opt, "num_layers_D", 4))
             self.fpD = FlatParams(dev)
             self.netD = BNMultiscaleDiscriminator(self.ctx, self.fpD, 1 + cond_nc, getattr(opt, "ndf", 64),
-                                                  self.num_layers_D, 2)
+                                                  self.num_layers_D, 2, norm_layer=getattr(opt, "norm_layer", "batch"))
             self.fpD.materialize()
             self.netD.init_reference(torch.Generator().manual_seed(getattr(opt, "init_seed", 0) + 1))
             self.optimizer_D = FusedAdam(self.ctx, self.fpD, self.old_lr, (getattr(opt, "beta1", 0.9), 0.999))
@@ -796,6 +875,7 @@ class TwoStreamAE_mask(object):
         for k, v in self.fpG.state_dict().items():
             mk, rest = k.split(".", 1)
             net.setdefault(mk, OrderedDict())[rest] = v
+        net.setdefault("conv_encoder_1", OrderedDict())       # InstanceNorm2d(affine=False): an empty state dict
         net.setdefault("conv_encoder_2", OrderedDict())
         return net
 

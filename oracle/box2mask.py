@@ -28,10 +28,18 @@ DIM_LIST_TAIL = [96, 128, 256, 512]   # MaskTwoStreamConv_NET.py:25 ("this part 
 _BN_MODE = [None]
 
 
+_NORM = ["batch"]            # norm_layer of the current forward pass: 'batch' | 'instance' (layer_util.py:19-26)
+
+
 def batch_norm(sd, key, x, eps=1e-5):
-    """nn.BatchNorm2d(affine=True) (layer_util.py:19-21 with norm_layer == 'batch').  Training mode: biased batch
+    """The network's norm layer.  norm_layer == 'instance': nn.InstanceNorm2d(affine=False), no parameters, no buffers.
+    norm_layer == 'batch': nn.BatchNorm2d(affine=True) (layer_util.py:19-21).  Training mode: biased batch
     statistics over (N, H, W); the running buffers (momentum 0.1, unbiased variance) do not enter the result.  Eval mode:
     the running buffers."""
+    if _NORM[0] == "instance":
+        mean = x.mean(dim=(2, 3), keepdim=True)
+        var = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+        return (x - mean) / torch.sqrt(var + eps)
     g, b = sd[key + ".weight"].view(1, -1, 1, 1), sd[key + ".bias"].view(1, -1, 1, 1)
     if _BN_MODE[0] == "eval":
         mean, var = sd[key + ".running_mean"].view(1, -1, 1, 1), sd[key + ".running_var"].view(1, -1, 1, 1)
@@ -82,19 +90,29 @@ def resnet_block(sd, p, x):
     return x + batch_norm(sd, p + ".conv_block.6", h)
 
 
-def two_stream_forward(sd, cond, num_layers=3, n_blocks=6, conv_size=4, no_comb=False, bn_mode=None):
+def dilated_resnet_block(sd, p, x, d):
+    """DilatedResnetBlock(dim, dim, dilation=(d, d), activation_fn=norm) (layer_util.py:260-293): conv3x3 (no bias, padding
+    = dilation = d), norm, ReLU, conv3x3, norm, + x, ReLU."""
+    out = F.conv2d(x, sd[p + ".conv1.weight"], None, padding=d, dilation=d)
+    out = F.relu(batch_norm(sd, p + ".bn1", out))
+    out = F.conv2d(out, sd[p + ".conv2.weight"], None, padding=d, dilation=d)
+    return F.relu(batch_norm(sd, p + ".bn2", out) + x)
+
+
+def two_stream_forward(sd, cond, num_layers=3, n_blocks=6, conv_size=4, no_comb=False, bn_mode=None, norm_layer="batch",
+                       add_dilated_layers=False):
     """MaskTwoStreamConv_NET.forward (:159-219), which_stream == 'obj_context'; no_comb: MaskTwoStreamConvSwitch_NET
     (--no_comb), the same network whose forward returns the context stream as it is (:208).
     cond: [B, input_nc, S, S] (cond_in 'ctx_obj': object box mask in its class channel | one-hot context).
     bn_mode: see _BN_MODE.  Returns (comb_logit, comb_logprob, obj_logit, obj_prob)."""
-    _BN_MODE[0] = bn_mode
+    _BN_MODE[0], _NORM[0] = bn_mode, norm_layer
     try:
-        return _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb)
+        return _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb, add_dilated_layers)
     finally:
-        _BN_MODE[0] = None
+        _BN_MODE[0], _NORM[0] = None, "batch"
 
 
-def _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb):
+def _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb, add_dilated_layers=False):
     # shared encoder (:63-90): Conv 7x7 stride 2 pad 3, norm, ReLU, then num_layers ConvResnetBlocks
     h = F.conv2d(cond, sd["conv_encoder_0.weight"], sd["conv_encoder_0.bias"], stride=2, padding=3)
     h = F.relu(batch_norm(sd, "conv_encoder_1", h))
@@ -104,8 +122,13 @@ def _two_stream_forward(sd, cond, num_layers, n_blocks, conv_size, no_comb):
         enc_features[-1] = prev_rectified             # the kept feature was rectified in place by this block
         if i < num_layers - 1:
             enc_features.append(h)
+    j0 = 0
+    if add_dilated_layers:                            # --add_dilated_layers (MaskTwoStreamConvSwitch_NET.py:101-104)
+        h = dilated_resnet_block(sd, "latent_encoder.0", h, 2)
+        h = dilated_resnet_block(sd, "latent_encoder.1", h, 4)
+        j0 = 2
     for j in range(n_blocks // 2):                    # latent encoder (:92-106)
-        h = resnet_block(sd, "latent_encoder.%d" % j, h)
+        h = resnet_block(sd, "latent_encoder.%d" % (j0 + j), h)
     latent = h
 
     def decode(stream, skips):

@@ -45,7 +45,67 @@ def build_switch(cfg):
     return net, LU, ML
 
 
+def ade_case():
+    """The flag set of scripts/train_box2mask_ade.sh that differs from the Cityscapes one: --norm_layer instance
+    (InstanceNorm2d(affine=False) everywhere) and --add_dilated_layers (two DilatedResnetBlocks, dilation 2 and 4, in front
+    of the latent encoder, MaskTwoStreamConvSwitch_NET.py:101-104).  Stored: the four outputs, both reconstruction losses
+    and the gradient of their sum w.r.t. every parameter (full tensors up to 4096 elements, sum / L1 / projection beyond)."""
+    from oracle.weights import named_param
+    cfg = dict(G.CFG, norm_layer="instance")
+    torch.manual_seed(7)
+    G.import_reference()
+    import MaskTwoStreamConvSwitch_NET as MS
+    import mask_losses as ML
+    opt = types.SimpleNamespace(add_dilated_layers=True, **cfg)
+    net = MS.MaskTwoStreamConvSwitch_NET(opt)
+    net.conv_encoder_modules = net.get_conv_encoder()
+    net.latent_encoder = net.get_latent_encoder()
+    net.obj_conv_decoder_modules = net.get_conv_decoder(output_nc=1, skip_layers=None)
+    net.obj_latent_decoder = net.get_latent_decoder()
+    net.ctx_conv_decoder_modules = net.get_conv_decoder(output_nc=net.output_nc, skip_layers=net.skip_layers)
+    net.ctx_latent_decoder = net.get_latent_decoder()
+    net.params_dict = net.get_params_dict()
+
+    class ClampReLU(nn.Module):
+        def forward(self, x):
+            return x.clamp(min=0)
+    assert type(net.conv_encoder_modules[2]).__name__ == "ReLU" and not net.conv_encoder_modules[2].inplace
+    net.conv_encoder_modules[2] = ClampReLU()
+    names, params = [], []
+    for mk, mod in net.params_dict.items():
+        with torch.no_grad():
+            for k, p in mod.named_parameters():
+                p.copy_(named_param(mk + "." + k, p.shape))
+                names.append(mk + "." + k)
+                params.append(p)
+        mod.train()
+    a = G.synthetic(cfg, 3, seed=47)
+    cond, onehot = G.encode(cfg, a)
+    lo, lp, oo, op = net.forward(cond, onehot)
+    gt = a["label_map"].view(-1, a["label_map"].size(2), a["label_map"].size(3)).long()
+    loss_comb = ML.MaskReconLoss()(lp, gt, a["mask_out"])
+    loss_obj = nn.BCELoss()(op * a["mask_out"], a["mask_obj_inst"])
+    grads = torch.autograd.grad(loss_obj + loss_comb, params, allow_unused=True)
+    out = dict(param_names=np.array(names), param_shapes=np.array([";".join(str(v) for v in p.shape) for p in params]),
+               comb_logit=lo.detach().numpy(), comb_prob=lp.detach().numpy(), obj_logit=oo.detach().numpy(),
+               obj_prob=op.detach().numpy(), loss_comb=float(loss_comb), loss_obj=float(loss_obj))
+    for k, v in a.items():
+        out["in::" + k] = v.numpy()
+    for n_, g_ in zip(names, grads):
+        assert g_ is not None, n_
+        if g_.numel() <= 4096:
+            out["g::" + n_] = g_.numpy()
+        else:
+            r = named_param("proj::" + n_ + ".bias", g_.shape)
+            out["gs::" + n_] = np.array([float(g_.sum()), float(g_.abs().sum()), float((g_ * r).sum())])
+    np.savez_compressed(os.path.join(G.OUT, "box2mask_switch_ade_small.npz"), **out)
+    print("wrote box2mask_switch_ade_small.npz:", len(names), "parameters; losses", float(loss_comb), float(loss_obj))
+    print([n for n in names if n.startswith("latent_encoder.")][:8])
+
+
 def main():
+    if "ade" in sys.argv[1:]:
+        return ade_case()
     from oracle.weights import named_param
     cfg = dict(G.CFG)
     torch.manual_seed(6)

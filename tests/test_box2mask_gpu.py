@@ -517,3 +517,60 @@ def test_box2mask_alternate_precision_modes_track_the_parity_mode(precision):
         assert err < (tol0 if it == 0 else 5e-2), (it, a, b)
     torch.cuda.synchronize()
     alt.ctx.check_pipeline()
+
+
+def test_box2mask_ade_flag_set_against_the_reference_class_golden(golden_dir):
+    """--norm_layer instance --add_dilated_layers --no_comb (scripts/train_box2mask_ade.sh): outputs, losses and the
+    gradients of all 66 parameters against the golden generated from the reference's own MaskTwoStreamConvSwitch_NET;
+    then two --use_gan --lr_control training iterations (InstanceNorm discriminator) run and stay finite."""
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_switch_ade_small.npz"))
+    kw = dict(label_nc=6, output_nc=6, conv_dim=32, n_blocks=2, no_comb=True, norm_layer="instance", add_dilated_layers=True)
+    m = _model(**kw)
+    sd = {str(n): named_param(str(n), tuple(int(v) for v in str(s).split(";")))
+          for n, s in zip(z["param_names"], z["param_shapes"])}
+    assert set(sd) == set(m.fpG.params), sorted(set(sd) ^ set(m.fpG.params))[:6]
+    assert not m.fpG.buffers
+    m.fpG.load_state_dict(sd)
+    ins = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in::")}
+    losses, out = m.forward(ins["label_map"], None, ins["mask_ctx_in"], None, ins["mask_out"], ins["mask_obj_inst"], ins["cls"],
+                            ins["mask_in"], train=False)
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    for k in ("comb_logit", "comb_prob", "obj_logit", "obj_prob"):
+        e = rel(out[k], z[k])
+        assert e < 1e-3, (k, e)
+    assert abs(float(losses[0]) - float(z["loss_comb"])) < 1e-3 * abs(float(z["loss_comb"]))
+    assert abs(float(losses[1]) - float(z["loss_obj"])) < 1e-3 * abs(float(z["loss_obj"]))
+    m.optimizer.zero_grad()
+    m.backward_losses()
+    torch.cuda.synchronize()
+    m.ctx.check_pipeline()
+    worst = []
+    for k, p in m.fpG.params.items():
+        g = p.grad.detach().double().cpu()
+        if "g::" + k in z.files:
+            ref = torch.from_numpy(z["g::" + k]).double()
+            if k.endswith("bias") and float(ref.abs().max()) < 1e-6:
+                assert float(g.abs().max()) < 1e-6, k
+            else:
+                worst.append((float((g - ref).abs().max() / ref.abs().max()), k))
+        else:
+            s_, a_, p_ = (float(v) for v in z["gs::" + k])
+            r = named_param("proj::" + k + ".bias", g.shape).double()
+            worst.append((abs(float(g.abs().sum()) - a_) / a_, k + " |.|1"))
+            worst.append((abs(float((g * r).sum()) - p_) / (a_ * 0.05), k + " proj"))
+    worst.sort(reverse=True)
+    print("box2mask ADE flag set, gradients vs reference autograd: worst", ["%.1e %s" % w for w in worst[:4]])
+    assert worst[0][0] < 1e-2, worst[:8]
+    # the GAN half of the ADE script: InstanceNorm discriminator + lr_control (eager iterations)
+    m2 = _model(use_gan=True, which_gan="patch_multiscale", gan_weight=0.1, num_layers_D=3, ndf=16, use_ganFeat_loss=True,
+                lambda_feat=1.0, lr_control=True, **kw)
+    assert not any(k.endswith(".1.weight") for k in m2.fpD.params)          # no norm parameters in the discriminator
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(2):
+            ls, _ = m2.forward(ins["label_map"], None, ins["mask_ctx_in"], None, ins["mask_out"], ins["mask_obj_inst"],
+                               ins["cls"], ins["mask_in"])
+    vals = [float(v) for v in ls]
+    assert all(v == v and abs(v) < 1e4 for v in vals) and m2._graph is False, vals
+    m2.ctx.check_pipeline()

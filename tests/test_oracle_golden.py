@@ -385,3 +385,39 @@ def test_image_pool_against_the_reference_model(golden_dir):
         if k.endswith("bias") and float(gD[k].abs().max()) < 1e-3 * float(gD[k[:-4] + "weight"].abs().max()):
             continue
         close(gi.float(), gD[k], 2e-4)
+
+
+def test_box2mask_ade_flag_set_against_the_reference_class(golden_dir):
+    """--norm_layer instance --add_dilated_layers --no_comb (what scripts/train_box2mask_ade.sh adds to the Cityscapes flag
+    set): outputs, losses and all 66 parameter gradients against the reference's own MaskTwoStreamConvSwitch_NET
+    (oracle/make_golden_box2mask_switch.py ade)."""
+    from oracle import box2mask as B2
+    from oracle.weights import named_param
+    z = np.load(os.path.join(golden_dir, "box2mask_switch_ade_small.npz"))
+    sd = {str(n): named_param(str(n), tuple(int(v) for v in str(s_).split(";"))).double().requires_grad_(True)
+          for n, s_ in zip(z["param_names"], z["param_shapes"])}
+    a = {k[4:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("in::")}
+    cond, _ = B2.encode_input(6, a["mask_ctx_in"], a["mask_in"], a["cls"])
+    outs = B2.two_stream_forward(sd, cond.double(), num_layers=3, n_blocks=2, no_comb=True, norm_layer="instance",
+                                 add_dilated_layers=True)
+    for got, k in zip(outs, ("comb_logit", "comb_prob", "obj_logit", "obj_prob")):
+        ref = torch.from_numpy(z[k]).double()
+        assert float((got.detach() - ref).abs().max() / ref.abs().max()) < 2e-5, k
+    lc = B2.mask_recon_loss(outs[1], a["label_map"], a["mask_out"])
+    lo = B2.obj_recon_loss(outs[3], a["mask_out"], a["mask_obj_inst"])
+    assert abs(float(lc) - float(z["loss_comb"])) < 2e-5 and abs(float(lo) - float(z["loss_obj"])) < 2e-5
+    names = list(sd)
+    grads = torch.autograd.grad(lo + lc, [sd[k] for k in names])
+    n_full = n_proj = 0
+    for k, g in zip(names, grads):
+        if "g::" + k in z.files:
+            ref = torch.from_numpy(z["g::" + k]).double()
+            assert float((g - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-6, k
+            n_full += 1
+        else:
+            s_, a_, p_ = (float(v) for v in z["gs::" + k])
+            r = named_param("proj::" + k + ".bias", g.shape).double()
+            assert abs(float(g.abs().sum()) - a_) <= 2e-3 * a_, k
+            assert abs(float((g * r).sum()) - p_) <= 2e-3 * a_ * 0.05 + 1e-6, k
+            n_proj += 1
+    assert n_full + n_proj == 66
