@@ -313,7 +313,8 @@ int hm_adam_step_dev(float* param, const float* grad, float* m, float* v, long n
  *   TwoStreamAE_mask.forward :188-203: acc[0] += sum of NLL over pixels with mask_out >= 0.5 (mask_losses.py:12-27),
  *   acc[1] += their count, acc[2] += sum of BCE(obj_prob [* mask_out when gated], inst) terms (logs clamped at -100).
  *   `use_gate` is a bit set: bit 0 = --use_output_gate; bit 1 = --no_comb (MaskTwoStreamConvSwitch_NET.forward :208: the
- *   context logits are returned as they are, comb = ctx), in hm_box2mask_head_bwd too. */
+ *   context logits are returned as they are, comb = ctx); bit 2 = --objReconLoss l1 (acc[2] accumulates |q - inst|
+ *   instead of the BCE terms, TwoStreamAE_mask.py:50-51); in hm_box2mask_head_bwd too. */
 int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const float* cls, int B, int H, int W, int label_nc,
                        void* o_hi, void* o_lo, int o_cs, void* stream);
 int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,

@@ -11,7 +11,7 @@
                             `evaluate` (:257-335); `save` / `load` / `delete_model` / `update_learning_rate` in the
                             reference's checkpoint layout (:106-118, 359-383); `--norm_layer instance` and
                             `--add_dilated_layers` (what scripts/train_box2mask_ade.sh adds).  `which_gan` 'patch' /
-                            'patch_res' and `objReconLoss l1` raise.
+                            'patch_res' raise.
 
 Parameter names are the reference's own ('<params_dict key>.<state_dict key>': conv_encoder_3.deep.1.weight,
 ctx_conv_decoder_1.shortcut.0.weight, latent_encoder.0.conv_block.1.weight, ...), OIHW / IOHW fp32 like the reference, so
@@ -613,8 +613,8 @@ class TwoStreamAE_mask(object):
         if self.use_gan and getattr(opt, "which_gan", "patch") != "patch_multiscale":
             raise NotImplementedError("--which_gan: only 'patch_multiscale' (the shipped setting, TwoStreamAE_mask.py:83-92) "
                                       "is built; 'patch' / 'patch_res' use the conditional single-scale discriminators")
-        if getattr(opt, "objReconLoss", "bce") != "bce":
-            raise NotImplementedError("objReconLoss: only 'bce' (the shipped setting) is built")
+        # :48-55 criterionObjRecon: 'l1' -> nn.L1Loss, 'bce' -> nn.BCELoss, anything else -> no object-mask loss
+        self.obj_loss = getattr(opt, "objReconLoss", "bce")
         self.fpG = FlatParams(dev)
         self.netG = MaskTwoStreamConvNet(self.ctx, self.fpG, opt.label_nc, opt.output_nc, opt.conv_dim, opt.num_layers,
                                          opt.conv_size, opt.n_blocks, opt.cond_in, opt.which_stream,
@@ -733,9 +733,11 @@ class TwoStreamAE_mask(object):
                    obj_logit=obj_logit[..., :1].permute(0, 3, 1, 2), obj_prob=torch.empty(B, 1, H, W, device=self.device))
         self.acc.zero_()
         ops.box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, gate, out["comb_logit"], out["comb_prob"],
-                          out["obj_prob"], self.acc, no_comb=self.no_comb)
+                          out["obj_prob"], self.acc, no_comb=self.no_comb, l1=(self.obj_loss == "l1"))
         loss_comb = (self.acc[0] / self.acc[1].clamp_min(1.0)).float()       # NLLLoss2d mean over non-ignored pixels
-        loss_obj = (self.acc[2] / float(B * H * W)).float()                  # BCELoss mean
+        loss_obj = (self.acc[2] / float(B * H * W)).float()                  # BCELoss / L1Loss mean
+        if self.obj_loss not in ("bce", "l1"):
+            loss_obj = loss_obj * 0.0                                        # criterionObjRecon is None: loss_recon_obj = 0
         self._last = dict(tape=tape, ctx_logit=ctx_logit, obj_logit=obj_logit, label_map=label_map, mask_out=mask_out,
                           inst=inst, gate=gate)
         zero = torch.zeros((), device=self.device)
@@ -796,7 +798,8 @@ class TwoStreamAE_mask(object):
         if self.use_gan:    # gan_weight * loss_G_GAN through the discriminator's data path down to the generated mask
             g_prob = self.netD.backward(s["d_fake"], 1.0, self.gan_weight, False)
         ops.box2mask_head_bwd(ctx, s["ctx_logit"], s["obj_logit"], s["label_map"], s["mask_out"], s["inst"], s["gate"],
-                              self.acc, self.rec_weight, 1.0, d_ctx, d_obj, g_prob=g_prob, no_comb=self.no_comb)
+                              self.acc, self.rec_weight, 1.0 if self.obj_loss in ("bce", "l1") else 0.0, d_ctx, d_obj,
+                              g_prob=g_prob, no_comb=self.no_comb, l1=(self.obj_loss == "l1"))
         self.netG.backward(s["tape"], d_ctx, d_obj)
 
     # ---- inference (vis_box2mask.py:36-60, train_box2mask.py:90-100) -------------------------------------------------

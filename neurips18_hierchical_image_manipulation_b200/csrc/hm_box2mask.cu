@@ -190,8 +190,12 @@ __global__ void b2m_head_kernel(const float* __restrict__ ctx_logit /*[N,H,W,C]*
     if (inst) {
       const float q = use_gate ? pr * mo : pr;
       const float t = __ldg(inst + i);
-      const float lq = fmaxf(logf(q), -100.f), l1q = fmaxf(logf(1.f - q), -100.f);   // nn.BCELoss clamps its logs at -100
-      bce -= double(t * lq + (1.f - t) * l1q);
+      if (flags & 4) {                       // --objReconLoss l1 (nn.L1Loss, TwoStreamAE_mask.py:50-51)
+        bce += double(fabsf(q - t));
+      } else {
+        const float lq = fmaxf(logf(q), -100.f), l1q = fmaxf(logf(1.f - q), -100.f);   // nn.BCELoss clamps its logs at -100
+        bce -= double(t * lq + (1.f - t) * l1q);
+      }
     }
   }
   __shared__ double sh[3][kBlock];
@@ -288,8 +292,12 @@ __global__ void b2m_head_bwd_kernel(const float* __restrict__ ctx_logit, const f
       const float q = use_gate ? pr * mo : pr;
       const float t = __ldg(inst + i);
       float dq = 0.f;
-      if (logf(q) > -100.f) dq -= t / q;
-      if (logf(1.f - q) > -100.f) dq += (1.f - t) / (1.f - q);
+      if (flags & 4) {                       // --objReconLoss l1: sign(q - t), 0 at equality like torch
+        dq = q > t ? 1.f : (q < t ? -1.f : 0.f);
+      } else {
+        if (logf(q) > -100.f) dq -= t / q;
+        if (logf(1.f - q) > -100.f) dq += (1.f - t) / (1.f - q);
+      }
       dp += w_obj * inv_n * dq * (use_gate ? mo : 1.f);
     }
     // GAN term (--use_gan): g_prob is the gradient w.r.t. channel 0 of the discriminator input = p * mask^2 (gated)

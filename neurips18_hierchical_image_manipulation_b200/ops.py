@@ -480,10 +480,11 @@ def upsample2_add(ctx, small, deep, out):
 
 
 def box2mask_head(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, comb_logit, comb_logprob, obj_prob, acc,
-                  no_comb=False):
+                  no_comb=False, l1=False):
     N, H, W, Cc = ctx_logit.shape
     L.check(ctx.lib.hm_box2mask_head(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1], _ptr(label_map),
-                                     _ptr(mask_out), _ptr(inst), N, H, W, Cc, (1 if use_gate else 0) | (2 if no_comb else 0),
+                                     _ptr(mask_out), _ptr(inst), N, H, W, Cc,
+                                     (1 if use_gate else 0) | (2 if no_comb else 0) | (4 if l1 else 0),
                                      _ptr(comb_logit),
                                      _ptr(comb_logprob), _ptr(obj_prob), _ptr(acc), _stream()), "hm_box2mask_head")
     ctx.launches += 1
@@ -509,11 +510,11 @@ def upsample2_bwd(ctx, g, dsmall):
 
 
 def box2mask_head_bwd(ctx, ctx_logit, obj_logit, label_map, mask_out, inst, use_gate, acc, w_comb, w_obj, d_ctx, d_obj,
-                      g_prob=None, no_comb=False):
+                      g_prob=None, no_comb=False, l1=False):
     N, H, W, Cc = ctx_logit.shape
     L.check(ctx.lib.hm_box2mask_head_bwd(ctx_logit.data_ptr(), obj_logit.data_ptr(), obj_logit.shape[-1],
                                          label_map.data_ptr(), _ptr(mask_out), inst.data_ptr(), N, H, W, Cc,
-                                         (1 if use_gate else 0) | (2 if no_comb else 0), acc.data_ptr(), float(w_comb),
+                                         (1 if use_gate else 0) | (2 if no_comb else 0) | (4 if l1 else 0), acc.data_ptr(), float(w_comb),
                                          float(w_obj), _ptr(g_prob),
                                          g_prob.shape[-1] if g_prob is not None else 0, d_ctx.hi.data_ptr(), _ptr(d_ctx.lo),
                                          d_ctx.cs, d_obj.hi.data_ptr(), _ptr(d_obj.lo), d_obj.cs, _stream()),

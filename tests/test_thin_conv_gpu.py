@@ -183,3 +183,37 @@ def test_dilated_conv3x3_forward_and_gradients(cin, cout, d, h, w, split):
     ctx.check_pipeline()
     assert rel(gin.cpu().permute(0, 3, 1, 2).double(), xd.grad) < tol
     assert rel(conv.weight.grad.cpu().double(), wd.grad) < tol
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(256, 128, 8, 8), (192, 64, 16, 16), (64, 32, 32, 32), (40, 24, 9, 13)])
+def test_conv_transpose_4x4_s2_forward_and_gradients(cin, cout, h, w):
+    """nn.ConvTranspose2d(cin, cout, 4, stride=2, padding=1) -- DeconvResnetBlock's deep branch (layer_util.py:210-222) --
+    forward, data gradient and weight gradient through ConvP against torch CPU fp64."""
+    from neurips18_hierchical_image_manipulation_b200 import ops
+    from neurips18_hierchical_image_manipulation_b200.networks import ConvP, FlatParams
+    ctx = ops.Ctx("cuda:0", split=True)
+    fp = FlatParams(ctx.device)
+    conv = ConvP(ctx, fp, "c", cin, cout, 4, 2, 1, transposed=True)
+    fp.materialize()
+    conv.init_reference(torch.Generator().manual_seed(6))
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(3, cin, h, w, generator=g)
+    xin = _operand(ctx, x, 0, reflect=False)
+    y = torch.full((3, 2 * h, 2 * w, cout), float("nan"), device="cuda")
+    conv.forward(xin, 0, out32=y)
+    xd = x.double().requires_grad_(True)
+    wd = conv.weight.detach().cpu().double().requires_grad_(True)
+    ref = F.conv_transpose2d(xd, wd, conv.bias.detach().cpu().double(), stride=2, padding=1)
+    torch.cuda.synchronize()
+    assert rel(y.cpu().permute(0, 3, 1, 2).double(), ref.detach()) < 1e-4
+    dy = torch.randn(3, cout, 2 * h, 2 * w, generator=g)
+    ref.backward(dy.double())
+    dyo = _operand(ctx, dy, 0, reflect=False, grad=True)
+    fp.grad.zero_()
+    conv.wgrad(xin, dyo, 0, bias_grad=False)
+    gin = torch.full((3, h, w, cin), float("nan"), device="cuda")
+    conv.dgrad(dyo, h, w, 0, gin)
+    torch.cuda.synchronize()
+    ctx.check_pipeline()
+    assert rel(gin.cpu().permute(0, 3, 1, 2).double(), xd.grad) < 1e-4
+    assert rel(conv.weight.grad.cpu().double(), wd.grad) < 1e-4
