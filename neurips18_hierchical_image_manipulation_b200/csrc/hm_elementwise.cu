@@ -399,7 +399,8 @@ __device__ __forceinline__ void load_chan_stats(const BwdArgs& a, int n, int c, 
 // constants (F_* mask): with run-time flags the loop body re-tested ~10 pointers and rebuilt every 64-bit address
 // per pixel (~160 instructions per 4-channel pixel, issue bound at 25-35 % of HBM bandwidth; ncu r01).  BWD_GENERIC
 // keeps the run-time tests for the combinations that are not instantiated.
-enum : int { F_IN = 1, F_G1D = 2, F_G1B = 4, F_G2 = 8, F_Z = 16, F_TREF = 32, F_MASK = 64, BWD_GENERIC = 128 };
+enum : int { F_IN = 1, F_G1D = 2, F_G1B = 4, F_G2 = 8, F_Z = 16, F_TREF = 32, F_MASK = 64, BWD_GENERIC = 128, F_BN = 256 };
+// F_BN: the affine (BatchNorm) form as a compile-time variant: gamma is known to be present
 template <int F> __device__ __forceinline__ bool has_in(const BwdArgs& a) { return (F & BWD_GENERIC) ? a.y != nullptr : (F & F_IN) != 0; }
 template <int F> __device__ __forceinline__ bool has_g1d(const BwdArgs& a) { return (F & BWD_GENERIC) ? (a.g1 && a.g1_border == 0) : (F & F_G1D) != 0; }
 template <int F> __device__ __forceinline__ bool has_g1b(const BwdArgs& a) { return (F & BWD_GENERIC) ? (a.g1 && a.g1_border != 0) : (F & F_G1B) != 0; }
@@ -475,7 +476,7 @@ __device__ __forceinline__ void bwd_dyhat(const BwdArgs& a, const ChanStats<V>& 
     loadv<V>(a.y + pix * a.C, c, a.C, yh);
 #pragma unroll
     for (int j = 0; j < V; ++j) { yh[j] = (yh[j] - cs.mu[j]) * cs.rs[j]; src[j] = yh[j]; }
-    if ((F & BWD_GENERIC) && a.gamma) {
+    if ((F & F_BN) || ((F & BWD_GENERIC) && a.gamma)) {
 #pragma unroll
       for (int j = 0; j < V; ++j)
         if (c + j < a.C) src[j] = yh[j] * __ldg(a.gamma + c + j) + (a.beta ? __ldg(a.beta + c + j) : 0.f);
@@ -579,8 +580,11 @@ __global__ void __launch_bounds__(kBlock) in_bwd_reduce_kernel(BwdArgs a, int gx
     for (int j = 0; j < V; ++j) { dst[j] = sm[tx * 2 * V + j]; dst[C8 + j] = sm[tx * 2 * V + V + j]; }
   }
 }
+// BatchNorm (N == 1): the same sums are d(beta) = sum dact and d(gamma) = sum dact * xhat -- accumulated here when asked
+// for (C valid channels), which saves the separate bn_param_grad launch per layer.
 __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N, int nblk, int C8, int HW,
-                                       float* __restrict__ sums /*[N][2][C8] means*/) {
+                                       float* __restrict__ sums /*[N][2][C8] means*/, float* __restrict__ dgamma = nullptr,
+                                       float* __restrict__ dbeta = nullptr, int C = 0) {
   __shared__ double ss[8][32], sq[8][32];
   const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cl;
@@ -600,6 +604,10 @@ __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, int N,
     for (int k = 1; k < 8; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
     sums[(size_t(n) * 2) * C8 + c] = float(s / HW);
     sums[(size_t(n) * 2 + 1) * C8 + c] = float(q / HW);
+    if (n == 0 && c < C) {
+      if (dbeta) dbeta[c] += float(s);
+      if (dgamma) dgamma[c] += float(q);
+    }
   }
 }
 // same thread decomposition; grid (pixel blocks, N, cgroups) with a grid-stride loop over the pixels of image n
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(kBlock) in_bwd_apply_kernel(BwdArgs a, int gx_
       if (sums) {
 #pragma unroll
         for (int j = 0; j < V; ++j) dy[j] = (V == 4 || c + j < a.C) ? cs.rs[j] * (dyh[j] - m1[j] - yh[j] * m2[j]) : 0.f;
-        if ((F & BWD_GENERIC) && a.gamma) {
+        if ((F & F_BN) || ((F & BWD_GENERIC) && a.gamma)) {
 #pragma unroll
           for (int j = 0; j < V; ++j) if (c + j < a.C) dy[j] *= __ldg(a.gamma + c + j);
         }
@@ -1213,18 +1221,12 @@ int hm_in_apply(const float* y, const float* mean, const float* rstd, const floa
 }  // extern "C"
 
 namespace {
-__global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, int C8, float count, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (dbeta) dbeta[c] += sums[c] * count;            // sum of dact
-  if (dgamma) dgamma[c] += sums[C8 + c] * count;     // sum of dact * xhat
-}
 
 int in_bwd_impl(const float* y, const float* mean, const float* rstd, const float* z, const void* mask_hi, int mask_cs,
                 const float* g1, int g1_border, int g1_ld, int g1_coff, const float* g2, const float* tref, float l1coef,
                 int N, int H, int W, int C, int act, float slope, float* ws, void* o_hi, void* o_lo, int o_cs,
-                float* out32, const float* gamma, const float* beta, float** sums_out, void* stream) {
+                float* out32, const float* gamma, const float* beta, float** sums_out, void* stream,
+                float* dgamma = nullptr, float* dbeta = nullptr) {
   if ((!o_hi && !out32) || (o_hi && ((o_cs & 7) || o_cs < C))) return HM_ERR_INVALID;
   if (mean && (!y || !ws)) return HM_ERR_INVALID;
   if (g1 && g1_border > 0 && (g1_border >= H || g1_border >= W)) return HM_ERR_INVALID;
@@ -1243,12 +1245,13 @@ int in_bwd_impl(const float* y, const float* mean, const float* rstd, const floa
   const int V = v4 ? 4 : 8;
   // presence mask of this call; instantiated combinations run with compile-time flags (the affine / BatchNorm form
   // always takes the generic kernels: -1 matches no instantiated case)
-  const int F = gamma ? -1 :
+  const int F = (gamma ? F_BN : 0) |
                 (y ? F_IN : 0) | ((g1 && g1_border == 0) ? F_G1D : 0) | ((g1 && g1_border != 0) ? F_G1B : 0) |
                 (g2 ? F_G2 : 0) | (z ? F_Z : 0) | (tref ? F_TREF : 0) | ((mask_hi && !y && !z) ? F_MASK : 0);
 #define HM_BWD_CASES(X)                                                                                      \
   X(F_IN | F_G2) X(F_IN | F_G1D) X(F_IN | F_G1B) X(F_IN | F_G1D | F_Z) X(F_IN | F_G1D | F_Z | F_TREF)          \
-  X(F_G1D | F_Z) X(F_G1D | F_Z | F_TREF) X(F_Z | F_TREF) X(F_Z | F_TREF | F_G2) X(F_MASK | F_G2) X(F_MASK)
+  X(F_G1D | F_Z) X(F_G1D | F_Z | F_TREF) X(F_Z | F_TREF) X(F_Z | F_TREF | F_G2) X(F_MASK | F_G2) X(F_MASK)       \
+  X(F_BN | F_IN | F_G1D) X(F_BN | F_IN | F_G1D | F_G2) X(F_BN | F_IN | F_G2)
   if (mean) {
     stats_geometry(C, V, &gx_log2, &cgroups);
     const int nblk = stats_nblk(N, H * W, cgroups);
@@ -1266,7 +1269,7 @@ int in_bwd_impl(const float* y, const float* mean, const float* rstd, const floa
     } else {
       in_bwd_reduce_kernel<8, BWD_GENERIC><<<grid, kBlock, 0, st>>>(a, gx_log2, ws);
     }
-    in_bwd_finalize_kernel<<<(N * C8 + 31) / 32, 256, 0, st>>>(ws, N, nblk, C8, H * W, sums);
+    in_bwd_finalize_kernel<<<(N * C8 + 31) / 32, 256, 0, st>>>(ws, N, nblk, C8, H * W, sums, dgamma, dbeta, C);
   }
   const int Cout = o_hi ? o_cs : C8;
   stats_geometry(Cout, V, &gx_log2, &cgroups);
@@ -1313,14 +1316,10 @@ int hm_bn_bwd(const float* y, const float* mean, const float* rstd, const float*
               void* stream) {
   if (!y || !mean || !rstd || !gamma || !ws || long(N) * H > 0x7fffffffL) return HM_ERR_INVALID;
   float* sums = nullptr;
+  // d(gamma) / d(beta) are accumulated by the finalize launch of the reduction (N == 1: one "sample" of N*H*W pixels)
   int rc = in_bwd_impl(y, mean, rstd, z, mask_hi, mask_cs, g1, 0, C, 0, g2, nullptr, 0.f, 1, N * H, W, C, act, slope, ws,
-                       o_hi, o_lo, o_cs, out32, gamma, beta, &sums, stream);
+                       o_hi, o_lo, o_cs, out32, gamma, beta, &sums, stream, dgamma, dbeta);
   if (rc != HM_OK) return rc;
-  if (dgamma || dbeta) {
-    const int C8 = (C + 7) & ~7;
-    bn_param_grad_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, C, C8, float(N) * H * W,
-                                                                                         dgamma, dbeta);
-  }
   return HM_LAUNCH_OK();
 }
 

@@ -500,7 +500,7 @@ def bn_bwd(ctx, y, mean, rstd, gamma, beta, act, g1, g2=None, z=None, mask_op=No
                               W, Cc, act, slope, ws.data_ptr(), _ptr(out_op.hi) if out_op else None,
                               _ptr(out_op.lo) if out_op else None, out_op.cs if out_op else 0, _ptr(out32), _ptr(dgamma),
                               _ptr(dbeta), _stream()), "hm_bn_bwd")
-    ctx.launches += 4
+    ctx.launches += 3
 
 
 def upsample2_bwd(ctx, g, dsmall):
