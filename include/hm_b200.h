@@ -320,6 +320,13 @@ int hm_box2mask_encode(const float* mask_ctx_in, const float* mask_in, const flo
 int hm_bn_fold(const float* mean, const float* rstd, const float* gamma, const float* beta, int N, int C, float* mean_out,
                float* rstd_out, float* running_mean, float* running_var, long long* num_batches_tracked, float count,
                float momentum, float eps, int repeat, void* stream);
+/* hm_bn_stats = hm_in_stats over the batch-folded tensor (one sample of N*HW pixels) + hm_bn_fold in two launches instead of
+ * three: y fp32 [N, HW, C]; mean / rstd [C] (the batch statistics hm_bn_bwd needs), mean_rows / rstd_rows [N][C] for
+ * hm_in_apply, optional running-buffer update (both or neither; unbiased variance, momentum, `repeat` evaluations).
+ * ws: hm_in_ws_bytes(1, N*HW, C). */
+int hm_bn_stats(const float* y, int N, int HW, int C, float eps, float* ws, float* mean, float* rstd, const float* gamma,
+                const float* beta, float* mean_rows, float* rstd_rows, float* running_mean, float* running_var,
+                long long* num_batches_tracked, float momentum, int repeat, void* stream);
 int hm_upsample2_add(const float* small, const float* deep, int N, int h, int w, int C, float* out, void* stream);
 /* Backward halves (training step of TwoStreamAE_mask.forward :233-248 without the GAN terms):
  * hm_bn_bwd: BatchNorm2d(affine) + activation backward, batch statistics (mean / rstd [C] over N*H*W): the gradient w.r.t.

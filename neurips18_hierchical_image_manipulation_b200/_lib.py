@@ -104,6 +104,7 @@ PROTOTYPES = {
     "hm_sn_weight_grad": (_i, [_vp, _i, _i, _i, _vp]),
     "hm_box2mask_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "hm_bn_fold": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _vp]),
+    "hm_bn_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp]),
     "hm_upsample2_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "hm_box2mask_head": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp,

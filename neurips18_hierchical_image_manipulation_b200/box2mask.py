@@ -76,10 +76,9 @@ class _BN(object):
         """Returns the statistics (mean, rstd) [1, C] the tensor was normalised with (the backward pass needs the batch
         statistics).  repeat: how many times the reference evaluates this module on this batch (buffer update count)."""
         N, H, W, C = y.shape
-        if self.training:
-            mean, rstd = ops.in_stats(ctx, y.view(1, N * H, W, C), eps=self.EPS)          # statistics over (N, H, W)
-            mean_n, rstd_n = ops.bn_fold(ctx, mean, rstd, self.gamma, self.beta, N, running=self.running, count=N * H * W,
-                                         repeat=repeat, momentum=self.MOMENTUM, eps=self.EPS)
+        if self.training:                                                                 # statistics over (N, H, W)
+            mean, rstd, mean_n, rstd_n = ops.bn_stats(ctx, y, self.gamma, self.beta, running=self.running, repeat=repeat,
+                                                      momentum=self.MOMENTUM, eps=self.EPS)
         else:
             rm, rv, _ = self.running
             mean, rstd = rm.view(1, C), torch.rsqrt(rv + self.EPS).view(1, C)

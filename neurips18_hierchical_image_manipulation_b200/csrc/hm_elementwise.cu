@@ -258,6 +258,55 @@ __global__ void in_stats_finalize_kernel(const float* __restrict__ y, const floa
   }
 }
 
+// BatchNorm2d in training mode (box2mask): finalize of the batch-folded statistics (one "sample" of P = N * HW pixels) fused
+// with what hm_bn_fold does -- per-(n, c) rows for hm_in_apply (rstd' = rstd * gamma, mean' = mean - beta / rstd') and the
+// module's running-buffer update (momentum, unbiased variance, `repeat` evaluations) -- one launch instead of two.
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ y, const float* __restrict__ partial, int nblk, int C, int P,
+                                         float eps, float* __restrict__ mean, float* __restrict__ rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, int N,
+                                         float* __restrict__ mean_rows, float* __restrict__ rstd_rows, float* running_mean,
+                                         float* running_var, long long* num_batches_tracked, float momentum, int repeat) {
+  __shared__ double ss[8][32], sq[8][32];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool ok = c < C;
+  double s = 0, q = 0;
+  if (ok) {
+    for (int b = bl; b < nblk; b += 8) {
+      const float* p = partial + (size_t(b) * 2) * C + c;
+      s += p[0]; q += p[C];
+    }
+  }
+  ss[bl][cl] = s; sq[bl][cl] = q;
+  __syncthreads();
+  if (bl == 0 && ok) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
+    const double m = s / P;                                // mean of (x - pivot)
+    double var = q / P - m * m;
+    if (var < 0) var = 0;
+    const float mu = float(m + double(__ldg(y + c)));
+    const float rs = float(1.0 / sqrt(var + double(eps)));
+    mean[c] = mu;
+    rstd[c] = rs;
+    const float rsg = rs * (gamma ? gamma[c] : 1.f);
+    const float b = beta ? beta[c] : 0.f;
+    const float mg = (rsg != 0.f) ? mu - b / rsg : mu;
+    for (int n = 0; n < N; ++n) { rstd_rows[size_t(n) * C + c] = rsg; mean_rows[size_t(n) * C + c] = mg; }
+    if (running_mean && running_var) {
+      const float var_u = P > 1 ? float(var) * (float(P) / float(P - 1)) : float(var);
+      float rm = running_mean[c], rv = running_var[c];
+      for (int k = 0; k < repeat; ++k) {
+        rm = (1.f - momentum) * rm + momentum * mu;
+        rv = (1.f - momentum) * rv + momentum * var_u;
+      }
+      running_mean[c] = rm;
+      running_var[c] = rv;
+      if (c == 0 && num_batches_tracked) *num_batches_tracked += repeat;
+    }
+  }
+}
+
 // ================================================================================================
 // K7  normalise + activation (+ residual) + operand emission with materialised border
 //   out = act((y - mean) * rstd) [+ skip]     (Pix2Pix_NET.py:74-90, layer_util.py:341-378, Discriminator_NET.py:80-90)
@@ -1188,6 +1237,24 @@ int hm_encode_input(const float* label, const float* inst, const float* image, c
 size_t hm_in_ws_bytes(int N, int HW, int C) {
   const int C8 = (C + 7) & ~7;
   return size_t(N) * stats_nblk_max(N, HW) * 2 * C8 * sizeof(float) + size_t(N) * 2 * C8 * sizeof(float);
+}
+
+int hm_bn_stats(const float* y, int N, int HW, int C, float eps, float* ws, float* mean, float* rstd, const float* gamma,
+                const float* beta, float* mean_rows, float* rstd_rows, float* running_mean, float* running_var,
+                long long* num_batches_tracked, float momentum, int repeat, void* stream) {
+  if (!y || !ws || !mean || !rstd || !mean_rows || !rstd_rows || (C & 3) || N <= 0 || (!running_mean != !running_var) ||
+      long(N) * HW > 0x7fffffffL)
+    return HM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int gx_log2, cgroups;
+  stats_geometry(C, 4, &gx_log2, &cgroups);
+  const int P = N * HW;                                   // the batch folded into one "sample" of N * HW pixels
+  const int nblk = stats_nblk(1, P, cgroups);
+  in_stats_kernel<<<dim3(nblk, 1, cgroups), kBlock, 0, st>>>(y, P, C, gx_log2, ws);
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(y, ws, nblk, C, P, eps, mean, rstd, gamma, beta, N, mean_rows,
+                                                          rstd_rows, running_mean, running_var, num_batches_tracked,
+                                                          momentum, repeat);
+  return HM_LAUNCH_OK();
 }
 
 int hm_in_stats(const float* y, int N, int HW, int C, float eps, float* ws, float* mean, float* rstd, void* stream) {

@@ -471,6 +471,23 @@ def bn_fold(ctx, mean, rstd, gamma, beta, N, running=None, count=0, repeat=1, mo
     return mo, ro
 
 
+def bn_stats(ctx, y, gamma, beta, running=None, repeat=1, momentum=0.1, eps=1e-5):
+    """BatchNorm2d (training mode) statistics of y fp32 [N,H,W,C] + the per-(n, c) rows for in_apply + the running-buffer
+    update, in two launches.  Returns (mean [1,C], rstd [1,C], mean_rows [N,C], rstd_rows [N,C])."""
+    N, H, W, Cc = y.shape
+    ws = ctx.ws("in", ctx.lib.hm_in_ws_bytes(1, N * H * W, Cc))
+    mean = torch.empty(1, Cc, dtype=torch.float32, device=ctx.device)
+    rstd = torch.empty(1, Cc, dtype=torch.float32, device=ctx.device)
+    mo = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    ro = torch.empty(N, Cc, dtype=torch.float32, device=ctx.device)
+    rm, rv, nbt = running if running is not None else (None, None, None)
+    L.check(ctx.lib.hm_bn_stats(y.data_ptr(), N, H * W, Cc, float(eps), ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                _ptr(gamma), _ptr(beta), mo.data_ptr(), ro.data_ptr(), _ptr(rm), _ptr(rv), _ptr(nbt),
+                                float(momentum), int(repeat), _stream()), "hm_bn_stats")
+    ctx.launches += 2
+    return mean, rstd, mo, ro
+
+
 def upsample2_add(ctx, small, deep, out):
     N, h, w, Cc = small.shape
     assert tuple(deep.shape) == (N, 2 * h, 2 * w, Cc) == tuple(out.shape)
